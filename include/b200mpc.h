@@ -1,0 +1,154 @@
+/*
+ * b200mpc.h — C ABI of libb200mpc.so: batched nonlinear-MPC solve on B200 (sm_100a), FP64.
+ *
+ * Drop-in boundary for the per-control-step solve of nitesh-subedi/ros2_mpc.  Each entry point names the
+ * reference interface it replaces (paths under the reference repository):
+ *
+ *   b200mpc_create        <- Mpc.__init__            ros2_mpc/planner/local_planner_point_stabilization.py:12-57
+ *                                                    ros2_mpc/mpc_point_stabilization.py:10-44
+ *                                                    ros2_mpc/planner/local_planner_tracking.py:12-53
+ *                            (casadi.Opti problem construction + opti.solver("ipopt", opts))
+ *   b200mpc_solve_batch   <- Mpc.perform_mpc         local_planner_point_stabilization.py:69-87,
+ *                                                    mpc_point_stabilization.py:55-68, local_planner_tracking.py:65-80
+ *                            (opti.set_initial / set_value / solve / sol.value), batched over independent problems
+ *   b200mpc_solve_batch_device  same, caller-owned device buffers, asynchronous on a CUDA stream
+ *   b200mpc_eval_batch    <- the NLP functions CasADi evaluates inside opti.solve():
+ *                            rk4 :136-148, euler_integration (tracking) :132-137, define_cost_function :104-127,
+ *                            define_obstacles_cost_function (mpc_point_stabilization.py:46-53)
+ *   b200mpc_destroy       <- garbage collection of the Mpc / Opti object
+ *
+ * Conventions: plain pointers and sizes only; no C++ exceptions cross the boundary; functions return 0 on
+ * success and a negative B200MPC_E_* code otherwise (text via b200mpc_last_error).  Per-problem solver outcomes
+ * are reported in status_out with IPOPT's ApplicationReturnStatus values (the reference raises RuntimeError from
+ * opti.solve() for any status other than Solve_Succeeded / Solved_To_Acceptable_Level).
+ * A handle is bound to one device and is not thread-safe (one handle per thread and device), matching the
+ * reference's one-Mpc-per-process usage.  There is no CPU fallback: every entry point fails if no CUDA device
+ * is available.
+ *
+ * Layouts (all FP64, problem-major, "stage-major" inside a problem):
+ *   x0      [B][3]                 initial state (x, y, theta)                       = P[0:3]
+ *   xref    [B][3]   (ref_kind 0)  goal state                                        = P[3:6]
+ *           [B][3N]  (ref_kind 1)  state reference ref_1..ref_N                      = P_X[3:]
+ *   uref    [B][2N]  (ref_kind 1)  control reference, NULL otherwise                 = P_U
+ *   obs_x/y [B][M] with obs_stride = M, or one shared list [M] with obs_stride = 0   = obstacles_x / obstacles_y
+ *   u_init  [B][N][2] or NULL (= zeros)      the u0 argument of perform_mpc (casadi shape (2,N), column-major)
+ *   X_out   [B][N+1][3]   predicted states, X_out[b][0] == x0[b]      (sol.value(X) is its transpose, (3,N+1))
+ *   U_out   [B][N][2]     optimal controls                            (sol.value(U) is its transpose, (2,N))
+ *   cost_out[B]           objective value at the returned point
+ *   status_out[B], iters_out[B] (accepted interior-point iterations), ls_out[B] (extra line-search trial evaluations)
+ */
+#ifndef B200MPC_H
+#define B200MPC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MPC_ABI_VERSION 1
+#define B200MPC_MAX_N 127 /* horizon limit of the warp-per-problem kernel (4 stages per lane) */
+#define B200MPC_MAX_M 1024 /* obstacle slots staged in shared memory per problem */
+
+/* integrator */
+#define B200MPC_RK4 0
+#define B200MPC_EULER 1
+/* obstacle cost form */
+#define B200MPC_OBS_NONE 0
+#define B200MPC_OBS_GAUSS 1  /* c*exp(-s),  s = ((x-ox)^2+(y-oy)^2)/r^2 */
+#define B200MPC_OBS_EXPLOG 2 /* exp(c/s) = exp(c*exp(-log(s))) */
+/* reference kind */
+#define B200MPC_REF_GOAL 0
+#define B200MPC_REF_TRAJ 1
+
+/* per-problem status: IPOPT ApplicationReturnStatus */
+#define B200MPC_SOLVE_SUCCEEDED 0
+#define B200MPC_SOLVED_TO_ACCEPTABLE_LEVEL 1
+#define B200MPC_MAXITER_EXCEEDED (-1)
+#define B200MPC_RESTORATION_FAILED (-2)
+#define B200MPC_ERROR_IN_STEP_COMPUTATION (-3)
+#define B200MPC_INVALID_NUMBER_DETECTED (-13)
+
+/* library error codes */
+#define B200MPC_E_ARG (-1)
+#define B200MPC_E_CUDA (-2)
+#define B200MPC_E_NODEVICE (-3)
+#define B200MPC_E_NOMEM (-4)
+
+typedef struct b200mpc_params {
+    int32_t N;          /* horizon, params.yaml "N" */
+    int32_t M;          /* obstacle slots: int(costmap_size*2/resolution)*2 */
+    double dt;          /* params.yaml "dt" */
+    int32_t integrator; /* B200MPC_RK4 | B200MPC_EULER */
+    int32_t ref_kind;   /* B200MPC_REF_GOAL | B200MPC_REF_TRAJ */
+    double Q[3];        /* diagonal state weights */
+    double R[2];        /* diagonal control weights */
+    double kappa;       /* exponent of the reverse penalty (1/exp(v))**kappa */
+    int32_t obs_form;   /* B200MPC_OBS_* */
+    int32_t obs_k0;     /* first stage carrying the obstacle sum */
+    int32_t obs_k1;     /* last stage carrying the obstacle sum (inclusive) */
+    int32_t max_iter;   /* ipopt max_iter (3000) */
+    double obs_c;       /* obstacle cost factor */
+    double obs_r;       /* inflation radius */
+    double u_lo[2];     /* lower bounds on (v, omega) */
+    double u_hi[2];     /* upper bounds on (v, omega) */
+    double tol;             /* ipopt tol (1e-8) */
+    double acceptable_tol;  /* 1e-6 */
+    double mu_init;         /* 0.1 */
+    int32_t acceptable_iter; /* 15 */
+    int32_t max_soc;         /* 4 */
+} b200mpc_params;
+
+typedef struct b200mpc_handle b200mpc_handle;
+
+/* Fills the solver options with IPOPT's defaults (tol, max_iter, acceptable_*, mu_init, max_soc). */
+void b200mpc_default_options(b200mpc_params *p);
+
+/* Creates a solver bound to CUDA device `device`.  Returns NULL on failure (see b200mpc_last_error(NULL)). */
+b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device);
+void b200mpc_destroy(b200mpc_handle *h);
+
+/* Last error text of the handle (or of the last failed b200mpc_create when h == NULL). */
+const char *b200mpc_last_error(const b200mpc_handle *h);
+
+/* Host-buffer solve: copies inputs host->device, runs the solve kernel, copies results back, blocks until done.
+ * Any of cost_out / iters_out / ls_out may be NULL. */
+int b200mpc_solve_batch(b200mpc_handle *h, int B, const double *x0, const double *xref, const double *uref,
+                        const double *obs_x, const double *obs_y, int obs_stride, const double *u_init,
+                        double *X_out, double *U_out, double *cost_out, int32_t *status_out, int32_t *iters_out,
+                        int32_t *ls_out);
+
+/* Device-buffer solve: every pointer is a device pointer on the handle's device; the kernel is enqueued on
+ * `stream` (a cudaStream_t passed as void*, NULL = the legacy default stream) and the call returns without
+ * synchronising.  Same NULL rules as above. */
+int b200mpc_solve_batch_device(b200mpc_handle *h, int B, const double *x0, const double *xref, const double *uref,
+                               const double *obs_x, const double *obs_y, int obs_stride, const double *u_init,
+                               double *X_out, double *U_out, double *cost_out, int32_t *status_out,
+                               int32_t *iters_out, int32_t *ls_out, void *stream);
+
+/* NLP function evaluation at given points (host buffers, blocking): for each problem b, X[b][N+1][3] (X[b][0]
+ * must equal x0[b]), U[b][N][2], lam[b][N][3] (multipliers of c_k = X_k - F(X_{k-1},U_{k-1}), k = 1..N; NULL = 0):
+ *   f_out[B]              objective
+ *   c_out[B][N][3]        shooting defects
+ *   grad_out[B][5N]       objective gradient w.r.t. (X_1..X_N, U_0..U_{N-1})
+ *   stage_out[B][N+1][36] per stage: a13,a23,b11,b12,b21,b22, Lagrangian Hessian 5x5 row-major on
+ *                         (x,y,theta,v,omega), c_{k+1}[3], 2 pad.
+ * Any output pointer may be NULL. */
+int b200mpc_eval_batch(b200mpc_handle *h, int B, const double *x0, const double *xref, const double *uref,
+                       const double *obs_x, const double *obs_y, int obs_stride, const double *X,
+                       const double *U, const double *lam, double obj_scale, double *f_out, double *c_out,
+                       double *grad_out, double *stage_out);
+
+/* Number of kernel launches issued by this handle so far (bench.py reports it as gpu_launches). */
+long long b200mpc_launch_count(const b200mpc_handle *h);
+/* Device time [ms] of the most recent solve kernel measured with CUDA events on its own stream
+ * (valid after the stream has been synchronised; host-buffer solves synchronise themselves). */
+float b200mpc_last_kernel_ms(b200mpc_handle *h);
+
+int b200mpc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

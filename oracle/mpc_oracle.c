@@ -752,19 +752,27 @@ void orc_default_options(orc_params *p) {
 #define DW_INC_FIRST 100.0
 #define DW_INC 8.0
 #define DW_DEC (1.0 / 3.0)
-#define MAX_FILTER 64
+#define MAX_FILTER 32
 #define OBJ_MAX_INC 5.0
 #define MAX_RESTO 20
 
+/* Filter: MAX_FILTER slots (phi, theta, valid).  A new entry evicts the entries it dominates and takes the
+ * lowest free slot; when every slot is taken it overwrites slot (ring++ % MAX_FILTER). */
 typedef struct {
     double phi[MAX_FILTER], theta[MAX_FILTER];
-    int n;
+    int valid[MAX_FILTER];
+    int ring;
 } filter_t;
 
 static int cmp_le(double lhs, double rhs, double bas) { return lhs - rhs <= 10.0 * DBL_EPSILON * fabs(bas); }
 
+static void filter_reset(filter_t *f) {
+    for (int i = 0; i < MAX_FILTER; i++) f->valid[i] = 0;
+}
+
 static int filter_acceptable(const filter_t *f, double phi, double theta) {
-    for (int i = 0; i < f->n; i++) {
+    for (int i = 0; i < MAX_FILTER; i++) {
+        if (!f->valid[i]) continue;
         int ok = cmp_le(phi, f->phi[i], f->phi[i]) || cmp_le(theta, f->theta[i], f->theta[i]);
         if (!ok) return 0;
     }
@@ -772,21 +780,15 @@ static int filter_acceptable(const filter_t *f, double phi, double theta) {
 }
 
 static void filter_add(filter_t *f, double phi, double theta) {
-    int m = 0;
-    for (int i = 0; i < f->n; i++) {
-        if (f->phi[i] >= phi && f->theta[i] >= theta) continue; /* dominated by the new entry */
-        f->phi[m] = f->phi[i];
-        f->theta[m] = f->theta[i];
-        m++;
+    int slot = -1;
+    for (int i = 0; i < MAX_FILTER; i++) {
+        if (f->valid[i] && f->phi[i] >= phi && f->theta[i] >= theta) f->valid[i] = 0; /* dominated */
+        if (!f->valid[i] && slot < 0) slot = i;
     }
-    if (m == MAX_FILTER) { /* overflow: drop the oldest */
-        memmove(f->phi, f->phi + 1, sizeof(double) * (MAX_FILTER - 1));
-        memmove(f->theta, f->theta + 1, sizeof(double) * (MAX_FILTER - 1));
-        m--;
-    }
-    f->phi[m] = phi;
-    f->theta[m] = theta;
-    f->n = m + 1;
+    if (slot < 0) slot = (f->ring++) % MAX_FILTER;
+    f->phi[slot] = phi;
+    f->theta[slot] = theta;
+    f->valid[slot] = 1;
 }
 
 /* line-search reference values of the current iterate */
@@ -944,7 +946,8 @@ int orc_solve(const orc_params *p, const double *x0, const double *xref, const d
     double mu = p->mu_init, tau = fmax(TAU_MIN, 1.0 - mu);
     const double mu_floor = fmin(p->tol, 1e-4) / (K_EPS + 1.0);
     filter_t filt;
-    filt.n = 0;
+    filt.ring = 0;
+    filter_reset(&filt);
     double theta_max = -1, theta_min = -1;
     double dw_last = 0.0;
     int acceptable_count = 0;
@@ -1035,7 +1038,7 @@ int orc_solve(const orc_params *p, const double *x0, const double *xref, const d
             if (nm == mu) break;
             mu = nm;
             tau = fmax(TAU_MIN, 1.0 - mu);
-            filt.n = 0;
+            filter_reset(&filt);
         }
 
         /* ---- search direction with inertia correction (PDPerturbationHandler, delta_x = delta_s) ---- */

@@ -1,0 +1,184 @@
+"""ctypes binding of libb200mpc.so (include/b200mpc.h).  Thin: argument marshalling only.
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is present, construction fails with
+a RuntimeError naming the cause."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200mpc.so")
+_LIB = None
+
+RK4, EULER = 0, 1
+OBS_NONE, OBS_GAUSS, OBS_EXPLOG = 0, 1, 2
+REF_GOAL, REF_TRAJ = 0, 1
+
+STATUS_NAMES = {
+    0: "Solve_Succeeded", 1: "Solved_To_Acceptable_Level", -1: "Maximum_Iterations_Exceeded",
+    -2: "Restoration_Failed", -3: "Error_In_Step_Computation", -13: "Invalid_Number_Detected",
+}
+SUCCESS_STATUSES = (0, 1)  # CasADi's return_success(): Solve_Succeeded, Solved_To_Acceptable_Level
+
+
+class Params(C.Structure):
+    """struct b200mpc_params"""
+    _fields_ = [
+        ("N", C.c_int32), ("M", C.c_int32), ("dt", C.c_double), ("integrator", C.c_int32), ("ref_kind", C.c_int32),
+        ("Q", C.c_double * 3), ("R", C.c_double * 2), ("kappa", C.c_double),
+        ("obs_form", C.c_int32), ("obs_k0", C.c_int32), ("obs_k1", C.c_int32), ("max_iter", C.c_int32),
+        ("obs_c", C.c_double), ("obs_r", C.c_double), ("u_lo", C.c_double * 2), ("u_hi", C.c_double * 2),
+        ("tol", C.c_double), ("acceptable_tol", C.c_double), ("mu_init", C.c_double),
+        ("acceptable_iter", C.c_int32), ("max_soc", C.c_int32),
+    ]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  ros2_mpc_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p
+        L.b200mpc_abi_version.restype = C.c_int
+        L.b200mpc_default_options.argtypes = [C.POINTER(Params)]
+        L.b200mpc_default_options.restype = None
+        L.b200mpc_create.argtypes = [C.POINTER(Params), C.c_int]
+        L.b200mpc_create.restype = vp
+        L.b200mpc_destroy.argtypes = [vp]
+        L.b200mpc_destroy.restype = None
+        L.b200mpc_last_error.argtypes = [vp]
+        L.b200mpc_last_error.restype = C.c_char_p
+        L.b200mpc_solve_batch.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, C.c_int, dp, dp, dp, dp, ip, ip, ip]
+        L.b200mpc_solve_batch.restype = C.c_int
+        # device entry point: raw addresses
+        L.b200mpc_solve_batch_device.argtypes = [vp, C.c_int] + [vp] * 5 + [C.c_int] + [vp] * 7 + [vp]
+        L.b200mpc_solve_batch_device.restype = C.c_int
+        L.b200mpc_eval_batch.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, C.c_int, dp, dp, dp, C.c_double,
+                                         dp, dp, dp, dp]
+        L.b200mpc_eval_batch.restype = C.c_int
+        L.b200mpc_launch_count.argtypes = [vp]
+        L.b200mpc_launch_count.restype = C.c_longlong
+        L.b200mpc_last_kernel_ms.argtypes = [vp]
+        L.b200mpc_last_kernel_ms.restype = C.c_float
+        _LIB = L
+    return _LIB
+
+
+def default_params():
+    p = Params()
+    lib().b200mpc_default_options(C.byref(p))
+    return p
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _f64(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class Solver:
+    """Owns one b200mpc_handle (one CUDA device)."""
+
+    def __init__(self, params, device=0):
+        self._L = lib()
+        self.params = params
+        self._h = self._L.b200mpc_create(C.byref(params), int(device))
+        if not self._h:
+            raise RuntimeError("b200mpc_create failed: " + self._L.b200mpc_last_error(None).decode())
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200mpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"b200mpc error {rc}: " + self._L.b200mpc_last_error(self._h).decode())
+
+    @property
+    def launch_count(self):
+        return int(self._L.b200mpc_launch_count(self._h))
+
+    def last_kernel_ms(self):
+        return float(self._L.b200mpc_last_kernel_ms(self._h))
+
+    def solve_batch(self, x0, xref, uref=None, obs_x=None, obs_y=None, u_init=None, out=None):
+        """Host-buffer solve.  x0 (B,3); xref (B,3)|(B,3N); uref (B,2N); obs_x/obs_y (B,M) or (M,) shared;
+        u_init (B,N,2).  Returns dict X (B,N+1,3), U (B,N,2), cost, status, iters, ls."""
+        p = self.params
+        N = p.N
+        x0 = _f64(x0)
+        B = x0.shape[0] if x0.ndim == 2 else 1
+        x0 = x0.reshape(B, 3)
+        nref = 3 if p.ref_kind == REF_GOAL else 3 * N
+        xref = _f64(xref, (B, nref))
+        uref = _f64(uref, (B, 2 * N)) if uref is not None else None
+        stride = 0
+        if obs_x is not None:
+            obs_x, obs_y = _f64(obs_x), _f64(obs_y)
+            if obs_x.shape[-1] != p.M or obs_y.shape != obs_x.shape:
+                raise ValueError(f"obstacle lists must have {p.M} slots")
+            stride = 0 if obs_x.ndim == 1 else p.M
+            if obs_x.ndim == 2 and obs_x.shape[0] != B:
+                raise ValueError("obstacle lists: batch size mismatch")
+        u_init = _f64(u_init, (B, N, 2)) if u_init is not None else None
+        if out is None:
+            out = dict(X=np.empty((B, N + 1, 3)), U=np.empty((B, N, 2)), cost=np.empty(B),
+                       status=np.empty(B, np.int32), iters=np.empty(B, np.int32), ls=np.empty(B, np.int32))
+        rc = self._L.b200mpc_solve_batch(self._h, B, _dp(x0), _dp(xref), _dp(uref), _dp(obs_x), _dp(obs_y), stride,
+                                         _dp(u_init), _dp(out["X"]), _dp(out["U"]), _dp(out["cost"]),
+                                         _ip(out["status"]), _ip(out["iters"]), _ip(out["ls"]))
+        self._check(rc)
+        return out
+
+    def solve_batch_device(self, B, x0, xref, uref, obs_x, obs_y, obs_stride, u_init, X, U, cost, status, iters, ls,
+                           stream=0):
+        """Device-buffer solve: every argument is a raw device address (int, 0 = NULL); asynchronous on `stream`."""
+        v = lambda a: C.c_void_p(int(a) if a else None)  # noqa: E731
+        rc = self._L.b200mpc_solve_batch_device(self._h, int(B), v(x0), v(xref), v(uref), v(obs_x), v(obs_y),
+                                                int(obs_stride), v(u_init), v(X), v(U), v(cost), v(status),
+                                                v(iters), v(ls), v(stream))
+        self._check(rc)
+
+    def eval_batch(self, x0, xref, X, U, uref=None, obs_x=None, obs_y=None, lam=None, obj_scale=1.0):
+        """NLP functions at given points.  X (B,N+1,3), U (B,N,2), lam (B,N,3)."""
+        p = self.params
+        N = p.N
+        x0 = _f64(x0)
+        B = x0.shape[0]
+        nref = 3 if p.ref_kind == REF_GOAL else 3 * N
+        xref = _f64(xref, (B, nref))
+        uref = _f64(uref, (B, 2 * N)) if uref is not None else None
+        stride = 0
+        if obs_x is not None:
+            obs_x, obs_y = _f64(obs_x), _f64(obs_y)
+            stride = 0 if obs_x.ndim == 1 else p.M
+        X, U = _f64(X, (B, N + 1, 3)), _f64(U, (B, N, 2))
+        lam = _f64(lam, (B, N, 3)) if lam is not None else None
+        f = np.empty(B); c = np.empty((B, N, 3)); g = np.empty((B, 5 * N)); st = np.empty((B, N + 1, 36))
+        rc = self._L.b200mpc_eval_batch(self._h, B, _dp(x0), _dp(xref), _dp(uref), _dp(obs_x), _dp(obs_y), stride,
+                                        _dp(X), _dp(U), _dp(lam), float(obj_scale), _dp(f), _dp(c), _dp(g), _dp(st))
+        self._check(rc)
+        return dict(f=f, c=c, grad=g, stages=st)

@@ -1,0 +1,1477 @@
+// b200mpc.cu — batched nonlinear-MPC solve for B200 (sm_100a), FP64, one warp per problem.
+//
+// Replaces the CasADi/IPOPT call stack behind ros2_mpc's Mpc.perform_mpc
+// (ros2_mpc/planner/local_planner_point_stabilization.py:69-87 and its two sibling variants):
+//   K1 multiple-shooting transcription (rk4 :136-148 / euler_integration local_planner_tracking.py:132-137)
+//   K2 unicycle RK4 step with analytic first and second derivatives (get_system_function :159-178)
+//   K3 obstacle-cost value / gradient / Hessian over the obstacle list staged in shared memory
+//      (define_obstacles_cost_function mpc_point_stabilization.py:46-53, local_planner_point_stabilization.py:60-67)
+//   K4 primal-dual interior-point Newton iteration (what opti.solve() :84 runs inside IPOPT): stage-wise KKT
+//      assembly, Riccati factorisation, fraction-to-the-boundary rule, filter line search with second-order
+//      correction, inertia correction, monotone barrier update.
+//
+// Mapping: stage k of the horizon lives in lane k / J, slot k % J (J = ceil((N+1)/32) stages per lane), all
+// per-stage quantities in registers.  Stage-parallel work (dynamics, cost, obstacle sums, residuals, trial
+// points) runs on all lanes; norms and merit values are butterfly-shuffle reductions (bitwise identical on
+// every lane, so all control flow is warp-uniform); the Riccati backward/forward recursions walk the lanes
+// serially, broadcasting the 3x3 cost-to-go with shuffles.  Warps pull problems from a global counter, so a
+// slow problem only delays its own warp.  No tensor cores: the blocks are 3x3 / 3x2.
+//
+// The algorithm and every constant are the same as in oracle/mpc_oracle.c (the CPU checker); the two share no code.
+#include "b200mpc.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+
+#define FULL 0xffffffffu
+
+// ---- IPOPT defaults (Waechter & Biegler 2006; IPOPT option documentation) -------------------------------
+#define K_EPS 10.0
+#define K_MU 0.2
+#define TH_MU 1.5
+#define TAU_MIN 0.99
+#define S_MAX 100.0
+#define GAMMA_THETA 1e-5
+#define GAMMA_PHI 1e-8
+#define ETA_PHI 1e-8
+#define S_THETA 1.1
+#define S_PHI 2.3
+#define DELTA_LS 1.0
+#define ALPHA_MIN_FRAC 0.05
+#define KAPPA_SOC 0.99
+#define KAPPA_SIGMA 1e10
+#define BOUND_PUSH 0.01
+#define BOUND_FRAC 0.01
+#define BOUND_RELAX 1e-8
+#define DW_INIT 1e-4
+#define DW_MIN 1e-20
+#define DW_MAX 1e20
+#define DW_INC_FIRST 100.0
+#define DW_INC 8.0
+#define DW_DEC (1.0 / 3.0)
+#define OBJ_MAX_INC 5.0
+#define MAX_RESTO 20
+#define DBL_EPS 2.220446049250313e-16
+
+struct KParams {
+    int N, M, integrator, ref_kind, obs_form, obs_k0, obs_k1, max_iter, acceptable_iter, max_soc;
+    double dt, Q[3], R[2], kappa, obs_c, obs_r, u_lo[2], u_hi[2], tol, acceptable_tol, mu_init;
+    double sL[2], sU[2], inv_r2, mu_floor;
+};
+
+struct BatchArgs {
+    int B, obs_stride;
+    const double *x0, *xref, *uref, *ox, *oy, *u_init;
+    double *X, *U, *cost;
+    int *status, *iters, *ls;
+    unsigned int *counter;
+};
+
+struct EvalArgs {
+    int B, obs_stride;
+    const double *x0, *xref, *uref, *ox, *oy, *X, *U, *lam;
+    double obj_scale;
+    double *f, *c, *grad, *stage;
+};
+
+// ---- warp reductions (butterfly: every lane ends with the same bits) ------------------------------------
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double wmax(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double wmin(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ int wor(int v) { return __any_sync(FULL, v); }
+
+__device__ __forceinline__ bool cmp_le(double lhs, double rhs, double bas) {
+    return lhs - rhs <= 10.0 * DBL_EPS * fabs(bas);
+}
+
+// ---- K3: obstacle sum at one predicted position ---------------------------------------------------------
+// ox/oy are the problem's obstacle list staged in shared memory (all lanes read the same address: broadcast).
+template <bool DERIV>
+__device__ __forceinline__ void obstacle_sum(const KParams &P, const double *__restrict__ sox,
+                                             const double *__restrict__ soy, double x, double y, double &val,
+                                             double &gx, double &gy, double &hxx, double &hxy, double &hyy) {
+    const double ir2 = P.inv_r2, c = P.obs_c;
+    double v = 0, ax = 0, ay = 0, bxx = 0, bxy = 0, byy = 0;
+    if (P.obs_form == B200MPC_OBS_EXPLOG) {
+#pragma unroll 2
+        for (int j = 0; j < P.M; j++) {
+            double dx = x - sox[j], dy = y - soy[j];
+            double s = (dx * dx + dy * dy) * ir2;
+            double is = 1.0 / s;
+            double q = c * is;
+            double e = exp(q);
+            v += e;
+            if (DERIV) {
+                double t = q * is;          // c / s^2
+                double p1 = -t * e;         // phi'
+                double p2 = t * (2.0 * is + t) * e; // phi'' = c(2s+c)/s^4 * e
+                double sx = 2.0 * dx * ir2, sy = 2.0 * dy * ir2;
+                ax += p1 * sx;
+                ay += p1 * sy;
+                bxx += p2 * sx * sx + p1 * 2.0 * ir2;
+                bxy += p2 * sx * sy;
+                byy += p2 * sy * sy + p1 * 2.0 * ir2;
+            }
+        }
+    } else {
+#pragma unroll 2
+        for (int j = 0; j < P.M; j++) {
+            double dx = x - sox[j], dy = y - soy[j];
+            double s = (dx * dx + dy * dy) * ir2;
+            double e = c * exp(-s);
+            v += e;
+            if (DERIV) {
+                double sx = 2.0 * dx * ir2, sy = 2.0 * dy * ir2;
+                ax -= e * sx;
+                ay -= e * sy;
+                bxx += e * sx * sx - e * 2.0 * ir2;
+                bxy += e * sx * sy;
+                byy += e * sy * sy - e * 2.0 * ir2;
+            }
+        }
+    }
+    val = v;
+    if (DERIV) { gx = ax; gy = ay; hxx = bxx; hxy = bxy; hyy = byy; }
+}
+
+// ---- per-stage register state ----------------------------------------------------------------------------
+struct Step {
+    double dX[3], dU[2], dS[2], dlam[3], dyd[2];
+};
+
+struct Stg {
+    // iterate
+    double X[3], U[2], S[2], lam[3], yd[2], vL[2], vU[2];
+    // references
+    double r[3], ub[2];
+    // K2 stage derivatives: A = I + a13 e1e3' + a23 e2e3',  B = [[b11,b12],[b21,b22],[0,dt]]
+    double a13, a23, b11, b12, b21, b22;
+    // Lagrangian Hessian nonzeros on (x,y,th,v,w)
+    double hxx, hxy, hyy, htt, htv, htw, hvv, hvw, hww;
+    double g[5];  // scaled objective gradient
+    double c[3];  // c_{k+1} = X_{k+1} - F(X_k,U_k)
+    double rx[3], ru[2]; // grad_lag_x
+    double Dsig[2], rs[2];
+    // Riccati factors
+    double K[6], kf[2], P[6], pv[3];
+    // trial point
+    double Xt[3], Ut[2], St[2], ct[3];
+};
+
+// K1+K2: value of the integration step F(x,u) (closed form of the staged RK4, identical to k1..k4 of rk4())
+__device__ __forceinline__ void dyn_value(const KParams &P, const double X[3], const double U[2], double F[3]) {
+    const double dt = P.dt, th = X[2], v = U[0], w = U[1];
+    if (P.integrator == B200MPC_EULER) {
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        F[0] = X[0] + dt * v * cs;
+        F[1] = X[1] + dt * v * sn;
+        F[2] = th + dt * w;
+    } else {
+        double s0, c0, sm, cm, se, ce;
+        sincos(th, &s0, &c0);
+        sincos(th + 0.5 * dt * w, &sm, &cm);
+        sincos(th + dt * w, &se, &ce);
+        const double h = dt / 6.0;
+        F[0] = X[0] + h * v * (c0 + 4.0 * cm + ce);
+        F[1] = X[1] + h * v * (s0 + 4.0 * sm + se);
+        F[2] = th + dt * w;
+    }
+}
+
+// Full stage evaluation: defect, Jacobian entries, objective gradient, Lagrangian Hessian, stage cost.
+// act: stage exists (k <= N); dyn: stage has controls and a successor (k < N); obs: obstacle sum on this stage.
+__device__ __forceinline__ double stage_full(const KParams &P, const double *sox, const double *soy, Stg &s,
+                                             const double Xn[3], const double ln[3], double df, bool act,
+                                             bool dyn, bool obs) {
+    double fval = 0;
+    s.a13 = s.a23 = s.b11 = s.b12 = s.b21 = s.b22 = 0;
+    s.hxx = s.hxy = s.hyy = s.htt = s.htv = s.htw = s.hvv = s.hvw = s.hww = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) s.g[i] = 0;
+    s.c[0] = s.c[1] = s.c[2] = 0;
+    if (dyn) {
+        const double dt = P.dt, th = s.X[2], v = s.U[0], w = s.U[1];
+        double F0, F1, d2x[6], d2y[6];
+        if (P.integrator == B200MPC_EULER) {
+            double sn, cs;
+            sincos(th, &sn, &cs);
+            F0 = s.X[0] + dt * v * cs;
+            F1 = s.X[1] + dt * v * sn;
+            s.a13 = -dt * v * sn; s.a23 = dt * v * cs;
+            s.b11 = dt * cs; s.b21 = dt * sn;
+            d2x[0] = -dt * v * cs; d2x[1] = -dt * sn; d2x[2] = d2x[3] = d2x[4] = d2x[5] = 0;
+            d2y[0] = -dt * v * sn; d2y[1] = dt * cs; d2y[2] = d2y[3] = d2y[4] = d2y[5] = 0;
+        } else {
+            double s0, c0, sm, cm, se, ce;
+            sincos(th, &s0, &c0);
+            sincos(th + 0.5 * dt * w, &sm, &cm);
+            sincos(th + dt * w, &se, &ce);
+            const double h = dt / 6.0;
+            const double C = c0 + 4.0 * cm + ce, S = s0 + 4.0 * sm + se;
+            const double C1 = 2.0 * cm + ce, S1 = 2.0 * sm + se, C2 = cm + ce, S2 = sm + se;
+            F0 = s.X[0] + h * v * C;
+            F1 = s.X[1] + h * v * S;
+            s.a13 = -h * v * S; s.a23 = h * v * C;
+            s.b11 = h * C; s.b21 = h * S;
+            s.b12 = -h * dt * v * S1; s.b22 = h * dt * v * C1;
+            d2x[0] = -h * v * C;        d2y[0] = -h * v * S;
+            d2x[1] = -h * S;            d2y[1] = h * C;
+            d2x[2] = -h * dt * v * C1;  d2y[2] = -h * dt * v * S1;
+            d2x[3] = 0;                 d2y[3] = 0;
+            d2x[4] = -h * dt * S1;      d2y[4] = h * dt * C1;
+            d2x[5] = -h * dt * dt * v * C2; d2y[5] = -h * dt * dt * v * S2;
+        }
+        s.c[0] = Xn[0] - F0;
+        s.c[1] = Xn[1] - F1;
+        s.c[2] = Xn[2] - (th + dt * w);
+        // stage cost (define_cost_function): tracking + control + reverse penalty
+        const double e0 = s.X[0] - s.r[0], e1 = s.X[1] - s.r[1], e2 = s.X[2] - s.r[2];
+        const double m0 = v - s.ub[0], m1 = w - s.ub[1];
+        const double er = exp(-P.kappa * v);
+        fval = e0 * P.Q[0] * e0 + e1 * P.Q[1] * e1 + e2 * P.Q[2] * e2 + m0 * P.R[0] * m0 + m1 * P.R[1] * m1 + er;
+        s.g[0] = df * 2.0 * P.Q[0] * e0;
+        s.g[1] = df * 2.0 * P.Q[1] * e1;
+        s.g[2] = df * 2.0 * P.Q[2] * e2;
+        s.g[3] = df * (2.0 * P.R[0] * m0 - P.kappa * er);
+        s.g[4] = df * 2.0 * P.R[1] * m1;
+        s.hxx = df * 2.0 * P.Q[0];
+        s.hyy = df * 2.0 * P.Q[1];
+        s.htt = df * 2.0 * P.Q[2] - (ln[0] * d2x[0] + ln[1] * d2y[0]);
+        s.htv = -(ln[0] * d2x[1] + ln[1] * d2y[1]);
+        s.htw = -(ln[0] * d2x[2] + ln[1] * d2y[2]);
+        s.hvv = df * (2.0 * P.R[0] + P.kappa * P.kappa * er) - (ln[0] * d2x[3] + ln[1] * d2y[3]);
+        s.hvw = -(ln[0] * d2x[4] + ln[1] * d2y[4]);
+        s.hww = df * 2.0 * P.R[1] - (ln[0] * d2x[5] + ln[1] * d2y[5]);
+    }
+    if (obs && act) {
+        double ov, gx, gy, oxx, oxy, oyy;
+        obstacle_sum<true>(P, sox, soy, s.X[0], s.X[1], ov, gx, gy, oxx, oxy, oyy);
+        fval += ov;
+        s.g[0] += df * gx;
+        s.g[1] += df * gy;
+        s.hxx += df * oxx;
+        s.hxy += df * oxy;
+        s.hyy += df * oyy;
+    }
+    return fval;
+}
+
+// Value-only evaluation of a trial stage: defect (3) and stage cost.
+__device__ __forceinline__ double stage_value(const KParams &P, const double *sox, const double *soy,
+                                              const double X[3], const double U[2], const double r[3],
+                                              const double ub[2], const double Xn[3], double ct[3], bool act,
+                                              bool dyn, bool obs) {
+    double fval = 0;
+    ct[0] = ct[1] = ct[2] = 0;
+    if (dyn) {
+        double F[3];
+        dyn_value(P, X, U, F);
+        ct[0] = Xn[0] - F[0];
+        ct[1] = Xn[1] - F[1];
+        ct[2] = Xn[2] - F[2];
+        const double e0 = X[0] - r[0], e1 = X[1] - r[1], e2 = X[2] - r[2];
+        const double m0 = U[0] - ub[0], m1 = U[1] - ub[1];
+        fval = e0 * P.Q[0] * e0 + e1 * P.Q[1] * e1 + e2 * P.Q[2] * e2 + m0 * P.R[0] * m0 + m1 * P.R[1] * m1 +
+               exp(-P.kappa * U[0]);
+    }
+    if (obs && act) {
+        double ov, d0, d1, d2, d3, d4;
+        obstacle_sum<false>(P, sox, soy, X[0], X[1], ov, d0, d1, d2, d3, d4);
+        fval += ov;
+    }
+    return fval;
+}
+
+// value of the next stage (k+1) for slot j: same lane if j+1 < J, else slot 0 of lane+1
+#define NEXT3(dst, field, j)                                                               \
+    do {                                                                                   \
+        if ((j) + 1 < J) {                                                                 \
+            dst[0] = s[((j) + 1 < J) ? (j) + 1 : 0].field[0];                              \
+            dst[1] = s[((j) + 1 < J) ? (j) + 1 : 0].field[1];                              \
+            dst[2] = s[((j) + 1 < J) ? (j) + 1 : 0].field[2];                              \
+        } else {                                                                           \
+            dst[0] = __shfl_down_sync(FULL, s[0].field[0], 1);                             \
+            dst[1] = __shfl_down_sync(FULL, s[0].field[1], 1);                             \
+            dst[2] = __shfl_down_sync(FULL, s[0].field[2], 1);                             \
+        }                                                                                  \
+    } while (0)
+
+// ---- K4: Riccati solve of the condensed stage-wise KKT system --------------------------------------------
+// Solves (IPOPT augmented system with ds, dyd eliminated stage-locally):
+//   (useW*W + dw) dx + Jc' dyc + Jd' dyd = -rx,  Dsig ds - dyd = -rs,  Jc dx = -rc,  Jd dx - ds = -rd
+// rc[j] = defect rhs of c_{k+1} held with stage k, rd[j] = rhs of U_k - S_k.
+// Returns false when a condensed Quu block is not positive definite (wrong inertia).
+template <int J>
+__device__ __forceinline__ bool kkt_solve(const KParams &P, Stg (&s)[J], const double (&rc)[J][3],
+                                          const double (&rd)[J][2], bool useW, double dw, Step (&o)[J],
+                                          int lane) {
+    const int N = P.N;
+    const double dt = P.dt;
+    const int lN = N / J;
+    double P00 = 0, P01 = 0, P02 = 0, P11 = 0, P12 = 0, P22 = 0, p0 = 0, p1 = 0, p2 = 0;
+    int okall = 1;
+    for (int l = lN; l >= 0; --l) {
+        double q00 = P00, q01 = P01, q02 = P02, q11 = P11, q12 = P12, q22 = P22, v0 = p0, v1 = p1, v2 = p2;
+        int ok = 1;
+        const bool mine = (lane == l);
+#pragma unroll
+        for (int j = J - 1; j >= 0; --j) {
+            const int ko = l * J + j; // stage of the owner lane (uniform)
+            if (ko > N) continue;
+            Stg &t = s[j];
+            const double hxx = useW ? t.hxx : 0.0, hxy = useW ? t.hxy : 0.0, hyy = useW ? t.hyy : 0.0;
+            const double htt = useW ? t.htt : 0.0, htv = useW ? t.htv : 0.0, htw = useW ? t.htw : 0.0;
+            const double hvv = useW ? t.hvv : 0.0, hvw = useW ? t.hvw : 0.0, hww = useW ? t.hww : 0.0;
+            if (ko == N) {
+                q00 = hxx + dw; q01 = hxy; q02 = 0; q11 = hyy + dw; q12 = 0; q22 = htt + dw;
+                v0 = t.rx[0]; v1 = t.rx[1]; v2 = t.rx[2];
+            } else {
+                const double a = t.a13, b = t.a23, b11 = t.b11, b12 = t.b12, b21 = t.b21, b22 = t.b22;
+                const double d0 = -rc[j][0], d1 = -rc[j][1], d2 = -rc[j][2];
+                // w = P d + p
+                const double w0 = q00 * d0 + q01 * d1 + q02 * d2 + v0;
+                const double w1 = q01 * d0 + q11 * d1 + q12 * d2 + v1;
+                const double w2 = q02 * d0 + q12 * d1 + q22 * d2 + v2;
+                // t = P[:,2] + a P[:,0] + b P[:,1]
+                const double t0 = q02 + a * q00 + b * q01;
+                const double t1 = q12 + a * q01 + b * q11;
+                const double t2 = q22 + a * q02 + b * q12;
+                // Qxx = Hxx + A'PA
+                const double x00 = hxx + dw + q00, x01 = hxy + q01, x11 = hyy + dw + q11;
+                const double x02 = t0, x12 = t1, x22 = htt + dw + t2 + a * t0 + b * t1;
+                // PB columns
+                const double e0 = b11 * q00 + b21 * q01, e1 = b11 * q01 + b21 * q11, e2 = b11 * q02 + b21 * q12;
+                const double f0 = b12 * q00 + b22 * q01 + dt * q02, f1 = b12 * q01 + b22 * q11 + dt * q12,
+                             f2 = b12 * q02 + b22 * q12 + dt * q22;
+                // Qux = Hux + B'PA
+                const double u00 = e0, u01 = e1, u02 = htv + b11 * t0 + b21 * t1;
+                const double u10 = f0, u11 = f1, u12 = htw + b12 * t0 + b22 * t1 + dt * t2;
+                // Quu = Huu + Dsig + B'PB
+                const double r00 = hvv + dw + t.Dsig[0] + b11 * e0 + b21 * e1;
+                const double r01 = hvw + b11 * f0 + b21 * f1;
+                const double r11 = hww + dw + t.Dsig[1] + b12 * f0 + b22 * f1 + dt * f2;
+                // gradients
+                const bool first = (ko == 0);
+                const double gx0 = (first ? 0.0 : t.rx[0]) + w0;
+                const double gx1 = (first ? 0.0 : t.rx[1]) + w1;
+                const double gx2 = (first ? 0.0 : t.rx[2]) + a * w0 + b * w1 + w2;
+                const double qu0 = t.ru[0] + t.Dsig[0] * rd[j][0] + t.rs[0];
+                const double qu1 = t.ru[1] + t.Dsig[1] * rd[j][1] + t.rs[1];
+                const double gu0 = qu0 + b11 * w0 + b21 * w1;
+                const double gu1 = qu1 + b12 * w0 + b22 * w1 + dt * w2;
+                const double det = r00 * r11 - r01 * r01;
+                if (!(r00 > 0.0) || !(det > 0.0)) ok = 0;
+                const double idet = 1.0 / det;
+                const double i00 = r11 * idet, i01 = -r01 * idet, i11 = r00 * idet;
+                const double K00 = -(i00 * u00 + i01 * u10), K01 = -(i00 * u01 + i01 * u11),
+                             K02 = -(i00 * u02 + i01 * u12);
+                const double K10 = -(i01 * u00 + i11 * u10), K11 = -(i01 * u01 + i11 * u11),
+                             K12 = -(i01 * u02 + i11 * u12);
+                const double k0 = -(i00 * gu0 + i01 * gu1), k1 = -(i01 * gu0 + i11 * gu1);
+                if (mine) {
+                    t.K[0] = K00; t.K[1] = K01; t.K[2] = K02; t.K[3] = K10; t.K[4] = K11; t.K[5] = K12;
+                    t.kf[0] = k0; t.kf[1] = k1;
+                }
+                // P' = Qxx + Qux'K (symmetrised), p' = gx + Qux' kf
+                q00 = x00 + u00 * K00 + u10 * K10;
+                q11 = x11 + u01 * K01 + u11 * K11;
+                q22 = x22 + u02 * K02 + u12 * K12;
+                q01 = x01 + 0.5 * ((u00 * K01 + u10 * K11) + (u01 * K00 + u11 * K10));
+                q02 = x02 + 0.5 * ((u00 * K02 + u10 * K12) + (u02 * K00 + u12 * K10));
+                q12 = x12 + 0.5 * ((u01 * K02 + u11 * K12) + (u02 * K01 + u12 * K11));
+                v0 = gx0 + u00 * k0 + u10 * k1;
+                v1 = gx1 + u01 * k0 + u11 * k1;
+                v2 = gx2 + u02 * k0 + u12 * k1;
+            }
+            if (mine) {
+                t.P[0] = q00; t.P[1] = q01; t.P[2] = q02; t.P[3] = q11; t.P[4] = q12; t.P[5] = q22;
+                t.pv[0] = v0; t.pv[1] = v1; t.pv[2] = v2;
+            }
+        }
+        P00 = __shfl_sync(FULL, q00, l); P01 = __shfl_sync(FULL, q01, l); P02 = __shfl_sync(FULL, q02, l);
+        P11 = __shfl_sync(FULL, q11, l); P12 = __shfl_sync(FULL, q12, l); P22 = __shfl_sync(FULL, q22, l);
+        p0 = __shfl_sync(FULL, v0, l); p1 = __shfl_sync(FULL, v1, l); p2 = __shfl_sync(FULL, v2, l);
+        okall = __shfl_sync(FULL, ok, l);
+        if (!okall) return false;
+    }
+    // forward sweep
+    double x0 = 0, x1 = 0, x2 = 0;
+    for (int l = 0; l <= lN; ++l) {
+        double y0 = x0, y1 = x1, y2 = x2;
+        const bool mine = (lane == l);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int ko = l * J + j;
+            if (ko > N) continue;
+            Stg &t = s[j];
+            if (mine) { o[j].dX[0] = y0; o[j].dX[1] = y1; o[j].dX[2] = y2; }
+            if (ko < N) {
+                const double du0 = t.kf[0] + t.K[0] * y0 + t.K[1] * y1 + t.K[2] * y2;
+                const double du1 = t.kf[1] + t.K[3] * y0 + t.K[4] * y1 + t.K[5] * y2;
+                if (mine) { o[j].dU[0] = du0; o[j].dU[1] = du1; }
+                const double n0 = y0 + t.a13 * y2 + t.b11 * du0 + t.b12 * du1 - rc[j][0];
+                const double n1 = y1 + t.a23 * y2 + t.b21 * du0 + t.b22 * du1 - rc[j][1];
+                const double n2 = y2 + dt * du1 - rc[j][2];
+                y0 = n0; y1 = n1; y2 = n2;
+            }
+        }
+        x0 = __shfl_sync(FULL, y0, l); x1 = __shfl_sync(FULL, y1, l); x2 = __shfl_sync(FULL, y2, l);
+    }
+    // multiplier and slack steps (stage-parallel)
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int k = lane * J + j;
+        Stg &t = s[j];
+        const bool act = (k <= N), dyn = (k < N);
+        const double a0 = o[j].dX[0], a1 = o[j].dX[1], a2 = o[j].dX[2];
+        const double l0 = -(t.pv[0] + t.P[0] * a0 + t.P[1] * a1 + t.P[2] * a2);
+        const double l1 = -(t.pv[1] + t.P[1] * a0 + t.P[3] * a1 + t.P[4] * a2);
+        const double l2 = -(t.pv[2] + t.P[2] * a0 + t.P[4] * a1 + t.P[5] * a2);
+        const bool hasl = act && (k >= 1);
+        o[j].dlam[0] = hasl ? l0 : 0.0; o[j].dlam[1] = hasl ? l1 : 0.0; o[j].dlam[2] = hasl ? l2 : 0.0;
+        if (!act) { o[j].dX[0] = o[j].dX[1] = o[j].dX[2] = 0; }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const double ds = dyn ? (o[j].dU[i] + rd[j][i]) : 0.0;
+            o[j].dS[i] = ds;
+            o[j].dyd[i] = dyn ? (t.Dsig[i] * ds + t.rs[i]) : 0.0;
+            if (!dyn) o[j].dU[i] = 0;
+        }
+    }
+    return true;
+}
+
+// fraction-to-the-boundary step for the slacks
+template <int J>
+__device__ __forceinline__ double frac_to_bound(const KParams &P, const Stg (&s)[J], const Step (&o)[J], double tau,
+                                                int lane) {
+    double a = 1.0;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const bool dyn = (lane * J + j) < P.N;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const double sl = s[j].S[i] - P.sL[i], su = P.sU[i] - s[j].S[i], ds = o[j].dS[i];
+            if (dyn && ds < 0) a = fmin(a, -tau * sl / ds);
+            if (dyn && ds > 0) a = fmin(a, tau * su / ds);
+        }
+    }
+    return wmin(a);
+}
+
+// trial point curr + alpha*step: theta (1-norm) and barrier objective, both warp-uniform
+template <int J>
+__device__ __forceinline__ void trial_eval(const KParams &P, const double *sox, const double *soy, Stg (&s)[J],
+                                           const Step (&o)[J], double alpha, double mu, double df, int lane,
+                                           double &th_t, double &phi_t) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        Stg &t = s[j];
+#pragma unroll
+        for (int i = 0; i < 3; i++) t.Xt[i] = t.X[i] + alpha * o[j].dX[i];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            t.Ut[i] = t.U[i] + alpha * o[j].dU[i];
+            t.St[i] = t.S[i] + alpha * o[j].dS[i];
+        }
+    }
+    double th = 0, ph = 0;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int k = lane * J + j;
+        const bool act = (k <= P.N), dyn = (k < P.N);
+        const bool obs = P.obs_form != B200MPC_OBS_NONE && k >= P.obs_k0 && k <= P.obs_k1;
+        Stg &t = s[j];
+        double Xn[3];
+        NEXT3(Xn, Xt, j);
+        const double fv = stage_value(P, sox, soy, t.Xt, t.Ut, t.r, t.ub, Xn, t.ct, act, dyn, obs);
+        double bar = 0, thl = 0;
+        if (dyn) {
+            thl = fabs(t.ct[0]) + fabs(t.ct[1]) + fabs(t.ct[2]) + fabs(t.Ut[0] - t.St[0]) + fabs(t.Ut[1] - t.St[1]);
+            bar = -mu * (log(t.St[0] - P.sL[0]) + log(P.sU[0] - t.St[0]) + log(t.St[1] - P.sL[1]) +
+                         log(P.sU[1] - t.St[1]));
+        }
+        th += thl;
+        ph += df * fv + bar;
+    }
+    th_t = wsum(th);
+    phi_t = wsum(ph);
+}
+
+struct LsRef {
+    double phi, theta, gbd, theta_min, theta_max;
+};
+
+// FilterLSAcceptor::CheckAcceptabilityOfTrialPoint; the filter lives one entry per lane.
+__device__ __forceinline__ bool ls_acceptable(const LsRef &r, double alpha_test, double phi_t, double th_t,
+                                              double fphi, double ftheta, bool fvalid, bool &ftype_armijo) {
+    ftype_armijo = false;
+    if (!isfinite(th_t) || !isfinite(phi_t)) return false;
+    if (th_t > r.theta_max) return false;
+    const bool ftype = (r.gbd < 0) && (alpha_test * pow(-r.gbd, S_PHI) > DELTA_LS * pow(r.theta, S_THETA));
+    const bool armijo = cmp_le(phi_t - r.phi, ETA_PHI * alpha_test * r.gbd, r.phi);
+    ftype_armijo = ftype && armijo;
+    bool ok;
+    if (alpha_test > 0 && ftype && r.theta <= r.theta_min) {
+        ok = armijo;
+    } else {
+        if (phi_t > r.phi) {
+            double bas = 1.0;
+            if (fabs(r.phi) > 10.0) bas = log10(fabs(r.phi));
+            if (log10(phi_t - r.phi) > OBJ_MAX_INC + bas) return false;
+        }
+        ok = cmp_le(th_t, (1 - GAMMA_THETA) * r.theta, r.theta) || cmp_le(phi_t - r.phi, -GAMMA_PHI * r.theta, r.phi);
+    }
+    if (!ok) return false;
+    const bool rej = fvalid && !(cmp_le(phi_t, fphi, fphi) || cmp_le(th_t, ftheta, ftheta));
+    return !__any_sync(FULL, rej);
+}
+
+__device__ __forceinline__ void filter_add(double phi, double theta, double &fphi, double &ftheta, bool &fvalid,
+                                           int &ring, int lane) {
+    if (fvalid && fphi >= phi && ftheta >= theta) fvalid = false; // dominated by the new entry
+    const unsigned freem = __ballot_sync(FULL, !fvalid);
+    int slot;
+    if (freem) slot = __ffs(freem) - 1;
+    else { slot = ring & 31; ring++; }
+    if (lane == slot) { fphi = phi; ftheta = theta; fvalid = true; }
+}
+
+// ---- the per-problem solve ----------------------------------------------------------------------------------
+template <int J>
+__device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane, double *sox, double *soy) {
+    const int N = P.N;
+    Stg s[J];
+    Step st[J], soc[J];
+    double rc[J][3], rd[J][2], csoc[J][3], dsoc[J][2];
+
+    // ---- load the problem (coalesced: consecutive lanes read consecutive stages) ----
+    const double x00 = A.x0[3 * (size_t)b], x01 = A.x0[3 * (size_t)b + 1], x02 = A.x0[3 * (size_t)b + 2];
+    if (P.obs_form != B200MPC_OBS_NONE) {
+        const double *gx = A.ox + (size_t)A.obs_stride * b, *gy = A.oy + (size_t)A.obs_stride * b;
+        for (int i = lane; i < P.M; i += 32) { sox[i] = gx[i]; soy[i] = gy[i]; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int k = lane * J + j;
+        Stg &t = s[j];
+        const bool dyn = k < N;
+        t.X[0] = (k == 0) ? x00 : 0.0; t.X[1] = (k == 0) ? x01 : 0.0; t.X[2] = (k == 0) ? x02 : 0.0;
+        t.U[0] = t.U[1] = 0;
+        t.r[0] = t.r[1] = t.r[2] = 0; t.ub[0] = t.ub[1] = 0;
+        if (dyn) {
+            if (A.u_init) {
+                t.U[0] = A.u_init[(size_t)b * 2 * N + 2 * k];
+                t.U[1] = A.u_init[(size_t)b * 2 * N + 2 * k + 1];
+            }
+            if (P.ref_kind == B200MPC_REF_GOAL) {
+                t.r[0] = A.xref[3 * (size_t)b]; t.r[1] = A.xref[3 * (size_t)b + 1]; t.r[2] = A.xref[3 * (size_t)b + 2];
+            } else {
+                const double *xr = A.xref + (size_t)b * 3 * N + 3 * k;
+                t.r[0] = xr[0]; t.r[1] = xr[1]; t.r[2] = xr[2];
+                t.ub[0] = A.uref[(size_t)b * 2 * N + 2 * k];
+                t.ub[1] = A.uref[(size_t)b * 2 * N + 2 * k + 1];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) t.lam[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            // slack initialisation: s = d(x) pushed into the interior; bound multipliers 1
+            const double lo = P.sL[i], hi = P.sU[i];
+            const double pl = fmin(BOUND_PUSH * fmax(1.0, fabs(lo)), BOUND_FRAC * (hi - lo));
+            const double pu = fmin(BOUND_PUSH * fmax(1.0, fabs(hi)), BOUND_FRAC * (hi - lo));
+            double sv = t.U[i];
+            if (sv < lo + pl) sv = lo + pl;
+            if (sv > hi - pu) sv = hi - pu;
+            t.S[i] = dyn ? sv : 0.5 * (lo + hi);
+            t.vL[i] = 1.0; t.vU[i] = 1.0; t.yd[i] = 0;
+            t.Dsig[i] = 1.0; t.rs[i] = 0;
+        }
+    }
+
+    int status = B200MPC_MAXITER_EXCEEDED;
+    int iter = 0, ls_extra = 0, n_resto = 0;
+    double df = 1.0;
+    double fcur = 0;
+
+    // full evaluation of the current point; returns the objective value (unscaled, warp-uniform)
+    auto eval_point = [&](double dfv) -> double {
+        double Xn0[3], ln0[3];
+        double fl = 0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int k = lane * J + j;
+            const bool act = (k <= N), dyn = (k < N);
+            const bool obs = P.obs_form != B200MPC_OBS_NONE && k >= P.obs_k0 && k <= P.obs_k1;
+            NEXT3(Xn0, X, j);
+            NEXT3(ln0, lam, j);
+            fl += stage_full(P, sox, soy, s[j], Xn0, ln0, dfv, act, dyn, obs);
+        }
+        return wsum(fl);
+    };
+
+    // ---- objective scaling from the gradient at the starting point; invalid-number check ----
+    {
+        fcur = eval_point(1.0);
+        double gmax = 0;
+        int bad = 0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int k = lane * J + j;
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                const bool use = (i < 3) ? (k >= 1 && k <= N) : (k < N);
+                if (use) {
+                    if (!isfinite(s[j].g[i])) bad = 1;
+                    gmax = fmax(gmax, fabs(s[j].g[i]));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                if (k < N && !isfinite(s[j].c[i])) bad = 1;
+        }
+        gmax = wmax(gmax);
+        bad = wor(bad);
+        if (bad || !isfinite(fcur)) {
+            status = B200MPC_INVALID_NUMBER_DETECTED;
+            goto finish;
+        }
+        if (gmax > 100.0) df = fmax(100.0 / gmax, 1e-8);
+    }
+
+    // ---- least-squares multiplier estimate ----
+    {
+        fcur = eval_point(df);
+        double ymax = 0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) { s[j].rx[i] = s[j].g[i]; rc[j][i] = 0; }
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                s[j].ru[i] = s[j].g[3 + i];
+                s[j].rs[i] = -s[j].vL[i] + s[j].vU[i];
+                s[j].Dsig[i] = 1.0;
+                rd[j][i] = 0;
+            }
+        }
+        const bool ok = kkt_solve<J>(P, s, rc, rd, false, 1.0, st, lane);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) ymax = fmax(ymax, fabs(st[j].dlam[i]));
+#pragma unroll
+            for (int i = 0; i < 2; i++) ymax = fmax(ymax, fabs(st[j].dyd[i]));
+        }
+        ymax = wmax(ymax);
+        const bool keep = ok && (ymax <= 1e3);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) s[j].lam[i] = keep ? st[j].dlam[i] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 2; i++) s[j].yd[i] = keep ? st[j].dyd[i] : 0.0;
+        }
+    }
+
+    {
+        double mu = P.mu_init, tau = fmax(TAU_MIN, 1.0 - mu);
+        double theta_max = -1, theta_min = -1, dw_last = 0;
+        int acceptable_count = 0;
+        // filter: one entry per lane
+        double fphi = 0, ftheta = 0;
+        bool fvalid = false;
+        int ring = 0;
+
+        for (;;) {
+            // ---- evaluate the current point ----
+            fcur = eval_point(df);
+            double theta, prim_inf, dual_inf, sum_y, sum_z, compl0;
+            {
+                double th = 0, pi = 0, di = 0, sy = 0, sz = 0, c0 = 0;
+                double ln0[3];
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int k = lane * J + j;
+                    const bool act = (k <= N), dyn = (k < N);
+                    Stg &t = s[j];
+                    NEXT3(ln0, lam, j);
+                    if (!dyn) { ln0[0] = ln0[1] = ln0[2] = 0; }
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        rc[j][i] = t.c[i];
+                        th += fabs(t.c[i]);
+                        pi = fmax(pi, fabs(t.c[i]));
+                    }
+                    // grad_lag_x
+                    const bool hasx = act && k >= 1;
+                    double r0 = t.g[0] + t.lam[0] - ln0[0];
+                    double r1 = t.g[1] + t.lam[1] - ln0[1];
+                    double r2 = t.g[2] + t.lam[2] - (t.a13 * ln0[0] + t.a23 * ln0[1] + ln0[2]);
+                    t.rx[0] = hasx ? r0 : 0.0; t.rx[1] = hasx ? r1 : 0.0; t.rx[2] = hasx ? r2 : 0.0;
+                    if (hasx) {
+                        di = fmax(di, fmax(fabs(r0), fmax(fabs(r1), fabs(r2))));
+                        sy += fabs(t.lam[0]) + fabs(t.lam[1]) + fabs(t.lam[2]);
+                    }
+                    double q0 = t.g[3] - (t.b11 * ln0[0] + t.b21 * ln0[1]) + t.yd[0];
+                    double q1 = t.g[4] - (t.b12 * ln0[0] + t.b22 * ln0[1] + P.dt * ln0[2]) + t.yd[1];
+                    t.ru[0] = dyn ? q0 : 0.0; t.ru[1] = dyn ? q1 : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        rd[j][i] = dyn ? (t.U[i] - t.S[i]) : 0.0;
+                        if (dyn) {
+                            th += fabs(rd[j][i]);
+                            pi = fmax(pi, fabs(rd[j][i]));
+                            di = fmax(di, fabs(t.ru[i]));
+                            const double gs = -t.yd[i] - t.vL[i] + t.vU[i];
+                            di = fmax(di, fabs(gs));
+                            sy += fabs(t.yd[i]);
+                            sz += fabs(t.vL[i]) + fabs(t.vU[i]);
+                            const double sl = t.S[i] - P.sL[i], su = P.sU[i] - t.S[i];
+                            c0 = fmax(c0, fmax(fabs(sl * t.vL[i]), fabs(su * t.vU[i])));
+                        }
+                    }
+                }
+                theta = wsum(th); prim_inf = wmax(pi); dual_inf = wmax(di);
+                sum_y = wsum(sy); sum_z = wsum(sz); compl0 = wmax(c0);
+            }
+            if (theta_max < 0) {
+                theta_max = 1e4 * fmax(1.0, theta);
+                theta_min = 1e-4 * fmax(1.0, theta);
+            }
+            const double sd = fmax(S_MAX, (sum_y + sum_z) / (double)(9 * N)) / S_MAX;
+            const double sc = fmax(S_MAX, sum_z / (double)(4 * N)) / S_MAX;
+            const double E0 = fmax(dual_inf / sd, fmax(prim_inf, compl0 / sc));
+            if (!isfinite(E0)) { status = B200MPC_INVALID_NUMBER_DETECTED; break; }
+
+            // ---- convergence ----
+            if (E0 <= P.tol && dual_inf / df <= 1.0 && prim_inf <= 1e-4 && compl0 / df <= 1e-4) {
+                status = B200MPC_SOLVE_SUCCEEDED;
+                break;
+            }
+            if (P.acceptable_iter > 0 && E0 <= P.acceptable_tol && dual_inf / df <= 1e10 && prim_inf <= 1e-2 &&
+                compl0 / df <= 1e-2) {
+                acceptable_count++;
+                if (acceptable_count >= P.acceptable_iter) { status = B200MPC_SOLVED_TO_ACCEPTABLE_LEVEL; break; }
+            } else {
+                acceptable_count = 0;
+            }
+            if (iter >= P.max_iter) { status = B200MPC_MAXITER_EXCEEDED; break; }
+
+            // ---- barrier parameter update ----
+            for (;;) {
+                double cm = 0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const bool dyn = (lane * J + j) < N;
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const double sl = s[j].S[i] - P.sL[i], su = P.sU[i] - s[j].S[i];
+                        if (dyn) cm = fmax(cm, fmax(fabs(sl * s[j].vL[i] - mu), fabs(su * s[j].vU[i] - mu)));
+                    }
+                }
+                cm = wmax(cm);
+                const double Emu = fmax(dual_inf / sd, fmax(prim_inf, cm / sc));
+                if (!(Emu <= K_EPS * mu)) break;
+                const double nm = fmax(fmin(K_MU * mu, pow(mu, TH_MU)), P.mu_floor);
+                if (nm == mu) break;
+                mu = nm;
+                tau = fmax(TAU_MIN, 1.0 - mu);
+                fvalid = false;
+            }
+
+            // ---- search direction with inertia correction ----
+            double dw = 0.0;
+            bool solved = false;
+            for (;;) {
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const double sl = s[j].S[i] - P.sL[i], su = P.sU[i] - s[j].S[i];
+                        s[j].rs[i] = -s[j].yd[i] - mu / sl + mu / su;
+                        s[j].Dsig[i] = s[j].vL[i] / sl + s[j].vU[i] / su + dw;
+                    }
+                }
+                if (kkt_solve<J>(P, s, rc, rd, true, dw, st, lane)) { solved = true; break; }
+                if (dw == 0.0) dw = (dw_last == 0.0) ? DW_INIT : fmax(DW_MIN, dw_last * DW_DEC);
+                else dw = (dw_last == 0.0 || 1e5 * dw_last < dw) ? dw * DW_INC_FIRST : dw * DW_INC;
+                if (dw > DW_MAX) break;
+            }
+            if (!solved) { status = B200MPC_ERROR_IN_STEP_COMPUTATION; break; }
+            if (dw > 0.0) dw_last = dw;
+            {
+                int bad = 0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++)
+                        if (!isfinite(st[j].dX[i]) || !isfinite(st[j].dlam[i])) bad = 1;
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+                        if (!isfinite(st[j].dU[i]) || !isfinite(st[j].dS[i]) || !isfinite(st[j].dyd[i])) bad = 1;
+                }
+                if (wor(bad)) { status = B200MPC_ERROR_IN_STEP_COMPUTATION; break; }
+            }
+
+            // ---- filter line search ----
+            const double a_max = frac_to_bound<J>(P, s, st, tau, lane);
+            LsRef ref;
+            {
+                double bar = 0, gb = 0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int k = lane * J + j;
+                    const bool dyn = k < N;
+                    if (dyn) {
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            const double sl = s[j].S[i] - P.sL[i], su = P.sU[i] - s[j].S[i];
+                            bar -= mu * (log(sl) + log(su));
+                            gb += (-mu / sl + mu / su) * st[j].dS[i];
+                            gb += s[j].g[3 + i] * st[j].dU[i];
+                        }
+                    }
+                    if (k >= 1 && k <= N) {
+#pragma unroll
+                        for (int i = 0; i < 3; i++) gb += s[j].g[i] * st[j].dX[i];
+                    }
+                }
+                ref.phi = df * fcur + wsum(bar);
+                ref.gbd = wsum(gb);
+                ref.theta = theta; ref.theta_min = theta_min; ref.theta_max = theta_max;
+            }
+            double a_min = GAMMA_THETA;
+            if (ref.gbd < 0) {
+                a_min = fmin(GAMMA_THETA, GAMMA_PHI * theta / (-ref.gbd));
+                if (theta <= theta_min) a_min = fmin(a_min, DELTA_LS * pow(theta, S_THETA) / pow(-ref.gbd, S_PHI));
+            }
+            a_min *= ALPHA_MIN_FRAC;
+
+            double alpha = a_max, alpha_acc = 0;
+            int acc = 0; // 0 none, 1 newton step, 2 corrected step
+            bool fa = false;
+            int ntrial = 0;
+            while (!acc) {
+                double th_t, phi_t;
+                trial_eval<J>(P, sox, soy, s, st, alpha, mu, df, lane, th_t, phi_t);
+                if (ntrial++ > 0) ls_extra++;
+                if (ls_acceptable(ref, alpha, phi_t, th_t, fphi, ftheta, fvalid, fa)) { acc = 1; alpha_acc = alpha; break; }
+                if (ntrial == 1 && P.max_soc > 0 && isfinite(th_t) && th_t >= theta) {
+                    // second-order correction
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+#pragma unroll
+                        for (int i = 0; i < 3; i++) csoc[j][i] = rc[j][i];
+#pragma unroll
+                        for (int i = 0; i < 2; i++) dsoc[j][i] = rd[j][i];
+                    }
+                    double alpha_soc = alpha, theta_soc_old = 0, th_trial = th_t;
+                    int count = 0;
+                    while (count < P.max_soc && !acc && (count == 0 || th_trial <= KAPPA_SOC * theta_soc_old)) {
+                        theta_soc_old = th_trial;
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            const bool dyn = (lane * J + j) < N;
+#pragma unroll
+                            for (int i = 0; i < 3; i++) csoc[j][i] = alpha_soc * csoc[j][i] + s[j].ct[i];
+#pragma unroll
+                            for (int i = 0; i < 2; i++)
+                                dsoc[j][i] = dyn ? (alpha_soc * dsoc[j][i] + (s[j].Ut[i] - s[j].St[i])) : 0.0;
+                        }
+                        if (!kkt_solve<J>(P, s, csoc, dsoc, true, dw, soc, lane)) break;
+                        alpha_soc = frac_to_bound<J>(P, s, soc, tau, lane);
+                        double phi_s;
+                        trial_eval<J>(P, sox, soy, s, soc, alpha_soc, mu, df, lane, th_trial, phi_s);
+                        ls_extra++;
+                        if (ls_acceptable(ref, alpha, phi_s, th_trial, fphi, ftheta, fvalid, fa)) { acc = 2; alpha_acc = alpha_soc; }
+                        else count++;
+                    }
+                    if (acc) break;
+                }
+                alpha *= 0.5;
+                if (alpha < a_min) break;
+            }
+
+            if (!acc) {
+                // restoration stand-in: roll the controls out (closed-form feasible point), restart multipliers
+                if (theta <= 1e-10 || n_resto >= MAX_RESTO) { status = B200MPC_RESTORATION_FAILED; break; }
+                filter_add(ref.phi - GAMMA_PHI * theta, (1 - GAMMA_THETA) * theta, fphi, ftheta, fvalid, ring, lane);
+                double zm = 0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const bool dyn = (lane * J + j) < N;
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        if (dyn) { s[j].U[i] = s[j].S[i]; zm = fmax(zm, fmax(s[j].vL[i], s[j].vU[i])); }
+                        s[j].yd[i] = 0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 3; i++) s[j].lam[i] = 0;
+                }
+                zm = wmax(zm);
+                if (zm > 1e3) {
+#pragma unroll
+                    for (int j = 0; j < J; ++j) { s[j].vL[0] = s[j].vL[1] = 1.0; s[j].vU[0] = s[j].vU[1] = 1.0; }
+                }
+                // serial rollout X_{k+1} = F(X_k, U_k)
+                double y[3] = {x00, x01, x02};
+                for (int l = 0; l <= N / J; ++l) {
+                    double z[3] = {y[0], y[1], y[2]};
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        const int ko = l * J + j;
+                        if (ko > N) continue;
+                        if (lane == l) { s[j].X[0] = z[0]; s[j].X[1] = z[1]; s[j].X[2] = z[2]; }
+                        if (ko < N) {
+                            double F[3];
+                            dyn_value(P, z, s[j].U, F);
+                            z[0] = F[0]; z[1] = F[1]; z[2] = F[2];
+                        }
+                    }
+                    y[0] = __shfl_sync(FULL, z[0], l); y[1] = __shfl_sync(FULL, z[1], l); y[2] = __shfl_sync(FULL, z[2], l);
+                }
+                n_resto++;
+                iter++;
+                continue;
+            }
+
+            // ---- accept the trial point ----
+            if (!fa) filter_add(ref.phi - GAMMA_PHI * theta, (1 - GAMMA_THETA) * theta, fphi, ftheta, fvalid, ring, lane);
+            double a_z = 1.0;
+            double dvL[J][2], dvU[J][2];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const bool dyn = (lane * J + j) < N;
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const double ds = (acc == 2) ? soc[j].dS[i] : st[j].dS[i];
+                    const double sl = s[j].S[i] - P.sL[i], su = P.sU[i] - s[j].S[i];
+                    dvL[j][i] = mu / sl - s[j].vL[i] - s[j].vL[i] / sl * ds;
+                    dvU[j][i] = mu / su - s[j].vU[i] + s[j].vU[i] / su * ds;
+                    if (dyn && dvL[j][i] < 0) a_z = fmin(a_z, -tau * s[j].vL[i] / dvL[j][i]);
+                    if (dyn && dvU[j][i] < 0) a_z = fmin(a_z, -tau * s[j].vU[i] / dvU[j][i]);
+                }
+            }
+            a_z = wmin(a_z);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int k = lane * J + j;
+                const bool dyn = k < N;
+                Stg &t = s[j];
+                const Step &q = (acc == 2) ? soc[j] : st[j];
+                if (k >= 1 && k <= N) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        t.X[i] += alpha_acc * q.dX[i];
+                        t.lam[i] += alpha_acc * q.dlam[i];
+                    }
+                }
+                if (dyn) {
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        t.U[i] += alpha_acc * q.dU[i];
+                        t.S[i] += alpha_acc * q.dS[i];
+                        t.yd[i] += alpha_acc * q.dyd[i];
+                        t.vL[i] += a_z * dvL[j][i];
+                        t.vU[i] += a_z * dvU[j][i];
+                        const double sl = t.S[i] - P.sL[i], su = P.sU[i] - t.S[i];
+                        t.vL[i] = fmax(fmin(t.vL[i], KAPPA_SIGMA * mu / sl), mu / (KAPPA_SIGMA * sl));
+                        t.vU[i] = fmax(fmin(t.vU[i], KAPPA_SIGMA * mu / su), mu / (KAPPA_SIGMA * su));
+                    }
+                }
+            }
+            iter++;
+        }
+    }
+
+finish:
+    // ---- store results (coalesced) ----
+    {
+        // objective at the returned point (value-only evaluation of the current iterate)
+        double fl = 0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int k = lane * J + j;
+            const bool act = (k <= N), dyn = (k < N);
+            const bool obs = P.obs_form != B200MPC_OBS_NONE && k >= P.obs_k0 && k <= P.obs_k1;
+            double Xn[3], ct[3];
+            NEXT3(Xn, X, j);
+            fl += stage_value(P, sox, soy, s[j].X, s[j].U, s[j].r, s[j].ub, Xn, ct, act, dyn, obs);
+        }
+        const double fsum = wsum(fl);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int k = lane * J + j;
+            if (k <= N) {
+                double *xo = A.X + (size_t)b * 3 * (N + 1) + 3 * k;
+                xo[0] = s[j].X[0]; xo[1] = s[j].X[1]; xo[2] = s[j].X[2];
+            }
+            if (k < N) {
+                double *uo = A.U + (size_t)b * 2 * N + 2 * k;
+                uo[0] = s[j].U[0]; uo[1] = s[j].U[1];
+            }
+        }
+        if (lane == 0) {
+            if (A.cost) A.cost[b] = fsum;
+            A.status[b] = status;
+            if (A.iters) A.iters[b] = iter;
+            if (A.ls) A.ls[b] = ls_extra;
+        }
+    }
+    __syncwarp();
+}
+
+template <int J>
+__global__ void __launch_bounds__(128) mpc_solve_kernel(const KParams P, const BatchArgs A) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int Mpad = (P.M + 3) & ~3;
+    double *sox = smem + (size_t)wid * 2 * Mpad, *soy = sox + Mpad;
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = (int)atomicAdd(A.counter, 1u);
+        b = __shfl_sync(FULL, b, 0);
+        if (b >= A.B) break;
+        solve_one<J>(P, A, b, lane, sox, soy);
+    }
+}
+
+// ---- NLP function evaluation kernel (K1-K3 only), one warp per problem -----------------------------------
+template <int J>
+__global__ void __launch_bounds__(128) mpc_eval_kernel(const KParams P, const EvalArgs A) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int Mpad = (P.M + 3) & ~3;
+    double *sox = smem + (size_t)wid * 2 * Mpad, *soy = sox + Mpad;
+    const int N = P.N;
+    const int b = blockIdx.x * (blockDim.x >> 5) + wid;
+    if (b >= A.B) return;
+    if (P.obs_form != B200MPC_OBS_NONE) {
+        const double *gx = A.ox + (size_t)A.obs_stride * b, *gy = A.oy + (size_t)A.obs_stride * b;
+        for (int i = lane; i < P.M; i += 32) { sox[i] = gx[i]; soy[i] = gy[i]; }
+    }
+    __syncwarp();
+    Stg s[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int k = lane * J + j;
+        Stg &t = s[j];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            t.X[i] = (k <= N) ? A.X[(size_t)b * 3 * (N + 1) + 3 * k + i] : 0.0;
+            t.lam[i] = (k >= 1 && k <= N && A.lam) ? A.lam[(size_t)b * 3 * N + 3 * (k - 1) + i] : 0.0;
+            t.r[i] = 0;
+        }
+        t.U[0] = t.U[1] = t.ub[0] = t.ub[1] = 0;
+        if (k < N) {
+            t.U[0] = A.U[(size_t)b * 2 * N + 2 * k];
+            t.U[1] = A.U[(size_t)b * 2 * N + 2 * k + 1];
+            if (P.ref_kind == B200MPC_REF_GOAL) {
+                for (int i = 0; i < 3; i++) t.r[i] = A.xref[3 * (size_t)b + i];
+            } else {
+                for (int i = 0; i < 3; i++) t.r[i] = A.xref[(size_t)b * 3 * N + 3 * k + i];
+                t.ub[0] = A.uref[(size_t)b * 2 * N + 2 * k];
+                t.ub[1] = A.uref[(size_t)b * 2 * N + 2 * k + 1];
+            }
+        }
+    }
+    double fl = 0;
+    double Xn0[3], ln0[3];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int k = lane * J + j;
+        const bool act = (k <= N), dyn = (k < N);
+        const bool obs = P.obs_form != B200MPC_OBS_NONE && k >= P.obs_k0 && k <= P.obs_k1;
+        NEXT3(Xn0, X, j);
+        NEXT3(ln0, lam, j);
+        fl += stage_full(P, sox, soy, s[j], Xn0, ln0, A.obj_scale, act, dyn, obs);
+    }
+    const double f = wsum(fl);
+    if (lane == 0 && A.f) A.f[b] = f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int k = lane * J + j;
+        const Stg &t = s[j];
+        if (k < N && A.c)
+            for (int i = 0; i < 3; i++) A.c[(size_t)b * 3 * N + 3 * k + i] = t.c[i];
+        if (A.grad) {
+            if (k >= 1 && k <= N)
+                for (int i = 0; i < 3; i++) A.grad[(size_t)b * 5 * N + 3 * (k - 1) + i] = t.g[i];
+            if (k < N)
+                for (int i = 0; i < 2; i++) A.grad[(size_t)b * 5 * N + 3 * N + 2 * k + i] = t.g[3 + i];
+        }
+        if (k <= N && A.stage) {
+            double *o = A.stage + ((size_t)b * (N + 1) + k) * 36;
+            o[0] = t.a13; o[1] = t.a23; o[2] = t.b11; o[3] = t.b12; o[4] = t.b21; o[5] = t.b22;
+            double H[25];
+            for (int i = 0; i < 25; i++) H[i] = 0;
+            H[0] = t.hxx; H[1] = t.hxy; H[5] = t.hxy; H[6] = t.hyy; H[12] = t.htt;
+            H[13] = t.htv; H[17] = t.htv; H[14] = t.htw; H[22] = t.htw; H[18] = t.hvv;
+            H[19] = t.hvw; H[23] = t.hvw; H[24] = t.hww;
+            for (int i = 0; i < 25; i++) o[6 + i] = H[i];
+            for (int i = 0; i < 3; i++) o[31 + i] = t.c[i];
+            o[34] = o[35] = 0;
+        }
+    }
+}
+
+// =============================================================================================================
+// Host side: C ABI
+// =============================================================================================================
+
+static std::mutex g_err_mtx;
+static std::string g_create_err;
+
+struct b200mpc_handle {
+    b200mpc_params prm;
+    KParams kp;
+    int device;
+    int J;
+    int sm_count;
+    int ctas;
+    size_t smem_bytes;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    unsigned int *d_counter;
+    // staging buffers for the host-pointer entry points
+    char *d_buf;
+    size_t d_cap;
+    long long launches;
+    std::string err;
+};
+
+static int set_err(b200mpc_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    else {
+        std::lock_guard<std::mutex> g(g_err_mtx);
+        g_create_err = msg;
+    }
+    return code;
+}
+
+#define CU_TRY(h, call)                                                                              \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return set_err(h, B200MPC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+
+extern "C" int b200mpc_abi_version(void) { return B200MPC_ABI_VERSION; }
+
+extern "C" void b200mpc_default_options(b200mpc_params *p) {
+    p->tol = 1e-8;
+    p->max_iter = 3000;
+    p->acceptable_tol = 1e-6;
+    p->acceptable_iter = 15;
+    p->mu_init = 0.1;
+    p->max_soc = 4;
+}
+
+extern "C" const char *b200mpc_last_error(const b200mpc_handle *h) {
+    if (h) return h->err.c_str();
+    std::lock_guard<std::mutex> g(g_err_mtx);
+    return g_create_err.c_str();
+}
+
+template <int J>
+static cudaError_t configure_kernels(size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(mpc_solve_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(mpc_eval_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+template <int J>
+static cudaError_t occupancy(int *blocks, size_t smem) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, mpc_solve_kernel<J>, 128, smem);
+}
+
+extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
+    if (!p) { set_err(nullptr, B200MPC_E_ARG, "params is NULL"); return nullptr; }
+    if (p->N < 1 || p->N > B200MPC_MAX_N) { set_err(nullptr, B200MPC_E_ARG, "N out of range [1,127]"); return nullptr; }
+    if (p->obs_form != B200MPC_OBS_NONE && (p->M < 1 || p->M > B200MPC_MAX_M)) {
+        set_err(nullptr, B200MPC_E_ARG, "M out of range [1,1024]");
+        return nullptr;
+    }
+    if (!(p->dt > 0) || !(p->u_lo[0] < p->u_hi[0]) || !(p->u_lo[1] < p->u_hi[1])) {
+        set_err(nullptr, B200MPC_E_ARG, "dt must be > 0 and u_lo < u_hi");
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_err(nullptr, B200MPC_E_NODEVICE,
+                std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { set_err(nullptr, B200MPC_E_ARG, "device index out of range"); return nullptr; }
+    b200mpc_handle *h = new b200mpc_handle();
+    h->prm = *p;
+    h->device = device;
+    h->launches = 0;
+    h->d_buf = nullptr;
+    h->d_cap = 0;
+    KParams &k = h->kp;
+    memset(&k, 0, sizeof(k));
+    k.N = p->N; k.M = (p->obs_form == B200MPC_OBS_NONE) ? 0 : p->M;
+    k.integrator = p->integrator; k.ref_kind = p->ref_kind; k.obs_form = p->obs_form;
+    k.obs_k0 = p->obs_k0; k.obs_k1 = p->obs_k1; k.max_iter = p->max_iter;
+    k.acceptable_iter = p->acceptable_iter; k.max_soc = p->max_soc;
+    k.dt = p->dt; k.kappa = p->kappa; k.obs_c = p->obs_c; k.obs_r = p->obs_r;
+    k.tol = p->tol; k.acceptable_tol = p->acceptable_tol; k.mu_init = p->mu_init;
+    for (int i = 0; i < 3; i++) k.Q[i] = p->Q[i];
+    for (int i = 0; i < 2; i++) {
+        k.R[i] = p->R[i]; k.u_lo[i] = p->u_lo[i]; k.u_hi[i] = p->u_hi[i];
+        k.sL[i] = p->u_lo[i] - BOUND_RELAX * fmax(1.0, fabs(p->u_lo[i]));
+        k.sU[i] = p->u_hi[i] + BOUND_RELAX * fmax(1.0, fabs(p->u_hi[i]));
+    }
+    k.inv_r2 = 1.0 / (p->obs_r * p->obs_r);
+    k.mu_floor = fmin(p->tol, 1e-4) / (K_EPS + 1.0);
+    h->J = (p->N + 1 + 31) / 32;
+    const int Mpad = (k.M + 3) & ~3;
+    h->smem_bytes = (size_t)4 * 2 * Mpad * sizeof(double);
+    auto fail = [&](const std::string &m) -> b200mpc_handle * {
+        set_err(nullptr, B200MPC_E_CUDA, m);
+        delete h;
+        return nullptr;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(cudaGetErrorString(e));
+    h->sm_count = prop.multiProcessorCount;
+    int blocks = 0;
+    switch (h->J) {
+        case 1: e = configure_kernels<1>(h->smem_bytes); if (e == cudaSuccess) e = occupancy<1>(&blocks, h->smem_bytes); break;
+        case 2: e = configure_kernels<2>(h->smem_bytes); if (e == cudaSuccess) e = occupancy<2>(&blocks, h->smem_bytes); break;
+        case 3: e = configure_kernels<3>(h->smem_bytes); if (e == cudaSuccess) e = occupancy<3>(&blocks, h->smem_bytes); break;
+        default: e = configure_kernels<4>(h->smem_bytes); if (e == cudaSuccess) e = occupancy<4>(&blocks, h->smem_bytes); break;
+    }
+    if (e != cudaSuccess) return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
+    if (blocks < 1) blocks = 1;
+    h->ctas = blocks * h->sm_count; // persistent grid: a multiple of the SM count (148 on B200)
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cudaGetErrorString(e));
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail(cudaGetErrorString(e));
+    if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail(cudaGetErrorString(e));
+    if ((e = cudaMalloc(&h->d_counter, sizeof(unsigned int))) != cudaSuccess) return fail(cudaGetErrorString(e));
+    return h;
+}
+
+extern "C" void b200mpc_destroy(b200mpc_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->d_buf) cudaFree(h->d_buf);
+    cudaFree(h->d_counter);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" long long b200mpc_launch_count(const b200mpc_handle *h) { return h ? h->launches : 0; }
+
+extern "C" float b200mpc_last_kernel_ms(b200mpc_handle *h) {
+    if (!h) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+static int check_args(b200mpc_handle *h, int B, const double *x0, const double *xref, const double *uref,
+                      const double *obs_x, const double *obs_y, int obs_stride) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0) return set_err(h, B200MPC_E_ARG, "B < 0");
+    if (B > 0 && (!x0 || !xref)) return set_err(h, B200MPC_E_ARG, "x0 / xref is NULL");
+    if (h->prm.ref_kind == B200MPC_REF_TRAJ && B > 0 && !uref) return set_err(h, B200MPC_E_ARG, "uref is NULL for a trajectory reference");
+    if (h->prm.obs_form != B200MPC_OBS_NONE && B > 0) {
+        if (!obs_x || !obs_y) return set_err(h, B200MPC_E_ARG, "obstacle lists are required: the obstacle cost is active");
+        if (obs_stride != 0 && obs_stride < h->prm.M) return set_err(h, B200MPC_E_ARG, "obs_stride must be 0 or >= M");
+    }
+    return 0;
+}
+
+static int launch_solve(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stream) {
+    CU_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), stream));
+    int grid = h->ctas;
+    const int need = (a.B + 3) / 4;
+    if (need < grid) grid = need;
+    if (grid < 1) grid = 1;
+    CU_TRY(h, cudaEventRecord(h->ev0, stream));
+    switch (h->J) {
+        case 1: mpc_solve_kernel<1><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a); break;
+        case 2: mpc_solve_kernel<2><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a); break;
+        case 3: mpc_solve_kernel<3><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a); break;
+        default: mpc_solve_kernel<4><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a); break;
+    }
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->ev1, stream));
+    h->launches++;
+    return 0;
+}
+
+extern "C" int b200mpc_solve_batch_device(b200mpc_handle *h, int B, const double *x0, const double *xref,
+                                          const double *uref, const double *obs_x, const double *obs_y,
+                                          int obs_stride, const double *u_init, double *X_out, double *U_out,
+                                          double *cost_out, int32_t *status_out, int32_t *iters_out,
+                                          int32_t *ls_out, void *stream) {
+    int rc = check_args(h, B, x0, xref, uref, obs_x, obs_y, obs_stride);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!X_out || !U_out || !status_out) return set_err(h, B200MPC_E_ARG, "X_out / U_out / status_out is NULL");
+    CU_TRY(h, cudaSetDevice(h->device));
+    BatchArgs a;
+    a.B = B; a.obs_stride = obs_stride;
+    a.x0 = x0; a.xref = xref; a.uref = uref; a.ox = obs_x; a.oy = obs_y; a.u_init = u_init;
+    a.X = X_out; a.U = U_out; a.cost = cost_out; a.status = status_out; a.iters = iters_out; a.ls = ls_out;
+    a.counter = h->d_counter;
+    return launch_solve(h, a, (cudaStream_t)stream);
+}
+
+static int ensure_buf(b200mpc_handle *h, size_t bytes) {
+    if (bytes <= h->d_cap) return 0;
+    if (h->d_buf) { cudaFree(h->d_buf); h->d_buf = nullptr; h->d_cap = 0; }
+    size_t cap = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&h->d_buf, cap);
+    if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    h->d_cap = cap;
+    return 0;
+}
+
+static size_t al256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+extern "C" int b200mpc_solve_batch(b200mpc_handle *h, int B, const double *x0, const double *xref, const double *uref,
+                                   const double *obs_x, const double *obs_y, int obs_stride, const double *u_init,
+                                   double *X_out, double *U_out, double *cost_out, int32_t *status_out,
+                                   int32_t *iters_out, int32_t *ls_out) {
+    int rc = check_args(h, B, x0, xref, uref, obs_x, obs_y, obs_stride);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!X_out || !U_out || !status_out) return set_err(h, B200MPC_E_ARG, "X_out / U_out / status_out is NULL");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int N = h->prm.N, M = h->prm.M;
+    const bool traj = h->prm.ref_kind == B200MPC_REF_TRAJ, obs = h->prm.obs_form != B200MPC_OBS_NONE;
+    const size_t nb = (size_t)B;
+    const size_t sz_x0 = al256(nb * 3 * 8), sz_xref = al256(nb * (traj ? 3 * N : 3) * 8);
+    const size_t sz_uref = traj ? al256(nb * 2 * N * 8) : 0;
+    const size_t n_obs = obs ? (obs_stride ? nb * obs_stride : (size_t)M) : 0;
+    const size_t sz_obs = al256(n_obs * 8);
+    const size_t sz_ui = u_init ? al256(nb * 2 * N * 8) : 0;
+    const size_t sz_X = al256(nb * 3 * (N + 1) * 8), sz_U = al256(nb * 2 * N * 8), sz_c = al256(nb * 8), sz_i = al256(nb * 4);
+    const size_t total = sz_x0 + sz_xref + sz_uref + 2 * sz_obs + sz_ui + sz_X + sz_U + sz_c + 3 * sz_i;
+    rc = ensure_buf(h, total);
+    if (rc) return rc;
+    char *p = h->d_buf;
+    auto take = [&](size_t n) { char *r = p; p += n; return r; };
+    double *d_x0 = (double *)take(sz_x0), *d_xref = (double *)take(sz_xref);
+    double *d_uref = traj ? (double *)take(sz_uref) : nullptr;
+    double *d_ox = obs ? (double *)take(sz_obs) : nullptr, *d_oy = obs ? (double *)take(sz_obs) : nullptr;
+    double *d_ui = u_init ? (double *)take(sz_ui) : nullptr;
+    double *d_X = (double *)take(sz_X), *d_U = (double *)take(sz_U), *d_c = (double *)take(sz_c);
+    int *d_st = (int *)take(sz_i), *d_it = (int *)take(sz_i), *d_ls = (int *)take(sz_i);
+    cudaStream_t s = h->stream;
+    CU_TRY(h, cudaMemcpyAsync(d_x0, x0, nb * 3 * 8, cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaMemcpyAsync(d_xref, xref, nb * (traj ? 3 * N : 3) * 8, cudaMemcpyHostToDevice, s));
+    if (traj) CU_TRY(h, cudaMemcpyAsync(d_uref, uref, nb * 2 * N * 8, cudaMemcpyHostToDevice, s));
+    if (obs) {
+        CU_TRY(h, cudaMemcpyAsync(d_ox, obs_x, n_obs * 8, cudaMemcpyHostToDevice, s));
+        CU_TRY(h, cudaMemcpyAsync(d_oy, obs_y, n_obs * 8, cudaMemcpyHostToDevice, s));
+    }
+    if (u_init) CU_TRY(h, cudaMemcpyAsync(d_ui, u_init, nb * 2 * N * 8, cudaMemcpyHostToDevice, s));
+    BatchArgs a;
+    a.B = B; a.obs_stride = obs_stride;
+    a.x0 = d_x0; a.xref = d_xref; a.uref = d_uref; a.ox = d_ox; a.oy = d_oy; a.u_init = d_ui;
+    a.X = d_X; a.U = d_U; a.cost = d_c; a.status = d_st; a.iters = d_it; a.ls = d_ls;
+    a.counter = h->d_counter;
+    rc = launch_solve(h, a, s);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(X_out, d_X, nb * 3 * (N + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaMemcpyAsync(U_out, d_U, nb * 2 * N * 8, cudaMemcpyDeviceToHost, s));
+    if (cost_out) CU_TRY(h, cudaMemcpyAsync(cost_out, d_c, nb * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaMemcpyAsync(status_out, d_st, nb * 4, cudaMemcpyDeviceToHost, s));
+    if (iters_out) CU_TRY(h, cudaMemcpyAsync(iters_out, d_it, nb * 4, cudaMemcpyDeviceToHost, s));
+    if (ls_out) CU_TRY(h, cudaMemcpyAsync(ls_out, d_ls, nb * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int b200mpc_eval_batch(b200mpc_handle *h, int B, const double *x0, const double *xref, const double *uref,
+                                  const double *obs_x, const double *obs_y, int obs_stride, const double *X,
+                                  const double *U, const double *lam, double obj_scale, double *f_out, double *c_out,
+                                  double *grad_out, double *stage_out) {
+    int rc = check_args(h, B, x0, xref, uref, obs_x, obs_y, obs_stride);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (!X || !U) return set_err(h, B200MPC_E_ARG, "X / U is NULL");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int N = h->prm.N, M = h->prm.M;
+    const bool traj = h->prm.ref_kind == B200MPC_REF_TRAJ, obs = h->prm.obs_form != B200MPC_OBS_NONE;
+    const size_t nb = (size_t)B;
+    const size_t sz_x0 = al256(nb * 3 * 8), sz_xref = al256(nb * (traj ? 3 * N : 3) * 8);
+    const size_t sz_uref = traj ? al256(nb * 2 * N * 8) : 0;
+    const size_t n_obs = obs ? (obs_stride ? nb * obs_stride : (size_t)M) : 0;
+    const size_t sz_obs = al256(n_obs * 8);
+    const size_t sz_X = al256(nb * 3 * (N + 1) * 8), sz_U = al256(nb * 2 * N * 8), sz_l = al256(nb * 3 * N * 8);
+    const size_t sz_f = al256(nb * 8), sz_g = al256(nb * 5 * N * 8), sz_s = al256(nb * (N + 1) * 36 * 8);
+    const size_t total = sz_x0 + sz_xref + sz_uref + 2 * sz_obs + sz_X + sz_U + sz_l + sz_f + sz_l + sz_g + sz_s;
+    rc = ensure_buf(h, total);
+    if (rc) return rc;
+    char *p = h->d_buf;
+    auto take = [&](size_t n) { char *r = p; p += n; return r; };
+    double *d_x0 = (double *)take(sz_x0), *d_xref = (double *)take(sz_xref);
+    double *d_uref = traj ? (double *)take(sz_uref) : nullptr;
+    double *d_ox = obs ? (double *)take(sz_obs) : nullptr, *d_oy = obs ? (double *)take(sz_obs) : nullptr;
+    double *d_X = (double *)take(sz_X), *d_U = (double *)take(sz_U), *d_lam = (double *)take(sz_l);
+    double *d_f = (double *)take(sz_f), *d_c = (double *)take(sz_l), *d_g = (double *)take(sz_g), *d_s = (double *)take(sz_s);
+    cudaStream_t s = h->stream;
+    CU_TRY(h, cudaMemcpyAsync(d_x0, x0, nb * 3 * 8, cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaMemcpyAsync(d_xref, xref, nb * (traj ? 3 * N : 3) * 8, cudaMemcpyHostToDevice, s));
+    if (traj) CU_TRY(h, cudaMemcpyAsync(d_uref, uref, nb * 2 * N * 8, cudaMemcpyHostToDevice, s));
+    if (obs) {
+        CU_TRY(h, cudaMemcpyAsync(d_ox, obs_x, n_obs * 8, cudaMemcpyHostToDevice, s));
+        CU_TRY(h, cudaMemcpyAsync(d_oy, obs_y, n_obs * 8, cudaMemcpyHostToDevice, s));
+    }
+    CU_TRY(h, cudaMemcpyAsync(d_X, X, nb * 3 * (N + 1) * 8, cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaMemcpyAsync(d_U, U, nb * 2 * N * 8, cudaMemcpyHostToDevice, s));
+    if (lam) CU_TRY(h, cudaMemcpyAsync(d_lam, lam, nb * 3 * N * 8, cudaMemcpyHostToDevice, s));
+    EvalArgs a;
+    a.B = B; a.obs_stride = obs_stride;
+    a.x0 = d_x0; a.xref = d_xref; a.uref = d_uref; a.ox = d_ox; a.oy = d_oy;
+    a.X = d_X; a.U = d_U; a.lam = lam ? d_lam : nullptr; a.obj_scale = obj_scale;
+    a.f = d_f; a.c = d_c; a.grad = d_g; a.stage = d_s;
+    const int grid = (B + 3) / 4;
+    switch (h->J) {
+        case 1: mpc_eval_kernel<1><<<grid, 128, h->smem_bytes, s>>>(h->kp, a); break;
+        case 2: mpc_eval_kernel<2><<<grid, 128, h->smem_bytes, s>>>(h->kp, a); break;
+        case 3: mpc_eval_kernel<3><<<grid, 128, h->smem_bytes, s>>>(h->kp, a); break;
+        default: mpc_eval_kernel<4><<<grid, 128, h->smem_bytes, s>>>(h->kp, a); break;
+    }
+    CU_TRY(h, cudaGetLastError());
+    h->launches++;
+    if (f_out) CU_TRY(h, cudaMemcpyAsync(f_out, d_f, nb * 8, cudaMemcpyDeviceToHost, s));
+    if (c_out) CU_TRY(h, cudaMemcpyAsync(c_out, d_c, nb * 3 * N * 8, cudaMemcpyDeviceToHost, s));
+    if (grad_out) CU_TRY(h, cudaMemcpyAsync(grad_out, d_g, nb * 5 * N * 8, cudaMemcpyDeviceToHost, s));
+    if (stage_out) CU_TRY(h, cudaMemcpyAsync(stage_out, d_s, nb * (N + 1) * 36 * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaStreamSynchronize(s));
+    return 0;
+}
