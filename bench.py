@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — converged MPC solves/sec (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W          the CUDA path (libb200mpc.so through the C ABI)
+  python bench.py --impl reference ...                   the CPU restatement (oracle/) on the box's host cores
+
+Workload: 4096 robots on map_carto (PCG64 seed 0: random free-space poses and
+goals, scan-derived obstacle lists) x `seeds` warm-start seeds, u_init = clip(N(0,0.05^2), bounds) from
+PCG64(1+s): one "step" = one batched solve of robots*seeds problems on every GPU (weak scaling: rank r uses the
+seed block [r*seeds, (r+1)*seeds)).  Default seeds=256 -> 1,048,576 problems per GPU per step, the reference
+horizon N=30, variant B (ros2_mpc/planner/local_planner_point_stabilization.py — the Mpc the launched node uses).
+`value` counts converged problems only (status Solve_Succeeded / Solved_To_Acceptable_Level).
+
+Timing: W>=3 untimed steps, then K steps between CUDA events on the launch stream, bracketed by barrier +
+synchronize, max over ranks.  Inputs (>500 MB per step) exceed the 126 MB L2.  `e2e` repeats the K steps through
+the host-buffer C-ABI call with pinned host arrays (H2D + kernel + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "converged_mpc_solves_per_sec"
+UNIT = "solves/s"
+T_FLOP = 20.0  # flop-equivalents per transcendental (SURVEY.md 8d convention)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="B", choices=["A", "B", "C"])
+    ap.add_argument("--robots", type=int, default=4096)
+    ap.add_argument("--seeds", type=int, default=256, help="warm-start seeds per robot per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample", type=int, default=0, help="problems per step of the reference arm (0 = auto)")
+    return ap.parse_args()
+
+
+def algorithmic_flops(p, iters, ls):
+    """W = I*W_iter + L*W_ls per problem."""
+    N, M = p.N, p.M
+    Ko = 0 if p.obs_form == 0 else (p.obs_k1 - p.obs_k0 + 1)
+    c_o = 24.0 if p.obs_form == 1 else 34.0
+    w_iter = 548.0 * N + c_o * Ko * M + T_FLOP * (7 * N + Ko * M)
+    w_ls = 31.0 * N + 7 * T_FLOP * N + (8 + T_FLOP) * Ko * M
+    return iters.astype(np.float64) * w_iter + ls.astype(np.float64) * w_ls
+
+
+def io_bytes_per_solve(p, per_problem_obstacles):
+    N, M = p.N, p.M
+    nref = 3 if p.ref_kind == 0 else 3 * N
+    inb = 8 * (3 + nref + 2 * N + (2 * N if p.ref_kind == 1 else 0))
+    if p.obs_form != 0 and per_problem_obstacles:
+        inb += 8 * 2 * M
+    outb = 8 * (3 * (N + 1) + 2 * N + 1) + 4 * 3
+    return inb, outb
+
+
+def build_workload(variant, robots, seeds, seed_offset, params):
+    """Returns host arrays for robots*seeds problems (problem index = seed-major: b = s*robots + r)."""
+    from ros2_mpc_b200 import synth  # noqa: PLC0415
+    w = synth.robots_on_map(B=robots, seed=0, params=params)
+    B = robots * seeds
+    N = params["N"]
+    from ros2_mpc_b200 import make_params  # noqa: PLC0415
+    p = make_params(variant, params)
+    ui = synth.warm_start_seeds(seeds, N, list(p.u_lo), list(p.u_hi), first_seed=1 + seed_offset)
+    out = dict(B=B, p=p)
+    out["x0"] = np.tile(w["x0"], (seeds, 1))
+    if variant == "C":
+        pxf, puf = synth.straight_reference(w["x0"], w["goal"], N)
+        out["xref"] = np.tile(pxf, (seeds, 1))
+        out["uref"] = np.tile(puf, (seeds, 1))
+    else:
+        out["xref"] = np.tile(w["goal"], (seeds, 1))
+        out["uref"] = None
+    out["u_init"] = np.repeat(ui, robots, axis=0).reshape(B, N, 2)
+    if variant == "A":
+        out["obs_x"] = np.tile(w["obs_x"], (seeds, 1))
+        out["obs_y"] = np.tile(w["obs_y"], (seeds, 1))
+    else:
+        out["obs_x"] = out["obs_y"] = None
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(variant, params, wl, budget_s=12.0):
+    """Oracle (CPU restatement) on all host cores over a bounded prefix of the same workload."""
+    from oracle import oracle as O  # noqa: PLC0415
+    po = O.variant_params(variant, params)
+    cores = len(os.sched_getaffinity(0))
+
+    def run(n):
+        kw = {}
+        if wl["obs_x"] is not None:
+            kw = dict(obs_x=wl["obs_x"][:n], obs_y=wl["obs_y"][:n])
+        if wl["uref"] is not None:
+            kw["uref"] = wl["uref"][:n]
+        t = time.perf_counter()
+        r = O.solve_batch(po, wl["x0"][:n], wl["xref"][:n], u_init=wl["u_init"][:n].reshape(n, -1), nthreads=cores, **kw)
+        return time.perf_counter() - t, r
+
+    n0 = min(wl["B"], 2048)
+    t0, _ = run(n0)
+    n = int(min(wl["B"], max(n0, n0 * budget_s / max(t0, 1e-6))))
+    t1, r = run(n)
+    conv = int(np.isin(r["status"], (0, 1)).sum())
+    return {"value": conv / t1, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n} problems of the step's batch, {t1:.1f} s, {conv}/{n} converged, "
+                      f"oracle/mpc_oracle.c (Riccati backend), one problem per thread"}, po
+
+
+def run_reference(args, params):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O  # noqa: PLC0415
+    cores = len(os.sched_getaffinity(0))
+    wl = build_workload(args.variant, args.robots, 1 if args.ref_sample else 2, 0, params)
+    po = O.variant_params(args.variant, params)
+    n = args.ref_sample or min(wl["B"], 8192)
+
+    def step():
+        kw = {}
+        if wl["obs_x"] is not None:
+            kw = dict(obs_x=wl["obs_x"][:n], obs_y=wl["obs_y"][:n])
+        if wl["uref"] is not None:
+            kw["uref"] = wl["uref"][:n]
+        return O.solve_batch(po, wl["x0"][:n], wl["xref"][:n], u_init=wl["u_init"][:n].reshape(n, -1), nthreads=cores, **kw)
+
+    for _ in range(args.warmup):
+        step()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        r = step()
+    dt = time.perf_counter() - t
+    conv = int(np.isin(r["status"], (0, 1)).sum())
+    value = conv * args.steps / dt
+    sample = f"{n} problems per step (prefix of the config-4 batch), {cores} host threads, oracle/mpc_oracle.c"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, params), "reference_impl": "CPU restatement of the CasADi/IPOPT path "
+                       "(casadi is not installable offline); bounded sample per step"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args, params):
+    return (f"config4: {args.robots} robots on map_carto (PCG64 seed 0) x {args.seeds} warm-start seeds = "
+            f"{args.robots * args.seeds} problems per GPU per step, variant {args.variant}, N={params['N']}, M=160")
+
+
+def main():
+    args = parse_args()
+    from ros2_mpc_b200 import load_params  # noqa: PLC0415
+    params = load_params()
+    if args.impl == "reference":
+        run_reference(args, params)
+        return
+
+    import torch  # noqa: PLC0415
+    import torch.distributed as dist  # noqa: PLC0415
+    from ros2_mpc_b200 import _shim  # noqa: PLC0415
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: ros2_mpc_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = build_workload(args.variant, args.robots, args.seeds, rank * args.seeds, params)
+    p, B, N = wl["p"], wl["B"], params["N"]
+    solver = _shim.Solver(p, device=local_rank)
+
+    # ---- device-resident buffers ----
+    def to_dev(a):
+        return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    d = {k: to_dev(wl[k]) for k in ("x0", "xref", "uref", "u_init", "obs_x", "obs_y")}
+    dX = torch.empty((B, N + 1, 3), dtype=torch.float64, device=dev)
+    dU = torch.empty((B, N, 2), dtype=torch.float64, device=dev)
+    dcost = torch.empty(B, dtype=torch.float64, device=dev)
+    dstat = torch.empty(B, dtype=torch.int32, device=dev)
+    dit = torch.empty(B, dtype=torch.int32, device=dev)
+    dls = torch.empty(B, dtype=torch.int32, device=dev)
+    ptr = lambda t: 0 if t is None else t.data_ptr()  # noqa: E731
+    stride = p.M if d["obs_x"] is not None else 0
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        solver.solve_batch_device(B, ptr(d["x0"]), ptr(d["xref"]), ptr(d["uref"]), ptr(d["obs_x"]), ptr(d["obs_y"]), stride,
+                                  ptr(d["u_init"]), ptr(dX), ptr(dU), ptr(dcost), ptr(dstat), ptr(dit), ptr(dls),
+                                  stream=stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    fp64_peak = solver.measure_fp64_peak() if rank == 0 else 0.0
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = solver.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = solver.launch_count - launches0
+    kernel_ms.append(solver.last_kernel_ms())
+    status = dstat.cpu().numpy()
+    iters = dit.cpu().numpy()
+    ls = dls.cpu().numpy()
+    conv_local = int(np.isin(status, (0, 1)).sum())
+    conv_total = sum_over_ranks(float(conv_local))
+    value = conv_total * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end: pinned host buffers through the host-pointer C-ABI call ----
+    def pinned(a):
+        if a is None:
+            return None
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy()
+
+    h = {k: pinned(wl[k]) for k in ("x0", "xref", "uref", "u_init", "obs_x", "obs_y")}
+    out = dict(X=torch.empty((B, N + 1, 3), dtype=torch.float64).pin_memory().numpy(),
+               U=torch.empty((B, N, 2), dtype=torch.float64).pin_memory().numpy(),
+               cost=torch.empty(B, dtype=torch.float64).pin_memory().numpy(),
+               status=torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
+               iters=torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
+               ls=torch.empty(B, dtype=torch.int32).pin_memory().numpy())
+
+    def step_host():
+        solver.solve_batch(h["x0"], h["xref"], uref=h["uref"], obs_x=h["obs_x"], obs_y=h["obs_y"], u_init=h["u_init"], out=out)
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    conv_e2e = sum_over_ranks(float(np.isin(out["status"], (0, 1)).sum()))
+    e2e_value = conv_e2e * args.steps / e2e_s
+    h2d = sum(a.nbytes for a in h.values() if a is not None)
+    d2h = sum(a.nbytes for a in out.values())
+    assert np.array_equal(out["status"], status), "host-buffer and device-buffer paths disagree"
+
+    if rank == 0:
+        W = algorithmic_flops(p, iters, ls)
+        k_ms = float(np.mean(kernel_ms))
+        achieved = float(W.sum()) / (k_ms * 1e-3) / 1e12
+        inb, outb = io_bytes_per_solve(p, wl["obs_x"] is not None)
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(f"{args.variant}_{B}")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, params), "l2": f"inputs {h2d / 1e6:.0f} MB per step exceed the 126 MB L2",
+                       "converged_fraction": conv_local / B, "mean_iterations": float(iters.mean()),
+                       "max_iterations": int(iters.max()), "mean_extra_ls_trials": float(ls.mean())},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
+                         "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "kernel": "mpc_solve_kernel", "kernel_ms": k_ms,
+                         "algorithmic_flops_per_launch": float(W.sum()),
+                         "hbm": {"achieved": (inb + outb) * B / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "algorithmic_bytes_per_solve": inb + outb,
+                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback"}},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_baseline(args.variant, params, wl)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

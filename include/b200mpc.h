@@ -146,7 +146,13 @@ long long b200mpc_launch_count(const b200mpc_handle *h);
  * (valid after the stream has been synchronised; host-buffer solves synchronise themselves). */
 float b200mpc_last_kernel_ms(b200mpc_handle *h);
 
+/* Measures the device's FP64 FMA throughput [TFLOP/s] with a register-resident DFMA loop on every SM.
+ * bench.py uses it as the roofline denominator of the solve kernel (which is FP64-pipe / latency bound). */
+int b200mpc_measure_fp64_peak(b200mpc_handle *h, double *tflops_out);
+
 int b200mpc_abi_version(void);
+/* sizeof(struct b200mpc_params) as compiled, so a binding can verify its struct layout. */
+int b200mpc_sizeof_params(void);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,11 @@ def lib():
         L.b200mpc_launch_count.restype = C.c_longlong
         L.b200mpc_last_kernel_ms.argtypes = [vp]
         L.b200mpc_last_kernel_ms.restype = C.c_float
+        L.b200mpc_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+        L.b200mpc_measure_fp64_peak.restype = C.c_int
+        L.b200mpc_sizeof_params.restype = C.c_int
+        if L.b200mpc_sizeof_params() != C.sizeof(Params):
+            raise RuntimeError("b200mpc_params layout mismatch between _shim.Params and libb200mpc.so")
         _LIB = L
     return _LIB
 
@@ -123,6 +128,12 @@ class Solver:
 
     def last_kernel_ms(self):
         return float(self._L.b200mpc_last_kernel_ms(self._h))
+
+    def measure_fp64_peak(self):
+        """FP64 FMA peak of the device [TFLOP/s], measured with a DFMA-saturating micro-kernel."""
+        v = C.c_double(0.0)
+        self._check(self._L.b200mpc_measure_fp64_peak(self._h, C.byref(v)))
+        return float(v.value)
 
     def solve_batch(self, x0, xref, uref=None, obs_x=None, obs_y=None, u_init=None, out=None):
         """Host-buffer solve.  x0 (B,3); xref (B,3)|(B,3N); uref (B,2N); obs_x/obs_y (B,M) or (M,) shared;

@@ -359,7 +359,7 @@ __device__ __forceinline__ bool kkt_solve(const KParams &P, Stg (&s)[J], const d
                 const double x00 = hxx + dw + q00, x01 = hxy + q01, x11 = hyy + dw + q11;
                 const double x02 = t0, x12 = t1, x22 = htt + dw + t2 + a * t0 + b * t1;
                 // PB columns
-                const double e0 = b11 * q00 + b21 * q01, e1 = b11 * q01 + b21 * q11, e2 = b11 * q02 + b21 * q12;
+                const double e0 = b11 * q00 + b21 * q01, e1 = b11 * q01 + b21 * q11;
                 const double f0 = b12 * q00 + b22 * q01 + dt * q02, f1 = b12 * q01 + b22 * q11 + dt * q12,
                              f2 = b12 * q02 + b22 * q12 + dt * q22;
                 // Qux = Hux + B'PA
@@ -1288,6 +1288,44 @@ extern "C" void b200mpc_destroy(b200mpc_handle *h) {
     cudaStreamDestroy(h->stream);
     delete h;
 }
+
+// ---- FP64 DFMA peak micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 entry) ----------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+    double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double b = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" int b200mpc_measure_fp64_peak(b200mpc_handle *h, double *tflops_out) {
+    if (!h || !tflops_out) return B200MPC_E_ARG;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int blocks = h->sm_count * 8, threads = 256, iters = 1 << 15;
+    double *d_out = nullptr;
+    CU_TRY(h, cudaMalloc(&d_out, sizeof(double) * (size_t)blocks * threads));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CU_TRY(h, cudaEventRecord(h->ev0, h->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(d_out, iters);
+        CU_TRY(h, cudaGetLastError());
+        CU_TRY(h, cudaEventRecord(h->ev1, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        float ms = 0;
+        CU_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        if (rep > 0 && ms < best) best = ms;
+        h->launches++;
+    }
+    cudaFree(d_out);
+    const double flops = (double)blocks * threads * (double)iters * 8.0 * 2.0;
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    return 0;
+}
+
+extern "C" int b200mpc_sizeof_params(void) { return (int)sizeof(b200mpc_params); }
 
 extern "C" long long b200mpc_launch_count(const b200mpc_handle *h) { return h ? h->launches : 0; }
 

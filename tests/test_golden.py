@@ -1,0 +1,127 @@
+"""The oracle and the host-side obstacle builder against fixtures generated from the reference itself
+(tests/golden/make_golden.py: the reference's unmodified Mpc sources traced through a casadi stand-in, its numba
+helpers run on seeded scans, and its perform_mpc run end to end with scipy SLSQP substituted for IPOPT)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from ros2_mpc_b200 import obstacles as ob
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def nlp():
+    return np.load(os.path.join(G, "nlp_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def sol():
+    return np.load(os.path.join(G, "solve_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def obsg():
+    return np.load(os.path.join(G, "obstacles_golden.npz"))
+
+
+@pytest.mark.parametrize("variant", ["A", "B", "C"])
+def test_oracle_nlp_functions_match_reference_sources(nlp, variant):
+    """Objective and shooting defects of the oracle == those of the reference's own Opti problem."""
+    p = O.variant_params(variant)
+    v = variant
+    x0 = nlp[f"{v}_x0"]
+    kw = {}
+    xref = nlp[f"{v}_goal"]
+    if v == "C":
+        xref = nlp["C_pf"]; kw["uref"] = nlp["C_puf"]
+    if v == "A":
+        kw.update(obs_x=nlp["A_obs_x"], obs_y=nlp["A_obs_y"])
+    for i in range(nlp[f"{v}_X"].shape[0]):
+        e = O.evaluate(p, x0, xref, nlp[f"{v}_X"][i], nlp[f"{v}_U"][i], **kw)
+        assert abs(e["f"] - nlp[f"{v}_f"][i]) <= 1e-12 * abs(nlp[f"{v}_f"][i])
+        assert np.allclose(e["c"], nlp[f"{v}_c"][i], rtol=0, atol=1e-13)
+        # the inequality rows of the reference are exactly the controls, with the variant's box
+        assert np.array_equal(nlp[f"{v}_h"][i], np.r_[nlp[f"{v}_U"][i][:, 0], nlp[f"{v}_U"][i][:, 1]])
+    N = p.N
+    assert np.array_equal(nlp[f"{v}_h_lo"], np.r_[np.full(N, p.u_lo[0]), np.full(N, p.u_lo[1])])
+    assert np.array_equal(nlp[f"{v}_h_hi"], np.r_[np.full(N, p.u_hi[0]), np.full(N, p.u_hi[1])])
+
+
+def _check(r, X, U, cost):
+    assert r["status"] == 0
+    assert abs(r["cost"] - cost) <= 1e-5 * abs(cost)
+    assert np.max(np.abs(r["U"] - U)) <= 1e-4
+    assert np.max(np.abs(r["X"] - X)) <= 1e-4
+
+
+@pytest.mark.parametrize("tag", ["B1", "B2", "B3"])
+def test_oracle_optimum_matches_reference_perform_mpc_variant_b(sol, tag):
+    p = O.variant_params("B")
+    r = O.solve(p, sol[f"{tag}_x0"], sol[f"{tag}_goal"])
+    _check(r, sol[f"{tag}_X"], sol[f"{tag}_U"], float(sol[f"{tag}_cost"]))
+    assert np.max(np.abs(r["U"][:, 0] - sol[f"{tag}_u0"])) <= 1e-4
+
+
+@pytest.mark.parametrize("tag", ["A1", "A2"])
+def test_oracle_optimum_matches_reference_perform_mpc_variant_a(sol, tag):
+    p = O.variant_params("A")
+    r = O.solve(p, sol[f"{tag}_x0"], sol[f"{tag}_goal"], obs_x=sol[f"{tag}_obs_x"], obs_y=sol[f"{tag}_obs_y"])
+    _check(r, sol[f"{tag}_X"], sol[f"{tag}_U"], float(sol[f"{tag}_cost"]))
+
+
+def test_oracle_optimum_matches_reference_perform_mpc_variant_c(sol):
+    p = O.variant_params("C")
+    r = O.solve(p, sol["C1_x0"], sol["C1_pf"], uref=sol["C1_puf"])
+    _check(r, sol["C1_X"], sol["C1_U"], float(sol["C1_cost"]))
+    assert np.max(np.abs(r["U"][:, 0] - sol["C1_u0"])) <= 1e-4
+
+
+def test_scan_to_grid_cells_bit_exact(obsg):
+    S = obsg["scans"].shape[0]
+    grids = np.unpackbits(obsg["grid_bits"])[:S * 80 * 80].reshape(S, 80, 80)
+    for i in range(S):
+        g = ob.scan_to_occupancy_grid(obsg["scans"][i][None], obsg["angles"][i], 0.05, 4.0)[0]
+        assert np.array_equal((g == 100).astype(np.uint8), grids[i]), f"scan {i}"
+        assert set(np.unique(g)) <= {0.0, 100.0}
+
+
+def test_get_obstacles_matches_reference(obsg):
+    S = obsg["scans"].shape[0]
+    ox, oy, cnt = ob.get_obstacles(obsg["scans"], obsg["angles"], 2.0, 0.05, obsg["pos"], obsg["yaw"], 160)
+    assert np.array_equal(cnt, obsg["count"])
+    assert np.allclose(ox, obsg["obs_x"], rtol=0, atol=1e-12)
+    assert np.allclose(oy, obsg["obs_y"], rtol=0, atol=1e-12)
+    # quirks: no hit -> sentinel 100.0; all-inf scan -> a single cell next to the robot centre
+    none = np.where(cnt == 0)[0]
+    assert len(none) >= 1 and np.all(ox[none] == 100.0) and np.all(oy[none] == 100.0)
+    i = 2
+    # cell (40,40) becomes (39,39) after the 180-degree rotation: one grid cell (0.05, 0.05) off the robot centre
+    assert cnt[i] == 1
+    assert np.allclose(np.hypot(ox[i] - obsg["pos"][i, 0], oy[i] - obsg["pos"][i, 1]), 0.05 * np.sqrt(2), atol=1e-12)
+    # overflow: the reference raises ValueError (more cells than slots)
+    over = np.where(cnt > 160)[0]
+    assert len(over) >= 1
+    with pytest.raises(ValueError):
+        ob.get_obstacles(obsg["scans"][over[0]], obsg["angles"][over[0]], 2.0, 0.05, obsg["pos"][over[0]],
+                         obsg["yaw"][over[0]], 160, overflow="raise")
+
+
+def test_get_obstacles_live_against_reference_numba(obsg):
+    """When the reference checkout is present (build container), run its numba helpers live as well."""
+    path = "/root/reference/ros2_mpc/utils/utils.py"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present (GPU box)")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_utils_live", path)
+    ru = importlib.util.module_from_spec(spec); spec.loader.exec_module(ru)
+    rng = np.random.default_rng(99)
+    for _ in range(20):
+        sc = np.round(rng.uniform(0.1, 3.5, 360), 2)
+        sc[rng.random(360) < 0.05] = np.inf
+        a = np.array([0.0, 6.28])
+        g_ref = ru.convert_laser_scan_to_occupancy_grid(sc.copy(), a, 0.05, 4.0)
+        g = ob.scan_to_occupancy_grid(sc[None], a, 0.05, 4.0)[0]
+        assert np.array_equal(g, g_ref)
