@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200mpc.so")
+# B200MPC_LIB selects an alternative build of the same library (kernel-tuning experiments)
+LIB_PATH = os.environ.get("B200MPC_LIB") or os.path.join(_HERE, "libb200mpc.so")
 _LIB = None
 
 RK4, EULER = 0, 1

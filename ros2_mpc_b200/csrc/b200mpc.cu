@@ -30,6 +30,9 @@
 #include <string>
 
 #define FULL 0xffffffffu
+#ifndef B200MPC_MIN_CTAS
+#define B200MPC_MIN_CTAS 2
+#endif
 
 // ---- IPOPT defaults (Waechter & Biegler 2006; IPOPT option documentation) -------------------------------
 #define K_EPS 10.0
@@ -1044,7 +1047,7 @@ finish:
 }
 
 template <int J>
-__global__ void __launch_bounds__(128) mpc_solve_kernel(const KParams P, const BatchArgs A) {
+__global__ void __launch_bounds__(128, B200MPC_MIN_CTAS) mpc_solve_kernel(const KParams P, const BatchArgs A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int Mpad = (P.M + 3) & ~3;
