@@ -70,6 +70,12 @@ extern "C" {
 #define B200MPC_ERROR_IN_STEP_COMPUTATION (-3)
 #define B200MPC_INVALID_NUMBER_DETECTED (-13)
 
+/* solve kernels (b200mpc_set_kernel) */
+#define B200MPC_KERNEL_AUTO 0 /* by batch size: lane-per-problem from B200MPC_LANE_KERNEL_MIN_BATCH problems on */
+#define B200MPC_KERNEL_WARP 1 /* one warp per problem, horizon in registers: small batches, single-solve latency */
+#define B200MPC_KERNEL_LANE 2 /* one lane per problem, horizon streamed through an HBM workspace: large batches */
+#define B200MPC_LANE_KERNEL_MIN_BATCH 16384
+
 /* library error codes */
 #define B200MPC_E_ARG (-1)
 #define B200MPC_E_CUDA (-2)
@@ -139,6 +145,13 @@ int b200mpc_eval_batch(b200mpc_handle *h, int B, const double *x0, const double 
                        const double *obs_x, const double *obs_y, int obs_stride, const double *X,
                        const double *U, const double *lam, double obj_scale, double *f_out, double *c_out,
                        double *grad_out, double *stage_out);
+
+/* Forces one of the two solve kernels (default B200MPC_KERNEL_AUTO; the environment variable B200MPC_KERNEL=warp|lane
+ * sets the default of new handles).  Both kernels run the same algorithm; results agree to rounding.  The
+ * lane-per-problem kernel does not carry the obstacle cost (obs_form != NONE always uses the warp kernel). */
+int b200mpc_set_kernel(b200mpc_handle *h, int kind);
+/* B200MPC_KERNEL_WARP / _LANE: the kernel the most recent solve used. */
+int b200mpc_last_kernel_kind(const b200mpc_handle *h);
 
 /* Number of kernel launches issued by this handle so far (bench.py reports it as gpu_launches). */
 long long b200mpc_launch_count(const b200mpc_handle *h);

@@ -15,6 +15,7 @@ _LIB = None
 RK4, EULER = 0, 1
 OBS_NONE, OBS_GAUSS, OBS_EXPLOG = 0, 1, 2
 REF_GOAL, REF_TRAJ = 0, 1
+KERNEL_AUTO, KERNEL_WARP, KERNEL_LANE = 0, 1, 2
 
 STATUS_NAMES = {
     0: "Solve_Succeeded", 1: "Solved_To_Acceptable_Level", -1: "Maximum_Iterations_Exceeded",
@@ -67,6 +68,10 @@ def lib():
         L.b200mpc_last_kernel_ms.restype = C.c_float
         L.b200mpc_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
         L.b200mpc_measure_fp64_peak.restype = C.c_int
+        L.b200mpc_set_kernel.argtypes = [vp, C.c_int]
+        L.b200mpc_set_kernel.restype = C.c_int
+        L.b200mpc_last_kernel_kind.argtypes = [vp]
+        L.b200mpc_last_kernel_kind.restype = C.c_int
         L.b200mpc_sizeof_params.restype = C.c_int
         if L.b200mpc_sizeof_params() != C.sizeof(Params):
             raise RuntimeError("b200mpc_params layout mismatch between _shim.Params and libb200mpc.so")
@@ -129,6 +134,14 @@ class Solver:
 
     def last_kernel_ms(self):
         return float(self._L.b200mpc_last_kernel_ms(self._h))
+
+    def set_kernel(self, kind):
+        """KERNEL_AUTO (by batch size), KERNEL_WARP (warp per problem) or KERNEL_LANE (lane per problem)."""
+        self._check(self._L.b200mpc_set_kernel(self._h, int(kind)))
+
+    @property
+    def last_kernel_kind(self):
+        return int(self._L.b200mpc_last_kernel_kind(self._h))
 
     def measure_fp64_peak(self):
         """FP64 FMA peak of the device [TFLOP/s], measured with a DFMA-saturating micro-kernel."""

@@ -33,6 +33,9 @@
 #ifndef B200MPC_MIN_CTAS
 #define B200MPC_MIN_CTAS 2
 #endif
+#ifndef B200MPC_TPP_MIN_CTAS
+#define B200MPC_TPP_MIN_CTAS 3
+#endif
 
 // ---- IPOPT defaults (Waechter & Biegler 2006; IPOPT option documentation) -------------------------------
 #define K_EPS 10.0
@@ -1140,6 +1143,8 @@ __global__ void __launch_bounds__(128) mpc_eval_kernel(const KParams P, const Ev
     }
 }
 
+#include "tpp_kernel.cuh"
+
 // =============================================================================================================
 // Host side: C ABI
 // =============================================================================================================
@@ -1162,6 +1167,11 @@ struct b200mpc_handle {
     char *d_buf;
     size_t d_cap;
     long long launches;
+    // lane-per-problem kernel (tpp_kernel.cuh): persistent grid and its HBM workspace
+    int kernel_kind;   // B200MPC_KERNEL_AUTO / _WARP / _LANE
+    int last_kind;     // kernel used by the most recent solve
+    int tpp_ctas;
+    double *d_ws, *d_filt;
     std::string err;
 };
 
@@ -1235,6 +1245,15 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     h->launches = 0;
     h->d_buf = nullptr;
     h->d_cap = 0;
+    h->kernel_kind = B200MPC_KERNEL_AUTO;
+    h->last_kind = B200MPC_KERNEL_WARP;
+    h->tpp_ctas = 0;
+    h->d_ws = nullptr;
+    h->d_filt = nullptr;
+    if (const char *ek = getenv("B200MPC_KERNEL")) {
+        if (!strcmp(ek, "warp")) h->kernel_kind = B200MPC_KERNEL_WARP;
+        else if (!strcmp(ek, "lane")) h->kernel_kind = B200MPC_KERNEL_LANE;
+    }
     KParams &k = h->kp;
     memset(&k, 0, sizeof(k));
     k.N = p->N; k.M = (p->obs_form == B200MPC_OBS_NONE) ? 0 : p->M;
@@ -1273,6 +1292,11 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     if (e != cudaSuccess) return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
     if (blocks < 1) blocks = 1;
     h->ctas = blocks * h->sm_count; // persistent grid: a multiple of the SM count (148 on B200)
+    int tblocks = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tblocks, mpc_solve_tpp_kernel, 128, 0)) != cudaSuccess)
+        return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
+    if (tblocks < 1) tblocks = 1;
+    h->tpp_ctas = tblocks * h->sm_count;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cudaGetErrorString(e));
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail(cudaGetErrorString(e));
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail(cudaGetErrorString(e));
@@ -1285,6 +1309,8 @@ extern "C" void b200mpc_destroy(b200mpc_handle *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->d_buf) cudaFree(h->d_buf);
+    if (h->d_ws) cudaFree(h->d_ws);
+    if (h->d_filt) cudaFree(h->d_filt);
     cudaFree(h->d_counter);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
@@ -1352,7 +1378,53 @@ static int check_args(b200mpc_handle *h, int B, const double *x0, const double *
     return 0;
 }
 
+extern "C" int b200mpc_set_kernel(b200mpc_handle *h, int kind) {
+    if (!h) return B200MPC_E_ARG;
+    if (kind != B200MPC_KERNEL_AUTO && kind != B200MPC_KERNEL_WARP && kind != B200MPC_KERNEL_LANE)
+        return set_err(h, B200MPC_E_ARG, "unknown kernel kind");
+    if (kind == B200MPC_KERNEL_LANE && h->prm.obs_form != B200MPC_OBS_NONE)
+        return set_err(h, B200MPC_E_ARG, "the lane-per-problem kernel does not carry the obstacle cost");
+    h->kernel_kind = kind;
+    return 0;
+}
+
+extern "C" int b200mpc_last_kernel_kind(const b200mpc_handle *h) { return h ? h->last_kind : B200MPC_E_ARG; }
+
+// Lane-per-problem kernel: persistent grid, one workspace stripe per warp (allocated on first use).
+static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stream) {
+    const int N = h->prm.N;
+    const size_t nwarps = (size_t)h->tpp_ctas * 4;
+    if (!h->d_ws) {
+        const size_t ws_bytes = nwarps * (size_t)(N + 1) * TPP_NF * 32 * sizeof(double);
+        cudaError_t e = cudaMalloc(&h->d_ws, ws_bytes);
+        if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e));
+        e = cudaMalloc(&h->d_filt, nwarps * 64 * 32 * sizeof(double));
+        if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc(filter): ") + cudaGetErrorString(e));
+    }
+    CU_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), stream));
+    int grid = h->tpp_ctas;
+    const int need = (a.B + 127) / 128;
+    if (need < grid) grid = need;
+    if (grid < 1) grid = 1;
+    TppArgs t;
+    t.a = a; t.ws = h->d_ws; t.filt = h->d_filt;
+    CU_TRY(h, cudaEventRecord(h->ev0, stream));
+    mpc_solve_tpp_kernel<<<grid, 128, 0, stream>>>(h->kp, t);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->ev1, stream));
+    h->launches++;
+    h->last_kind = B200MPC_KERNEL_LANE;
+    return 0;
+}
+
 static int launch_solve(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stream) {
+    // Kernel choice: the lane-per-problem kernel needs enough problems to fill the machine with lanes; below that
+    // (and whenever the obstacle cost is active) the warp-per-problem kernel is used.
+    int kind = h->kernel_kind;
+    if (h->prm.obs_form != B200MPC_OBS_NONE) kind = B200MPC_KERNEL_WARP;
+    else if (kind == B200MPC_KERNEL_AUTO) kind = (a.B >= B200MPC_LANE_KERNEL_MIN_BATCH) ? B200MPC_KERNEL_LANE : B200MPC_KERNEL_WARP;
+    if (kind == B200MPC_KERNEL_LANE) return launch_solve_tpp(h, a, stream);
+    h->last_kind = B200MPC_KERNEL_WARP;
     CU_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), stream));
     int grid = h->ctas;
     const int need = (a.B + 3) / 4;

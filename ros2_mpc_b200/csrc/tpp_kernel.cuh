@@ -1,0 +1,888 @@
+// tpp_kernel.cuh — large-batch solve kernel: one LANE per problem, horizon streamed through a per-warp workspace.
+//
+// The warp-per-problem kernel (mpc_solve_kernel in b200mpc.cu) keeps one problem in the registers of a warp; its
+// Riccati recursion is serial over the horizon, so 31 of 32 lanes idle during more than half of the issued
+// instructions (profiles/r1_v1_*).  For large batches this kernel turns the mapping around: every lane runs the
+// complete interior-point method of its own problem, so each warp instruction advances 32 problems and every
+// phase — linearisation, Riccati sweeps, trial points — runs at full lane utilisation.
+//
+// Data layout.  A problem's iterate, Riccati factors and steps (TPP_NF doubles per stage) do not fit on chip for
+// enough problems, so they live in an HBM workspace private to the warp:
+//     ws[warp][stage k][field f][lane]            (doubles)
+// A field row is 32 consecutive doubles = 256 B = two full 128-byte lines, every access of the kernel is such a
+// row (fully coalesced, compile-time field offsets from one per-stage pointer), and a stage record is one
+// contiguous 18-20 KB block.  The kernel is HBM-bound by construction (about 110 doubles per stage and iteration),
+// not FP64-bound.  Each interior-point iteration is three streaming sweeps over the stages:
+//     B  backward  k = N..0   read iterate, re-linearise, condense, Riccati recursion        -> K, kf, P, pv
+//     F  forward   k = 0..N   read K, kf, P, pv (+ iterate), roll the step out              -> dX, dU, dlam,
+//                             fraction-to-the-boundary step sizes, directional derivative
+//     T  trial     k = N..0   read iterate + step, write curr + alpha*step into the OTHER iterate buffer, and
+//                             evaluate that point: filter quantities (theta, phi) and all KKT residual norms
+// The trial point is written speculatively; if the line search accepts it (99 % of first trials) the lane just
+// flips its buffer index and already holds the convergence norms of the new iterate, so there is no separate
+// "accept" or "evaluate" sweep.  Sweeps are LIFO against each other (F reads what B wrote last, T what F wrote
+// last), which is what the 126 MB L2 can exploit.
+//
+// Control flow.  Lanes of a warp solve different problems whose line searches, inertia corrections and iteration
+// counts differ.  Every lane carries a phase (LOAD, B, F, T); one trip of the main loop executes the blocks
+// L, B, F, T in that order, each for the lanes that are in that phase.  A regular iteration is one trip.  A lane
+// that needs something extra (another trial step size, a second-order correction, a larger delta_w) simply sits
+// out the blocks it does not need in the next trip; it never forces the other 31 lanes to wait for it.  A lane
+// whose problem finishes pulls the next problem from a global counter in the next trip.
+//
+// The algorithm, constants and every decision are those of the warp-per-problem kernel and of oracle/mpc_oracle.c
+// (the CPU checker); only the summation order of the reductions over stages differs (sequential here).
+#pragma once
+
+enum {
+    I_X = 0, I_U = 3, I_S = 5, I_LAM = 7, I_YD = 10, I_VL = 12, I_VU = 14, I_NF = 16, // one iterate buffer; two of them
+    F_K = 32, F_KF = 38, F_P = 40, F_PV = 46,   // Riccati factors
+    F_DX = 49, F_DU = 52, F_DL = 54,            // Newton step (dX, dU, dlam)
+    F_SX = 57, F_SU = 60, F_SL = 62,            // second-order-correction step
+    F_CS = 65, F_DS = 68,                       // second-order-correction right-hand sides
+    F_R = 70, F_UB = 73,                        // per-stage references (trajectory tracking only)
+    TPP_NF = 75
+};
+
+enum { PH_LOAD = 0, PH_B = 1, PH_F = 2, PH_T = 3, PH_BACKTRACK = 4, PH_TOP = 5, PH_FIN = 6, PH_DONE = 7 };
+enum { BM_NEWTON = 0, BM_SOC = 1, BM_LSQ = 2 };
+enum { TM_EVAL0 = 0, TM_EVAL = 1, TM_LSQ = 2, TM_STEP = 3, TM_STEP_SOC = 4 };
+
+#define WF(p, f) (p)[(f) * 32]
+
+// Per-lane mode words are loop-invariant, so the compiler would "unswitch" the stage loops into one copy per mode:
+// lanes of a warp that are in different modes (a freshly loaded problem next to one in mid-solve) would then run
+// their sweeps one after the other, and the code would outgrow the instruction cache.  Passing the mode through an
+// empty volatile asm every stage keeps one loop whose mode-specific parts are short, reconverging branches.
+// The same is done with the phase word at every block of the main loop, together with a __syncwarp(): otherwise
+// the compiler threads the jump "end of block F, phase := T" straight into block T, and the lanes that arrive
+// there by different routes execute the sweep as separate groups (measured: 10.6 active lanes per instruction).
+__device__ __forceinline__ int tpp_opaque(int v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+__device__ __noinline__ double tpp_pow(double a, double b) { return pow(a, b); }
+__device__ __noinline__ double tpp_log10(double a) { return log10(a); }
+
+struct TppArgs {
+    BatchArgs a;
+    double *ws;   // [nwarps][N+1][TPP_NF][32]
+    double *filt; // [nwarps][64][32]: 32 filter entries (phi, theta) per lane
+};
+
+struct TppNorms {
+    double theta, prim_inf, dual_inf, sum_y, sum_z, pmin, pmax, f;
+};
+
+struct TppLane {
+    int b, phase, bmode, tmode;
+    int status, iter, ls_extra, n_resto, acceptable_count, ntrial, soc_count, cur, ring;
+    unsigned fmask;
+    bool keep, soc_first;
+    double df, mu, tau, theta_max, theta_min, dw, dw_last;
+    TppNorms n;                                    // residual norms of the current iterate
+    double ref_phi, ref_gbd, alpha, a_min, a_z;    // line-search reference values, Newton step sizes
+    double alpha_soc, a_z_soc, theta_soc_old;      // second-order correction
+    double r[3];                                   // goal (ref_kind GOAL)
+};
+
+struct TppLin {
+    double a13, a23, b11, b12, b21, b22, F0, F1, F2;
+    double hxx, hyy, htt, htv, htw, hvv, hvw, hww;
+    double g[5], f;
+};
+
+// K1+K2 of a stage with controls (k < N): integration step, Jacobian entries, stage cost and its gradient; with
+// HESS also the Lagrangian Hessian block (ln = multiplier of the defect X_{k+1} - F(X_k, U_k)).
+template <bool HESS>
+__device__ __forceinline__ void tpp_lin(const KParams &P, const double r[3], const double ub[2], const double X[3],
+                                        const double U[2], const double ln[3], double df, TppLin &o) {
+    const double dt = P.dt, th = X[2], v = U[0], w = U[1];
+    o.b12 = 0; o.b22 = 0;
+    o.htw = 0; o.hvw = 0; o.hww = 0;
+    if (P.integrator == B200MPC_EULER) {
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        o.F0 = X[0] + dt * v * cs;
+        o.F1 = X[1] + dt * v * sn;
+        o.a13 = -dt * v * sn; o.a23 = dt * v * cs;
+        o.b11 = dt * cs; o.b21 = dt * sn;
+        if (HESS) {
+            o.htt = -(ln[0] * (-dt * v * cs) + ln[1] * (-dt * v * sn));
+            o.htv = -(ln[0] * (-dt * sn) + ln[1] * (dt * cs));
+        }
+    } else {
+        double s0, c0, sm, cm, se, ce;
+        sincos(th, &s0, &c0);
+        sincos(th + 0.5 * dt * w, &sm, &cm);
+        sincos(th + dt * w, &se, &ce);
+        const double h = dt / 6.0;
+        const double C = c0 + 4.0 * cm + ce, S = s0 + 4.0 * sm + se;
+        const double C1 = 2.0 * cm + ce, S1 = 2.0 * sm + se;
+        o.F0 = X[0] + h * v * C;
+        o.F1 = X[1] + h * v * S;
+        o.a13 = -h * v * S; o.a23 = h * v * C;
+        o.b11 = h * C; o.b21 = h * S;
+        o.b12 = -h * dt * v * S1; o.b22 = h * dt * v * C1;
+        if (HESS) {
+            const double C2 = cm + ce, S2 = sm + se;
+            o.htt = -(ln[0] * (-h * v * C) + ln[1] * (-h * v * S));
+            o.htv = -(ln[0] * (-h * S) + ln[1] * (h * C));
+            o.htw = -(ln[0] * (-h * dt * v * C1) + ln[1] * (-h * dt * v * S1));
+            o.hvw = -(ln[0] * (-h * dt * S1) + ln[1] * (h * dt * C1));
+            o.hww = -(ln[0] * (-h * dt * dt * v * C2) + ln[1] * (-h * dt * dt * v * S2));
+        }
+    }
+    o.F2 = th + dt * w;
+    const double e0 = X[0] - r[0], e1 = X[1] - r[1], e2 = X[2] - r[2];
+    const double m0 = v - ub[0], m1 = w - ub[1];
+    const double er = exp(-P.kappa * v);
+    o.f = e0 * P.Q[0] * e0 + e1 * P.Q[1] * e1 + e2 * P.Q[2] * e2 + m0 * P.R[0] * m0 + m1 * P.R[1] * m1 + er;
+    o.g[0] = df * 2.0 * P.Q[0] * e0;
+    o.g[1] = df * 2.0 * P.Q[1] * e1;
+    o.g[2] = df * 2.0 * P.Q[2] * e2;
+    o.g[3] = df * (2.0 * P.R[0] * m0 - P.kappa * er);
+    o.g[4] = df * 2.0 * P.R[1] * m1;
+    if (HESS) {
+        o.hxx = df * 2.0 * P.Q[0];
+        o.hyy = df * 2.0 * P.Q[1];
+        o.htt = df * 2.0 * P.Q[2] + o.htt;
+        o.hvv = df * (2.0 * P.R[0] + P.kappa * P.kappa * er);
+        o.hww = df * 2.0 * P.R[1] + o.hww;
+    }
+}
+
+__device__ __forceinline__ void tpp_ref(const KParams &P, const TppLane &L, const double *p, double r[3], double ub[2]) {
+    if (P.ref_kind == B200MPC_REF_GOAL) {
+        r[0] = L.r[0]; r[1] = L.r[1]; r[2] = L.r[2];
+        ub[0] = 0; ub[1] = 0;
+    } else {
+        r[0] = WF(p, F_R); r[1] = WF(p, F_R + 1); r[2] = WF(p, F_R + 2);
+        ub[0] = WF(p, F_UB); ub[1] = WF(p, F_UB + 1);
+    }
+}
+
+// ---- sweep B: condensed stage-wise KKT system, Riccati backward recursion -----------------------------------------
+// bmode NEWTON: right-hand side = KKT residual of the current iterate.
+// bmode SOC:    same matrix; the defect right-hand sides are advanced in the same sweep from the last trial point
+//               (csoc = a*csoc + c(trial), dsoc = a*dsoc + (U_t - S_t)) and stored for the forward sweep.
+// bmode LSQ:    least-squares multiplier estimate (W = 0, delta = 1, Sigma = 1, rhs = objective gradient).
+// Returns false when a condensed Quu block is not positive definite (wrong inertia).
+__device__ __forceinline__ bool tpp_backward(const KParams &P, double *wb, const TppLane &L) {
+    const int N = P.N;
+    const double dt = P.dt;
+    const double dw = (L.bmode != BM_LSQ) ? L.dw : 1.0;
+    const double df = L.df, mu = L.mu;
+    const int co = L.cur * I_NF;
+    const int sfx = L.soc_first ? F_DX : F_SX, sfu = L.soc_first ? F_DU : F_SU;
+    const double at = L.soc_first ? L.alpha : L.alpha_soc;
+    double Xn[3] = {0, 0, 0}, ln[3] = {0, 0, 0}, Xtn[3] = {0, 0, 0};
+    double q00 = 0, q01 = 0, q02 = 0, q11 = 0, q12 = 0, q22 = 0, v0 = 0, v1 = 0, v2 = 0;
+    bool ok = true;
+#pragma unroll 1
+    for (int k = N; k >= 0; --k) {
+        const int mode = tpp_opaque(L.bmode);
+        const bool useW = (mode != BM_LSQ);
+        double *p = wb + (size_t)k * (TPP_NF * 32);
+        const double *pc = p + co * 32;
+        const double X[3] = {WF(pc, I_X), WF(pc, I_X + 1), WF(pc, I_X + 2)};
+        double lam[3] = {0, 0, 0};
+        if (k >= 1) { lam[0] = WF(pc, I_LAM); lam[1] = WF(pc, I_LAM + 1); lam[2] = WF(pc, I_LAM + 2); }
+        if (k == N) {
+            // terminal stage: no cost, no controls
+            q00 = dw; q01 = 0; q02 = 0; q11 = dw; q12 = 0; q22 = dw;
+            if (mode == BM_LSQ) { v0 = 0; v1 = 0; v2 = 0; }
+            else { v0 = lam[0]; v1 = lam[1]; v2 = lam[2]; }
+            if (mode == BM_SOC) {
+                Xtn[0] = X[0] + at * WF(p, sfx); Xtn[1] = X[1] + at * WF(p, sfx + 1); Xtn[2] = X[2] + at * WF(p, sfx + 2);
+            }
+        } else {
+            const double U[2] = {WF(pc, I_U), WF(pc, I_U + 1)};
+            double r[3], ub[2];
+            tpp_ref(P, L, p, r, ub);
+            TppLin o;
+            tpp_lin<true>(P, r, ub, X, U, ln, df, o);
+            const double c0 = Xn[0] - o.F0, c1 = Xn[1] - o.F1, c2 = Xn[2] - o.F2;
+            double rx0, rx1, rx2, ru[2], Dsig[2], rs[2], rd[2], rc[3];
+            if (mode == BM_LSQ) {
+                rx0 = o.g[0]; rx1 = o.g[1]; rx2 = o.g[2];
+                ru[0] = o.g[3]; ru[1] = o.g[4];
+                Dsig[0] = Dsig[1] = 1.0; rs[0] = rs[1] = 0.0; rd[0] = rd[1] = 0.0;
+                rc[0] = rc[1] = rc[2] = 0.0;
+            } else {
+                rx0 = o.g[0] + lam[0] - ln[0];
+                rx1 = o.g[1] + lam[1] - ln[1];
+                rx2 = o.g[2] + lam[2] - (o.a13 * ln[0] + o.a23 * ln[1] + ln[2]);
+                const double S[2] = {WF(pc, I_S), WF(pc, I_S + 1)};
+                const double yd[2] = {WF(pc, I_YD), WF(pc, I_YD + 1)};
+                const double vL[2] = {WF(pc, I_VL), WF(pc, I_VL + 1)};
+                const double vU[2] = {WF(pc, I_VU), WF(pc, I_VU + 1)};
+                ru[0] = o.g[3] - (o.b11 * ln[0] + o.b21 * ln[1]) + yd[0];
+                ru[1] = o.g[4] - (o.b12 * ln[0] + o.b22 * ln[1] + dt * ln[2]) + yd[1];
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const double sl = S[i] - P.sL[i], su = P.sU[i] - S[i];
+                    rs[i] = -yd[i] - mu / sl + mu / su;
+                    Dsig[i] = vL[i] / sl + vU[i] / su + dw;
+                    rd[i] = U[i] - S[i];
+                }
+                rc[0] = c0; rc[1] = c1; rc[2] = c2;
+                if (mode == BM_SOC) {
+                    // defects of the last trial point curr + at*step
+                    double Xt[3], Ut[2], St[2], Ft[3];
+                    Xt[0] = X[0] + at * WF(p, sfx); Xt[1] = X[1] + at * WF(p, sfx + 1); Xt[2] = X[2] + at * WF(p, sfx + 2);
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const double du = WF(p, sfu + i);
+                        const double rdp = (sfu == F_DU) ? rd[i] : WF(p, F_DS + i);
+                        Ut[i] = U[i] + at * du;
+                        St[i] = S[i] + at * (du + rdp);
+                        rd[i] = at * rdp + (Ut[i] - St[i]);
+                        WF(p, F_DS + i) = rd[i];
+                    }
+                    dyn_value(P, Xt, Ut, Ft);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        const double base = (sfu == F_DU) ? rc[i] : WF(p, F_CS + i);
+                        rc[i] = at * base + (Xtn[i] - Ft[i]);
+                        WF(p, F_CS + i) = rc[i];
+                        Xtn[i] = Xt[i];
+                    }
+                }
+            }
+            const double hxx = useW ? o.hxx : 0.0, hyy = useW ? o.hyy : 0.0;
+            const double htt = useW ? o.htt : 0.0, htv = useW ? o.htv : 0.0, htw = useW ? o.htw : 0.0;
+            const double hvv = useW ? o.hvv : 0.0, hvw = useW ? o.hvw : 0.0, hww = useW ? o.hww : 0.0;
+            const double a = o.a13, b = o.a23, b11 = o.b11, b12 = o.b12, b21 = o.b21, b22 = o.b22;
+            const double d0 = -rc[0], d1 = -rc[1], d2 = -rc[2];
+            // w = P d + p
+            const double w0 = q00 * d0 + q01 * d1 + q02 * d2 + v0;
+            const double w1 = q01 * d0 + q11 * d1 + q12 * d2 + v1;
+            const double w2 = q02 * d0 + q12 * d1 + q22 * d2 + v2;
+            // t = P[:,2] + a P[:,0] + b P[:,1]
+            const double t0 = q02 + a * q00 + b * q01;
+            const double t1 = q12 + a * q01 + b * q11;
+            const double t2 = q22 + a * q02 + b * q12;
+            // Qxx = Hxx + A'PA
+            const double x00 = hxx + dw + q00, x01 = q01, x11 = hyy + dw + q11;
+            const double x02 = t0, x12 = t1, x22 = htt + dw + t2 + a * t0 + b * t1;
+            // PB columns
+            const double e0 = b11 * q00 + b21 * q01, e1 = b11 * q01 + b21 * q11;
+            const double f0 = b12 * q00 + b22 * q01 + dt * q02, f1 = b12 * q01 + b22 * q11 + dt * q12,
+                         f2 = b12 * q02 + b22 * q12 + dt * q22;
+            // Qux = Hux + B'PA
+            const double u00 = e0, u01 = e1, u02 = htv + b11 * t0 + b21 * t1;
+            const double u10 = f0, u11 = f1, u12 = htw + b12 * t0 + b22 * t1 + dt * t2;
+            // Quu = Huu + Dsig + B'PB
+            const double r00 = hvv + dw + Dsig[0] + b11 * e0 + b21 * e1;
+            const double r01 = hvw + b11 * f0 + b21 * f1;
+            const double r11 = hww + dw + Dsig[1] + b12 * f0 + b22 * f1 + dt * f2;
+            const bool first = (k == 0);
+            const double gx0 = (first ? 0.0 : rx0) + w0;
+            const double gx1 = (first ? 0.0 : rx1) + w1;
+            const double gx2 = (first ? 0.0 : rx2) + a * w0 + b * w1 + w2;
+            const double qu0 = ru[0] + Dsig[0] * rd[0] + rs[0];
+            const double qu1 = ru[1] + Dsig[1] * rd[1] + rs[1];
+            const double gu0 = qu0 + b11 * w0 + b21 * w1;
+            const double gu1 = qu1 + b12 * w0 + b22 * w1 + dt * w2;
+            const double det = r00 * r11 - r01 * r01;
+            if (!(r00 > 0.0) || !(det > 0.0)) ok = false;
+            const double idet = 1.0 / det;
+            const double i00 = r11 * idet, i01 = -r01 * idet, i11 = r00 * idet;
+            const double K00 = -(i00 * u00 + i01 * u10), K01 = -(i00 * u01 + i01 * u11), K02 = -(i00 * u02 + i01 * u12);
+            const double K10 = -(i01 * u00 + i11 * u10), K11 = -(i01 * u01 + i11 * u11), K12 = -(i01 * u02 + i11 * u12);
+            const double k0 = -(i00 * gu0 + i01 * gu1), k1 = -(i01 * gu0 + i11 * gu1);
+            WF(p, F_K) = K00; WF(p, F_K + 1) = K01; WF(p, F_K + 2) = K02;
+            WF(p, F_K + 3) = K10; WF(p, F_K + 4) = K11; WF(p, F_K + 5) = K12;
+            WF(p, F_KF) = k0; WF(p, F_KF + 1) = k1;
+            // P' = Qxx + Qux'K (symmetrised), p' = gx + Qux' kf
+            q00 = x00 + u00 * K00 + u10 * K10;
+            q11 = x11 + u01 * K01 + u11 * K11;
+            q22 = x22 + u02 * K02 + u12 * K12;
+            q01 = x01 + 0.5 * ((u00 * K01 + u10 * K11) + (u01 * K00 + u11 * K10));
+            q02 = x02 + 0.5 * ((u00 * K02 + u10 * K12) + (u02 * K00 + u12 * K10));
+            q12 = x12 + 0.5 * ((u01 * K02 + u11 * K12) + (u02 * K01 + u12 * K11));
+            v0 = gx0 + u00 * k0 + u10 * k1;
+            v1 = gx1 + u01 * k0 + u11 * k1;
+            v2 = gx2 + u02 * k0 + u12 * k1;
+        }
+        if (k >= 1) {
+            WF(p, F_P) = q00; WF(p, F_P + 1) = q01; WF(p, F_P + 2) = q02;
+            WF(p, F_P + 3) = q11; WF(p, F_P + 4) = q12; WF(p, F_P + 5) = q22;
+            WF(p, F_PV) = v0; WF(p, F_PV + 1) = v1; WF(p, F_PV + 2) = v2;
+        }
+        Xn[0] = X[0]; Xn[1] = X[1]; Xn[2] = X[2];
+        ln[0] = lam[0]; ln[1] = lam[1]; ln[2] = lam[2];
+    }
+    return ok;
+}
+
+struct TppFwd {
+    double a_max, a_z, gbd, bar, ymax;
+    int bad;
+};
+
+// ---- sweep F: forward roll-out of the step; step sizes and directional derivative ----------------------------------
+__device__ __forceinline__ void tpp_forward(const KParams &P, double *wb, const TppLane &L, TppFwd &o) {
+    const int N = P.N;
+    const double dt = P.dt, mu = L.mu, tau = L.tau, df = L.df;
+    const int co = L.cur * I_NF;
+    const int fx = (L.bmode == BM_SOC) ? F_SX : F_DX, fu = (L.bmode == BM_SOC) ? F_SU : F_DU, fl = (L.bmode == BM_SOC) ? F_SL : F_DL;
+    double y0 = 0, y1 = 0, y2 = 0;
+    o.a_max = 1.0; o.a_z = 1.0; o.gbd = 0; o.bar = 0; o.ymax = 0; o.bad = 0;
+    double X[3] = {WF(wb + co * 32, I_X), WF(wb + co * 32, I_X + 1), WF(wb + co * 32, I_X + 2)};
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+        const int mode = tpp_opaque(L.bmode);
+        double *p = wb + (size_t)k * (TPP_NF * 32);
+        const double *pc = p + co * 32;
+        WF(p, fx) = y0; WF(p, fx + 1) = y1; WF(p, fx + 2) = y2;
+        if (!isfinite(y0) || !isfinite(y1) || !isfinite(y2)) o.bad = 1;
+        if (k >= 1) {
+            const double P0 = WF(p, F_P), P1 = WF(p, F_P + 1), P2 = WF(p, F_P + 2), P3 = WF(p, F_P + 3),
+                         P4 = WF(p, F_P + 4), P5 = WF(p, F_P + 5);
+            const double l0 = -(WF(p, F_PV) + P0 * y0 + P1 * y1 + P2 * y2);
+            const double l1 = -(WF(p, F_PV + 1) + P1 * y0 + P3 * y1 + P4 * y2);
+            const double l2 = -(WF(p, F_PV + 2) + P2 * y0 + P4 * y1 + P5 * y2);
+            WF(p, fl) = l0; WF(p, fl + 1) = l1; WF(p, fl + 2) = l2;
+            if (!isfinite(l0) || !isfinite(l1) || !isfinite(l2)) o.bad = 1;
+            if (mode == BM_LSQ) o.ymax = fmax(o.ymax, fmax(fabs(l0), fmax(fabs(l1), fabs(l2))));
+        }
+        if (k < N) {
+            const double du0 = WF(p, F_KF) + WF(p, F_K) * y0 + WF(p, F_K + 1) * y1 + WF(p, F_K + 2) * y2;
+            const double du1 = WF(p, F_KF + 1) + WF(p, F_K + 3) * y0 + WF(p, F_K + 4) * y1 + WF(p, F_K + 5) * y2;
+            WF(p, fu) = du0; WF(p, fu + 1) = du1;
+            if (!isfinite(du0) || !isfinite(du1)) o.bad = 1;
+            const double du[2] = {du0, du1};
+            const double U[2] = {WF(pc, I_U), WF(pc, I_U + 1)};
+            const double *pn = pc + TPP_NF * 32;
+            const double Xn[3] = {WF(pn, I_X), WF(pn, I_X + 1), WF(pn, I_X + 2)};
+            double r[3], ub[2];
+            tpp_ref(P, L, p, r, ub);
+            const double ln0[3] = {0, 0, 0};
+            TppLin q;
+            tpp_lin<false>(P, r, ub, X, U, ln0, df, q);
+            double rc0, rc1, rc2;
+            if (mode == BM_LSQ) {
+                rc0 = rc1 = rc2 = 0;
+                o.ymax = fmax(o.ymax, fmax(fabs(du0), fabs(du1))); // dyd = Sigma*dS + rs with Sigma = 1, rd = rs = 0
+            } else {
+                if (mode == BM_SOC) { rc0 = WF(p, F_CS); rc1 = WF(p, F_CS + 1); rc2 = WF(p, F_CS + 2); }
+                else { rc0 = Xn[0] - q.F0; rc1 = Xn[1] - q.F1; rc2 = Xn[2] - q.F2; }
+                if (mode == BM_NEWTON && k >= 1) o.gbd += q.g[0] * y0 + q.g[1] * y1 + q.g[2] * y2;
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const double S = WF(pc, I_S + i), vL = WF(pc, I_VL + i), vU = WF(pc, I_VU + i);
+                    const double rd = (mode == BM_SOC) ? WF(p, F_DS + i) : (U[i] - S);
+                    const double ds = du[i] + rd;
+                    const double sl = S - P.sL[i], su = P.sU[i] - S;
+                    if (ds < 0) o.a_max = fmin(o.a_max, -tau * sl / ds);
+                    if (ds > 0) o.a_max = fmin(o.a_max, tau * su / ds);
+                    const double dvL = mu / sl - vL - vL / sl * ds;
+                    const double dvU = mu / su - vU + vU / su * ds;
+                    if (dvL < 0) o.a_z = fmin(o.a_z, -tau * vL / dvL);
+                    if (dvU < 0) o.a_z = fmin(o.a_z, -tau * vU / dvU);
+                    if (!isfinite(ds) || !isfinite(dvL) || !isfinite(dvU)) o.bad = 1;
+                    if (mode == BM_NEWTON) {
+                        o.bar -= mu * (log(sl) + log(su));
+                        o.gbd += (-mu / sl + mu / su) * ds + q.g[3 + i] * du[i];
+                    }
+                }
+            }
+            const double n0 = y0 + q.a13 * y2 + q.b11 * du0 + q.b12 * du1 - rc0;
+            const double n1 = y1 + q.a23 * y2 + q.b21 * du0 + q.b22 * du1 - rc1;
+            const double n2 = y2 + dt * du1 - rc2;
+            y0 = n0; y1 = n1; y2 = n2;
+            X[0] = Xn[0]; X[1] = Xn[1]; X[2] = Xn[2];
+        }
+    }
+}
+
+struct TppTrial {
+    double th, phi, gmax;
+    TppNorms n;
+    int bad;
+};
+
+// ---- sweep T: write curr + alpha*step into the other iterate buffer and evaluate that point -------------------------
+// tmode EVAL0 / EVAL: no step, evaluates the current buffer in place (EVAL0 also returns the largest gradient entry).
+// tmode LSQ:          new = current with the least-squares multiplier estimate (or zeros) for lam, yd.
+// tmode STEP(_SOC):   new = current + alpha*(dX,dU,dS,dlam,dyd) and bound multipliers + a_z*(dvL,dvU), clamped.
+__device__ __forceinline__ void tpp_trial(const KParams &P, double *wb, const TppLane &L, TppTrial &o) {
+    const int N = P.N;
+    const double dt = P.dt, mu = L.mu, df = L.df, dw = L.dw;
+    const bool soc0 = (L.tmode == TM_STEP_SOC);
+    const double alpha = soc0 ? L.alpha_soc : L.alpha, a_z = soc0 ? L.a_z_soc : L.a_z;
+    const int co = L.cur * I_NF, no = I_NF - co;
+    const int fx = soc0 ? F_SX : F_DX, fu = soc0 ? F_SU : F_DU, fl = soc0 ? F_SL : F_DL;
+    double Xn[3] = {0, 0, 0}, ln[3] = {0, 0, 0};
+    double th = 0, ph = 0, pi = 0, di = 0, sy = 0, sz = 0, pmin = 1e300, pmax = -1e300, fs = 0, gmax = 0;
+    int bad = 0;
+#pragma unroll 1
+    for (int k = N; k >= 0; --k) {
+        const int mode = tpp_opaque(L.tmode);
+        const bool step = (mode >= TM_STEP), soc = (mode == TM_STEP_SOC), write = (mode >= TM_LSQ);
+        const bool keep = tpp_opaque((int)L.keep) != 0;
+        double *p = wb + (size_t)k * (TPP_NF * 32);
+        const double *pc = p + co * 32;
+        double *pw = p + no * 32;
+        double X[3] = {WF(pc, I_X), WF(pc, I_X + 1), WF(pc, I_X + 2)};
+        double lam[3] = {0, 0, 0};
+        if (k >= 1) {
+            lam[0] = WF(pc, I_LAM); lam[1] = WF(pc, I_LAM + 1); lam[2] = WF(pc, I_LAM + 2);
+            if (step) {
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    X[i] += alpha * WF(p, fx + i);
+                    lam[i] += alpha * WF(p, fl + i);
+                }
+            } else if (mode == TM_LSQ) {
+#pragma unroll
+                for (int i = 0; i < 3; i++) lam[i] = keep ? WF(p, F_DL + i) : 0.0;
+            }
+        }
+        if (write) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) { WF(pw, I_X + i) = X[i]; WF(pw, I_LAM + i) = lam[i]; }
+        }
+        if (k < N) {
+            double U[2], S[2], yd[2], vL[2], vU[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                U[i] = WF(pc, I_U + i); S[i] = WF(pc, I_S + i); yd[i] = WF(pc, I_YD + i);
+                vL[i] = WF(pc, I_VL + i); vU[i] = WF(pc, I_VU + i);
+                if (step) {
+                    const double du = WF(p, fu + i);
+                    const double rd = soc ? WF(p, F_DS + i) : (U[i] - S[i]);
+                    const double ds = du + rd;
+                    const double sl = S[i] - P.sL[i], su = P.sU[i] - S[i];
+                    const double Dsig = vL[i] / sl + vU[i] / su + dw;
+                    const double rs = -yd[i] - mu / sl + mu / su;
+                    const double dvL = mu / sl - vL[i] - vL[i] / sl * ds;
+                    const double dvU = mu / su - vU[i] + vU[i] / su * ds;
+                    U[i] += alpha * du;
+                    S[i] += alpha * ds;
+                    yd[i] += alpha * (Dsig * ds + rs);
+                    vL[i] += a_z * dvL;
+                    vU[i] += a_z * dvU;
+                    const double sl2 = S[i] - P.sL[i], su2 = P.sU[i] - S[i];
+                    vL[i] = fmax(fmin(vL[i], KAPPA_SIGMA * mu / sl2), mu / (KAPPA_SIGMA * sl2));
+                    vU[i] = fmax(fmin(vU[i], KAPPA_SIGMA * mu / su2), mu / (KAPPA_SIGMA * su2));
+                } else if (mode == TM_LSQ) {
+                    yd[i] = keep ? WF(p, F_DU + i) : 0.0;
+                }
+                if (write) {
+                    WF(pw, I_U + i) = U[i]; WF(pw, I_S + i) = S[i]; WF(pw, I_YD + i) = yd[i];
+                    WF(pw, I_VL + i) = vL[i]; WF(pw, I_VU + i) = vU[i];
+                }
+            }
+            double r[3], ub[2];
+            tpp_ref(P, L, p, r, ub);
+            TppLin q;
+            tpp_lin<false>(P, r, ub, X, U, ln, df, q);
+            const double c[3] = {Xn[0] - q.F0, Xn[1] - q.F1, Xn[2] - q.F2};
+            fs += q.f;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                th += fabs(c[i]);
+                pi = fmax(pi, fabs(c[i]));
+                if (!isfinite(c[i])) bad = 1;
+            }
+            if (k >= 1) {
+                const double r0 = q.g[0] + lam[0] - ln[0];
+                const double r1 = q.g[1] + lam[1] - ln[1];
+                const double r2 = q.g[2] + lam[2] - (q.a13 * ln[0] + q.a23 * ln[1] + ln[2]);
+                di = fmax(di, fmax(fabs(r0), fmax(fabs(r1), fabs(r2))));
+                sy += fabs(lam[0]) + fabs(lam[1]) + fabs(lam[2]);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    if (!isfinite(q.g[i])) bad = 1;
+                    gmax = fmax(gmax, fabs(q.g[i]));
+                }
+            }
+            const double ru0 = q.g[3] - (q.b11 * ln[0] + q.b21 * ln[1]) + yd[0];
+            const double ru1 = q.g[4] - (q.b12 * ln[0] + q.b22 * ln[1] + dt * ln[2]) + yd[1];
+            di = fmax(di, fmax(fabs(ru0), fabs(ru1)));
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const double rd = U[i] - S[i];
+                const double sl = S[i] - P.sL[i], su = P.sU[i] - S[i];
+                th += fabs(rd);
+                pi = fmax(pi, fabs(rd));
+                ph -= mu * (log(sl) + log(su));
+                di = fmax(di, fabs(-yd[i] - vL[i] + vU[i]));
+                sy += fabs(yd[i]);
+                sz += fabs(vL[i]) + fabs(vU[i]);
+                const double pl = sl * vL[i], pu = su * vU[i];
+                pmin = fmin(pmin, fmin(pl, pu));
+                pmax = fmax(pmax, fmax(pl, pu));
+                if (!isfinite(q.g[3 + i])) bad = 1;
+                gmax = fmax(gmax, fabs(q.g[3 + i]));
+            }
+        } else if (k >= 1) {
+            // terminal state: no cost; its stationarity residual is the multiplier itself
+            di = fmax(di, fmax(fabs(lam[0]), fmax(fabs(lam[1]), fabs(lam[2]))));
+            sy += fabs(lam[0]) + fabs(lam[1]) + fabs(lam[2]);
+        }
+        Xn[0] = X[0]; Xn[1] = X[1]; Xn[2] = X[2];
+        ln[0] = lam[0]; ln[1] = lam[1]; ln[2] = lam[2];
+    }
+    o.th = th;
+    o.phi = df * fs + ph;
+    o.gmax = gmax;
+    o.bad = bad;
+    o.n.theta = th; o.n.prim_inf = pi; o.n.dual_inf = di; o.n.sum_y = sy; o.n.sum_z = sz;
+    o.n.pmin = pmin; o.n.pmax = pmax; o.n.f = fs;
+}
+
+// ---- filter (32 entries per lane, kept in the workspace) --------------------------------------------------------------
+__device__ __forceinline__ bool tpp_filter_ok(const double *fl, unsigned mask, double phi, double th) {
+    while (mask) {
+        const int i = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const double fp = fl[(2 * i) * 32], ft = fl[(2 * i + 1) * 32];
+        if (!(cmp_le(phi, fp, fp) || cmp_le(th, ft, ft))) return false;
+    }
+    return true;
+}
+
+__device__ __forceinline__ void tpp_filter_add(double *fl, unsigned &mask, int &ring, double phi, double th) {
+    unsigned m = mask;
+    while (m) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1;
+        if (fl[(2 * i) * 32] >= phi && fl[(2 * i + 1) * 32] >= th) mask &= ~(1u << i); // dominated by the new entry
+    }
+    int slot;
+    if (~mask) slot = __ffs(~mask) - 1;
+    else { slot = ring & 31; ring++; }
+    fl[(2 * slot) * 32] = phi;
+    fl[(2 * slot + 1) * 32] = th;
+    mask |= 1u << slot;
+}
+
+// FilterLSAcceptor::CheckAcceptabilityOfTrialPoint (same tests as ls_acceptable of the warp kernel)
+__device__ __forceinline__ bool tpp_ls_acceptable(const TppLane &L, const double *fl, double alpha_test, double phi_t,
+                                                  double th_t, bool &ftype_armijo) {
+    ftype_armijo = false;
+    if (!isfinite(th_t) || !isfinite(phi_t)) return false;
+    if (th_t > L.theta_max) return false;
+    const double gbd = L.ref_gbd, theta = L.n.theta, phi = L.ref_phi;
+    const bool ftype = (gbd < 0) && (alpha_test * tpp_pow(-gbd, S_PHI) > DELTA_LS * tpp_pow(theta, S_THETA));
+    const bool armijo = cmp_le(phi_t - phi, ETA_PHI * alpha_test * gbd, phi);
+    ftype_armijo = ftype && armijo;
+    bool ok;
+    if (alpha_test > 0 && ftype && theta <= L.theta_min) {
+        ok = armijo;
+    } else {
+        if (phi_t > phi) {
+            double bas = 1.0;
+            if (fabs(phi) > 10.0) bas = tpp_log10(fabs(phi));
+            if (tpp_log10(phi_t - phi) > OBJ_MAX_INC + bas) return false;
+        }
+        ok = cmp_le(th_t, (1 - GAMMA_THETA) * theta, theta) || cmp_le(phi_t - phi, -GAMMA_PHI * theta, phi);
+    }
+    if (!ok) return false;
+    return tpp_filter_ok(fl, L.fmask, phi_t, th_t);
+}
+
+// Line search gave up on the Newton direction (alpha < alpha_min): restoration stand-in of the warp kernel — roll
+// the controls out (closed-form feasible point), restart the multipliers.
+__device__ __forceinline__ void tpp_restore(const KParams &P, double *wb, double *fl, TppLane &L) {
+    const int N = P.N;
+    if (L.n.theta <= 1e-10 || L.n_resto >= MAX_RESTO) { L.status = B200MPC_RESTORATION_FAILED; L.phase = PH_FIN; return; }
+    tpp_filter_add(fl, L.fmask, L.ring, L.ref_phi - GAMMA_PHI * L.n.theta, (1 - GAMMA_THETA) * L.n.theta);
+    const int co = L.cur * I_NF;
+    double zm = 0;
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+        const double *pc = wb + (size_t)k * (TPP_NF * 32) + co * 32;
+        zm = fmax(zm, fmax(fmax(WF(pc, I_VL), WF(pc, I_VL + 1)), fmax(WF(pc, I_VU), WF(pc, I_VU + 1))));
+    }
+    double y[3] = {WF(wb + co * 32, I_X), WF(wb + co * 32, I_X + 1), WF(wb + co * 32, I_X + 2)};
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+        double *pc = wb + (size_t)k * (TPP_NF * 32) + co * 32;
+        WF(pc, I_X) = y[0]; WF(pc, I_X + 1) = y[1]; WF(pc, I_X + 2) = y[2];
+        WF(pc, I_LAM) = 0; WF(pc, I_LAM + 1) = 0; WF(pc, I_LAM + 2) = 0;
+        if (k < N) {
+            const double U[2] = {WF(pc, I_S), WF(pc, I_S + 1)};
+            WF(pc, I_U) = U[0]; WF(pc, I_U + 1) = U[1];
+            WF(pc, I_YD) = 0; WF(pc, I_YD + 1) = 0;
+            if (zm > 1e3) { WF(pc, I_VL) = 1.0; WF(pc, I_VL + 1) = 1.0; WF(pc, I_VU) = 1.0; WF(pc, I_VU + 1) = 1.0; }
+            double F[3];
+            dyn_value(P, y, U, F);
+            y[0] = F[0]; y[1] = F[1]; y[2] = F[2];
+        }
+    }
+    L.n_resto++;
+    L.iter++;
+    L.tmode = TM_EVAL;
+    L.phase = PH_T;
+}
+
+// Top of an interior-point iteration: convergence tests, barrier update; leaves the lane in phase B (Newton) or
+// finishes the problem.  L.n holds the residual norms of the current iterate.
+__device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L) {
+    const int N = P.N;
+    const TppNorms &n = L.n;
+    if (L.theta_max < 0) {
+        L.theta_max = 1e4 * fmax(1.0, n.theta);
+        L.theta_min = 1e-4 * fmax(1.0, n.theta);
+    }
+    const double df = L.df;
+    const double sd = fmax(S_MAX, (n.sum_y + n.sum_z) / (double)(9 * N)) / S_MAX;
+    const double sc = fmax(S_MAX, n.sum_z / (double)(4 * N)) / S_MAX;
+    const double compl0 = fmax(fabs(n.pmin), fabs(n.pmax));
+    const double E0 = fmax(n.dual_inf / sd, fmax(n.prim_inf, compl0 / sc));
+    L.phase = PH_FIN;
+    if (!isfinite(E0)) { L.status = B200MPC_INVALID_NUMBER_DETECTED; return; }
+    if (E0 <= P.tol && n.dual_inf / df <= 1.0 && n.prim_inf <= 1e-4 && compl0 / df <= 1e-4) {
+        L.status = B200MPC_SOLVE_SUCCEEDED;
+        return;
+    }
+    if (P.acceptable_iter > 0 && E0 <= P.acceptable_tol && n.dual_inf / df <= 1e10 && n.prim_inf <= 1e-2 &&
+        compl0 / df <= 1e-2) {
+        L.acceptable_count++;
+        if (L.acceptable_count >= P.acceptable_iter) { L.status = B200MPC_SOLVED_TO_ACCEPTABLE_LEVEL; return; }
+    } else {
+        L.acceptable_count = 0;
+    }
+    if (L.iter >= P.max_iter) { L.status = B200MPC_MAXITER_EXCEEDED; return; }
+    // barrier parameter update
+    for (;;) {
+        const double mu = L.mu;
+        const double cm = fmax(fabs(n.pmax - mu), fabs(n.pmin - mu));
+        const double Emu = fmax(n.dual_inf / sd, fmax(n.prim_inf, cm / sc));
+        if (!(Emu <= K_EPS * mu)) break;
+        const double nm = fmax(fmin(K_MU * mu, tpp_pow(mu, TH_MU)), P.mu_floor);
+        if (nm == mu) break;
+        L.mu = nm;
+        L.tau = fmax(TAU_MIN, 1.0 - nm);
+        L.fmask = 0;
+    }
+    L.dw = 0.0;
+    L.bmode = BM_NEWTON;
+    L.phase = PH_B;
+}
+
+__global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kernel(const KParams P, const TppArgs T) {
+    const BatchArgs &A = T.a;
+    const int N = P.N;
+    const int lane = threadIdx.x & 31;
+    const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    double *wb = T.ws + gw * ((size_t)(N + 1) * TPP_NF * 32) + lane;
+    double *fl = T.filt + gw * (64 * 32) + lane;
+    TppLane L;
+    L.phase = PH_LOAD;
+    L.b = -1;
+
+    for (;;) {
+        // ---- block L: pull the next problem, write the starting point ----
+        __syncwarp();
+        if (tpp_opaque(L.phase) == PH_LOAD) {
+            const int b = (int)atomicAdd(A.counter, 1u);
+            if (b >= A.B) {
+                L.phase = PH_DONE;
+            } else {
+                L.b = b;
+                const double x0[3] = {A.x0[3 * (size_t)b], A.x0[3 * (size_t)b + 1], A.x0[3 * (size_t)b + 2]};
+                if (P.ref_kind == B200MPC_REF_GOAL) {
+                    L.r[0] = A.xref[3 * (size_t)b]; L.r[1] = A.xref[3 * (size_t)b + 1]; L.r[2] = A.xref[3 * (size_t)b + 2];
+                } else {
+                    L.r[0] = L.r[1] = L.r[2] = 0;
+                }
+                L.cur = 0;
+#pragma unroll 1
+                for (int k = 0; k <= N; ++k) {
+                    double *p = wb + (size_t)k * (TPP_NF * 32);
+                    WF(p, I_X) = (k == 0) ? x0[0] : 0.0; WF(p, I_X + 1) = (k == 0) ? x0[1] : 0.0; WF(p, I_X + 2) = (k == 0) ? x0[2] : 0.0;
+                    WF(p, I_LAM) = 0; WF(p, I_LAM + 1) = 0; WF(p, I_LAM + 2) = 0;
+                    if (k < N) {
+                        double u[2] = {0, 0};
+                        if (A.u_init) { u[0] = A.u_init[(size_t)b * 2 * N + 2 * k]; u[1] = A.u_init[(size_t)b * 2 * N + 2 * k + 1]; }
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            // slack initialisation: s = d(x) pushed into the interior; bound multipliers 1
+                            const double lo = P.sL[i], hi = P.sU[i];
+                            const double pl = fmin(BOUND_PUSH * fmax(1.0, fabs(lo)), BOUND_FRAC * (hi - lo));
+                            const double pu = fmin(BOUND_PUSH * fmax(1.0, fabs(hi)), BOUND_FRAC * (hi - lo));
+                            double sv = u[i];
+                            if (sv < lo + pl) sv = lo + pl;
+                            if (sv > hi - pu) sv = hi - pu;
+                            WF(p, I_U + i) = u[i]; WF(p, I_S + i) = sv; WF(p, I_YD + i) = 0;
+                            WF(p, I_VL + i) = 1.0; WF(p, I_VU + i) = 1.0;
+                        }
+                        if (P.ref_kind == B200MPC_REF_TRAJ) {
+                            const double *xr = A.xref + (size_t)b * 3 * N + 3 * k;
+                            WF(p, F_R) = xr[0]; WF(p, F_R + 1) = xr[1]; WF(p, F_R + 2) = xr[2];
+                            WF(p, F_UB) = A.uref[(size_t)b * 2 * N + 2 * k]; WF(p, F_UB + 1) = A.uref[(size_t)b * 2 * N + 2 * k + 1];
+                        }
+                    }
+                }
+                L.status = B200MPC_MAXITER_EXCEEDED;
+                L.iter = 0; L.ls_extra = 0; L.n_resto = 0; L.acceptable_count = 0; L.ntrial = 0; L.soc_count = 0;
+                L.ring = 0; L.fmask = 0; L.keep = false; L.soc_first = true;
+                L.df = 1.0; L.mu = P.mu_init; L.tau = fmax(TAU_MIN, 1.0 - P.mu_init);
+                L.theta_max = -1; L.theta_min = -1; L.dw = 0; L.dw_last = 0;
+                L.alpha = 0; L.a_z = 0; L.alpha_soc = 0; L.a_z_soc = 0; L.a_min = 0; L.theta_soc_old = 0;
+                L.ref_phi = 0; L.ref_gbd = 0;
+                L.bmode = BM_LSQ;
+                L.tmode = TM_EVAL0;
+                L.phase = PH_T;
+            }
+        }
+        if (__all_sync(FULL, L.phase == PH_DONE)) break;
+
+        // ---- block B ----
+        __syncwarp();
+        if (tpp_opaque(L.phase) == PH_B) {
+            const bool ok = tpp_backward(P, wb, L);
+            if (L.bmode == BM_LSQ) {
+                if (ok) L.phase = PH_F;
+                else { L.keep = false; L.tmode = TM_LSQ; L.phase = PH_T; }
+            } else if (ok) {
+                if (L.bmode == BM_NEWTON && L.dw > 0.0) L.dw_last = L.dw;
+                L.phase = PH_F;
+            } else if (L.bmode == BM_SOC) {
+                L.phase = PH_BACKTRACK; // correction abandoned: continue with the Newton direction
+            } else {
+                // inertia correction
+                if (L.dw == 0.0) L.dw = (L.dw_last == 0.0) ? DW_INIT : fmax(DW_MIN, L.dw_last * DW_DEC);
+                else L.dw = (L.dw_last == 0.0 || 1e5 * L.dw_last < L.dw) ? L.dw * DW_INC_FIRST : L.dw * DW_INC;
+                if (L.dw > DW_MAX) { L.status = B200MPC_ERROR_IN_STEP_COMPUTATION; L.phase = PH_FIN; }
+            }
+        }
+
+        // ---- block F ----
+        __syncwarp();
+        if (tpp_opaque(L.phase) == PH_F) {
+            TppFwd f;
+            tpp_forward(P, wb, L, f);
+            if (L.bmode == BM_LSQ) {
+                L.keep = (f.ymax <= 1e3);
+                L.tmode = TM_LSQ;
+                L.phase = PH_T;
+            } else if (L.bmode == BM_NEWTON) {
+                if (f.bad) {
+                    L.status = B200MPC_ERROR_IN_STEP_COMPUTATION;
+                    L.phase = PH_FIN;
+                } else {
+                    const double theta = L.n.theta;
+                    L.ref_phi = L.df * L.n.f + f.bar;
+                    L.ref_gbd = f.gbd;
+                    double a_min = GAMMA_THETA;
+                    if (f.gbd < 0) {
+                        a_min = fmin(GAMMA_THETA, GAMMA_PHI * theta / (-f.gbd));
+                        if (theta <= L.theta_min) a_min = fmin(a_min, DELTA_LS * tpp_pow(theta, S_THETA) / tpp_pow(-f.gbd, S_PHI));
+                    }
+                    L.a_min = a_min * ALPHA_MIN_FRAC;
+                    L.alpha = f.a_max;
+                    L.a_z = f.a_z;
+                    L.ntrial = 0;
+                    L.tmode = TM_STEP;
+                    L.phase = PH_T;
+                }
+            } else {
+                L.alpha_soc = f.a_max;
+                L.a_z_soc = f.a_z;
+                L.tmode = TM_STEP_SOC;
+                L.phase = PH_T;
+            }
+        }
+
+        // ---- block T ----
+        __syncwarp();
+        if (tpp_opaque(L.phase) == PH_T) {
+            TppTrial t;
+            tpp_trial(P, wb, L, t);
+            const int tm = L.tmode;
+            if (tm == TM_EVAL0) {
+                // objective scaling from the gradient at the starting point; invalid-number check
+                L.n = t.n;
+                if (t.bad || !isfinite(t.n.f)) {
+                    L.status = B200MPC_INVALID_NUMBER_DETECTED;
+                    L.phase = PH_FIN;
+                } else {
+                    if (t.gmax > 100.0) L.df = fmax(100.0 / t.gmax, 1e-8);
+                    L.bmode = BM_LSQ;
+                    L.phase = PH_B;
+                }
+            } else if (tm == TM_EVAL) {
+                L.n = t.n;
+                L.phase = PH_TOP;
+            } else if (tm == TM_LSQ) {
+                L.n = t.n;
+                L.cur ^= 1;
+                L.phase = PH_TOP;
+            } else {
+                const bool soc = (tm == TM_STEP_SOC);
+                if (soc || L.ntrial++ > 0) L.ls_extra++;
+                bool fa;
+                if (tpp_ls_acceptable(L, fl, L.alpha, t.phi, t.th, fa)) {
+                    if (!fa) tpp_filter_add(fl, L.fmask, L.ring, L.ref_phi - GAMMA_PHI * L.n.theta, (1 - GAMMA_THETA) * L.n.theta);
+                    L.n = t.n;
+                    L.cur ^= 1;
+                    L.iter++;
+                    L.phase = PH_TOP;
+                } else if (!soc) {
+                    if (L.ntrial == 1 && P.max_soc > 0 && isfinite(t.th) && t.th >= L.n.theta) {
+                        // second-order correction, first round: right-hand sides from this trial point
+                        L.soc_count = 0;
+                        L.soc_first = true;
+                        L.theta_soc_old = t.th;
+                        L.bmode = BM_SOC;
+                        L.phase = PH_B;
+                    } else {
+                        L.phase = PH_BACKTRACK;
+                    }
+                } else {
+                    L.soc_count++;
+                    if (L.soc_count < P.max_soc && t.th <= KAPPA_SOC * L.theta_soc_old) {
+                        L.theta_soc_old = t.th;
+                        L.soc_first = false;
+                        L.bmode = BM_SOC;
+                        L.phase = PH_B;
+                    } else {
+                        L.phase = PH_BACKTRACK;
+                    }
+                }
+            }
+        }
+
+        // ---- rare: backtracking / restoration stand-in ----
+        __syncwarp();
+        if (tpp_opaque(L.phase) == PH_BACKTRACK) {
+            L.alpha *= 0.5;
+            if (L.alpha < L.a_min) {
+                tpp_restore(P, wb, fl, L);
+            } else {
+                L.tmode = TM_STEP;
+                L.phase = PH_T;
+            }
+        }
+
+        // ---- top of the next iteration: convergence tests, barrier update ----
+        __syncwarp();
+        if (tpp_opaque(L.phase) == PH_TOP) tpp_iterate_top(P, L);
+
+        // ---- result store, release of the lane ----
+        __syncwarp();
+        if (tpp_opaque(L.phase) == PH_FIN) {
+            const size_t b = (size_t)L.b;
+            const int co = L.cur * I_NF;
+            double *xo = A.X + b * 3 * (N + 1), *uo = A.U + b * 2 * N;
+#pragma unroll 1
+            for (int k = 0; k <= N; ++k) {
+                const double *pc = wb + (size_t)k * (TPP_NF * 32) + co * 32;
+                xo[3 * k] = WF(pc, I_X); xo[3 * k + 1] = WF(pc, I_X + 1); xo[3 * k + 2] = WF(pc, I_X + 2);
+                if (k < N) { uo[2 * k] = WF(pc, I_U); uo[2 * k + 1] = WF(pc, I_U + 1); }
+            }
+            if (A.cost) A.cost[b] = L.n.f;
+            A.status[b] = L.status;
+            if (A.iters) A.iters[b] = L.iter;
+            if (A.ls) A.ls[b] = L.ls_extra;
+            L.phase = PH_LOAD;
+        }
+    }
+}
