@@ -34,7 +34,7 @@
 #define B200MPC_MIN_CTAS 2
 #endif
 #ifndef B200MPC_TPP_MIN_CTAS
-#define B200MPC_TPP_MIN_CTAS 3
+#define B200MPC_TPP_MIN_CTAS 4
 #endif
 
 // ---- IPOPT defaults (Waechter & Biegler 2006; IPOPT option documentation) -------------------------------
@@ -1293,7 +1293,10 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     if (blocks < 1) blocks = 1;
     h->ctas = blocks * h->sm_count; // persistent grid: a multiple of the SM count (148 on B200)
     int tblocks = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tblocks, mpc_solve_tpp_kernel, 128, 0)) != cudaSuccess)
+    const size_t tpp_smem = (size_t)128 * TPP_LANE_STRIDE * sizeof(double);
+    if ((e = cudaFuncSetAttribute(mpc_solve_tpp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tpp_smem)) != cudaSuccess)
+        return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tblocks, mpc_solve_tpp_kernel, 128, tpp_smem)) != cudaSuccess)
         return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
     if (tblocks < 1) tblocks = 1;
     h->tpp_ctas = tblocks * h->sm_count;
@@ -1409,7 +1412,7 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t 
     TppArgs t;
     t.a = a; t.ws = h->d_ws; t.filt = h->d_filt;
     CU_TRY(h, cudaEventRecord(h->ev0, stream));
-    mpc_solve_tpp_kernel<<<grid, 128, 0, stream>>>(h->kp, t);
+    mpc_solve_tpp_kernel<<<grid, 128, (size_t)128 * TPP_LANE_STRIDE * sizeof(double), stream>>>(h->kp, t);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev1, stream));
     h->launches++;

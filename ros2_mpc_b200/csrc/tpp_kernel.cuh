@@ -10,28 +10,32 @@
 // enough problems, so they live in an HBM workspace private to the warp:
 //     ws[warp][stage k][field f][lane]            (doubles)
 // A field row is 32 consecutive doubles = 256 B = two full 128-byte lines, every access of the kernel is such a
-// row (fully coalesced, compile-time field offsets from one per-stage pointer), and a stage record is one
-// contiguous 18-20 KB block.  The kernel is HBM-bound by construction (about 110 doubles per stage and iteration),
-// not FP64-bound.  Each interior-point iteration is three streaming sweeps over the stages:
+// row (fully coalesced, compile-time field offsets from one per-stage pointer, L1 bypassed), and a stage record is
+// one contiguous block whose next-needed rows are prefetched into L2 one stage ahead.  Each interior-point
+// iteration is three streaming sweeps over the stages:
 //     B  backward  k = N..0   read iterate, re-linearise, condense, Riccati recursion        -> K, kf, P, pv
 //     F  forward   k = 0..N   read K, kf, P, pv (+ iterate), roll the step out              -> dX, dU, dlam,
 //                             fraction-to-the-boundary step sizes, directional derivative
 //     T  trial     k = N..0   read iterate + step, write curr + alpha*step into the OTHER iterate buffer, and
 //                             evaluate that point: filter quantities (theta, phi) and all KKT residual norms
-// The trial point is written speculatively; if the line search accepts it (99 % of first trials) the lane just
-// flips its buffer index and already holds the convergence norms of the new iterate, so there is no separate
-// "accept" or "evaluate" sweep.  Sweeps are LIFO against each other (F reads what B wrote last, T what F wrote
-// last), which is what the 126 MB L2 can exploit.
+// The trial point is written speculatively; if the line search accepts it (99 % of first trials) it simply is the
+// next iterate and the lane already holds its convergence norms, so there is no separate "accept" or "evaluate"
+// sweep.  The two iterate buffers swap roles every trip for the whole warp (so that every row access stays one
+// full row); the rare lane whose trial point was rejected copies its iterate across at the end of the trip.
 //
 // Control flow.  Lanes of a warp solve different problems whose line searches, inertia corrections and iteration
-// counts differ.  Every lane carries a phase (LOAD, B, F, T); one trip of the main loop executes the blocks
-// L, B, F, T in that order, each for the lanes that are in that phase.  A regular iteration is one trip.  A lane
-// that needs something extra (another trial step size, a second-order correction, a larger delta_w) simply sits
-// out the blocks it does not need in the next trip; it never forces the other 31 lanes to wait for it.  A lane
-// whose problem finishes pulls the next problem from a global counter in the next trip.
+// counts differ.  Every lane carries a phase; one trip of the main loop executes the blocks L(oad), B, F, T in
+// that order, each for the lanes that are in that phase.  A regular iteration is one trip.  A lane that needs
+// something extra (another trial step size, a second-order correction, a larger delta_w) sits out the blocks it
+// does not need in the next trip; it never makes the other 31 lanes wait.  A lane whose problem finishes pulls the
+// next problem from a global counter in the next trip.  The per-lane solver state (TppLane) lives in shared
+// memory so that the sweeps have the register file to themselves.
 //
 // The algorithm, constants and every decision are those of the warp-per-problem kernel and of oracle/mpc_oracle.c
-// (the CPU checker); only the summation order of the reductions over stages differs (sequential here).
+// (the CPU checker).  Arithmetic differs at rounding level only: sums over stages are sequential, x/s is
+// evaluated as x*(1/s), the barrier term uses one logarithm per stage (log of the product of the four slack
+// distances), sin/cos of the RK4 mid- and end-point angles come from the angle-addition formulas, and the
+// least-squares multiplier estimate is computed for the unscaled objective and scaled afterwards (it is linear).
 #pragma once
 
 enum {
@@ -46,9 +50,22 @@ enum {
 
 enum { PH_LOAD = 0, PH_B = 1, PH_F = 2, PH_T = 3, PH_BACKTRACK = 4, PH_TOP = 5, PH_FIN = 6, PH_DONE = 7 };
 enum { BM_NEWTON = 0, BM_SOC = 1, BM_LSQ = 2 };
-enum { TM_EVAL0 = 0, TM_EVAL = 1, TM_LSQ = 2, TM_STEP = 3, TM_STEP_SOC = 4 };
+enum { TM_EVAL = 1, TM_LSQ = 2, TM_STEP = 3, TM_STEP_SOC = 4 };
 
-#define WF(p, f) (p)[(f) * 32]
+#define TPP_STAGE (TPP_NF * 32)
+// workspace rows bypass L1 (each row is used once per sweep; L1 is left to the stack)
+#define LDW(p, f) __ldcg((p) + (f) * 32)
+#define STW(p, f, v) __stcg((p) + (f) * 32, (v))
+#ifndef TPP_PREFETCH
+#define TPP_PREFETCH 1
+#endif
+
+__device__ __forceinline__ void tpp_prefetch_rows(const double *p, int f0, int n) {
+#if TPP_PREFETCH
+#pragma unroll
+    for (int f = 0; f < n; f++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (f0 + f) * 32));
+#endif
+}
 
 // Per-lane mode words are loop-invariant, so the compiler would "unswitch" the stage loops into one copy per mode:
 // lanes of a warp that are in different modes (a freshly loaded problem next to one in mid-solve) would then run
@@ -71,20 +88,36 @@ struct TppArgs {
 };
 
 struct TppNorms {
-    double theta, prim_inf, dual_inf, sum_y, sum_z, pmin, pmax, f;
+    double theta, prim_inf, dual_inf, sum_y, sum_z, pmin, pmax, f, slog;
 };
 
+// Solver state of one lane (shared memory, one record per thread; the record stride is an odd multiple of 8 bytes
+// so that the 64-bit accesses of a half-warp fall into distinct banks).
 struct TppLane {
-    int b, phase, bmode, tmode;
-    int status, iter, ls_extra, n_resto, acceptable_count, ntrial, soc_count, cur, ring;
-    unsigned fmask;
-    bool keep, soc_first;
-    double df, mu, tau, theta_max, theta_min, dw, dw_last;
     TppNorms n;                                    // residual norms of the current iterate
+    double df, mu, tau, theta_max, theta_min, dw, dw_last;
     double ref_phi, ref_gbd, alpha, a_min, a_z;    // line-search reference values, Newton step sizes
     double alpha_soc, a_z_soc, theta_soc_old;      // second-order correction
     double r[3];                                   // goal (ref_kind GOAL)
+    int b, phase, bmode, tmode;
+    int status, iter, ls_extra, n_resto, acceptable_count, ntrial, soc_count, ring;
+    unsigned fmask;
+    int keep, soc_first, moved;
 };
+#define TPP_LANE_STRIDE (((sizeof(TppLane) + 7) / 8) | 1) /* in doubles, odd */
+
+// sin/cos of th, th + hw, th + 2 hw (RK4 stage angles) from two sincos evaluations
+__device__ __forceinline__ void tpp_trig(double th, double hw, double &s0, double &c0, double &sm, double &cm,
+                                         double &se, double &ce) {
+    double sh, ch;
+    sincos(th, &s0, &c0);
+    sincos(hw, &sh, &ch);
+    sm = s0 * ch + c0 * sh;
+    cm = c0 * ch - s0 * sh;
+    const double s2 = 2.0 * sh * ch, c2 = 1.0 - 2.0 * sh * sh;
+    se = s0 * c2 + c0 * s2;
+    ce = c0 * c2 - s0 * s2;
+}
 
 struct TppLin {
     double a13, a23, b11, b12, b21, b22, F0, F1, F2;
@@ -113,9 +146,7 @@ __device__ __forceinline__ void tpp_lin(const KParams &P, const double r[3], con
         }
     } else {
         double s0, c0, sm, cm, se, ce;
-        sincos(th, &s0, &c0);
-        sincos(th + 0.5 * dt * w, &sm, &cm);
-        sincos(th + dt * w, &se, &ce);
+        tpp_trig(th, 0.5 * dt * w, s0, c0, sm, cm, se, ce);
         const double h = dt / 6.0;
         const double C = c0 + 4.0 * cm + ce, S = s0 + 4.0 * sm + se;
         const double C1 = 2.0 * cm + ce, S1 = 2.0 * sm + se;
@@ -152,108 +183,145 @@ __device__ __forceinline__ void tpp_lin(const KParams &P, const double r[3], con
     }
 }
 
-__device__ __forceinline__ void tpp_ref(const KParams &P, const TppLane &L, const double *p, double r[3], double ub[2]) {
+// value of the integration step only (second-order-correction defects, restoration roll-out: rare paths)
+__device__ __noinline__ void tpp_dyn(const KParams &P, const double X[3], const double U[2], double F[3]) {
+    const double dt = P.dt, th = X[2], v = U[0], w = U[1];
+    if (P.integrator == B200MPC_EULER) {
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        F[0] = X[0] + dt * v * cs;
+        F[1] = X[1] + dt * v * sn;
+    } else {
+        double s0, c0, sm, cm, se, ce;
+        tpp_trig(th, 0.5 * dt * w, s0, c0, sm, cm, se, ce);
+        const double h = dt / 6.0;
+        F[0] = X[0] + h * v * (c0 + 4.0 * cm + ce);
+        F[1] = X[1] + h * v * (s0 + 4.0 * sm + se);
+    }
+    F[2] = th + dt * w;
+}
+
+__device__ __forceinline__ void tpp_ref(const KParams &P, const double goal[3], const double *p, double r[3], double ub[2]) {
     if (P.ref_kind == B200MPC_REF_GOAL) {
-        r[0] = L.r[0]; r[1] = L.r[1]; r[2] = L.r[2];
+        r[0] = goal[0]; r[1] = goal[1]; r[2] = goal[2];
         ub[0] = 0; ub[1] = 0;
     } else {
-        r[0] = WF(p, F_R); r[1] = WF(p, F_R + 1); r[2] = WF(p, F_R + 2);
-        ub[0] = WF(p, F_UB); ub[1] = WF(p, F_UB + 1);
+        r[0] = LDW(p, F_R); r[1] = LDW(p, F_R + 1); r[2] = LDW(p, F_R + 2);
+        ub[0] = LDW(p, F_UB); ub[1] = LDW(p, F_UB + 1);
     }
 }
+
+struct TppBwd {
+    double gmax, f;
+    int ok, bad;
+};
 
 // ---- sweep B: condensed stage-wise KKT system, Riccati backward recursion -----------------------------------------
 // bmode NEWTON: right-hand side = KKT residual of the current iterate.
 // bmode SOC:    same matrix; the defect right-hand sides are advanced in the same sweep from the last trial point
 //               (csoc = a*csoc + c(trial), dsoc = a*dsoc + (U_t - S_t)) and stored for the forward sweep.
-// bmode LSQ:    least-squares multiplier estimate (W = 0, delta = 1, Sigma = 1, rhs = objective gradient).
-// Returns false when a condensed Quu block is not positive definite (wrong inertia).
-__device__ __forceinline__ bool tpp_backward(const KParams &P, double *wb, const TppLane &L) {
+// bmode LSQ:    least-squares multiplier estimate (W = 0, delta = 1, Sigma = 1, rhs = objective gradient), on the
+//               unscaled objective (L.df is 1); also returns the largest gradient entry (objective scaling), the
+//               objective and the invalid-number flag of the starting point.
+// o.ok = 0 when a condensed Quu block is not positive definite (wrong inertia).
+__device__ __forceinline__ void tpp_backward(const KParams &P, double *wb, int cur, const TppLane &L, TppBwd &o) {
     const int N = P.N;
     const double dt = P.dt;
-    const double dw = (L.bmode != BM_LSQ) ? L.dw : 1.0;
+    const int bmode0 = L.bmode;
+    const double dw = (bmode0 != BM_LSQ) ? L.dw : 1.0;
     const double df = L.df, mu = L.mu;
-    const int co = L.cur * I_NF;
-    const int sfx = L.soc_first ? F_DX : F_SX, sfu = L.soc_first ? F_DU : F_SU;
-    const double at = L.soc_first ? L.alpha : L.alpha_soc;
+    const double goal[3] = {L.r[0], L.r[1], L.r[2]};
+    const int sfirst = L.soc_first;
+    const int sfx = sfirst ? F_DX : F_SX, sfu = sfirst ? F_DU : F_SU;
+    const double at = sfirst ? L.alpha : L.alpha_soc;
+    const int co = cur * I_NF;
     double Xn[3] = {0, 0, 0}, ln[3] = {0, 0, 0}, Xtn[3] = {0, 0, 0};
     double q00 = 0, q01 = 0, q02 = 0, q11 = 0, q12 = 0, q22 = 0, v0 = 0, v1 = 0, v2 = 0;
-    bool ok = true;
+    double gmax = 0, fs = 0;
+    int ok = 1, bad = 0;
 #pragma unroll 1
     for (int k = N; k >= 0; --k) {
-        const int mode = tpp_opaque(L.bmode);
+        const int mode = tpp_opaque(bmode0);
         const bool useW = (mode != BM_LSQ);
-        double *p = wb + (size_t)k * (TPP_NF * 32);
+        double *p = wb + (size_t)k * TPP_STAGE;
         const double *pc = p + co * 32;
-        const double X[3] = {WF(pc, I_X), WF(pc, I_X + 1), WF(pc, I_X + 2)};
+        if (k > 0) tpp_prefetch_rows(pc - TPP_STAGE, 0, I_NF);
+        const double X[3] = {LDW(pc, I_X), LDW(pc, I_X + 1), LDW(pc, I_X + 2)};
         double lam[3] = {0, 0, 0};
-        if (k >= 1) { lam[0] = WF(pc, I_LAM); lam[1] = WF(pc, I_LAM + 1); lam[2] = WF(pc, I_LAM + 2); }
+        if (k >= 1) { lam[0] = LDW(pc, I_LAM); lam[1] = LDW(pc, I_LAM + 1); lam[2] = LDW(pc, I_LAM + 2); }
         if (k == N) {
             // terminal stage: no cost, no controls
             q00 = dw; q01 = 0; q02 = 0; q11 = dw; q12 = 0; q22 = dw;
             if (mode == BM_LSQ) { v0 = 0; v1 = 0; v2 = 0; }
             else { v0 = lam[0]; v1 = lam[1]; v2 = lam[2]; }
             if (mode == BM_SOC) {
-                Xtn[0] = X[0] + at * WF(p, sfx); Xtn[1] = X[1] + at * WF(p, sfx + 1); Xtn[2] = X[2] + at * WF(p, sfx + 2);
+                Xtn[0] = X[0] + at * LDW(p, sfx); Xtn[1] = X[1] + at * LDW(p, sfx + 1); Xtn[2] = X[2] + at * LDW(p, sfx + 2);
             }
         } else {
-            const double U[2] = {WF(pc, I_U), WF(pc, I_U + 1)};
+            const double U[2] = {LDW(pc, I_U), LDW(pc, I_U + 1)};
             double r[3], ub[2];
-            tpp_ref(P, L, p, r, ub);
-            TppLin o;
-            tpp_lin<true>(P, r, ub, X, U, ln, df, o);
-            const double c0 = Xn[0] - o.F0, c1 = Xn[1] - o.F1, c2 = Xn[2] - o.F2;
+            tpp_ref(P, goal, p, r, ub);
+            TppLin q;
+            tpp_lin<true>(P, r, ub, X, U, ln, df, q);
+            const double c0 = Xn[0] - q.F0, c1 = Xn[1] - q.F1, c2 = Xn[2] - q.F2;
             double rx0, rx1, rx2, ru[2], Dsig[2], rs[2], rd[2], rc[3];
             if (mode == BM_LSQ) {
-                rx0 = o.g[0]; rx1 = o.g[1]; rx2 = o.g[2];
-                ru[0] = o.g[3]; ru[1] = o.g[4];
+                rx0 = q.g[0]; rx1 = q.g[1]; rx2 = q.g[2];
+                ru[0] = q.g[3]; ru[1] = q.g[4];
                 Dsig[0] = Dsig[1] = 1.0; rs[0] = rs[1] = 0.0; rd[0] = rd[1] = 0.0;
                 rc[0] = rc[1] = rc[2] = 0.0;
+                fs += q.f;
+                if (!isfinite(c0) || !isfinite(c1) || !isfinite(c2) || !isfinite(q.g[3]) || !isfinite(q.g[4])) bad = 1;
+                gmax = fmax(gmax, fmax(fabs(q.g[3]), fabs(q.g[4])));
+                if (k >= 1) {
+                    if (!isfinite(q.g[0]) || !isfinite(q.g[1]) || !isfinite(q.g[2])) bad = 1;
+                    gmax = fmax(gmax, fmax(fabs(q.g[0]), fmax(fabs(q.g[1]), fabs(q.g[2]))));
+                }
             } else {
-                rx0 = o.g[0] + lam[0] - ln[0];
-                rx1 = o.g[1] + lam[1] - ln[1];
-                rx2 = o.g[2] + lam[2] - (o.a13 * ln[0] + o.a23 * ln[1] + ln[2]);
-                const double S[2] = {WF(pc, I_S), WF(pc, I_S + 1)};
-                const double yd[2] = {WF(pc, I_YD), WF(pc, I_YD + 1)};
-                const double vL[2] = {WF(pc, I_VL), WF(pc, I_VL + 1)};
-                const double vU[2] = {WF(pc, I_VU), WF(pc, I_VU + 1)};
-                ru[0] = o.g[3] - (o.b11 * ln[0] + o.b21 * ln[1]) + yd[0];
-                ru[1] = o.g[4] - (o.b12 * ln[0] + o.b22 * ln[1] + dt * ln[2]) + yd[1];
+                rx0 = q.g[0] + lam[0] - ln[0];
+                rx1 = q.g[1] + lam[1] - ln[1];
+                rx2 = q.g[2] + lam[2] - (q.a13 * ln[0] + q.a23 * ln[1] + ln[2]);
+                const double S[2] = {LDW(pc, I_S), LDW(pc, I_S + 1)};
+                const double yd[2] = {LDW(pc, I_YD), LDW(pc, I_YD + 1)};
+                const double vL[2] = {LDW(pc, I_VL), LDW(pc, I_VL + 1)};
+                const double vU[2] = {LDW(pc, I_VU), LDW(pc, I_VU + 1)};
+                ru[0] = q.g[3] - (q.b11 * ln[0] + q.b21 * ln[1]) + yd[0];
+                ru[1] = q.g[4] - (q.b12 * ln[0] + q.b22 * ln[1] + dt * ln[2]) + yd[1];
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
-                    const double sl = S[i] - P.sL[i], su = P.sU[i] - S[i];
-                    rs[i] = -yd[i] - mu / sl + mu / su;
-                    Dsig[i] = vL[i] / sl + vU[i] / su + dw;
+                    const double isl = 1.0 / (S[i] - P.sL[i]), isu = 1.0 / (P.sU[i] - S[i]);
+                    rs[i] = -yd[i] - mu * isl + mu * isu;
+                    Dsig[i] = vL[i] * isl + vU[i] * isu + dw;
                     rd[i] = U[i] - S[i];
                 }
                 rc[0] = c0; rc[1] = c1; rc[2] = c2;
                 if (mode == BM_SOC) {
                     // defects of the last trial point curr + at*step
                     double Xt[3], Ut[2], St[2], Ft[3];
-                    Xt[0] = X[0] + at * WF(p, sfx); Xt[1] = X[1] + at * WF(p, sfx + 1); Xt[2] = X[2] + at * WF(p, sfx + 2);
+                    Xt[0] = X[0] + at * LDW(p, sfx); Xt[1] = X[1] + at * LDW(p, sfx + 1); Xt[2] = X[2] + at * LDW(p, sfx + 2);
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
-                        const double du = WF(p, sfu + i);
-                        const double rdp = (sfu == F_DU) ? rd[i] : WF(p, F_DS + i);
+                        const double du = LDW(p, sfu + i);
+                        const double rdp = sfirst ? rd[i] : LDW(p, F_DS + i);
                         Ut[i] = U[i] + at * du;
                         St[i] = S[i] + at * (du + rdp);
                         rd[i] = at * rdp + (Ut[i] - St[i]);
-                        WF(p, F_DS + i) = rd[i];
+                        STW(p, F_DS + i, rd[i]);
                     }
-                    dyn_value(P, Xt, Ut, Ft);
+                    tpp_dyn(P, Xt, Ut, Ft);
 #pragma unroll
                     for (int i = 0; i < 3; i++) {
-                        const double base = (sfu == F_DU) ? rc[i] : WF(p, F_CS + i);
+                        const double base = sfirst ? rc[i] : LDW(p, F_CS + i);
                         rc[i] = at * base + (Xtn[i] - Ft[i]);
-                        WF(p, F_CS + i) = rc[i];
+                        STW(p, F_CS + i, rc[i]);
                         Xtn[i] = Xt[i];
                     }
                 }
             }
-            const double hxx = useW ? o.hxx : 0.0, hyy = useW ? o.hyy : 0.0;
-            const double htt = useW ? o.htt : 0.0, htv = useW ? o.htv : 0.0, htw = useW ? o.htw : 0.0;
-            const double hvv = useW ? o.hvv : 0.0, hvw = useW ? o.hvw : 0.0, hww = useW ? o.hww : 0.0;
-            const double a = o.a13, b = o.a23, b11 = o.b11, b12 = o.b12, b21 = o.b21, b22 = o.b22;
+            const double hxx = useW ? q.hxx : 0.0, hyy = useW ? q.hyy : 0.0;
+            const double htt = useW ? q.htt : 0.0, htv = useW ? q.htv : 0.0, htw = useW ? q.htw : 0.0;
+            const double hvv = useW ? q.hvv : 0.0, hvw = useW ? q.hvw : 0.0, hww = useW ? q.hww : 0.0;
+            const double a = q.a13, b = q.a23, b11 = q.b11, b12 = q.b12, b21 = q.b21, b22 = q.b22;
             const double d0 = -rc[0], d1 = -rc[1], d2 = -rc[2];
             // w = P d + p
             const double w0 = q00 * d0 + q01 * d1 + q02 * d2 + v0;
@@ -286,15 +354,15 @@ __device__ __forceinline__ bool tpp_backward(const KParams &P, double *wb, const
             const double gu0 = qu0 + b11 * w0 + b21 * w1;
             const double gu1 = qu1 + b12 * w0 + b22 * w1 + dt * w2;
             const double det = r00 * r11 - r01 * r01;
-            if (!(r00 > 0.0) || !(det > 0.0)) ok = false;
+            if (!(r00 > 0.0) || !(det > 0.0)) ok = 0;
             const double idet = 1.0 / det;
             const double i00 = r11 * idet, i01 = -r01 * idet, i11 = r00 * idet;
             const double K00 = -(i00 * u00 + i01 * u10), K01 = -(i00 * u01 + i01 * u11), K02 = -(i00 * u02 + i01 * u12);
             const double K10 = -(i01 * u00 + i11 * u10), K11 = -(i01 * u01 + i11 * u11), K12 = -(i01 * u02 + i11 * u12);
             const double k0 = -(i00 * gu0 + i01 * gu1), k1 = -(i01 * gu0 + i11 * gu1);
-            WF(p, F_K) = K00; WF(p, F_K + 1) = K01; WF(p, F_K + 2) = K02;
-            WF(p, F_K + 3) = K10; WF(p, F_K + 4) = K11; WF(p, F_K + 5) = K12;
-            WF(p, F_KF) = k0; WF(p, F_KF + 1) = k1;
+            STW(p, F_K, K00); STW(p, F_K + 1, K01); STW(p, F_K + 2, K02);
+            STW(p, F_K + 3, K10); STW(p, F_K + 4, K11); STW(p, F_K + 5, K12);
+            STW(p, F_KF, k0); STW(p, F_KF + 1, k1);
             // P' = Qxx + Qux'K (symmetrised), p' = gx + Qux' kf
             q00 = x00 + u00 * K00 + u10 * K10;
             q11 = x11 + u01 * K01 + u11 * K11;
@@ -307,86 +375,92 @@ __device__ __forceinline__ bool tpp_backward(const KParams &P, double *wb, const
             v2 = gx2 + u02 * k0 + u12 * k1;
         }
         if (k >= 1) {
-            WF(p, F_P) = q00; WF(p, F_P + 1) = q01; WF(p, F_P + 2) = q02;
-            WF(p, F_P + 3) = q11; WF(p, F_P + 4) = q12; WF(p, F_P + 5) = q22;
-            WF(p, F_PV) = v0; WF(p, F_PV + 1) = v1; WF(p, F_PV + 2) = v2;
+            STW(p, F_P, q00); STW(p, F_P + 1, q01); STW(p, F_P + 2, q02);
+            STW(p, F_P + 3, q11); STW(p, F_P + 4, q12); STW(p, F_P + 5, q22);
+            STW(p, F_PV, v0); STW(p, F_PV + 1, v1); STW(p, F_PV + 2, v2);
         }
         Xn[0] = X[0]; Xn[1] = X[1]; Xn[2] = X[2];
         ln[0] = lam[0]; ln[1] = lam[1]; ln[2] = lam[2];
     }
-    return ok;
+    o.ok = ok; o.bad = bad; o.gmax = gmax; o.f = fs;
 }
 
 struct TppFwd {
-    double a_max, a_z, gbd, bar, ymax;
+    double a_max, a_z, gbd, ymax;
     int bad;
 };
 
 // ---- sweep F: forward roll-out of the step; step sizes and directional derivative ----------------------------------
-__device__ __forceinline__ void tpp_forward(const KParams &P, double *wb, const TppLane &L, TppFwd &o) {
+__device__ __forceinline__ void tpp_forward(const KParams &P, double *wb, int cur, const TppLane &L, TppFwd &o) {
     const int N = P.N;
     const double dt = P.dt, mu = L.mu, tau = L.tau, df = L.df;
-    const int co = L.cur * I_NF;
-    const int fx = (L.bmode == BM_SOC) ? F_SX : F_DX, fu = (L.bmode == BM_SOC) ? F_SU : F_DU, fl = (L.bmode == BM_SOC) ? F_SL : F_DL;
+    const double goal[3] = {L.r[0], L.r[1], L.r[2]};
+    const int bmode0 = L.bmode;
+    const int co = cur * I_NF;
+    const int fx = (bmode0 == BM_SOC) ? F_SX : F_DX, fu = (bmode0 == BM_SOC) ? F_SU : F_DU, fl = (bmode0 == BM_SOC) ? F_SL : F_DL;
     double y0 = 0, y1 = 0, y2 = 0;
-    o.a_max = 1.0; o.a_z = 1.0; o.gbd = 0; o.bar = 0; o.ymax = 0; o.bad = 0;
-    double X[3] = {WF(wb + co * 32, I_X), WF(wb + co * 32, I_X + 1), WF(wb + co * 32, I_X + 2)};
+    double a_max = 1.0, a_z = 1.0, gbd = 0, ymax = 0;
+    int bad = 0;
+    double X[3] = {LDW(wb + co * 32, I_X), LDW(wb + co * 32, I_X + 1), LDW(wb + co * 32, I_X + 2)};
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-        const int mode = tpp_opaque(L.bmode);
-        double *p = wb + (size_t)k * (TPP_NF * 32);
+        const int mode = tpp_opaque(bmode0);
+        double *p = wb + (size_t)k * TPP_STAGE;
         const double *pc = p + co * 32;
-        WF(p, fx) = y0; WF(p, fx + 1) = y1; WF(p, fx + 2) = y2;
-        if (!isfinite(y0) || !isfinite(y1) || !isfinite(y2)) o.bad = 1;
+        if (k < N) {
+            tpp_prefetch_rows(p + TPP_STAGE, F_K, F_DX - F_K);
+            tpp_prefetch_rows(pc + TPP_STAGE, I_U, 4);
+            tpp_prefetch_rows(pc + TPP_STAGE, I_VL, 4);
+            if (k + 1 < N) tpp_prefetch_rows(pc + 2 * TPP_STAGE, I_X, 3);
+        }
+        STW(p, fx, y0); STW(p, fx + 1, y1); STW(p, fx + 2, y2);
+        if (!isfinite(y0) || !isfinite(y1) || !isfinite(y2)) bad = 1;
         if (k >= 1) {
-            const double P0 = WF(p, F_P), P1 = WF(p, F_P + 1), P2 = WF(p, F_P + 2), P3 = WF(p, F_P + 3),
-                         P4 = WF(p, F_P + 4), P5 = WF(p, F_P + 5);
-            const double l0 = -(WF(p, F_PV) + P0 * y0 + P1 * y1 + P2 * y2);
-            const double l1 = -(WF(p, F_PV + 1) + P1 * y0 + P3 * y1 + P4 * y2);
-            const double l2 = -(WF(p, F_PV + 2) + P2 * y0 + P4 * y1 + P5 * y2);
-            WF(p, fl) = l0; WF(p, fl + 1) = l1; WF(p, fl + 2) = l2;
-            if (!isfinite(l0) || !isfinite(l1) || !isfinite(l2)) o.bad = 1;
-            if (mode == BM_LSQ) o.ymax = fmax(o.ymax, fmax(fabs(l0), fmax(fabs(l1), fabs(l2))));
+            const double P0 = LDW(p, F_P), P1 = LDW(p, F_P + 1), P2 = LDW(p, F_P + 2), P3 = LDW(p, F_P + 3),
+                         P4 = LDW(p, F_P + 4), P5 = LDW(p, F_P + 5);
+            const double l0 = -(LDW(p, F_PV) + P0 * y0 + P1 * y1 + P2 * y2);
+            const double l1 = -(LDW(p, F_PV + 1) + P1 * y0 + P3 * y1 + P4 * y2);
+            const double l2 = -(LDW(p, F_PV + 2) + P2 * y0 + P4 * y1 + P5 * y2);
+            STW(p, fl, l0); STW(p, fl + 1, l1); STW(p, fl + 2, l2);
+            if (!isfinite(l0) || !isfinite(l1) || !isfinite(l2)) bad = 1;
+            if (mode == BM_LSQ) ymax = fmax(ymax, fmax(fabs(l0), fmax(fabs(l1), fabs(l2))));
         }
         if (k < N) {
-            const double du0 = WF(p, F_KF) + WF(p, F_K) * y0 + WF(p, F_K + 1) * y1 + WF(p, F_K + 2) * y2;
-            const double du1 = WF(p, F_KF + 1) + WF(p, F_K + 3) * y0 + WF(p, F_K + 4) * y1 + WF(p, F_K + 5) * y2;
-            WF(p, fu) = du0; WF(p, fu + 1) = du1;
-            if (!isfinite(du0) || !isfinite(du1)) o.bad = 1;
+            const double du0 = LDW(p, F_KF) + LDW(p, F_K) * y0 + LDW(p, F_K + 1) * y1 + LDW(p, F_K + 2) * y2;
+            const double du1 = LDW(p, F_KF + 1) + LDW(p, F_K + 3) * y0 + LDW(p, F_K + 4) * y1 + LDW(p, F_K + 5) * y2;
+            STW(p, fu, du0); STW(p, fu + 1, du1);
+            if (!isfinite(du0) || !isfinite(du1)) bad = 1;
             const double du[2] = {du0, du1};
-            const double U[2] = {WF(pc, I_U), WF(pc, I_U + 1)};
-            const double *pn = pc + TPP_NF * 32;
-            const double Xn[3] = {WF(pn, I_X), WF(pn, I_X + 1), WF(pn, I_X + 2)};
+            const double U[2] = {LDW(pc, I_U), LDW(pc, I_U + 1)};
+            const double *pn = pc + TPP_STAGE;
+            const double Xn[3] = {LDW(pn, I_X), LDW(pn, I_X + 1), LDW(pn, I_X + 2)};
             double r[3], ub[2];
-            tpp_ref(P, L, p, r, ub);
+            tpp_ref(P, goal, p, r, ub);
             const double ln0[3] = {0, 0, 0};
             TppLin q;
             tpp_lin<false>(P, r, ub, X, U, ln0, df, q);
             double rc0, rc1, rc2;
             if (mode == BM_LSQ) {
                 rc0 = rc1 = rc2 = 0;
-                o.ymax = fmax(o.ymax, fmax(fabs(du0), fabs(du1))); // dyd = Sigma*dS + rs with Sigma = 1, rd = rs = 0
+                ymax = fmax(ymax, fmax(fabs(du0), fabs(du1))); // dyd = Sigma*dS + rs with Sigma = 1, rd = rs = 0
             } else {
-                if (mode == BM_SOC) { rc0 = WF(p, F_CS); rc1 = WF(p, F_CS + 1); rc2 = WF(p, F_CS + 2); }
+                if (mode == BM_SOC) { rc0 = LDW(p, F_CS); rc1 = LDW(p, F_CS + 1); rc2 = LDW(p, F_CS + 2); }
                 else { rc0 = Xn[0] - q.F0; rc1 = Xn[1] - q.F1; rc2 = Xn[2] - q.F2; }
-                if (mode == BM_NEWTON && k >= 1) o.gbd += q.g[0] * y0 + q.g[1] * y1 + q.g[2] * y2;
+                if (mode == BM_NEWTON && k >= 1) gbd += q.g[0] * y0 + q.g[1] * y1 + q.g[2] * y2;
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
-                    const double S = WF(pc, I_S + i), vL = WF(pc, I_VL + i), vU = WF(pc, I_VU + i);
-                    const double rd = (mode == BM_SOC) ? WF(p, F_DS + i) : (U[i] - S);
+                    const double S = LDW(pc, I_S + i), vL = LDW(pc, I_VL + i), vU = LDW(pc, I_VU + i);
+                    const double rd = (mode == BM_SOC) ? LDW(p, F_DS + i) : (U[i] - S);
                     const double ds = du[i] + rd;
                     const double sl = S - P.sL[i], su = P.sU[i] - S;
-                    if (ds < 0) o.a_max = fmin(o.a_max, -tau * sl / ds);
-                    if (ds > 0) o.a_max = fmin(o.a_max, tau * su / ds);
-                    const double dvL = mu / sl - vL - vL / sl * ds;
-                    const double dvU = mu / su - vU + vU / su * ds;
-                    if (dvL < 0) o.a_z = fmin(o.a_z, -tau * vL / dvL);
-                    if (dvU < 0) o.a_z = fmin(o.a_z, -tau * vU / dvU);
-                    if (!isfinite(ds) || !isfinite(dvL) || !isfinite(dvU)) o.bad = 1;
-                    if (mode == BM_NEWTON) {
-                        o.bar -= mu * (log(sl) + log(su));
-                        o.gbd += (-mu / sl + mu / su) * ds + q.g[3 + i] * du[i];
-                    }
+                    const double isl = 1.0 / sl, isu = 1.0 / su;
+                    if (ds != 0.0) a_max = fmin(a_max, tau * ((ds < 0) ? -sl : su) / ds);
+                    const double dvL = mu * isl - vL - vL * isl * ds;
+                    const double dvU = mu * isu - vU + vU * isu * ds;
+                    if (dvL < 0) a_z = fmin(a_z, -tau * vL / dvL);
+                    if (dvU < 0) a_z = fmin(a_z, -tau * vU / dvU);
+                    if (!isfinite(ds) || !isfinite(dvL) || !isfinite(dvU)) bad = 1;
+                    if (mode == BM_NEWTON) gbd += (-mu * isl + mu * isu) * ds + q.g[3 + i] * du[i];
                 }
             }
             const double n0 = y0 + q.a13 * y2 + q.b11 * du0 + q.b12 * du1 - rc0;
@@ -396,88 +470,89 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, double *wb, const 
             X[0] = Xn[0]; X[1] = Xn[1]; X[2] = Xn[2];
         }
     }
+    o.a_max = a_max; o.a_z = a_z; o.gbd = gbd; o.ymax = ymax; o.bad = bad;
 }
 
 struct TppTrial {
-    double th, phi, gmax;
+    double th, phi;
     TppNorms n;
-    int bad;
 };
 
 // ---- sweep T: write curr + alpha*step into the other iterate buffer and evaluate that point -------------------------
-// tmode EVAL0 / EVAL: no step, evaluates the current buffer in place (EVAL0 also returns the largest gradient entry).
-// tmode LSQ:          new = current with the least-squares multiplier estimate (or zeros) for lam, yd.
-// tmode STEP(_SOC):   new = current + alpha*(dX,dU,dS,dlam,dyd) and bound multipliers + a_z*(dvL,dvU), clamped.
-__device__ __forceinline__ void tpp_trial(const KParams &P, double *wb, const TppLane &L, TppTrial &o) {
+// tmode EVAL:        new = current (after the restoration stand-in).
+// tmode LSQ:         new = current with the least-squares multiplier estimate (scaled by df; or zeros) for lam, yd.
+// tmode STEP(_SOC):  new = current + alpha*(dX,dU,dS,dlam,dyd) and bound multipliers + a_z*(dvL,dvU), clamped.
+__device__ __forceinline__ void tpp_trial(const KParams &P, double *wb, int cur, const TppLane &L, TppTrial &o) {
     const int N = P.N;
     const double dt = P.dt, mu = L.mu, df = L.df, dw = L.dw;
-    const bool soc0 = (L.tmode == TM_STEP_SOC);
+    const double goal[3] = {L.r[0], L.r[1], L.r[2]};
+    const int tmode0 = L.tmode, keep0 = L.keep;
+    const bool soc0 = (tmode0 == TM_STEP_SOC);
     const double alpha = soc0 ? L.alpha_soc : L.alpha, a_z = soc0 ? L.a_z_soc : L.a_z;
-    const int co = L.cur * I_NF, no = I_NF - co;
+    const int co = cur * I_NF, no = I_NF - co;
     const int fx = soc0 ? F_SX : F_DX, fu = soc0 ? F_SU : F_DU, fl = soc0 ? F_SL : F_DL;
+    const double ikap = 1.0 / KAPPA_SIGMA;
     double Xn[3] = {0, 0, 0}, ln[3] = {0, 0, 0};
-    double th = 0, ph = 0, pi = 0, di = 0, sy = 0, sz = 0, pmin = 1e300, pmax = -1e300, fs = 0, gmax = 0;
-    int bad = 0;
+    double th = 0, slog = 0, pi = 0, di = 0, sy = 0, sz = 0, pmin = 1e300, pmax = -1e300, fs = 0;
 #pragma unroll 1
     for (int k = N; k >= 0; --k) {
-        const int mode = tpp_opaque(L.tmode);
-        const bool step = (mode >= TM_STEP), soc = (mode == TM_STEP_SOC), write = (mode >= TM_LSQ);
-        const bool keep = tpp_opaque((int)L.keep) != 0;
-        double *p = wb + (size_t)k * (TPP_NF * 32);
+        const int mode = tpp_opaque(tmode0);
+        const bool step = (mode >= TM_STEP), soc = (mode == TM_STEP_SOC);
+        double *p = wb + (size_t)k * TPP_STAGE;
         const double *pc = p + co * 32;
         double *pw = p + no * 32;
-        double X[3] = {WF(pc, I_X), WF(pc, I_X + 1), WF(pc, I_X + 2)};
+        if (k > 0) {
+            tpp_prefetch_rows(pc - TPP_STAGE, 0, I_NF);
+            tpp_prefetch_rows(p - TPP_STAGE, F_DX, F_SX - F_DX);
+        }
+        double X[3] = {LDW(pc, I_X), LDW(pc, I_X + 1), LDW(pc, I_X + 2)};
         double lam[3] = {0, 0, 0};
         if (k >= 1) {
-            lam[0] = WF(pc, I_LAM); lam[1] = WF(pc, I_LAM + 1); lam[2] = WF(pc, I_LAM + 2);
+            lam[0] = LDW(pc, I_LAM); lam[1] = LDW(pc, I_LAM + 1); lam[2] = LDW(pc, I_LAM + 2);
             if (step) {
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
-                    X[i] += alpha * WF(p, fx + i);
-                    lam[i] += alpha * WF(p, fl + i);
+                    X[i] += alpha * LDW(p, fx + i);
+                    lam[i] += alpha * LDW(p, fl + i);
                 }
             } else if (mode == TM_LSQ) {
 #pragma unroll
-                for (int i = 0; i < 3; i++) lam[i] = keep ? WF(p, F_DL + i) : 0.0;
+                for (int i = 0; i < 3; i++) lam[i] = keep0 ? df * LDW(p, F_DL + i) : 0.0;
             }
         }
-        if (write) {
 #pragma unroll
-            for (int i = 0; i < 3; i++) { WF(pw, I_X + i) = X[i]; WF(pw, I_LAM + i) = lam[i]; }
-        }
+        for (int i = 0; i < 3; i++) { STW(pw, I_X + i, X[i]); STW(pw, I_LAM + i, lam[i]); }
         if (k < N) {
             double U[2], S[2], yd[2], vL[2], vU[2];
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-                U[i] = WF(pc, I_U + i); S[i] = WF(pc, I_S + i); yd[i] = WF(pc, I_YD + i);
-                vL[i] = WF(pc, I_VL + i); vU[i] = WF(pc, I_VU + i);
+                U[i] = LDW(pc, I_U + i); S[i] = LDW(pc, I_S + i); yd[i] = LDW(pc, I_YD + i);
+                vL[i] = LDW(pc, I_VL + i); vU[i] = LDW(pc, I_VU + i);
                 if (step) {
-                    const double du = WF(p, fu + i);
-                    const double rd = soc ? WF(p, F_DS + i) : (U[i] - S[i]);
+                    const double du = LDW(p, fu + i);
+                    const double rd = soc ? LDW(p, F_DS + i) : (U[i] - S[i]);
                     const double ds = du + rd;
-                    const double sl = S[i] - P.sL[i], su = P.sU[i] - S[i];
-                    const double Dsig = vL[i] / sl + vU[i] / su + dw;
-                    const double rs = -yd[i] - mu / sl + mu / su;
-                    const double dvL = mu / sl - vL[i] - vL[i] / sl * ds;
-                    const double dvU = mu / su - vU[i] + vU[i] / su * ds;
+                    const double isl = 1.0 / (S[i] - P.sL[i]), isu = 1.0 / (P.sU[i] - S[i]);
+                    const double Dsig = vL[i] * isl + vU[i] * isu + dw;
+                    const double rs = -yd[i] - mu * isl + mu * isu;
+                    const double dvL = mu * isl - vL[i] - vL[i] * isl * ds;
+                    const double dvU = mu * isu - vU[i] + vU[i] * isu * ds;
                     U[i] += alpha * du;
                     S[i] += alpha * ds;
                     yd[i] += alpha * (Dsig * ds + rs);
                     vL[i] += a_z * dvL;
                     vU[i] += a_z * dvU;
-                    const double sl2 = S[i] - P.sL[i], su2 = P.sU[i] - S[i];
-                    vL[i] = fmax(fmin(vL[i], KAPPA_SIGMA * mu / sl2), mu / (KAPPA_SIGMA * sl2));
-                    vU[i] = fmax(fmin(vU[i], KAPPA_SIGMA * mu / su2), mu / (KAPPA_SIGMA * su2));
+                    const double ml = mu / (S[i] - P.sL[i]), mu_u = mu / (P.sU[i] - S[i]);
+                    vL[i] = fmax(fmin(vL[i], KAPPA_SIGMA * ml), ml * ikap);
+                    vU[i] = fmax(fmin(vU[i], KAPPA_SIGMA * mu_u), mu_u * ikap);
                 } else if (mode == TM_LSQ) {
-                    yd[i] = keep ? WF(p, F_DU + i) : 0.0;
+                    yd[i] = keep0 ? df * LDW(p, F_DU + i) : 0.0;
                 }
-                if (write) {
-                    WF(pw, I_U + i) = U[i]; WF(pw, I_S + i) = S[i]; WF(pw, I_YD + i) = yd[i];
-                    WF(pw, I_VL + i) = vL[i]; WF(pw, I_VU + i) = vU[i];
-                }
+                STW(pw, I_U + i, U[i]); STW(pw, I_S + i, S[i]); STW(pw, I_YD + i, yd[i]);
+                STW(pw, I_VL + i, vL[i]); STW(pw, I_VU + i, vU[i]);
             }
             double r[3], ub[2];
-            tpp_ref(P, L, p, r, ub);
+            tpp_ref(P, goal, p, r, ub);
             TppLin q;
             tpp_lin<false>(P, r, ub, X, U, ln, df, q);
             const double c[3] = {Xn[0] - q.F0, Xn[1] - q.F1, Xn[2] - q.F2};
@@ -486,7 +561,6 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, double *wb, const Tp
             for (int i = 0; i < 3; i++) {
                 th += fabs(c[i]);
                 pi = fmax(pi, fabs(c[i]));
-                if (!isfinite(c[i])) bad = 1;
             }
             if (k >= 1) {
                 const double r0 = q.g[0] + lam[0] - ln[0];
@@ -494,31 +568,29 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, double *wb, const Tp
                 const double r2 = q.g[2] + lam[2] - (q.a13 * ln[0] + q.a23 * ln[1] + ln[2]);
                 di = fmax(di, fmax(fabs(r0), fmax(fabs(r1), fabs(r2))));
                 sy += fabs(lam[0]) + fabs(lam[1]) + fabs(lam[2]);
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    if (!isfinite(q.g[i])) bad = 1;
-                    gmax = fmax(gmax, fabs(q.g[i]));
-                }
             }
             const double ru0 = q.g[3] - (q.b11 * ln[0] + q.b21 * ln[1]) + yd[0];
             const double ru1 = q.g[4] - (q.b12 * ln[0] + q.b22 * ln[1] + dt * ln[2]) + yd[1];
             di = fmax(di, fmax(fabs(ru0), fabs(ru1)));
+            double prod = 1.0;
+            bool inside = true;
 #pragma unroll
             for (int i = 0; i < 2; i++) {
                 const double rd = U[i] - S[i];
                 const double sl = S[i] - P.sL[i], su = P.sU[i] - S[i];
                 th += fabs(rd);
                 pi = fmax(pi, fabs(rd));
-                ph -= mu * (log(sl) + log(su));
+                prod *= sl * su;
+                inside = inside && (sl > 0.0) && (su > 0.0);
                 di = fmax(di, fabs(-yd[i] - vL[i] + vU[i]));
                 sy += fabs(yd[i]);
                 sz += fabs(vL[i]) + fabs(vU[i]);
                 const double pl = sl * vL[i], pu = su * vU[i];
                 pmin = fmin(pmin, fmin(pl, pu));
                 pmax = fmax(pmax, fmax(pl, pu));
-                if (!isfinite(q.g[3 + i])) bad = 1;
-                gmax = fmax(gmax, fabs(q.g[3 + i]));
             }
+            // barrier term: one logarithm per stage; a slack outside its bounds gives NaN like log(negative) would
+            slog += log(inside ? prod : -1.0);
         } else if (k >= 1) {
             // terminal state: no cost; its stationarity residual is the multiplier itself
             di = fmax(di, fmax(fabs(lam[0]), fmax(fabs(lam[1]), fabs(lam[2]))));
@@ -528,11 +600,9 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, double *wb, const Tp
         ln[0] = lam[0]; ln[1] = lam[1]; ln[2] = lam[2];
     }
     o.th = th;
-    o.phi = df * fs + ph;
-    o.gmax = gmax;
-    o.bad = bad;
+    o.phi = df * fs - mu * slog;
     o.n.theta = th; o.n.prim_inf = pi; o.n.dual_inf = di; o.n.sum_y = sy; o.n.sum_z = sz;
-    o.n.pmin = pmin; o.n.pmax = pmax; o.n.f = fs;
+    o.n.pmin = pmin; o.n.pmax = pmax; o.n.f = fs; o.n.slog = slog;
 }
 
 // ---- filter (32 entries per lane, kept in the workspace) --------------------------------------------------------------
@@ -546,7 +616,8 @@ __device__ __forceinline__ bool tpp_filter_ok(const double *fl, unsigned mask, d
     return true;
 }
 
-__device__ __forceinline__ void tpp_filter_add(double *fl, unsigned &mask, int &ring, double phi, double th) {
+__device__ __forceinline__ void tpp_filter_add(double *fl, TppLane &L, double phi, double th) {
+    unsigned mask = L.fmask;
     unsigned m = mask;
     while (m) {
         const int i = __ffs(m) - 1;
@@ -555,10 +626,10 @@ __device__ __forceinline__ void tpp_filter_add(double *fl, unsigned &mask, int &
     }
     int slot;
     if (~mask) slot = __ffs(~mask) - 1;
-    else { slot = ring & 31; ring++; }
+    else { slot = L.ring & 31; L.ring++; }
     fl[(2 * slot) * 32] = phi;
     fl[(2 * slot + 1) * 32] = th;
-    mask |= 1u << slot;
+    L.fmask = mask | (1u << slot);
 }
 
 // FilterLSAcceptor::CheckAcceptabilityOfTrialPoint (same tests as ls_acceptable of the warp kernel)
@@ -587,34 +658,39 @@ __device__ __forceinline__ bool tpp_ls_acceptable(const TppLane &L, const double
 }
 
 // Line search gave up on the Newton direction (alpha < alpha_min): restoration stand-in of the warp kernel — roll
-// the controls out (closed-form feasible point), restart the multipliers.
-__device__ __forceinline__ void tpp_restore(const KParams &P, double *wb, double *fl, TppLane &L) {
+// the controls out (closed-form feasible point), restart the multipliers.  Writes the other iterate buffer.
+__device__ __forceinline__ void tpp_restore(const KParams &P, double *wb, double *fl, int cur, TppLane &L) {
     const int N = P.N;
     if (L.n.theta <= 1e-10 || L.n_resto >= MAX_RESTO) { L.status = B200MPC_RESTORATION_FAILED; L.phase = PH_FIN; return; }
-    tpp_filter_add(fl, L.fmask, L.ring, L.ref_phi - GAMMA_PHI * L.n.theta, (1 - GAMMA_THETA) * L.n.theta);
-    const int co = L.cur * I_NF;
+    tpp_filter_add(fl, L, L.ref_phi - GAMMA_PHI * L.n.theta, (1 - GAMMA_THETA) * L.n.theta);
+    const int co = cur * I_NF, no = I_NF - co;
     double zm = 0;
 #pragma unroll 1
     for (int k = 0; k < N; ++k) {
-        const double *pc = wb + (size_t)k * (TPP_NF * 32) + co * 32;
-        zm = fmax(zm, fmax(fmax(WF(pc, I_VL), WF(pc, I_VL + 1)), fmax(WF(pc, I_VU), WF(pc, I_VU + 1))));
+        const double *pc = wb + (size_t)k * TPP_STAGE + co * 32;
+        zm = fmax(zm, fmax(fmax(LDW(pc, I_VL), LDW(pc, I_VL + 1)), fmax(LDW(pc, I_VU), LDW(pc, I_VU + 1))));
     }
-    double y[3] = {WF(wb + co * 32, I_X), WF(wb + co * 32, I_X + 1), WF(wb + co * 32, I_X + 2)};
+    double y[3] = {LDW(wb + co * 32, I_X), LDW(wb + co * 32, I_X + 1), LDW(wb + co * 32, I_X + 2)};
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-        double *pc = wb + (size_t)k * (TPP_NF * 32) + co * 32;
-        WF(pc, I_X) = y[0]; WF(pc, I_X + 1) = y[1]; WF(pc, I_X + 2) = y[2];
-        WF(pc, I_LAM) = 0; WF(pc, I_LAM + 1) = 0; WF(pc, I_LAM + 2) = 0;
+        const double *pc = wb + (size_t)k * TPP_STAGE + co * 32;
+        double *pw = wb + (size_t)k * TPP_STAGE + no * 32;
+        STW(pw, I_X, y[0]); STW(pw, I_X + 1, y[1]); STW(pw, I_X + 2, y[2]);
+        STW(pw, I_LAM, 0.0); STW(pw, I_LAM + 1, 0.0); STW(pw, I_LAM + 2, 0.0);
         if (k < N) {
-            const double U[2] = {WF(pc, I_S), WF(pc, I_S + 1)};
-            WF(pc, I_U) = U[0]; WF(pc, I_U + 1) = U[1];
-            WF(pc, I_YD) = 0; WF(pc, I_YD + 1) = 0;
-            if (zm > 1e3) { WF(pc, I_VL) = 1.0; WF(pc, I_VL + 1) = 1.0; WF(pc, I_VU) = 1.0; WF(pc, I_VU + 1) = 1.0; }
+            const double U[2] = {LDW(pc, I_S), LDW(pc, I_S + 1)};
+            STW(pw, I_U, U[0]); STW(pw, I_U + 1, U[1]);
+            STW(pw, I_S, U[0]); STW(pw, I_S + 1, U[1]);
+            STW(pw, I_YD, 0.0); STW(pw, I_YD + 1, 0.0);
+            const bool reset = zm > 1e3;
+            STW(pw, I_VL, reset ? 1.0 : LDW(pc, I_VL)); STW(pw, I_VL + 1, reset ? 1.0 : LDW(pc, I_VL + 1));
+            STW(pw, I_VU, reset ? 1.0 : LDW(pc, I_VU)); STW(pw, I_VU + 1, reset ? 1.0 : LDW(pc, I_VU + 1));
             double F[3];
-            dyn_value(P, y, U, F);
+            tpp_dyn(P, y, U, F);
             y[0] = F[0]; y[1] = F[1]; y[2] = F[2];
         }
     }
+    L.moved = 1;
     L.n_resto++;
     L.iter++;
     L.tmode = TM_EVAL;
@@ -625,7 +701,7 @@ __device__ __forceinline__ void tpp_restore(const KParams &P, double *wb, double
 // finishes the problem.  L.n holds the residual norms of the current iterate.
 __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L) {
     const int N = P.N;
-    const TppNorms &n = L.n;
+    const TppNorms n = L.n;
     if (L.theta_max < 0) {
         L.theta_max = 1e4 * fmax(1.0, n.theta);
         L.theta_min = 1e-4 * fmax(1.0, n.theta);
@@ -650,15 +726,20 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L) {
     }
     if (L.iter >= P.max_iter) { L.status = B200MPC_MAXITER_EXCEEDED; return; }
     // barrier parameter update
+    double mu = L.mu;
+    bool changed = false;
     for (;;) {
-        const double mu = L.mu;
         const double cm = fmax(fabs(n.pmax - mu), fabs(n.pmin - mu));
         const double Emu = fmax(n.dual_inf / sd, fmax(n.prim_inf, cm / sc));
         if (!(Emu <= K_EPS * mu)) break;
         const double nm = fmax(fmin(K_MU * mu, tpp_pow(mu, TH_MU)), P.mu_floor);
         if (nm == mu) break;
-        L.mu = nm;
-        L.tau = fmax(TAU_MIN, 1.0 - nm);
+        mu = nm;
+        changed = true;
+    }
+    if (changed) {
+        L.mu = mu;
+        L.tau = fmax(TAU_MIN, 1.0 - mu);
         L.fmask = 0;
     }
     L.dw = 0.0;
@@ -667,15 +748,18 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L) {
 }
 
 __global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kernel(const KParams P, const TppArgs T) {
+    extern __shared__ double tpp_smem[];
     const BatchArgs &A = T.a;
     const int N = P.N;
     const int lane = threadIdx.x & 31;
     const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    double *wb = T.ws + gw * ((size_t)(N + 1) * TPP_NF * 32) + lane;
+    double *wb = T.ws + gw * ((size_t)(N + 1) * TPP_STAGE) + lane;
     double *fl = T.filt + gw * (64 * 32) + lane;
-    TppLane L;
+    TppLane &L = *reinterpret_cast<TppLane *>(tpp_smem + (size_t)threadIdx.x * TPP_LANE_STRIDE);
     L.phase = PH_LOAD;
     L.b = -1;
+    L.moved = 0;
+    int cur = 0; // warp-uniform: the buffer holding the current iterates during this trip
 
     for (;;) {
         // ---- block L: pull the next problem, write the starting point ----
@@ -692,12 +776,13 @@ __global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kerne
                 } else {
                     L.r[0] = L.r[1] = L.r[2] = 0;
                 }
-                L.cur = 0;
+                const int co = cur * I_NF;
 #pragma unroll 1
                 for (int k = 0; k <= N; ++k) {
-                    double *p = wb + (size_t)k * (TPP_NF * 32);
-                    WF(p, I_X) = (k == 0) ? x0[0] : 0.0; WF(p, I_X + 1) = (k == 0) ? x0[1] : 0.0; WF(p, I_X + 2) = (k == 0) ? x0[2] : 0.0;
-                    WF(p, I_LAM) = 0; WF(p, I_LAM + 1) = 0; WF(p, I_LAM + 2) = 0;
+                    double *p = wb + (size_t)k * TPP_STAGE;
+                    double *pc = p + co * 32;
+                    STW(pc, I_X, (k == 0) ? x0[0] : 0.0); STW(pc, I_X + 1, (k == 0) ? x0[1] : 0.0); STW(pc, I_X + 2, (k == 0) ? x0[2] : 0.0);
+                    STW(pc, I_LAM, 0.0); STW(pc, I_LAM + 1, 0.0); STW(pc, I_LAM + 2, 0.0);
                     if (k < N) {
                         double u[2] = {0, 0};
                         if (A.u_init) { u[0] = A.u_init[(size_t)b * 2 * N + 2 * k]; u[1] = A.u_init[(size_t)b * 2 * N + 2 * k + 1]; }
@@ -710,26 +795,27 @@ __global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kerne
                             double sv = u[i];
                             if (sv < lo + pl) sv = lo + pl;
                             if (sv > hi - pu) sv = hi - pu;
-                            WF(p, I_U + i) = u[i]; WF(p, I_S + i) = sv; WF(p, I_YD + i) = 0;
-                            WF(p, I_VL + i) = 1.0; WF(p, I_VU + i) = 1.0;
+                            STW(pc, I_U + i, u[i]); STW(pc, I_S + i, sv); STW(pc, I_YD + i, 0.0);
+                            STW(pc, I_VL + i, 1.0); STW(pc, I_VU + i, 1.0);
                         }
                         if (P.ref_kind == B200MPC_REF_TRAJ) {
                             const double *xr = A.xref + (size_t)b * 3 * N + 3 * k;
-                            WF(p, F_R) = xr[0]; WF(p, F_R + 1) = xr[1]; WF(p, F_R + 2) = xr[2];
-                            WF(p, F_UB) = A.uref[(size_t)b * 2 * N + 2 * k]; WF(p, F_UB + 1) = A.uref[(size_t)b * 2 * N + 2 * k + 1];
+                            STW(p, F_R, xr[0]); STW(p, F_R + 1, xr[1]); STW(p, F_R + 2, xr[2]);
+                            STW(p, F_UB, A.uref[(size_t)b * 2 * N + 2 * k]); STW(p, F_UB + 1, A.uref[(size_t)b * 2 * N + 2 * k + 1]);
                         }
                     }
                 }
                 L.status = B200MPC_MAXITER_EXCEEDED;
                 L.iter = 0; L.ls_extra = 0; L.n_resto = 0; L.acceptable_count = 0; L.ntrial = 0; L.soc_count = 0;
-                L.ring = 0; L.fmask = 0; L.keep = false; L.soc_first = true;
+                L.ring = 0; L.fmask = 0; L.keep = 0; L.soc_first = 1; L.moved = 0;
                 L.df = 1.0; L.mu = P.mu_init; L.tau = fmax(TAU_MIN, 1.0 - P.mu_init);
                 L.theta_max = -1; L.theta_min = -1; L.dw = 0; L.dw_last = 0;
                 L.alpha = 0; L.a_z = 0; L.alpha_soc = 0; L.a_z_soc = 0; L.a_min = 0; L.theta_soc_old = 0;
                 L.ref_phi = 0; L.ref_gbd = 0;
+                L.n.f = 0; L.n.slog = 0; L.n.theta = 0;
                 L.bmode = BM_LSQ;
-                L.tmode = TM_EVAL0;
-                L.phase = PH_T;
+                L.tmode = TM_LSQ;
+                L.phase = PH_B;
             }
         }
         if (__all_sync(FULL, L.phase == PH_DONE)) break;
@@ -737,20 +823,33 @@ __global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kerne
         // ---- block B ----
         __syncwarp();
         if (tpp_opaque(L.phase) == PH_B) {
-            const bool ok = tpp_backward(P, wb, L);
-            if (L.bmode == BM_LSQ) {
-                if (ok) L.phase = PH_F;
-                else { L.keep = false; L.tmode = TM_LSQ; L.phase = PH_T; }
-            } else if (ok) {
-                if (L.bmode == BM_NEWTON && L.dw > 0.0) L.dw_last = L.dw;
+            TppBwd r;
+            tpp_backward(P, wb, cur, L, r);
+            const int bmode = L.bmode;
+            if (bmode == BM_LSQ) {
+                // objective scaling from the gradient at the starting point; invalid-number check
+                L.n.f = r.f;
+                if (r.bad || !isfinite(r.f)) {
+                    L.status = B200MPC_INVALID_NUMBER_DETECTED;
+                    L.phase = PH_FIN;
+                } else {
+                    if (r.gmax > 100.0) L.df = fmax(100.0 / r.gmax, 1e-8);
+                    if (r.ok) L.phase = PH_F;
+                    else { L.keep = 0; L.tmode = TM_LSQ; L.phase = PH_T; }
+                }
+            } else if (r.ok) {
+                if (bmode == BM_NEWTON && L.dw > 0.0) L.dw_last = L.dw;
                 L.phase = PH_F;
-            } else if (L.bmode == BM_SOC) {
+            } else if (bmode == BM_SOC) {
                 L.phase = PH_BACKTRACK; // correction abandoned: continue with the Newton direction
             } else {
                 // inertia correction
-                if (L.dw == 0.0) L.dw = (L.dw_last == 0.0) ? DW_INIT : fmax(DW_MIN, L.dw_last * DW_DEC);
-                else L.dw = (L.dw_last == 0.0 || 1e5 * L.dw_last < L.dw) ? L.dw * DW_INC_FIRST : L.dw * DW_INC;
-                if (L.dw > DW_MAX) { L.status = B200MPC_ERROR_IN_STEP_COMPUTATION; L.phase = PH_FIN; }
+                const double dw = L.dw, dwl = L.dw_last;
+                double nd;
+                if (dw == 0.0) nd = (dwl == 0.0) ? DW_INIT : fmax(DW_MIN, dwl * DW_DEC);
+                else nd = (dwl == 0.0 || 1e5 * dwl < dw) ? dw * DW_INC_FIRST : dw * DW_INC;
+                L.dw = nd;
+                if (nd > DW_MAX) { L.status = B200MPC_ERROR_IN_STEP_COMPUTATION; L.phase = PH_FIN; }
             }
         }
 
@@ -758,18 +857,19 @@ __global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kerne
         __syncwarp();
         if (tpp_opaque(L.phase) == PH_F) {
             TppFwd f;
-            tpp_forward(P, wb, L, f);
-            if (L.bmode == BM_LSQ) {
-                L.keep = (f.ymax <= 1e3);
+            tpp_forward(P, wb, cur, L, f);
+            const int bmode = L.bmode;
+            if (bmode == BM_LSQ) {
+                L.keep = (L.df * f.ymax <= 1e3) ? 1 : 0;
                 L.tmode = TM_LSQ;
                 L.phase = PH_T;
-            } else if (L.bmode == BM_NEWTON) {
+            } else if (bmode == BM_NEWTON) {
                 if (f.bad) {
                     L.status = B200MPC_ERROR_IN_STEP_COMPUTATION;
                     L.phase = PH_FIN;
                 } else {
                     const double theta = L.n.theta;
-                    L.ref_phi = L.df * L.n.f + f.bar;
+                    L.ref_phi = L.df * L.n.f - L.mu * L.n.slog;
                     L.ref_gbd = f.gbd;
                     double a_min = GAMMA_THETA;
                     if (f.gbd < 0) {
@@ -795,41 +895,27 @@ __global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kerne
         __syncwarp();
         if (tpp_opaque(L.phase) == PH_T) {
             TppTrial t;
-            tpp_trial(P, wb, L, t);
+            tpp_trial(P, wb, cur, L, t);
             const int tm = L.tmode;
-            if (tm == TM_EVAL0) {
-                // objective scaling from the gradient at the starting point; invalid-number check
+            if (tm == TM_EVAL || tm == TM_LSQ) {
                 L.n = t.n;
-                if (t.bad || !isfinite(t.n.f)) {
-                    L.status = B200MPC_INVALID_NUMBER_DETECTED;
-                    L.phase = PH_FIN;
-                } else {
-                    if (t.gmax > 100.0) L.df = fmax(100.0 / t.gmax, 1e-8);
-                    L.bmode = BM_LSQ;
-                    L.phase = PH_B;
-                }
-            } else if (tm == TM_EVAL) {
-                L.n = t.n;
-                L.phase = PH_TOP;
-            } else if (tm == TM_LSQ) {
-                L.n = t.n;
-                L.cur ^= 1;
+                L.moved = 1;
                 L.phase = PH_TOP;
             } else {
                 const bool soc = (tm == TM_STEP_SOC);
                 if (soc || L.ntrial++ > 0) L.ls_extra++;
                 bool fa;
                 if (tpp_ls_acceptable(L, fl, L.alpha, t.phi, t.th, fa)) {
-                    if (!fa) tpp_filter_add(fl, L.fmask, L.ring, L.ref_phi - GAMMA_PHI * L.n.theta, (1 - GAMMA_THETA) * L.n.theta);
+                    if (!fa) tpp_filter_add(fl, L, L.ref_phi - GAMMA_PHI * L.n.theta, (1 - GAMMA_THETA) * L.n.theta);
                     L.n = t.n;
-                    L.cur ^= 1;
+                    L.moved = 1;
                     L.iter++;
                     L.phase = PH_TOP;
                 } else if (!soc) {
                     if (L.ntrial == 1 && P.max_soc > 0 && isfinite(t.th) && t.th >= L.n.theta) {
                         // second-order correction, first round: right-hand sides from this trial point
                         L.soc_count = 0;
-                        L.soc_first = true;
+                        L.soc_first = 1;
                         L.theta_soc_old = t.th;
                         L.bmode = BM_SOC;
                         L.phase = PH_B;
@@ -840,7 +926,7 @@ __global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kerne
                     L.soc_count++;
                     if (L.soc_count < P.max_soc && t.th <= KAPPA_SOC * L.theta_soc_old) {
                         L.theta_soc_old = t.th;
-                        L.soc_first = false;
+                        L.soc_first = 0;
                         L.bmode = BM_SOC;
                         L.phase = PH_B;
                     } else {
@@ -855,7 +941,7 @@ __global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kerne
         if (tpp_opaque(L.phase) == PH_BACKTRACK) {
             L.alpha *= 0.5;
             if (L.alpha < L.a_min) {
-                tpp_restore(P, wb, fl, L);
+                tpp_restore(P, wb, fl, cur, L);
             } else {
                 L.tmode = TM_STEP;
                 L.phase = PH_T;
@@ -868,21 +954,37 @@ __global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kerne
 
         // ---- result store, release of the lane ----
         __syncwarp();
-        if (tpp_opaque(L.phase) == PH_FIN) {
-            const size_t b = (size_t)L.b;
-            const int co = L.cur * I_NF;
-            double *xo = A.X + b * 3 * (N + 1), *uo = A.U + b * 2 * N;
+        {
+            const int ph = tpp_opaque(L.phase);
+            if (ph == PH_FIN) {
+                const size_t b = (size_t)L.b;
+                const int co = (L.moved ? (1 - cur) : cur) * I_NF;
+                double *xo = A.X + b * 3 * (N + 1), *uo = A.U + b * 2 * N;
 #pragma unroll 1
-            for (int k = 0; k <= N; ++k) {
-                const double *pc = wb + (size_t)k * (TPP_NF * 32) + co * 32;
-                xo[3 * k] = WF(pc, I_X); xo[3 * k + 1] = WF(pc, I_X + 1); xo[3 * k + 2] = WF(pc, I_X + 2);
-                if (k < N) { uo[2 * k] = WF(pc, I_U); uo[2 * k + 1] = WF(pc, I_U + 1); }
+                for (int k = 0; k <= N; ++k) {
+                    const double *pc = wb + (size_t)k * TPP_STAGE + co * 32;
+                    xo[3 * k] = LDW(pc, I_X); xo[3 * k + 1] = LDW(pc, I_X + 1); xo[3 * k + 2] = LDW(pc, I_X + 2);
+                    if (k < N) { uo[2 * k] = LDW(pc, I_U); uo[2 * k + 1] = LDW(pc, I_U + 1); }
+                }
+                if (A.cost) A.cost[b] = L.n.f;
+                A.status[b] = L.status;
+                if (A.iters) A.iters[b] = L.iter;
+                if (A.ls) A.ls[b] = L.ls_extra;
+                L.phase = PH_LOAD;
+            } else if ((ph == PH_B || ph == PH_F || ph == PH_T) && !L.moved) {
+                // the iterate stays where it is but the warp's buffers swap: copy it across (rejected trial point,
+                // inertia-correction retry)
+                const int co = cur * I_NF, no = I_NF - co;
+#pragma unroll 1
+                for (int k = 0; k <= N; ++k) {
+                    const double *pc = wb + (size_t)k * TPP_STAGE + co * 32;
+                    double *pw = wb + (size_t)k * TPP_STAGE + no * 32;
+#pragma unroll
+                    for (int f = 0; f < I_NF; f++) STW(pw, f, LDW(pc, f));
+                }
             }
-            if (A.cost) A.cost[b] = L.n.f;
-            A.status[b] = L.status;
-            if (A.iters) A.iters[b] = L.iter;
-            if (A.ls) A.ls[b] = L.ls_extra;
-            L.phase = PH_LOAD;
+            L.moved = 0;
         }
+        cur ^= 1;
     }
 }
