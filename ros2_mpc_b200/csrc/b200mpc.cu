@@ -1293,10 +1293,10 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     if (blocks < 1) blocks = 1;
     h->ctas = blocks * h->sm_count; // persistent grid: a multiple of the SM count (148 on B200)
     int tblocks = 0;
-    const size_t tpp_smem = (size_t)128 * TPP_LANE_STRIDE * sizeof(double);
+    const size_t tpp_smem = (size_t)TPP_THREADS * TPP_LANE_STRIDE * sizeof(double);
     if ((e = cudaFuncSetAttribute(mpc_solve_tpp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tpp_smem)) != cudaSuccess)
         return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tblocks, mpc_solve_tpp_kernel, 128, tpp_smem)) != cudaSuccess)
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tblocks, mpc_solve_tpp_kernel, TPP_THREADS, tpp_smem)) != cudaSuccess)
         return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
     if (tblocks < 1) tblocks = 1;
     h->tpp_ctas = tblocks * h->sm_count;
@@ -1396,7 +1396,7 @@ extern "C" int b200mpc_last_kernel_kind(const b200mpc_handle *h) { return h ? h-
 // Lane-per-problem kernel: persistent grid, one workspace stripe per warp (allocated on first use).
 static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stream) {
     const int N = h->prm.N;
-    const size_t nwarps = (size_t)h->tpp_ctas * 4;
+    const size_t nwarps = (size_t)h->tpp_ctas * (TPP_THREADS / 32);
     if (!h->d_ws) {
         const size_t ws_bytes = nwarps * (size_t)(N + 1) * TPP_NF * 32 * sizeof(double);
         cudaError_t e = cudaMalloc(&h->d_ws, ws_bytes);
@@ -1406,13 +1406,13 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t 
     }
     CU_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), stream));
     int grid = h->tpp_ctas;
-    const int need = (a.B + 127) / 128;
+    const int need = (a.B + TPP_THREADS - 1) / TPP_THREADS;
     if (need < grid) grid = need;
     if (grid < 1) grid = 1;
     TppArgs t;
     t.a = a; t.ws = h->d_ws; t.filt = h->d_filt;
     CU_TRY(h, cudaEventRecord(h->ev0, stream));
-    mpc_solve_tpp_kernel<<<grid, 128, (size_t)128 * TPP_LANE_STRIDE * sizeof(double), stream>>>(h->kp, t);
+    mpc_solve_tpp_kernel<<<grid, TPP_THREADS, (size_t)TPP_THREADS * TPP_LANE_STRIDE * sizeof(double), stream>>>(h->kp, t);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev1, stream));
     h->launches++;

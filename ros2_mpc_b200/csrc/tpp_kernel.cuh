@@ -78,6 +78,19 @@ __device__ __forceinline__ int tpp_opaque(int v) {
     asm volatile("" : "+r"(v));
     return v;
 }
+// Reciprocal to within 1 ulp: hardware seed (MUFU.RCP64H) + two Newton steps.  Five instructions instead of the
+// ~25 of an IEEE division; the loop bodies have to stay small for the instruction cache.  The operands here
+// (slack distances, 2x2 determinants, step components) are normal, finite and non-zero.
+__device__ __forceinline__ double tpp_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+__device__ __noinline__ double tpp_exp(double a) { return exp(a); }
 __device__ __noinline__ double tpp_pow(double a, double b) { return pow(a, b); }
 __device__ __noinline__ double tpp_log10(double a) { return log10(a); }
 
@@ -106,12 +119,20 @@ struct TppLane {
 };
 #define TPP_LANE_STRIDE (((sizeof(TppLane) + 7) / 8) | 1) /* in doubles, odd */
 
+// sin/cos of th and hw: one out-of-line copy shared by all sweeps (instruction-cache footprint)
+struct TppSC { double s0, c0, sh, ch; };
+__device__ __noinline__ TppSC tpp_sincos2(double th, double hw) {
+    TppSC r;
+    sincos(th, &r.s0, &r.c0);
+    sincos(hw, &r.sh, &r.ch);
+    return r;
+}
 // sin/cos of th, th + hw, th + 2 hw (RK4 stage angles) from two sincos evaluations
 __device__ __forceinline__ void tpp_trig(double th, double hw, double &s0, double &c0, double &sm, double &cm,
                                          double &se, double &ce) {
-    double sh, ch;
-    sincos(th, &s0, &c0);
-    sincos(hw, &sh, &ch);
+    const TppSC t = tpp_sincos2(th, hw);
+    s0 = t.s0; c0 = t.c0;
+    const double sh = t.sh, ch = t.ch;
     sm = s0 * ch + c0 * sh;
     cm = c0 * ch - s0 * sh;
     const double s2 = 2.0 * sh * ch, c2 = 1.0 - 2.0 * sh * sh;
@@ -167,7 +188,7 @@ __device__ __forceinline__ void tpp_lin(const KParams &P, const double r[3], con
     o.F2 = th + dt * w;
     const double e0 = X[0] - r[0], e1 = X[1] - r[1], e2 = X[2] - r[2];
     const double m0 = v - ub[0], m1 = w - ub[1];
-    const double er = exp(-P.kappa * v);
+    const double er = tpp_exp(-P.kappa * v);
     o.f = e0 * P.Q[0] * e0 + e1 * P.Q[1] * e1 + e2 * P.Q[2] * e2 + m0 * P.R[0] * m0 + m1 * P.R[1] * m1 + er;
     o.g[0] = df * 2.0 * P.Q[0] * e0;
     o.g[1] = df * 2.0 * P.Q[1] * e1;
@@ -289,7 +310,7 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, double *wb, int c
                 ru[1] = q.g[4] - (q.b12 * ln[0] + q.b22 * ln[1] + dt * ln[2]) + yd[1];
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
-                    const double isl = 1.0 / (S[i] - P.sL[i]), isu = 1.0 / (P.sU[i] - S[i]);
+                    const double isl = tpp_rcp(S[i] - P.sL[i]), isu = tpp_rcp(P.sU[i] - S[i]);
                     rs[i] = -yd[i] - mu * isl + mu * isu;
                     Dsig[i] = vL[i] * isl + vU[i] * isu + dw;
                     rd[i] = U[i] - S[i];
@@ -355,7 +376,7 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, double *wb, int c
             const double gu1 = qu1 + b12 * w0 + b22 * w1 + dt * w2;
             const double det = r00 * r11 - r01 * r01;
             if (!(r00 > 0.0) || !(det > 0.0)) ok = 0;
-            const double idet = 1.0 / det;
+            const double idet = tpp_rcp(det);
             const double i00 = r11 * idet, i01 = -r01 * idet, i11 = r00 * idet;
             const double K00 = -(i00 * u00 + i01 * u10), K01 = -(i00 * u01 + i01 * u11), K02 = -(i00 * u02 + i01 * u12);
             const double K10 = -(i01 * u00 + i11 * u10), K11 = -(i01 * u01 + i11 * u11), K12 = -(i01 * u02 + i11 * u12);
@@ -453,12 +474,12 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, double *wb, int cu
                     const double rd = (mode == BM_SOC) ? LDW(p, F_DS + i) : (U[i] - S);
                     const double ds = du[i] + rd;
                     const double sl = S - P.sL[i], su = P.sU[i] - S;
-                    const double isl = 1.0 / sl, isu = 1.0 / su;
-                    if (ds != 0.0) a_max = fmin(a_max, tau * ((ds < 0) ? -sl : su) / ds);
+                    const double isl = tpp_rcp(sl), isu = tpp_rcp(su);
+                    if (ds != 0.0) a_max = fmin(a_max, tau * ((ds < 0) ? -sl : su) * tpp_rcp(ds));
                     const double dvL = mu * isl - vL - vL * isl * ds;
                     const double dvU = mu * isu - vU + vU * isu * ds;
-                    if (dvL < 0) a_z = fmin(a_z, -tau * vL / dvL);
-                    if (dvU < 0) a_z = fmin(a_z, -tau * vU / dvU);
+                    if (dvL < 0) a_z = fmin(a_z, -tau * vL * tpp_rcp(dvL));
+                    if (dvU < 0) a_z = fmin(a_z, -tau * vU * tpp_rcp(dvU));
                     if (!isfinite(ds) || !isfinite(dvL) || !isfinite(dvU)) bad = 1;
                     if (mode == BM_NEWTON) gbd += (-mu * isl + mu * isu) * ds + q.g[3 + i] * du[i];
                 }
@@ -532,7 +553,7 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, double *wb, int cur,
                     const double du = LDW(p, fu + i);
                     const double rd = soc ? LDW(p, F_DS + i) : (U[i] - S[i]);
                     const double ds = du + rd;
-                    const double isl = 1.0 / (S[i] - P.sL[i]), isu = 1.0 / (P.sU[i] - S[i]);
+                    const double isl = tpp_rcp(S[i] - P.sL[i]), isu = tpp_rcp(P.sU[i] - S[i]);
                     const double Dsig = vL[i] * isl + vU[i] * isu + dw;
                     const double rs = -yd[i] - mu * isl + mu * isu;
                     const double dvL = mu * isl - vL[i] - vL[i] * isl * ds;
@@ -542,7 +563,7 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, double *wb, int cur,
                     yd[i] += alpha * (Dsig * ds + rs);
                     vL[i] += a_z * dvL;
                     vU[i] += a_z * dvU;
-                    const double ml = mu / (S[i] - P.sL[i]), mu_u = mu / (P.sU[i] - S[i]);
+                    const double ml = mu * tpp_rcp(S[i] - P.sL[i]), mu_u = mu * tpp_rcp(P.sU[i] - S[i]);
                     vL[i] = fmax(fmin(vL[i], KAPPA_SIGMA * ml), ml * ikap);
                     vU[i] = fmax(fmin(vU[i], KAPPA_SIGMA * mu_u), mu_u * ikap);
                 } else if (mode == TM_LSQ) {
@@ -747,7 +768,20 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L) {
     L.phase = PH_B;
 }
 
-__global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kernel(const KParams P, const TppArgs T) {
+// With TPP_SYNC the warps of a CTA run the sweeps in lock-step (a __syncthreads() in front of every block), so the
+// SM's instruction cache holds one loop body at a time instead of the whole kernel.
+#ifndef TPP_THREADS
+#define TPP_THREADS 128
+#endif
+#ifndef TPP_SYNC
+#define TPP_SYNC 0
+#endif
+#if TPP_SYNC
+#define TPP_BLOCK_SYNC() __syncthreads()
+#else
+#define TPP_BLOCK_SYNC() __syncwarp()
+#endif
+__global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kernel(const KParams P, const TppArgs T) {
     extern __shared__ double tpp_smem[];
     const BatchArgs &A = T.a;
     const int N = P.N;
@@ -818,10 +852,14 @@ __global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kerne
                 L.phase = PH_B;
             }
         }
+#if TPP_SYNC
+        if (__syncthreads_and(L.phase == PH_DONE)) break;
+#else
         if (__all_sync(FULL, L.phase == PH_DONE)) break;
+#endif
 
         // ---- block B ----
-        __syncwarp();
+        TPP_BLOCK_SYNC();
         if (tpp_opaque(L.phase) == PH_B) {
             TppBwd r;
             tpp_backward(P, wb, cur, L, r);
@@ -854,7 +892,7 @@ __global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kerne
         }
 
         // ---- block F ----
-        __syncwarp();
+        TPP_BLOCK_SYNC();
         if (tpp_opaque(L.phase) == PH_F) {
             TppFwd f;
             tpp_forward(P, wb, cur, L, f);
@@ -892,7 +930,7 @@ __global__ void __launch_bounds__(128, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kerne
         }
 
         // ---- block T ----
-        __syncwarp();
+        TPP_BLOCK_SYNC();
         if (tpp_opaque(L.phase) == PH_T) {
             TppTrial t;
             tpp_trial(P, wb, cur, L, t);
