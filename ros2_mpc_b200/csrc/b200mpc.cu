@@ -34,7 +34,7 @@
 #define B200MPC_MIN_CTAS 2
 #endif
 #ifndef B200MPC_TPP_MIN_CTAS
-#define B200MPC_TPP_MIN_CTAS 4
+#define B200MPC_TPP_MIN_CTAS 2
 #endif
 
 // ---- IPOPT defaults (Waechter & Biegler 2006; IPOPT option documentation) -------------------------------
@@ -1293,7 +1293,7 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     if (blocks < 1) blocks = 1;
     h->ctas = blocks * h->sm_count; // persistent grid: a multiple of the SM count (148 on B200)
     int tblocks = 0;
-    const size_t tpp_smem = (size_t)TPP_THREADS * TPP_LANE_STRIDE * sizeof(double);
+    const size_t tpp_smem = TPP_SMEM_BYTES;
     if ((e = cudaFuncSetAttribute(mpc_solve_tpp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tpp_smem)) != cudaSuccess)
         return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tblocks, mpc_solve_tpp_kernel, TPP_THREADS, tpp_smem)) != cudaSuccess)
@@ -1398,7 +1398,7 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t 
     const int N = h->prm.N;
     const size_t nwarps = (size_t)h->tpp_ctas * (TPP_THREADS / 32);
     if (!h->d_ws) {
-        const size_t ws_bytes = nwarps * (size_t)(N + 1) * TPP_NF * 32 * sizeof(double);
+        const size_t ws_bytes = nwarps * (size_t)(N + 1) * TPP_STAGE_B;
         cudaError_t e = cudaMalloc(&h->d_ws, ws_bytes);
         if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e));
         e = cudaMalloc(&h->d_filt, nwarps * 64 * 32 * sizeof(double));
@@ -1412,7 +1412,7 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t 
     TppArgs t;
     t.a = a; t.ws = h->d_ws; t.filt = h->d_filt;
     CU_TRY(h, cudaEventRecord(h->ev0, stream));
-    mpc_solve_tpp_kernel<<<grid, TPP_THREADS, (size_t)TPP_THREADS * TPP_LANE_STRIDE * sizeof(double), stream>>>(h->kp, t);
+    mpc_solve_tpp_kernel<<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev1, stream));
     h->launches++;

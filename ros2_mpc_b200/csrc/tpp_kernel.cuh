@@ -38,33 +38,50 @@
 // least-squares multiplier estimate is computed for the unscaled objective and scaled afterwards (it is linear).
 #pragma once
 
+// Workspace rows.  A row holds one PAIR of fields for the 32 lanes of a warp: 32 x double2 = 512 B = four full
+// 128-byte lines; every workspace access of the kernel is one 128-bit load/store per lane of such a row.
 enum {
-    I_X = 0, I_U = 3, I_S = 5, I_LAM = 7, I_YD = 10, I_VL = 12, I_VU = 14, I_NF = 16, // one iterate buffer; two of them
-    F_K = 32, F_KF = 38, F_P = 40, F_PV = 46,   // Riccati factors
-    F_DX = 49, F_DU = 52, F_DL = 54,            // Newton step (dX, dU, dlam)
-    F_SX = 57, F_SU = 60, F_SL = 62,            // second-order-correction step
-    F_CS = 65, F_DS = 68,                       // second-order-correction right-hand sides
-    F_R = 70, F_UB = 73,                        // per-stage references (trajectory tracking only)
-    TPP_NF = 75
+    R_X01 = 0, R_X2L0 = 1, R_L12 = 2, R_U = 3, R_S = 4, R_YD = 5, R_VL = 6, R_VU = 7, // iterate: (X0,X1) (X2,lam0) (lam1,lam2) U S yd vL vU
+    R_ITER = 8,                                                                      // rows per iterate buffer; two buffers: rows 0-7, 8-15
+    R_K = 16,    // (K00,K01) (K02,K10) (K11,K12) (kf0,kf1)
+    R_P = 20,    // (P00,P01) (P02,P11) (P12,P22) (pv0,pv1) (pv2,-)
+    R_STEP = 25, // Newton step: (dX0,dX1) (dX2,dlam0) (dlam1,dlam2) (dU0,dU1)
+    R_SSTEP = 29, // second-order-correction step, same layout
+    R_CS = 33,   // second-order-correction right-hand sides: (cs0,cs1) (cs2,-) (ds0,ds1)
+    R_REF = 36,  // per-stage references (trajectory tracking only): (r0,r1) (r2,-) (ub0,ub1)
+    TPP_NR = 39
 };
+#define TPP_ROW_B 512
+#define TPP_STAGE_B (TPP_NR * TPP_ROW_B)
+#define TPP_STAGE_SLOTS 15                       /* staging rows per warp: the forward sweep needs 15 */
+#define TPP_STAGE_SMEM (TPP_STAGE_SLOTS * TPP_ROW_B) /* bytes of shared-memory staging per warp */
 
-enum { PH_LOAD = 0, PH_B = 1, PH_F = 2, PH_T = 3, PH_BACKTRACK = 4, PH_TOP = 5, PH_FIN = 6, PH_DONE = 7 };
+enum { PH_LOAD = 0, PH_B = 1, PH_F = 2, PH_T = 3, PH_BACKTRACK = 4, PH_FIN = 6, PH_DONE = 7 };
 enum { BM_NEWTON = 0, BM_SOC = 1, BM_LSQ = 2 };
 enum { TM_EVAL = 1, TM_LSQ = 2, TM_STEP = 3, TM_STEP_SOC = 4 };
 
-#define TPP_STAGE (TPP_NF * 32)
 // workspace rows bypass L1 (each row is used once per sweep; L1 is left to the stack)
-#define LDW(p, f) __ldcg((p) + (f) * 32)
-#define STW(p, f, v) __stcg((p) + (f) * 32, (v))
-#ifndef TPP_PREFETCH
-#define TPP_PREFETCH 1
-#endif
-
-__device__ __forceinline__ void tpp_prefetch_rows(const double *p, int f0, int n) {
-#if TPP_PREFETCH
-#pragma unroll
-    for (int f = 0; f < n; f++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (f0 + f) * 32));
-#endif
+__device__ __forceinline__ double2 tpp_ld2(const char *p, int row) {
+    return __ldcg(reinterpret_cast<const double2 *>(p + row * TPP_ROW_B));
+}
+__device__ __forceinline__ void tpp_st2(char *p, int row, double a, double b) {
+    __stcg(reinterpret_cast<double2 *>(p + row * TPP_ROW_B), make_double2(a, b));
+}
+// asynchronous global -> shared copy of this lane's 16 bytes of a row (LDGSTS, L1 bypassed); the data is private to
+// the lane, so completion needs only the lane's own cp.async.wait_group — no barrier, no warp synchronisation
+__device__ __forceinline__ void tpp_cp16(char *sdst, const char *gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void tpp_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tpp_cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ double2 tpp_sld(const char *sb, int slot) {
+    return *reinterpret_cast<const double2 *>(sb + slot * TPP_ROW_B);
+}
+// The staging buffer is single: the next stage's copy is issued as soon as this stage's values are in registers.
+// This empty asm makes "in registers" explicit (it consumes the values), so the copy cannot overtake the reads.
+__device__ __forceinline__ void tpp_consume(const double2 &a, const double2 &b, const double2 &c, const double2 &d) {
+    asm volatile("" ::"d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y), "d"(c.x), "d"(c.y), "d"(d.x), "d"(d.y) : "memory");
 }
 
 // Per-lane mode words are loop-invariant, so the compiler would "unswitch" the stage loops into one copy per mode:
@@ -100,6 +117,7 @@ struct TppArgs {
     double *filt; // [nwarps][64][32]: 32 filter entries (phi, theta) per lane
 };
 
+// Residual norms of an evaluated point (sweep T -> convergence tests of the same trip).
 struct TppNorms {
     double theta, prim_inf, dual_inf, sum_y, sum_z, pmin, pmax, f, slog;
 };
@@ -107,11 +125,10 @@ struct TppNorms {
 // Solver state of one lane (shared memory, one record per thread; the record stride is an odd multiple of 8 bytes
 // so that the 64-bit accesses of a half-warp fall into distinct banks).
 struct TppLane {
-    TppNorms n;                                    // residual norms of the current iterate
-    double df, mu, tau, theta_max, theta_min, dw, dw_last;
+    double theta, f, slog;                         // of the current iterate: constraint violation, objective, sum of log slacks
+    double df, mu, theta0, dw, dw_last;            // theta0 = max(1, theta at the starting point)
     double ref_phi, ref_gbd, alpha, a_min, a_z;    // line-search reference values, Newton step sizes
     double alpha_soc, a_z_soc, theta_soc_old;      // second-order correction
-    double r[3];                                   // goal (ref_kind GOAL)
     int b, phase, bmode, tmode;
     int status, iter, ls_extra, n_resto, acceptable_count, ntrial, soc_count, ring;
     unsigned fmask;
@@ -222,13 +239,23 @@ __device__ __noinline__ void tpp_dyn(const KParams &P, const double X[3], const 
     F[2] = th + dt * w;
 }
 
-__device__ __forceinline__ void tpp_ref(const KParams &P, const double goal[3], const double *p, double r[3], double ub[2]) {
+// per-stage references: the goal (registers) or the tracking reference rows of the stage
+__device__ __forceinline__ void tpp_ref(const KParams &P, const double goal[3], const char *p, double r[3], double ub[2]) {
     if (P.ref_kind == B200MPC_REF_GOAL) {
         r[0] = goal[0]; r[1] = goal[1]; r[2] = goal[2];
         ub[0] = 0; ub[1] = 0;
     } else {
-        r[0] = LDW(p, F_R); r[1] = LDW(p, F_R + 1); r[2] = LDW(p, F_R + 2);
-        ub[0] = LDW(p, F_UB); ub[1] = LDW(p, F_UB + 1);
+        const double2 a = tpp_ld2(p, R_REF), b = tpp_ld2(p, R_REF + 1), c = tpp_ld2(p, R_REF + 2);
+        r[0] = a.x; r[1] = a.y; r[2] = b.x;
+        ub[0] = c.x; ub[1] = c.y;
+    }
+}
+
+__device__ __forceinline__ void tpp_goal(const KParams &P, const BatchArgs &A, int b, double goal[3]) {
+    goal[0] = goal[1] = goal[2] = 0;
+    if (P.ref_kind == B200MPC_REF_GOAL) {
+        const double *xr = A.xref + 3 * (size_t)b;
+        goal[0] = xr[0]; goal[1] = xr[1]; goal[2] = xr[2];
     }
 }
 
@@ -245,41 +272,59 @@ struct TppBwd {
 //               unscaled objective (L.df is 1); also returns the largest gradient entry (objective scaling), the
 //               objective and the invalid-number flag of the starting point.
 // o.ok = 0 when a condensed Quu block is not positive definite (wrong inertia).
-__device__ __forceinline__ void tpp_backward(const KParams &P, double *wb, int cur, const TppLane &L, TppBwd &o) {
+__device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &A, char *wb, char *sb, int cur,
+                                             const TppLane &L, TppBwd &o) {
     const int N = P.N;
     const double dt = P.dt;
     const int bmode0 = L.bmode;
     const double dw = (bmode0 != BM_LSQ) ? L.dw : 1.0;
     const double df = L.df, mu = L.mu;
-    const double goal[3] = {L.r[0], L.r[1], L.r[2]};
+    double goal[3];
+    tpp_goal(P, A, L.b, goal);
     const int sfirst = L.soc_first;
-    const int sfx = sfirst ? F_DX : F_SX, sfu = sfirst ? F_DU : F_SU;
+    const int srow = sfirst ? R_STEP : R_SSTEP;
     const double at = sfirst ? L.alpha : L.alpha_soc;
-    const int co = cur * I_NF;
+    const int co = cur * R_ITER;
     double Xn[3] = {0, 0, 0}, ln[3] = {0, 0, 0}, Xtn[3] = {0, 0, 0};
     double q00 = 0, q01 = 0, q02 = 0, q11 = 0, q12 = 0, q22 = 0, v0 = 0, v1 = 0, v2 = 0;
     double gmax = 0, fs = 0;
     int ok = 1, bad = 0;
+    {
+        const char *pc = wb + (size_t)N * TPP_STAGE_B + co * TPP_ROW_B;
+#pragma unroll
+        for (int i = 0; i < R_ITER; i++) tpp_cp16(sb + i * TPP_ROW_B, pc + i * TPP_ROW_B);
+        tpp_cp_commit();
+    }
 #pragma unroll 1
     for (int k = N; k >= 0; --k) {
         const int mode = tpp_opaque(bmode0);
         const bool useW = (mode != BM_LSQ);
-        double *p = wb + (size_t)k * TPP_STAGE;
-        const double *pc = p + co * 32;
-        if (k > 0) tpp_prefetch_rows(pc - TPP_STAGE, 0, I_NF);
-        const double X[3] = {LDW(pc, I_X), LDW(pc, I_X + 1), LDW(pc, I_X + 2)};
+        char *p = wb + (size_t)k * TPP_STAGE_B;
+        tpp_cp_wait();
+        const double2 x01 = tpp_sld(sb, R_X01), x2l0 = tpp_sld(sb, R_X2L0), l12 = tpp_sld(sb, R_L12), u2 = tpp_sld(sb, R_U);
+        const double2 s2 = tpp_sld(sb, R_S), yd2 = tpp_sld(sb, R_YD), vl2 = tpp_sld(sb, R_VL), vu2 = tpp_sld(sb, R_VU);
+        tpp_consume(x01, x2l0, l12, u2);
+        tpp_consume(s2, yd2, vl2, vu2);
+        if (k > 0) {
+            const char *pc = p - TPP_STAGE_B + co * TPP_ROW_B;
+#pragma unroll
+            for (int i = 0; i < R_ITER; i++) tpp_cp16(sb + i * TPP_ROW_B, pc + i * TPP_ROW_B);
+            tpp_cp_commit();
+        }
+        const double X[3] = {x01.x, x01.y, x2l0.x};
         double lam[3] = {0, 0, 0};
-        if (k >= 1) { lam[0] = LDW(pc, I_LAM); lam[1] = LDW(pc, I_LAM + 1); lam[2] = LDW(pc, I_LAM + 2); }
+        if (k >= 1) { lam[0] = x2l0.y; lam[1] = l12.x; lam[2] = l12.y; }
         if (k == N) {
             // terminal stage: no cost, no controls
             q00 = dw; q01 = 0; q02 = 0; q11 = dw; q12 = 0; q22 = dw;
             if (mode == BM_LSQ) { v0 = 0; v1 = 0; v2 = 0; }
             else { v0 = lam[0]; v1 = lam[1]; v2 = lam[2]; }
             if (mode == BM_SOC) {
-                Xtn[0] = X[0] + at * LDW(p, sfx); Xtn[1] = X[1] + at * LDW(p, sfx + 1); Xtn[2] = X[2] + at * LDW(p, sfx + 2);
+                const double2 d01 = tpp_ld2(p, srow), d2 = tpp_ld2(p, srow + 1);
+                Xtn[0] = X[0] + at * d01.x; Xtn[1] = X[1] + at * d01.y; Xtn[2] = X[2] + at * d2.x;
             }
         } else {
-            const double U[2] = {LDW(pc, I_U), LDW(pc, I_U + 1)};
+            const double U[2] = {u2.x, u2.y};
             double r[3], ub[2];
             tpp_ref(P, goal, p, r, ub);
             TppLin q;
@@ -302,10 +347,7 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, double *wb, int c
                 rx0 = q.g[0] + lam[0] - ln[0];
                 rx1 = q.g[1] + lam[1] - ln[1];
                 rx2 = q.g[2] + lam[2] - (q.a13 * ln[0] + q.a23 * ln[1] + ln[2]);
-                const double S[2] = {LDW(pc, I_S), LDW(pc, I_S + 1)};
-                const double yd[2] = {LDW(pc, I_YD), LDW(pc, I_YD + 1)};
-                const double vL[2] = {LDW(pc, I_VL), LDW(pc, I_VL + 1)};
-                const double vU[2] = {LDW(pc, I_VU), LDW(pc, I_VU + 1)};
+                const double S[2] = {s2.x, s2.y}, yd[2] = {yd2.x, yd2.y}, vL[2] = {vl2.x, vl2.y}, vU[2] = {vu2.x, vu2.y};
                 ru[0] = q.g[3] - (q.b11 * ln[0] + q.b21 * ln[1]) + yd[0];
                 ru[1] = q.g[4] - (q.b12 * ln[0] + q.b22 * ln[1] + dt * ln[2]) + yd[1];
 #pragma unroll
@@ -318,25 +360,25 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, double *wb, int c
                 rc[0] = c0; rc[1] = c1; rc[2] = c2;
                 if (mode == BM_SOC) {
                     // defects of the last trial point curr + at*step
+                    const double2 d01 = tpp_ld2(p, srow), d2 = tpp_ld2(p, srow + 1), du2 = tpp_ld2(p, srow + 3);
+                    double2 dsp = make_double2(rd[0], rd[1]), cs01 = make_double2(rc[0], rc[1]), cs2 = make_double2(rc[2], 0.0);
+                    if (!sfirst) { dsp = tpp_ld2(p, R_CS + 2); cs01 = tpp_ld2(p, R_CS); cs2 = tpp_ld2(p, R_CS + 1); }
+                    const double du[2] = {du2.x, du2.y}, rdp[2] = {dsp.x, dsp.y}, base[3] = {cs01.x, cs01.y, cs2.x};
                     double Xt[3], Ut[2], St[2], Ft[3];
-                    Xt[0] = X[0] + at * LDW(p, sfx); Xt[1] = X[1] + at * LDW(p, sfx + 1); Xt[2] = X[2] + at * LDW(p, sfx + 2);
+                    Xt[0] = X[0] + at * d01.x; Xt[1] = X[1] + at * d01.y; Xt[2] = X[2] + at * d2.x;
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
-                        const double du = LDW(p, sfu + i);
-                        const double rdp = sfirst ? rd[i] : LDW(p, F_DS + i);
-                        Ut[i] = U[i] + at * du;
-                        St[i] = S[i] + at * (du + rdp);
-                        rd[i] = at * rdp + (Ut[i] - St[i]);
-                        STW(p, F_DS + i, rd[i]);
+                        Ut[i] = U[i] + at * du[i];
+                        St[i] = S[i] + at * (du[i] + rdp[i]);
+                        rd[i] = at * rdp[i] + (Ut[i] - St[i]);
                     }
                     tpp_dyn(P, Xt, Ut, Ft);
 #pragma unroll
                     for (int i = 0; i < 3; i++) {
-                        const double base = sfirst ? rc[i] : LDW(p, F_CS + i);
-                        rc[i] = at * base + (Xtn[i] - Ft[i]);
-                        STW(p, F_CS + i, rc[i]);
+                        rc[i] = at * base[i] + (Xtn[i] - Ft[i]);
                         Xtn[i] = Xt[i];
                     }
+                    tpp_st2(p, R_CS, rc[0], rc[1]); tpp_st2(p, R_CS + 1, rc[2], 0.0); tpp_st2(p, R_CS + 2, rd[0], rd[1]);
                 }
             }
             const double hxx = useW ? q.hxx : 0.0, hyy = useW ? q.hyy : 0.0;
@@ -353,7 +395,7 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, double *wb, int c
             const double t1 = q12 + a * q01 + b * q11;
             const double t2 = q22 + a * q02 + b * q12;
             // Qxx = Hxx + A'PA
-            const double x00 = hxx + dw + q00, x01 = q01, x11 = hyy + dw + q11;
+            const double x00 = hxx + dw + q00, x01_ = q01, x11 = hyy + dw + q11;
             const double x02 = t0, x12 = t1, x22 = htt + dw + t2 + a * t0 + b * t1;
             // PB columns
             const double e0 = b11 * q00 + b21 * q01, e1 = b11 * q01 + b21 * q11;
@@ -381,14 +423,13 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, double *wb, int c
             const double K00 = -(i00 * u00 + i01 * u10), K01 = -(i00 * u01 + i01 * u11), K02 = -(i00 * u02 + i01 * u12);
             const double K10 = -(i01 * u00 + i11 * u10), K11 = -(i01 * u01 + i11 * u11), K12 = -(i01 * u02 + i11 * u12);
             const double k0 = -(i00 * gu0 + i01 * gu1), k1 = -(i01 * gu0 + i11 * gu1);
-            STW(p, F_K, K00); STW(p, F_K + 1, K01); STW(p, F_K + 2, K02);
-            STW(p, F_K + 3, K10); STW(p, F_K + 4, K11); STW(p, F_K + 5, K12);
-            STW(p, F_KF, k0); STW(p, F_KF + 1, k1);
+            tpp_st2(p, R_K, K00, K01); tpp_st2(p, R_K + 1, K02, K10); tpp_st2(p, R_K + 2, K11, K12);
+            tpp_st2(p, R_K + 3, k0, k1);
             // P' = Qxx + Qux'K (symmetrised), p' = gx + Qux' kf
             q00 = x00 + u00 * K00 + u10 * K10;
             q11 = x11 + u01 * K01 + u11 * K11;
             q22 = x22 + u02 * K02 + u12 * K12;
-            q01 = x01 + 0.5 * ((u00 * K01 + u10 * K11) + (u01 * K00 + u11 * K10));
+            q01 = x01_ + 0.5 * ((u00 * K01 + u10 * K11) + (u01 * K00 + u11 * K10));
             q02 = x02 + 0.5 * ((u00 * K02 + u10 * K12) + (u02 * K00 + u12 * K10));
             q12 = x12 + 0.5 * ((u01 * K02 + u11 * K12) + (u02 * K01 + u12 * K11));
             v0 = gx0 + u00 * k0 + u10 * k1;
@@ -396,9 +437,8 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, double *wb, int c
             v2 = gx2 + u02 * k0 + u12 * k1;
         }
         if (k >= 1) {
-            STW(p, F_P, q00); STW(p, F_P + 1, q01); STW(p, F_P + 2, q02);
-            STW(p, F_P + 3, q11); STW(p, F_P + 4, q12); STW(p, F_P + 5, q22);
-            STW(p, F_PV, v0); STW(p, F_PV + 1, v1); STW(p, F_PV + 2, v2);
+            tpp_st2(p, R_P, q00, q01); tpp_st2(p, R_P + 1, q02, q11); tpp_st2(p, R_P + 2, q12, q22);
+            tpp_st2(p, R_P + 3, v0, v1); tpp_st2(p, R_P + 4, v2, 0.0);
         }
         Xn[0] = X[0]; Xn[1] = X[1]; Xn[2] = X[2];
         ln[0] = lam[0]; ln[1] = lam[1]; ln[2] = lam[2];
@@ -411,68 +451,96 @@ struct TppFwd {
     int bad;
 };
 
+// staging of the forward sweep: slots 0-8 = factor rows of stage k, 9-12 = U, S, vL, vU of stage k,
+// 13-14 = (X0,X1) (X2,lam0) of stage k+1
+__device__ __forceinline__ void tpp_forward_stage(char *sb, const char *p, int co, bool has_next) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) tpp_cp16(sb + i * TPP_ROW_B, p + (R_K + i) * TPP_ROW_B);
+    const char *pc = p + co * TPP_ROW_B;
+    tpp_cp16(sb + 9 * TPP_ROW_B, pc + R_U * TPP_ROW_B);
+    tpp_cp16(sb + 10 * TPP_ROW_B, pc + R_S * TPP_ROW_B);
+    tpp_cp16(sb + 11 * TPP_ROW_B, pc + R_VL * TPP_ROW_B);
+    tpp_cp16(sb + 12 * TPP_ROW_B, pc + R_VU * TPP_ROW_B);
+    if (has_next) {
+        tpp_cp16(sb + 13 * TPP_ROW_B, pc + TPP_STAGE_B + R_X01 * TPP_ROW_B);
+        tpp_cp16(sb + 14 * TPP_ROW_B, pc + TPP_STAGE_B + R_X2L0 * TPP_ROW_B);
+    }
+    tpp_cp_commit();
+}
+
 // ---- sweep F: forward roll-out of the step; step sizes and directional derivative ----------------------------------
-__device__ __forceinline__ void tpp_forward(const KParams &P, double *wb, int cur, const TppLane &L, TppFwd &o) {
+__device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A, char *wb, char *sb, int cur,
+                                            const TppLane &L, TppFwd &o) {
     const int N = P.N;
-    const double dt = P.dt, mu = L.mu, tau = L.tau, df = L.df;
-    const double goal[3] = {L.r[0], L.r[1], L.r[2]};
+    const double dt = P.dt, mu = L.mu, tau = fmax(TAU_MIN, 1.0 - L.mu), df = L.df;
+    double goal[3];
+    tpp_goal(P, A, L.b, goal);
     const int bmode0 = L.bmode;
-    const int co = cur * I_NF;
-    const int fx = (bmode0 == BM_SOC) ? F_SX : F_DX, fu = (bmode0 == BM_SOC) ? F_SU : F_DU, fl = (bmode0 == BM_SOC) ? F_SL : F_DL;
+    const int co = cur * R_ITER;
+    const int orow = (bmode0 == BM_SOC) ? R_SSTEP : R_STEP;
     double y0 = 0, y1 = 0, y2 = 0;
     double a_max = 1.0, a_z = 1.0, gbd = 0, ymax = 0;
     int bad = 0;
-    double X[3] = {LDW(wb + co * 32, I_X), LDW(wb + co * 32, I_X + 1), LDW(wb + co * 32, I_X + 2)};
+    double X[3];
+    {
+        const double2 a = tpp_ld2(wb + co * TPP_ROW_B, R_X01), b = tpp_ld2(wb + co * TPP_ROW_B, R_X2L0);
+        X[0] = a.x; X[1] = a.y; X[2] = b.x;
+    }
+    tpp_forward_stage(sb, wb, co, N > 0);
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
         const int mode = tpp_opaque(bmode0);
-        double *p = wb + (size_t)k * TPP_STAGE;
-        const double *pc = p + co * 32;
-        if (k < N) {
-            tpp_prefetch_rows(p + TPP_STAGE, F_K, F_DX - F_K);
-            tpp_prefetch_rows(pc + TPP_STAGE, I_U, 4);
-            tpp_prefetch_rows(pc + TPP_STAGE, I_VL, 4);
-            if (k + 1 < N) tpp_prefetch_rows(pc + 2 * TPP_STAGE, I_X, 3);
-        }
-        STW(p, fx, y0); STW(p, fx + 1, y1); STW(p, fx + 2, y2);
+        char *p = wb + (size_t)k * TPP_STAGE_B;
+        tpp_cp_wait();
+        const double2 k0_ = tpp_sld(sb, 0), k1_ = tpp_sld(sb, 1), k2_ = tpp_sld(sb, 2), kf_ = tpp_sld(sb, 3);
+        const double2 p0_ = tpp_sld(sb, 4), p1_ = tpp_sld(sb, 5), p2_ = tpp_sld(sb, 6), pv0_ = tpp_sld(sb, 7);
+        const double2 pv1_ = tpp_sld(sb, 8), u2 = tpp_sld(sb, 9), s2 = tpp_sld(sb, 10), vl2 = tpp_sld(sb, 11);
+        const double2 vu2 = tpp_sld(sb, 12), xn01 = tpp_sld(sb, 13), xn2 = tpp_sld(sb, 14);
+        tpp_consume(k0_, k1_, k2_, kf_);
+        tpp_consume(p0_, p1_, p2_, pv0_);
+        tpp_consume(pv1_, u2, s2, vl2);
+        tpp_consume(vu2, xn01, xn2, xn2);
+        if (k < N) tpp_forward_stage(sb, p + TPP_STAGE_B, co, k + 1 < N);
+        double l0 = 0, l1 = 0, l2 = 0;
         if (!isfinite(y0) || !isfinite(y1) || !isfinite(y2)) bad = 1;
         if (k >= 1) {
-            const double P0 = LDW(p, F_P), P1 = LDW(p, F_P + 1), P2 = LDW(p, F_P + 2), P3 = LDW(p, F_P + 3),
-                         P4 = LDW(p, F_P + 4), P5 = LDW(p, F_P + 5);
-            const double l0 = -(LDW(p, F_PV) + P0 * y0 + P1 * y1 + P2 * y2);
-            const double l1 = -(LDW(p, F_PV + 1) + P1 * y0 + P3 * y1 + P4 * y2);
-            const double l2 = -(LDW(p, F_PV + 2) + P2 * y0 + P4 * y1 + P5 * y2);
-            STW(p, fl, l0); STW(p, fl + 1, l1); STW(p, fl + 2, l2);
+            l0 = -(pv0_.x + p0_.x * y0 + p0_.y * y1 + p1_.x * y2);
+            l1 = -(pv0_.y + p0_.y * y0 + p1_.y * y1 + p2_.x * y2);
+            l2 = -(pv1_.x + p1_.x * y0 + p2_.x * y1 + p2_.y * y2);
             if (!isfinite(l0) || !isfinite(l1) || !isfinite(l2)) bad = 1;
             if (mode == BM_LSQ) ymax = fmax(ymax, fmax(fabs(l0), fmax(fabs(l1), fabs(l2))));
         }
+        tpp_st2(p, orow, y0, y1); tpp_st2(p, orow + 1, y2, l0); tpp_st2(p, orow + 2, l1, l2);
         if (k < N) {
-            const double du0 = LDW(p, F_KF) + LDW(p, F_K) * y0 + LDW(p, F_K + 1) * y1 + LDW(p, F_K + 2) * y2;
-            const double du1 = LDW(p, F_KF + 1) + LDW(p, F_K + 3) * y0 + LDW(p, F_K + 4) * y1 + LDW(p, F_K + 5) * y2;
-            STW(p, fu, du0); STW(p, fu + 1, du1);
+            const double du0 = kf_.x + k0_.x * y0 + k0_.y * y1 + k1_.x * y2;
+            const double du1 = kf_.y + k1_.y * y0 + k2_.x * y1 + k2_.y * y2;
+            tpp_st2(p, orow + 3, du0, du1);
             if (!isfinite(du0) || !isfinite(du1)) bad = 1;
             const double du[2] = {du0, du1};
-            const double U[2] = {LDW(pc, I_U), LDW(pc, I_U + 1)};
-            const double *pn = pc + TPP_STAGE;
-            const double Xn[3] = {LDW(pn, I_X), LDW(pn, I_X + 1), LDW(pn, I_X + 2)};
+            const double U[2] = {u2.x, u2.y}, Sv[2] = {s2.x, s2.y}, vLv[2] = {vl2.x, vl2.y}, vUv[2] = {vu2.x, vu2.y};
+            const double Xn[3] = {xn01.x, xn01.y, xn2.x};
             double r[3], ub[2];
             tpp_ref(P, goal, p, r, ub);
             const double ln0[3] = {0, 0, 0};
             TppLin q;
             tpp_lin<false>(P, r, ub, X, U, ln0, df, q);
-            double rc0, rc1, rc2;
+            double rc0, rc1, rc2, rdv[2] = {U[0] - Sv[0], U[1] - Sv[1]};
             if (mode == BM_LSQ) {
                 rc0 = rc1 = rc2 = 0;
                 ymax = fmax(ymax, fmax(fabs(du0), fabs(du1))); // dyd = Sigma*dS + rs with Sigma = 1, rd = rs = 0
             } else {
-                if (mode == BM_SOC) { rc0 = LDW(p, F_CS); rc1 = LDW(p, F_CS + 1); rc2 = LDW(p, F_CS + 2); }
-                else { rc0 = Xn[0] - q.F0; rc1 = Xn[1] - q.F1; rc2 = Xn[2] - q.F2; }
+                if (mode == BM_SOC) {
+                    const double2 c01 = tpp_ld2(p, R_CS), c2 = tpp_ld2(p, R_CS + 1), d2 = tpp_ld2(p, R_CS + 2);
+                    rc0 = c01.x; rc1 = c01.y; rc2 = c2.x;
+                    rdv[0] = d2.x; rdv[1] = d2.y;
+                } else {
+                    rc0 = Xn[0] - q.F0; rc1 = Xn[1] - q.F1; rc2 = Xn[2] - q.F2;
+                }
                 if (mode == BM_NEWTON && k >= 1) gbd += q.g[0] * y0 + q.g[1] * y1 + q.g[2] * y2;
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
-                    const double S = LDW(pc, I_S + i), vL = LDW(pc, I_VL + i), vU = LDW(pc, I_VU + i);
-                    const double rd = (mode == BM_SOC) ? LDW(p, F_DS + i) : (U[i] - S);
-                    const double ds = du[i] + rd;
+                    const double S = Sv[i], vL = vLv[i], vU = vUv[i];
+                    const double ds = du[i] + rdv[i];
                     const double sl = S - P.sL[i], su = P.sU[i] - S;
                     const double isl = tpp_rcp(sl), isu = tpp_rcp(su);
                     if (ds != 0.0) a_max = fmin(a_max, tau * ((ds < 0) ? -sl : su) * tpp_rcp(ds));
@@ -499,60 +567,79 @@ struct TppTrial {
     TppNorms n;
 };
 
+// staging of the trial sweep: slots 0-7 = current iterate of stage k, 8-11 = step rows of stage k
+__device__ __forceinline__ void tpp_trial_stage(char *sb, const char *p, int co, int srow) {
+#pragma unroll
+    for (int i = 0; i < R_ITER; i++) tpp_cp16(sb + i * TPP_ROW_B, p + (co + i) * TPP_ROW_B);
+#pragma unroll
+    for (int i = 0; i < 4; i++) tpp_cp16(sb + (R_ITER + i) * TPP_ROW_B, p + (srow + i) * TPP_ROW_B);
+    tpp_cp_commit();
+}
+
 // ---- sweep T: write curr + alpha*step into the other iterate buffer and evaluate that point -------------------------
 // tmode EVAL:        new = current (after the restoration stand-in).
 // tmode LSQ:         new = current with the least-squares multiplier estimate (scaled by df; or zeros) for lam, yd.
 // tmode STEP(_SOC):  new = current + alpha*(dX,dU,dS,dlam,dyd) and bound multipliers + a_z*(dvL,dvU), clamped.
-__device__ __forceinline__ void tpp_trial(const KParams &P, double *wb, int cur, const TppLane &L, TppTrial &o) {
+__device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, char *wb, char *sb, int cur,
+                                          const TppLane &L, TppTrial &o) {
     const int N = P.N;
     const double dt = P.dt, mu = L.mu, df = L.df, dw = L.dw;
-    const double goal[3] = {L.r[0], L.r[1], L.r[2]};
+    double goal[3];
+    tpp_goal(P, A, L.b, goal);
     const int tmode0 = L.tmode, keep0 = L.keep;
     const bool soc0 = (tmode0 == TM_STEP_SOC);
     const double alpha = soc0 ? L.alpha_soc : L.alpha, a_z = soc0 ? L.a_z_soc : L.a_z;
-    const int co = cur * I_NF, no = I_NF - co;
-    const int fx = soc0 ? F_SX : F_DX, fu = soc0 ? F_SU : F_DU, fl = soc0 ? F_SL : F_DL;
+    const int co = cur * R_ITER, no = R_ITER - co;
+    const int srow = soc0 ? R_SSTEP : R_STEP;
     const double ikap = 1.0 / KAPPA_SIGMA;
     double Xn[3] = {0, 0, 0}, ln[3] = {0, 0, 0};
     double th = 0, slog = 0, pi = 0, di = 0, sy = 0, sz = 0, pmin = 1e300, pmax = -1e300, fs = 0;
+    tpp_trial_stage(sb, wb + (size_t)N * TPP_STAGE_B, co, srow);
 #pragma unroll 1
     for (int k = N; k >= 0; --k) {
         const int mode = tpp_opaque(tmode0);
         const bool step = (mode >= TM_STEP), soc = (mode == TM_STEP_SOC);
-        double *p = wb + (size_t)k * TPP_STAGE;
-        const double *pc = p + co * 32;
-        double *pw = p + no * 32;
-        if (k > 0) {
-            tpp_prefetch_rows(pc - TPP_STAGE, 0, I_NF);
-            tpp_prefetch_rows(p - TPP_STAGE, F_DX, F_SX - F_DX);
-        }
-        double X[3] = {LDW(pc, I_X), LDW(pc, I_X + 1), LDW(pc, I_X + 2)};
+        char *p = wb + (size_t)k * TPP_STAGE_B;
+        char *pw = p + no * TPP_ROW_B;
+        tpp_cp_wait();
+        const double2 x01 = tpp_sld(sb, R_X01), x2l0 = tpp_sld(sb, R_X2L0), l12 = tpp_sld(sb, R_L12), u2 = tpp_sld(sb, R_U);
+        const double2 s2 = tpp_sld(sb, R_S), yd2 = tpp_sld(sb, R_YD), vl2 = tpp_sld(sb, R_VL), vu2 = tpp_sld(sb, R_VU);
+        const double2 dx01 = tpp_sld(sb, R_ITER), dx2l0 = tpp_sld(sb, R_ITER + 1), dl12 = tpp_sld(sb, R_ITER + 2),
+                      du2 = tpp_sld(sb, R_ITER + 3);
+        tpp_consume(x01, x2l0, l12, u2);
+        tpp_consume(s2, yd2, vl2, vu2);
+        tpp_consume(dx01, dx2l0, dl12, du2);
+        if (k > 0) tpp_trial_stage(sb, p - TPP_STAGE_B, co, srow);
+        double X[3] = {x01.x, x01.y, x2l0.x};
         double lam[3] = {0, 0, 0};
         if (k >= 1) {
-            lam[0] = LDW(pc, I_LAM); lam[1] = LDW(pc, I_LAM + 1); lam[2] = LDW(pc, I_LAM + 2);
+            lam[0] = x2l0.y; lam[1] = l12.x; lam[2] = l12.y;
+            const double dX[3] = {dx01.x, dx01.y, dx2l0.x}, dL[3] = {dx2l0.y, dl12.x, dl12.y};
             if (step) {
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
-                    X[i] += alpha * LDW(p, fx + i);
-                    lam[i] += alpha * LDW(p, fl + i);
+                    X[i] += alpha * dX[i];
+                    lam[i] += alpha * dL[i];
                 }
             } else if (mode == TM_LSQ) {
 #pragma unroll
-                for (int i = 0; i < 3; i++) lam[i] = keep0 ? df * LDW(p, F_DL + i) : 0.0;
+                for (int i = 0; i < 3; i++) lam[i] = keep0 ? df * dL[i] : 0.0;
             }
         }
-#pragma unroll
-        for (int i = 0; i < 3; i++) { STW(pw, I_X + i, X[i]); STW(pw, I_LAM + i, lam[i]); }
+        tpp_st2(pw, R_X01, X[0], X[1]); tpp_st2(pw, R_X2L0, X[2], lam[0]); tpp_st2(pw, R_L12, lam[1], lam[2]);
         if (k < N) {
-            double U[2], S[2], yd[2], vL[2], vU[2];
+            double U[2] = {u2.x, u2.y}, S[2] = {s2.x, s2.y}, yd[2] = {yd2.x, yd2.y}, vL[2] = {vl2.x, vl2.y}, vU[2] = {vu2.x, vu2.y};
+            const double duv[2] = {du2.x, du2.y};
+            double rdv[2] = {U[0] - S[0], U[1] - S[1]};
+            if (soc) {
+                const double2 d2 = tpp_ld2(p, R_CS + 2);
+                rdv[0] = d2.x; rdv[1] = d2.y;
+            }
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-                U[i] = LDW(pc, I_U + i); S[i] = LDW(pc, I_S + i); yd[i] = LDW(pc, I_YD + i);
-                vL[i] = LDW(pc, I_VL + i); vU[i] = LDW(pc, I_VU + i);
                 if (step) {
-                    const double du = LDW(p, fu + i);
-                    const double rd = soc ? LDW(p, F_DS + i) : (U[i] - S[i]);
-                    const double ds = du + rd;
+                    const double du = duv[i];
+                    const double ds = du + rdv[i];
                     const double isl = tpp_rcp(S[i] - P.sL[i]), isu = tpp_rcp(P.sU[i] - S[i]);
                     const double Dsig = vL[i] * isl + vU[i] * isu + dw;
                     const double rs = -yd[i] - mu * isl + mu * isu;
@@ -567,11 +654,11 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, double *wb, int cur,
                     vL[i] = fmax(fmin(vL[i], KAPPA_SIGMA * ml), ml * ikap);
                     vU[i] = fmax(fmin(vU[i], KAPPA_SIGMA * mu_u), mu_u * ikap);
                 } else if (mode == TM_LSQ) {
-                    yd[i] = keep0 ? df * LDW(p, F_DU + i) : 0.0;
+                    yd[i] = keep0 ? df * duv[i] : 0.0;
                 }
-                STW(pw, I_U + i, U[i]); STW(pw, I_S + i, S[i]); STW(pw, I_YD + i, yd[i]);
-                STW(pw, I_VL + i, vL[i]); STW(pw, I_VU + i, vU[i]);
             }
+            tpp_st2(pw, R_U, U[0], U[1]); tpp_st2(pw, R_S, S[0], S[1]); tpp_st2(pw, R_YD, yd[0], yd[1]);
+            tpp_st2(pw, R_VL, vL[0], vL[1]); tpp_st2(pw, R_VU, vU[0], vU[1]);
             double r[3], ub[2];
             tpp_ref(P, goal, p, r, ub);
             TppLin q;
@@ -658,13 +745,13 @@ __device__ __forceinline__ bool tpp_ls_acceptable(const TppLane &L, const double
                                                   double th_t, bool &ftype_armijo) {
     ftype_armijo = false;
     if (!isfinite(th_t) || !isfinite(phi_t)) return false;
-    if (th_t > L.theta_max) return false;
-    const double gbd = L.ref_gbd, theta = L.n.theta, phi = L.ref_phi;
+    if (th_t > 1e4 * L.theta0) return false;
+    const double gbd = L.ref_gbd, theta = L.theta, phi = L.ref_phi;
     const bool ftype = (gbd < 0) && (alpha_test * tpp_pow(-gbd, S_PHI) > DELTA_LS * tpp_pow(theta, S_THETA));
     const bool armijo = cmp_le(phi_t - phi, ETA_PHI * alpha_test * gbd, phi);
     ftype_armijo = ftype && armijo;
     bool ok;
-    if (alpha_test > 0 && ftype && theta <= L.theta_min) {
+    if (alpha_test > 0 && ftype && theta <= 1e-4 * L.theta0) {
         ok = armijo;
     } else {
         if (phi_t > phi) {
@@ -680,32 +767,35 @@ __device__ __forceinline__ bool tpp_ls_acceptable(const TppLane &L, const double
 
 // Line search gave up on the Newton direction (alpha < alpha_min): restoration stand-in of the warp kernel — roll
 // the controls out (closed-form feasible point), restart the multipliers.  Writes the other iterate buffer.
-__device__ __forceinline__ void tpp_restore(const KParams &P, double *wb, double *fl, int cur, TppLane &L) {
+__device__ __forceinline__ void tpp_restore(const KParams &P, char *wb, double *fl, int cur, TppLane &L) {
     const int N = P.N;
-    if (L.n.theta <= 1e-10 || L.n_resto >= MAX_RESTO) { L.status = B200MPC_RESTORATION_FAILED; L.phase = PH_FIN; return; }
-    tpp_filter_add(fl, L, L.ref_phi - GAMMA_PHI * L.n.theta, (1 - GAMMA_THETA) * L.n.theta);
-    const int co = cur * I_NF, no = I_NF - co;
+    if (L.theta <= 1e-10 || L.n_resto >= MAX_RESTO) { L.status = B200MPC_RESTORATION_FAILED; L.phase = PH_FIN; return; }
+    tpp_filter_add(fl, L, L.ref_phi - GAMMA_PHI * L.theta, (1 - GAMMA_THETA) * L.theta);
+    const int co = cur * R_ITER, no = R_ITER - co;
     double zm = 0;
-#pragma unroll 1
+#pragma unroll 2
     for (int k = 0; k < N; ++k) {
-        const double *pc = wb + (size_t)k * TPP_STAGE + co * 32;
-        zm = fmax(zm, fmax(fmax(LDW(pc, I_VL), LDW(pc, I_VL + 1)), fmax(LDW(pc, I_VU), LDW(pc, I_VU + 1))));
+        const char *pc = wb + (size_t)k * TPP_STAGE_B + co * TPP_ROW_B;
+        const double2 a = tpp_ld2(pc, R_VL), b = tpp_ld2(pc, R_VU);
+        zm = fmax(zm, fmax(fmax(a.x, a.y), fmax(b.x, b.y)));
     }
-    double y[3] = {LDW(wb + co * 32, I_X), LDW(wb + co * 32, I_X + 1), LDW(wb + co * 32, I_X + 2)};
+    double y[3];
+    {
+        const double2 a = tpp_ld2(wb + co * TPP_ROW_B, R_X01), b = tpp_ld2(wb + co * TPP_ROW_B, R_X2L0);
+        y[0] = a.x; y[1] = a.y; y[2] = b.x;
+    }
+    const bool reset = zm > 1e3;
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-        const double *pc = wb + (size_t)k * TPP_STAGE + co * 32;
-        double *pw = wb + (size_t)k * TPP_STAGE + no * 32;
-        STW(pw, I_X, y[0]); STW(pw, I_X + 1, y[1]); STW(pw, I_X + 2, y[2]);
-        STW(pw, I_LAM, 0.0); STW(pw, I_LAM + 1, 0.0); STW(pw, I_LAM + 2, 0.0);
+        const char *pc = wb + (size_t)k * TPP_STAGE_B + co * TPP_ROW_B;
+        char *pw = wb + (size_t)k * TPP_STAGE_B + no * TPP_ROW_B;
+        tpp_st2(pw, R_X01, y[0], y[1]); tpp_st2(pw, R_X2L0, y[2], 0.0); tpp_st2(pw, R_L12, 0.0, 0.0);
         if (k < N) {
-            const double U[2] = {LDW(pc, I_S), LDW(pc, I_S + 1)};
-            STW(pw, I_U, U[0]); STW(pw, I_U + 1, U[1]);
-            STW(pw, I_S, U[0]); STW(pw, I_S + 1, U[1]);
-            STW(pw, I_YD, 0.0); STW(pw, I_YD + 1, 0.0);
-            const bool reset = zm > 1e3;
-            STW(pw, I_VL, reset ? 1.0 : LDW(pc, I_VL)); STW(pw, I_VL + 1, reset ? 1.0 : LDW(pc, I_VL + 1));
-            STW(pw, I_VU, reset ? 1.0 : LDW(pc, I_VU)); STW(pw, I_VU + 1, reset ? 1.0 : LDW(pc, I_VU + 1));
+            const double2 s = tpp_ld2(pc, R_S), a = tpp_ld2(pc, R_VL), b = tpp_ld2(pc, R_VU);
+            const double U[2] = {s.x, s.y};
+            tpp_st2(pw, R_U, U[0], U[1]); tpp_st2(pw, R_S, U[0], U[1]); tpp_st2(pw, R_YD, 0.0, 0.0);
+            tpp_st2(pw, R_VL, reset ? 1.0 : a.x, reset ? 1.0 : a.y);
+            tpp_st2(pw, R_VU, reset ? 1.0 : b.x, reset ? 1.0 : b.y);
             double F[3];
             tpp_dyn(P, y, U, F);
             y[0] = F[0]; y[1] = F[1]; y[2] = F[2];
@@ -719,14 +809,11 @@ __device__ __forceinline__ void tpp_restore(const KParams &P, double *wb, double
 }
 
 // Top of an interior-point iteration: convergence tests, barrier update; leaves the lane in phase B (Newton) or
-// finishes the problem.  L.n holds the residual norms of the current iterate.
-__device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L) {
+// finishes the problem.  n = residual norms of the (new) current iterate.
+__device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L, const TppNorms &n) {
     const int N = P.N;
-    const TppNorms n = L.n;
-    if (L.theta_max < 0) {
-        L.theta_max = 1e4 * fmax(1.0, n.theta);
-        L.theta_min = 1e-4 * fmax(1.0, n.theta);
-    }
+    L.theta = n.theta; L.f = n.f; L.slog = n.slog;
+    if (L.theta0 < 0) L.theta0 = fmax(1.0, n.theta);
     const double df = L.df;
     const double sd = fmax(S_MAX, (n.sum_y + n.sum_z) / (double)(9 * N)) / S_MAX;
     const double sc = fmax(S_MAX, n.sum_z / (double)(4 * N)) / S_MAX;
@@ -760,7 +847,6 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L) {
     }
     if (changed) {
         L.mu = mu;
-        L.tau = fmax(TAU_MIN, 1.0 - mu);
         L.fmask = 0;
     }
     L.dw = 0.0;
@@ -771,25 +857,29 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L) {
 // With TPP_SYNC the warps of a CTA run the sweeps in lock-step (a __syncthreads() in front of every block), so the
 // SM's instruction cache holds one loop body at a time instead of the whole kernel.
 #ifndef TPP_THREADS
-#define TPP_THREADS 128
+#define TPP_THREADS 256
 #endif
 #ifndef TPP_SYNC
-#define TPP_SYNC 0
+#define TPP_SYNC 1
 #endif
 #if TPP_SYNC
 #define TPP_BLOCK_SYNC() __syncthreads()
 #else
 #define TPP_BLOCK_SYNC() __syncwarp()
 #endif
+#define TPP_SMEM_BYTES ((size_t)(TPP_THREADS / 32) * TPP_STAGE_SMEM + (size_t)TPP_THREADS * TPP_LANE_STRIDE * sizeof(double))
+
 __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kernel(const KParams P, const TppArgs T) {
-    extern __shared__ double tpp_smem[];
+    extern __shared__ __align__(16) char tpp_smem[];
     const BatchArgs &A = T.a;
     const int N = P.N;
-    const int lane = threadIdx.x & 31;
-    const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    double *wb = T.ws + gw * ((size_t)(N + 1) * TPP_STAGE) + lane;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + wid;
+    char *wb = reinterpret_cast<char *>(T.ws) + gw * ((size_t)(N + 1) * TPP_STAGE_B) + lane * 16;
     double *fl = T.filt + gw * (64 * 32) + lane;
-    TppLane &L = *reinterpret_cast<TppLane *>(tpp_smem + (size_t)threadIdx.x * TPP_LANE_STRIDE);
+    char *sb = tpp_smem + (size_t)wid * TPP_STAGE_SMEM + lane * 16;
+    TppLane &L = *reinterpret_cast<TppLane *>(tpp_smem + (size_t)(TPP_THREADS / 32) * TPP_STAGE_SMEM +
+                                              (size_t)threadIdx.x * TPP_LANE_STRIDE * sizeof(double));
     L.phase = PH_LOAD;
     L.b = -1;
     L.moved = 0;
@@ -805,48 +895,48 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             } else {
                 L.b = b;
                 const double x0[3] = {A.x0[3 * (size_t)b], A.x0[3 * (size_t)b + 1], A.x0[3 * (size_t)b + 2]};
-                if (P.ref_kind == B200MPC_REF_GOAL) {
-                    L.r[0] = A.xref[3 * (size_t)b]; L.r[1] = A.xref[3 * (size_t)b + 1]; L.r[2] = A.xref[3 * (size_t)b + 2];
-                } else {
-                    L.r[0] = L.r[1] = L.r[2] = 0;
-                }
-                const int co = cur * I_NF;
-#pragma unroll 1
+                const int co = cur * R_ITER;
+                const double2 *ui = A.u_init ? reinterpret_cast<const double2 *>(A.u_init + (size_t)b * 2 * N) : nullptr;
+#pragma unroll 4
                 for (int k = 0; k <= N; ++k) {
-                    double *p = wb + (size_t)k * TPP_STAGE;
-                    double *pc = p + co * 32;
-                    STW(pc, I_X, (k == 0) ? x0[0] : 0.0); STW(pc, I_X + 1, (k == 0) ? x0[1] : 0.0); STW(pc, I_X + 2, (k == 0) ? x0[2] : 0.0);
-                    STW(pc, I_LAM, 0.0); STW(pc, I_LAM + 1, 0.0); STW(pc, I_LAM + 2, 0.0);
+                    char *p = wb + (size_t)k * TPP_STAGE_B;
+                    char *pc = p + co * TPP_ROW_B;
+                    tpp_st2(pc, R_X01, (k == 0) ? x0[0] : 0.0, (k == 0) ? x0[1] : 0.0);
+                    tpp_st2(pc, R_X2L0, (k == 0) ? x0[2] : 0.0, 0.0);
+                    tpp_st2(pc, R_L12, 0.0, 0.0);
                     if (k < N) {
-                        double u[2] = {0, 0};
-                        if (A.u_init) { u[0] = A.u_init[(size_t)b * 2 * N + 2 * k]; u[1] = A.u_init[(size_t)b * 2 * N + 2 * k + 1]; }
+                        double2 u = make_double2(0.0, 0.0);
+                        if (ui) u = ui[k];
+                        const double uv[2] = {u.x, u.y};
+                        double sv[2];
 #pragma unroll
                         for (int i = 0; i < 2; i++) {
                             // slack initialisation: s = d(x) pushed into the interior; bound multipliers 1
                             const double lo = P.sL[i], hi = P.sU[i];
                             const double pl = fmin(BOUND_PUSH * fmax(1.0, fabs(lo)), BOUND_FRAC * (hi - lo));
                             const double pu = fmin(BOUND_PUSH * fmax(1.0, fabs(hi)), BOUND_FRAC * (hi - lo));
-                            double sv = u[i];
-                            if (sv < lo + pl) sv = lo + pl;
-                            if (sv > hi - pu) sv = hi - pu;
-                            STW(pc, I_U + i, u[i]); STW(pc, I_S + i, sv); STW(pc, I_YD + i, 0.0);
-                            STW(pc, I_VL + i, 1.0); STW(pc, I_VU + i, 1.0);
+                            double s = uv[i];
+                            if (s < lo + pl) s = lo + pl;
+                            if (s > hi - pu) s = hi - pu;
+                            sv[i] = s;
                         }
+                        tpp_st2(pc, R_U, uv[0], uv[1]); tpp_st2(pc, R_S, sv[0], sv[1]); tpp_st2(pc, R_YD, 0.0, 0.0);
+                        tpp_st2(pc, R_VL, 1.0, 1.0); tpp_st2(pc, R_VU, 1.0, 1.0);
                         if (P.ref_kind == B200MPC_REF_TRAJ) {
                             const double *xr = A.xref + (size_t)b * 3 * N + 3 * k;
-                            STW(p, F_R, xr[0]); STW(p, F_R + 1, xr[1]); STW(p, F_R + 2, xr[2]);
-                            STW(p, F_UB, A.uref[(size_t)b * 2 * N + 2 * k]); STW(p, F_UB + 1, A.uref[(size_t)b * 2 * N + 2 * k + 1]);
+                            const double *ur = A.uref + (size_t)b * 2 * N + 2 * k;
+                            tpp_st2(p, R_REF, xr[0], xr[1]); tpp_st2(p, R_REF + 1, xr[2], 0.0); tpp_st2(p, R_REF + 2, ur[0], ur[1]);
                         }
                     }
                 }
                 L.status = B200MPC_MAXITER_EXCEEDED;
                 L.iter = 0; L.ls_extra = 0; L.n_resto = 0; L.acceptable_count = 0; L.ntrial = 0; L.soc_count = 0;
                 L.ring = 0; L.fmask = 0; L.keep = 0; L.soc_first = 1; L.moved = 0;
-                L.df = 1.0; L.mu = P.mu_init; L.tau = fmax(TAU_MIN, 1.0 - P.mu_init);
-                L.theta_max = -1; L.theta_min = -1; L.dw = 0; L.dw_last = 0;
+                L.df = 1.0; L.mu = P.mu_init;
+                L.theta0 = -1; L.dw = 0; L.dw_last = 0;
                 L.alpha = 0; L.a_z = 0; L.alpha_soc = 0; L.a_z_soc = 0; L.a_min = 0; L.theta_soc_old = 0;
                 L.ref_phi = 0; L.ref_gbd = 0;
-                L.n.f = 0; L.n.slog = 0; L.n.theta = 0;
+                L.f = 0; L.slog = 0; L.theta = 0;
                 L.bmode = BM_LSQ;
                 L.tmode = TM_LSQ;
                 L.phase = PH_B;
@@ -862,11 +952,11 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
         TPP_BLOCK_SYNC();
         if (tpp_opaque(L.phase) == PH_B) {
             TppBwd r;
-            tpp_backward(P, wb, cur, L, r);
+            tpp_backward(P, A, wb, sb, cur, L, r);
             const int bmode = L.bmode;
             if (bmode == BM_LSQ) {
                 // objective scaling from the gradient at the starting point; invalid-number check
-                L.n.f = r.f;
+                L.f = r.f;
                 if (r.bad || !isfinite(r.f)) {
                     L.status = B200MPC_INVALID_NUMBER_DETECTED;
                     L.phase = PH_FIN;
@@ -895,7 +985,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
         TPP_BLOCK_SYNC();
         if (tpp_opaque(L.phase) == PH_F) {
             TppFwd f;
-            tpp_forward(P, wb, cur, L, f);
+            tpp_forward(P, A, wb, sb, cur, L, f);
             const int bmode = L.bmode;
             if (bmode == BM_LSQ) {
                 L.keep = (L.df * f.ymax <= 1e3) ? 1 : 0;
@@ -906,13 +996,13 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                     L.status = B200MPC_ERROR_IN_STEP_COMPUTATION;
                     L.phase = PH_FIN;
                 } else {
-                    const double theta = L.n.theta;
-                    L.ref_phi = L.df * L.n.f - L.mu * L.n.slog;
+                    const double theta = L.theta;
+                    L.ref_phi = L.df * L.f - L.mu * L.slog;
                     L.ref_gbd = f.gbd;
                     double a_min = GAMMA_THETA;
                     if (f.gbd < 0) {
                         a_min = fmin(GAMMA_THETA, GAMMA_PHI * theta / (-f.gbd));
-                        if (theta <= L.theta_min) a_min = fmin(a_min, DELTA_LS * tpp_pow(theta, S_THETA) / tpp_pow(-f.gbd, S_PHI));
+                        if (theta <= 1e-4 * L.theta0) a_min = fmin(a_min, DELTA_LS * tpp_pow(theta, S_THETA) / tpp_pow(-f.gbd, S_PHI));
                     }
                     L.a_min = a_min * ALPHA_MIN_FRAC;
                     L.alpha = f.a_max;
@@ -933,24 +1023,21 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
         TPP_BLOCK_SYNC();
         if (tpp_opaque(L.phase) == PH_T) {
             TppTrial t;
-            tpp_trial(P, wb, cur, L, t);
+            tpp_trial(P, A, wb, sb, cur, L, t);
             const int tm = L.tmode;
+            bool accepted = false;
             if (tm == TM_EVAL || tm == TM_LSQ) {
-                L.n = t.n;
-                L.moved = 1;
-                L.phase = PH_TOP;
+                accepted = true;
             } else {
                 const bool soc = (tm == TM_STEP_SOC);
                 if (soc || L.ntrial++ > 0) L.ls_extra++;
                 bool fa;
                 if (tpp_ls_acceptable(L, fl, L.alpha, t.phi, t.th, fa)) {
-                    if (!fa) tpp_filter_add(fl, L, L.ref_phi - GAMMA_PHI * L.n.theta, (1 - GAMMA_THETA) * L.n.theta);
-                    L.n = t.n;
-                    L.moved = 1;
+                    if (!fa) tpp_filter_add(fl, L, L.ref_phi - GAMMA_PHI * L.theta, (1 - GAMMA_THETA) * L.theta);
                     L.iter++;
-                    L.phase = PH_TOP;
+                    accepted = true;
                 } else if (!soc) {
-                    if (L.ntrial == 1 && P.max_soc > 0 && isfinite(t.th) && t.th >= L.n.theta) {
+                    if (L.ntrial == 1 && P.max_soc > 0 && isfinite(t.th) && t.th >= L.theta) {
                         // second-order correction, first round: right-hand sides from this trial point
                         L.soc_count = 0;
                         L.soc_first = 1;
@@ -972,6 +1059,11 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                     }
                 }
             }
+            if (accepted) {
+                // top of the next iteration: convergence tests, barrier update
+                L.moved = 1;
+                tpp_iterate_top(P, L, t.n);
+            }
         }
 
         // ---- rare: backtracking / restoration stand-in ----
@@ -986,25 +1078,23 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             }
         }
 
-        // ---- top of the next iteration: convergence tests, barrier update ----
-        __syncwarp();
-        if (tpp_opaque(L.phase) == PH_TOP) tpp_iterate_top(P, L);
-
         // ---- result store, release of the lane ----
         __syncwarp();
         {
             const int ph = tpp_opaque(L.phase);
             if (ph == PH_FIN) {
                 const size_t b = (size_t)L.b;
-                const int co = (L.moved ? (1 - cur) : cur) * I_NF;
-                double *xo = A.X + b * 3 * (N + 1), *uo = A.U + b * 2 * N;
-#pragma unroll 1
+                const int co = (L.moved ? (1 - cur) : cur) * R_ITER;
+                double *xo = A.X + b * 3 * (N + 1);
+                double2 *uo = reinterpret_cast<double2 *>(A.U + b * 2 * N);
+#pragma unroll 4
                 for (int k = 0; k <= N; ++k) {
-                    const double *pc = wb + (size_t)k * TPP_STAGE + co * 32;
-                    xo[3 * k] = LDW(pc, I_X); xo[3 * k + 1] = LDW(pc, I_X + 1); xo[3 * k + 2] = LDW(pc, I_X + 2);
-                    if (k < N) { uo[2 * k] = LDW(pc, I_U); uo[2 * k + 1] = LDW(pc, I_U + 1); }
+                    const char *pc = wb + (size_t)k * TPP_STAGE_B + co * TPP_ROW_B;
+                    const double2 a = tpp_ld2(pc, R_X01), c = tpp_ld2(pc, R_X2L0);
+                    xo[3 * k] = a.x; xo[3 * k + 1] = a.y; xo[3 * k + 2] = c.x;
+                    if (k < N) uo[k] = tpp_ld2(pc, R_U);
                 }
-                if (A.cost) A.cost[b] = L.n.f;
+                if (A.cost) A.cost[b] = L.f;
                 A.status[b] = L.status;
                 if (A.iters) A.iters[b] = L.iter;
                 if (A.ls) A.ls[b] = L.ls_extra;
@@ -1012,13 +1102,16 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             } else if ((ph == PH_B || ph == PH_F || ph == PH_T) && !L.moved) {
                 // the iterate stays where it is but the warp's buffers swap: copy it across (rejected trial point,
                 // inertia-correction retry)
-                const int co = cur * I_NF, no = I_NF - co;
-#pragma unroll 1
+                const int co = cur * R_ITER, no = R_ITER - co;
+#pragma unroll 2
                 for (int k = 0; k <= N; ++k) {
-                    const double *pc = wb + (size_t)k * TPP_STAGE + co * 32;
-                    double *pw = wb + (size_t)k * TPP_STAGE + no * 32;
+                    const char *pc = wb + (size_t)k * TPP_STAGE_B + co * TPP_ROW_B;
+                    char *pw = wb + (size_t)k * TPP_STAGE_B + no * TPP_ROW_B;
+                    double2 v[R_ITER];
 #pragma unroll
-                    for (int f = 0; f < I_NF; f++) STW(pw, f, LDW(pc, f));
+                    for (int f = 0; f < R_ITER; f++) v[f] = tpp_ld2(pc, f);
+#pragma unroll
+                    for (int f = 0; f < R_ITER; f++) tpp_st2(pw, f, v[f].x, v[f].y);
                 }
             }
             L.moved = 0;
