@@ -34,7 +34,7 @@
 #define B200MPC_MIN_CTAS 2
 #endif
 #ifndef B200MPC_TPP_MIN_CTAS
-#define B200MPC_TPP_MIN_CTAS 2
+#define B200MPC_TPP_MIN_CTAS 1
 #endif
 
 // ---- IPOPT defaults (Waechter & Biegler 2006; IPOPT option documentation) -------------------------------

@@ -129,6 +129,7 @@ struct TppLane {
     double df, mu, theta0, dw, dw_last;            // theta0 = max(1, theta at the starting point)
     double ref_phi, ref_gbd, alpha, a_min, a_z;    // line-search reference values, Newton step sizes
     double alpha_soc, a_z_soc, theta_soc_old;      // second-order correction
+    double goal[3];                                // goal state (ref_kind GOAL)
     int b, phase, bmode, tmode;
     int status, iter, ls_extra, n_resto, acceptable_count, ntrial, soc_count, ring;
     unsigned fmask;
@@ -251,13 +252,6 @@ __device__ __forceinline__ void tpp_ref(const KParams &P, const double goal[3], 
     }
 }
 
-__device__ __forceinline__ void tpp_goal(const KParams &P, const BatchArgs &A, int b, double goal[3]) {
-    goal[0] = goal[1] = goal[2] = 0;
-    if (P.ref_kind == B200MPC_REF_GOAL) {
-        const double *xr = A.xref + 3 * (size_t)b;
-        goal[0] = xr[0]; goal[1] = xr[1]; goal[2] = xr[2];
-    }
-}
 
 struct TppBwd {
     double gmax, f;
@@ -279,13 +273,12 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
     const int bmode0 = L.bmode;
     const double dw = (bmode0 != BM_LSQ) ? L.dw : 1.0;
     const double df = L.df, mu = L.mu;
-    double goal[3];
-    tpp_goal(P, A, L.b, goal);
+    const double *goal = L.goal;
     const int sfirst = L.soc_first;
     const int srow = sfirst ? R_STEP : R_SSTEP;
     const double at = sfirst ? L.alpha : L.alpha_soc;
     const int co = cur * R_ITER;
-    double Xn[3] = {0, 0, 0}, ln[3] = {0, 0, 0}, Xtn[3] = {0, 0, 0};
+    double Xn[3] = {0, 0, 0}, ln[3] = {0, 0, 0};
     double q00 = 0, q01 = 0, q02 = 0, q11 = 0, q12 = 0, q22 = 0, v0 = 0, v1 = 0, v2 = 0;
     double gmax = 0, fs = 0;
     int ok = 1, bad = 0;
@@ -301,34 +294,37 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
         const bool useW = (mode != BM_LSQ);
         char *p = wb + (size_t)k * TPP_STAGE_B;
         tpp_cp_wait();
+        // the stage's rows are read from the staging buffer where they are needed; the copy of the next stage is
+        // issued right after the last of them (TPP_BWD_PREFETCH), in front of the Riccati algebra
         const double2 x01 = tpp_sld(sb, R_X01), x2l0 = tpp_sld(sb, R_X2L0), l12 = tpp_sld(sb, R_L12), u2 = tpp_sld(sb, R_U);
-        const double2 s2 = tpp_sld(sb, R_S), yd2 = tpp_sld(sb, R_YD), vl2 = tpp_sld(sb, R_VL), vu2 = tpp_sld(sb, R_VU);
-        tpp_consume(x01, x2l0, l12, u2);
-        tpp_consume(s2, yd2, vl2, vu2);
-        if (k > 0) {
-            const char *pc = p - TPP_STAGE_B + co * TPP_ROW_B;
-#pragma unroll
-            for (int i = 0; i < R_ITER; i++) tpp_cp16(sb + i * TPP_ROW_B, pc + i * TPP_ROW_B);
-            tpp_cp_commit();
-        }
+#define TPP_BWD_PREFETCH()                                                                                   \
+    do {                                                                                                     \
+        if (k > 0) {                                                                                         \
+            const char *pcn = p - TPP_STAGE_B + co * TPP_ROW_B;                                              \
+            _Pragma("unroll") for (int i = 0; i < R_ITER; i++) tpp_cp16(sb + i * TPP_ROW_B, pcn + i * TPP_ROW_B); \
+            tpp_cp_commit();                                                                                 \
+        }                                                                                                    \
+    } while (0)
         const double X[3] = {x01.x, x01.y, x2l0.x};
         double lam[3] = {0, 0, 0};
         if (k >= 1) { lam[0] = x2l0.y; lam[1] = l12.x; lam[2] = l12.y; }
         if (k == N) {
             // terminal stage: no cost, no controls
+            tpp_consume(x01, x2l0, l12, u2);
+            TPP_BWD_PREFETCH();
             q00 = dw; q01 = 0; q02 = 0; q11 = dw; q12 = 0; q22 = dw;
             if (mode == BM_LSQ) { v0 = 0; v1 = 0; v2 = 0; }
             else { v0 = lam[0]; v1 = lam[1]; v2 = lam[2]; }
-            if (mode == BM_SOC) {
-                const double2 d01 = tpp_ld2(p, srow), d2 = tpp_ld2(p, srow + 1);
-                Xtn[0] = X[0] + at * d01.x; Xtn[1] = X[1] + at * d01.y; Xtn[2] = X[2] + at * d2.x;
-            }
         } else {
             const double U[2] = {u2.x, u2.y};
             double r[3], ub[2];
             tpp_ref(P, goal, p, r, ub);
             TppLin q;
             tpp_lin<true>(P, r, ub, X, U, ln, df, q);
+            const double2 s2 = tpp_sld(sb, R_S), yd2 = tpp_sld(sb, R_YD), vl2 = tpp_sld(sb, R_VL), vu2 = tpp_sld(sb, R_VU);
+            tpp_consume(x01, x2l0, l12, u2);
+            tpp_consume(s2, yd2, vl2, vu2);
+            TPP_BWD_PREFETCH();
             const double c0 = Xn[0] - q.F0, c1 = Xn[1] - q.F1, c2 = Xn[2] - q.F2;
             double rx0, rx1, rx2, ru[2], Dsig[2], rs[2], rd[2], rc[3];
             if (mode == BM_LSQ) {
@@ -364,6 +360,9 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
                     double2 dsp = make_double2(rd[0], rd[1]), cs01 = make_double2(rc[0], rc[1]), cs2 = make_double2(rc[2], 0.0);
                     if (!sfirst) { dsp = tpp_ld2(p, R_CS + 2); cs01 = tpp_ld2(p, R_CS); cs2 = tpp_ld2(p, R_CS + 1); }
                     const double du[2] = {du2.x, du2.y}, rdp[2] = {dsp.x, dsp.y}, base[3] = {cs01.x, cs01.y, cs2.x};
+                    // trial state of the successor stage (its step rows are still in the workspace)
+                    const double2 n01 = tpp_ld2(p + TPP_STAGE_B, srow), n2 = tpp_ld2(p + TPP_STAGE_B, srow + 1);
+                    const double Xtn[3] = {Xn[0] + at * n01.x, Xn[1] + at * n01.y, Xn[2] + at * n2.x};
                     double Xt[3], Ut[2], St[2], Ft[3];
                     Xt[0] = X[0] + at * d01.x; Xt[1] = X[1] + at * d01.y; Xt[2] = X[2] + at * d2.x;
 #pragma unroll
@@ -376,7 +375,6 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
 #pragma unroll
                     for (int i = 0; i < 3; i++) {
                         rc[i] = at * base[i] + (Xtn[i] - Ft[i]);
-                        Xtn[i] = Xt[i];
                     }
                     tpp_st2(p, R_CS, rc[0], rc[1]); tpp_st2(p, R_CS + 1, rc[2], 0.0); tpp_st2(p, R_CS + 2, rd[0], rd[1]);
                 }
@@ -443,6 +441,7 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
         Xn[0] = X[0]; Xn[1] = X[1]; Xn[2] = X[2];
         ln[0] = lam[0]; ln[1] = lam[1]; ln[2] = lam[2];
     }
+#undef TPP_BWD_PREFETCH
     o.ok = ok; o.bad = bad; o.gmax = gmax; o.f = fs;
 }
 
@@ -473,8 +472,7 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
                                             const TppLane &L, TppFwd &o) {
     const int N = P.N;
     const double dt = P.dt, mu = L.mu, tau = fmax(TAU_MIN, 1.0 - L.mu), df = L.df;
-    double goal[3];
-    tpp_goal(P, A, L.b, goal);
+    const double *goal = L.goal;
     const int bmode0 = L.bmode;
     const int co = cur * R_ITER;
     const int orow = (bmode0 == BM_SOC) ? R_SSTEP : R_STEP;
@@ -584,8 +582,7 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
                                           const TppLane &L, TppTrial &o) {
     const int N = P.N;
     const double dt = P.dt, mu = L.mu, df = L.df, dw = L.dw;
-    double goal[3];
-    tpp_goal(P, A, L.b, goal);
+    const double *goal = L.goal;
     const int tmode0 = L.tmode, keep0 = L.keep;
     const bool soc0 = (tmode0 == TM_STEP_SOC);
     const double alpha = soc0 ? L.alpha_soc : L.alpha, a_z = soc0 ? L.a_z_soc : L.a_z;
@@ -857,7 +854,7 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L, co
 // With TPP_SYNC the warps of a CTA run the sweeps in lock-step (a __syncthreads() in front of every block), so the
 // SM's instruction cache holds one loop body at a time instead of the whole kernel.
 #ifndef TPP_THREADS
-#define TPP_THREADS 256
+#define TPP_THREADS 384
 #endif
 #ifndef TPP_SYNC
 #define TPP_SYNC 1
@@ -875,7 +872,8 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
     const int N = P.N;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + wid;
-    char *wb = reinterpret_cast<char *>(T.ws) + gw * ((size_t)(N + 1) * TPP_STAGE_B) + lane * 16;
+    char *wbase = reinterpret_cast<char *>(T.ws) + gw * ((size_t)(N + 1) * TPP_STAGE_B); // the warp's workspace
+    char *wb = wbase + lane * 16;                                                        // this lane's column of it
     double *fl = T.filt + gw * (64 * 32) + lane;
     char *sb = tpp_smem + (size_t)wid * TPP_STAGE_SMEM + lane * 16;
     TppLane &L = *reinterpret_cast<TppLane *>(tpp_smem + (size_t)(TPP_THREADS / 32) * TPP_STAGE_SMEM +
@@ -886,48 +884,20 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
     int cur = 0; // warp-uniform: the buffer holding the current iterates during this trip
 
     for (;;) {
-        // ---- block L: pull the next problem, write the starting point ----
+        // ---- block L: pull the next problems; the warp writes each starting point together (lane <-> stage) ----
         __syncwarp();
+        int newb = -1;
         if (tpp_opaque(L.phase) == PH_LOAD) {
             const int b = (int)atomicAdd(A.counter, 1u);
             if (b >= A.B) {
                 L.phase = PH_DONE;
             } else {
+                newb = b;
                 L.b = b;
-                const double x0[3] = {A.x0[3 * (size_t)b], A.x0[3 * (size_t)b + 1], A.x0[3 * (size_t)b + 2]};
-                const int co = cur * R_ITER;
-                const double2 *ui = A.u_init ? reinterpret_cast<const double2 *>(A.u_init + (size_t)b * 2 * N) : nullptr;
-#pragma unroll 4
-                for (int k = 0; k <= N; ++k) {
-                    char *p = wb + (size_t)k * TPP_STAGE_B;
-                    char *pc = p + co * TPP_ROW_B;
-                    tpp_st2(pc, R_X01, (k == 0) ? x0[0] : 0.0, (k == 0) ? x0[1] : 0.0);
-                    tpp_st2(pc, R_X2L0, (k == 0) ? x0[2] : 0.0, 0.0);
-                    tpp_st2(pc, R_L12, 0.0, 0.0);
-                    if (k < N) {
-                        double2 u = make_double2(0.0, 0.0);
-                        if (ui) u = ui[k];
-                        const double uv[2] = {u.x, u.y};
-                        double sv[2];
-#pragma unroll
-                        for (int i = 0; i < 2; i++) {
-                            // slack initialisation: s = d(x) pushed into the interior; bound multipliers 1
-                            const double lo = P.sL[i], hi = P.sU[i];
-                            const double pl = fmin(BOUND_PUSH * fmax(1.0, fabs(lo)), BOUND_FRAC * (hi - lo));
-                            const double pu = fmin(BOUND_PUSH * fmax(1.0, fabs(hi)), BOUND_FRAC * (hi - lo));
-                            double s = uv[i];
-                            if (s < lo + pl) s = lo + pl;
-                            if (s > hi - pu) s = hi - pu;
-                            sv[i] = s;
-                        }
-                        tpp_st2(pc, R_U, uv[0], uv[1]); tpp_st2(pc, R_S, sv[0], sv[1]); tpp_st2(pc, R_YD, 0.0, 0.0);
-                        tpp_st2(pc, R_VL, 1.0, 1.0); tpp_st2(pc, R_VU, 1.0, 1.0);
-                        if (P.ref_kind == B200MPC_REF_TRAJ) {
-                            const double *xr = A.xref + (size_t)b * 3 * N + 3 * k;
-                            const double *ur = A.uref + (size_t)b * 2 * N + 2 * k;
-                            tpp_st2(p, R_REF, xr[0], xr[1]); tpp_st2(p, R_REF + 1, xr[2], 0.0); tpp_st2(p, R_REF + 2, ur[0], ur[1]);
-                        }
-                    }
+                L.goal[0] = L.goal[1] = L.goal[2] = 0;
+                if (P.ref_kind == B200MPC_REF_GOAL) {
+                    const double *xr = A.xref + 3 * (size_t)b;
+                    L.goal[0] = xr[0]; L.goal[1] = xr[1]; L.goal[2] = xr[2];
                 }
                 L.status = B200MPC_MAXITER_EXCEEDED;
                 L.iter = 0; L.ls_extra = 0; L.n_resto = 0; L.acceptable_count = 0; L.ntrial = 0; L.soc_count = 0;
@@ -942,6 +912,45 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 L.phase = PH_B;
             }
         }
+        __syncwarp();
+        for (unsigned m = __ballot_sync(FULL, newb >= 0); m; m &= m - 1) {
+            const int j = __ffs(m) - 1;                      // slot (lane) that receives the problem
+            const size_t b = (size_t)__shfl_sync(FULL, newb, j);
+            const double x00 = A.x0[3 * b], x01 = A.x0[3 * b + 1], x02 = A.x0[3 * b + 2];
+            const double2 *ui = A.u_init ? reinterpret_cast<const double2 *>(A.u_init + b * 2 * N) : nullptr;
+            for (int k = lane; k <= N; k += 32) {
+                char *p = wbase + (size_t)k * TPP_STAGE_B + j * 16;
+                char *pc = p + cur * R_ITER * TPP_ROW_B;
+                tpp_st2(pc, R_X01, (k == 0) ? x00 : 0.0, (k == 0) ? x01 : 0.0);
+                tpp_st2(pc, R_X2L0, (k == 0) ? x02 : 0.0, 0.0);
+                tpp_st2(pc, R_L12, 0.0, 0.0);
+                if (k < N) {
+                    double2 u = make_double2(0.0, 0.0);
+                    if (ui) u = ui[k];
+                    const double uv[2] = {u.x, u.y};
+                    double sv[2];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        // slack initialisation: s = d(x) pushed into the interior; bound multipliers 1
+                        const double lo = P.sL[i], hi = P.sU[i];
+                        const double pl = fmin(BOUND_PUSH * fmax(1.0, fabs(lo)), BOUND_FRAC * (hi - lo));
+                        const double pu = fmin(BOUND_PUSH * fmax(1.0, fabs(hi)), BOUND_FRAC * (hi - lo));
+                        double sx = uv[i];
+                        if (sx < lo + pl) sx = lo + pl;
+                        if (sx > hi - pu) sx = hi - pu;
+                        sv[i] = sx;
+                    }
+                    tpp_st2(pc, R_U, uv[0], uv[1]); tpp_st2(pc, R_S, sv[0], sv[1]); tpp_st2(pc, R_YD, 0.0, 0.0);
+                    tpp_st2(pc, R_VL, 1.0, 1.0); tpp_st2(pc, R_VU, 1.0, 1.0);
+                    if (P.ref_kind == B200MPC_REF_TRAJ) {
+                        const double *xr = A.xref + b * 3 * N + 3 * k;
+                        const double *ur = A.uref + b * 2 * N + 2 * k;
+                        tpp_st2(p, R_REF, xr[0], xr[1]); tpp_st2(p, R_REF + 1, xr[2], 0.0); tpp_st2(p, R_REF + 2, ur[0], ur[1]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
 #if TPP_SYNC
         if (__syncthreads_and(L.phase == PH_DONE)) break;
 #else
@@ -1078,35 +1087,46 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             }
         }
 
-        // ---- result store, release of the lane ----
+        // ---- result store and release of finished lanes; iterate copy for lanes that did not move ----
+        // Both are done by the whole warp for one lane at a time (lane <-> stage): one round trip per event instead
+        // of one per stage, and stage-contiguous result stores.
         __syncwarp();
         {
             const int ph = tpp_opaque(L.phase);
-            if (ph == PH_FIN) {
-                const size_t b = (size_t)L.b;
-                const int co = (L.moved ? (1 - cur) : cur) * R_ITER;
+            const bool fin = (ph == PH_FIN);
+            const bool cpy = (ph == PH_B || ph == PH_F || ph == PH_T) && !L.moved;
+            const int myco = (L.moved ? (1 - cur) : cur) * R_ITER;
+            for (unsigned m = __ballot_sync(FULL, fin); m; m &= m - 1) {
+                const int j = __ffs(m) - 1;
+                const size_t b = (size_t)__shfl_sync(FULL, L.b, j);
+                const int co = __shfl_sync(FULL, myco, j);
                 double *xo = A.X + b * 3 * (N + 1);
                 double2 *uo = reinterpret_cast<double2 *>(A.U + b * 2 * N);
-#pragma unroll 4
-                for (int k = 0; k <= N; ++k) {
-                    const char *pc = wb + (size_t)k * TPP_STAGE_B + co * TPP_ROW_B;
+                for (int k = lane; k <= N; k += 32) {
+                    const char *pc = wbase + (size_t)k * TPP_STAGE_B + co * TPP_ROW_B + j * 16;
                     const double2 a = tpp_ld2(pc, R_X01), c = tpp_ld2(pc, R_X2L0);
+                    double2 u = make_double2(0.0, 0.0);
+                    if (k < N) u = tpp_ld2(pc, R_U);
                     xo[3 * k] = a.x; xo[3 * k + 1] = a.y; xo[3 * k + 2] = c.x;
-                    if (k < N) uo[k] = tpp_ld2(pc, R_U);
+                    if (k < N) uo[k] = u;
                 }
+            }
+            if (fin) {
+                const size_t b = (size_t)L.b;
                 if (A.cost) A.cost[b] = L.f;
                 A.status[b] = L.status;
                 if (A.iters) A.iters[b] = L.iter;
                 if (A.ls) A.ls[b] = L.ls_extra;
                 L.phase = PH_LOAD;
-            } else if ((ph == PH_B || ph == PH_F || ph == PH_T) && !L.moved) {
-                // the iterate stays where it is but the warp's buffers swap: copy it across (rejected trial point,
-                // inertia-correction retry)
+            }
+            // the iterate stays where it is but the warp's buffers swap: copy it across (rejected trial point,
+            // inertia-correction retry)
+            for (unsigned m = __ballot_sync(FULL, cpy); m; m &= m - 1) {
+                const int j = __ffs(m) - 1;
                 const int co = cur * R_ITER, no = R_ITER - co;
-#pragma unroll 2
-                for (int k = 0; k <= N; ++k) {
-                    const char *pc = wb + (size_t)k * TPP_STAGE_B + co * TPP_ROW_B;
-                    char *pw = wb + (size_t)k * TPP_STAGE_B + no * TPP_ROW_B;
+                for (int k = lane; k <= N; k += 32) {
+                    const char *pc = wbase + (size_t)k * TPP_STAGE_B + co * TPP_ROW_B + j * 16;
+                    char *pw = wbase + (size_t)k * TPP_STAGE_B + no * TPP_ROW_B + j * 16;
                     double2 v[R_ITER];
 #pragma unroll
                     for (int f = 0; f < R_ITER; f++) v[f] = tpp_ld2(pc, f);
