@@ -153,6 +153,11 @@ int b200mpc_set_kernel(b200mpc_handle *h, int kind);
 /* B200MPC_KERNEL_WARP / _LANE: the kernel the most recent solve used. */
 int b200mpc_last_kernel_kind(const b200mpc_handle *h);
 
+/* Diagnostics of the lane-per-problem kernel, cumulative over the handle's life: out[2i], out[2i+1] = warp-level
+ * executions and active lanes of sweep i (0 backward, 1 forward, 2 trial) and of the trips (i = 3).  Counted only
+ * in library builds with -DTPP_STATS=1 (zeros otherwise). */
+int b200mpc_lane_kernel_stats(b200mpc_handle *h, unsigned long long out[8]);
+
 /* Number of kernel launches issued by this handle so far (bench.py reports it as gpu_launches). */
 long long b200mpc_launch_count(const b200mpc_handle *h);
 /* Device time [ms] of the most recent solve kernel measured with CUDA events on its own stream

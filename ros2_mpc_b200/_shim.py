@@ -72,6 +72,8 @@ def lib():
         L.b200mpc_set_kernel.restype = C.c_int
         L.b200mpc_last_kernel_kind.argtypes = [vp]
         L.b200mpc_last_kernel_kind.restype = C.c_int
+        L.b200mpc_lane_kernel_stats.argtypes = [vp, C.POINTER(C.c_ulonglong * 8)]
+        L.b200mpc_lane_kernel_stats.restype = C.c_int
         L.b200mpc_sizeof_params.restype = C.c_int
         if L.b200mpc_sizeof_params() != C.sizeof(Params):
             raise RuntimeError("b200mpc_params layout mismatch between _shim.Params and libb200mpc.so")
@@ -142,6 +144,13 @@ class Solver:
     @property
     def last_kernel_kind(self):
         return int(self._L.b200mpc_last_kernel_kind(self._h))
+
+    def lane_kernel_stats(self):
+        """Cumulative sweep statistics of the lane kernel (TPP_STATS builds): dict sweep -> (executions, mean lanes)."""
+        a = (C.c_ulonglong * 8)()
+        self._check(self._L.b200mpc_lane_kernel_stats(self._h, C.byref(a)))
+        return {n: (int(a[2 * i]), (a[2 * i + 1] / a[2 * i]) if a[2 * i] else 0.0)
+                for i, n in enumerate(("backward", "forward", "trial", "trip"))}
 
     def measure_fp64_peak(self):
         """FP64 FMA peak of the device [TFLOP/s], measured with a DFMA-saturating micro-kernel."""

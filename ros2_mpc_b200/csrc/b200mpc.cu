@@ -1172,6 +1172,7 @@ struct b200mpc_handle {
     int last_kind;     // kernel used by the most recent solve
     int tpp_ctas;
     double *d_ws, *d_filt;
+    unsigned long long *d_stats;
     std::string err;
 };
 
@@ -1250,6 +1251,7 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     h->tpp_ctas = 0;
     h->d_ws = nullptr;
     h->d_filt = nullptr;
+    h->d_stats = nullptr;
     if (const char *ek = getenv("B200MPC_KERNEL")) {
         if (!strcmp(ek, "warp")) h->kernel_kind = B200MPC_KERNEL_WARP;
         else if (!strcmp(ek, "lane")) h->kernel_kind = B200MPC_KERNEL_LANE;
@@ -1314,6 +1316,7 @@ extern "C" void b200mpc_destroy(b200mpc_handle *h) {
     if (h->d_buf) cudaFree(h->d_buf);
     if (h->d_ws) cudaFree(h->d_ws);
     if (h->d_filt) cudaFree(h->d_filt);
+    if (h->d_stats) cudaFree(h->d_stats);
     cudaFree(h->d_counter);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
@@ -1393,6 +1396,17 @@ extern "C" int b200mpc_set_kernel(b200mpc_handle *h, int kind) {
 
 extern "C" int b200mpc_last_kernel_kind(const b200mpc_handle *h) { return h ? h->last_kind : B200MPC_E_ARG; }
 
+// Diagnostics of the lane-per-problem kernel (only counted in builds with -DTPP_STATS=1): cumulative
+// {executions, active lanes} of the sweeps B, F, T and of the trips; zeros otherwise.
+extern "C" int b200mpc_lane_kernel_stats(b200mpc_handle *h, unsigned long long out[8]) {
+    if (!h || !out) return B200MPC_E_ARG;
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    if (!h->d_stats) return 0;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaMemcpy(out, h->d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // Lane-per-problem kernel: persistent grid, one workspace stripe per warp (allocated on first use).
 static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stream) {
     const int N = h->prm.N;
@@ -1403,6 +1417,9 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t 
         if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e));
         e = cudaMalloc(&h->d_filt, nwarps * 64 * 32 * sizeof(double));
         if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc(filter): ") + cudaGetErrorString(e));
+        e = cudaMalloc(&h->d_stats, 8 * sizeof(unsigned long long));
+        if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc(stats): ") + cudaGetErrorString(e));
+        cudaMemset(h->d_stats, 0, 8 * sizeof(unsigned long long));
     }
     CU_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), stream));
     int grid = h->tpp_ctas;
@@ -1410,7 +1427,7 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t 
     if (need < grid) grid = need;
     if (grid < 1) grid = 1;
     TppArgs t;
-    t.a = a; t.ws = h->d_ws; t.filt = h->d_filt;
+    t.a = a; t.ws = h->d_ws; t.filt = h->d_filt; t.stats = h->d_stats;
     CU_TRY(h, cudaEventRecord(h->ev0, stream));
     mpc_solve_tpp_kernel<<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
     CU_TRY(h, cudaGetLastError());

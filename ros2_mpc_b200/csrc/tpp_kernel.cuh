@@ -37,6 +37,9 @@
 // distances), sin/cos of the RK4 mid- and end-point angles come from the angle-addition formulas, and the
 // least-squares multiplier estimate is computed for the unscaled objective and scaled afterwards (it is linear).
 #pragma once
+#ifndef TPP_BWD_EAGER
+#define TPP_BWD_EAGER 1 /* backward sweep: read all staged rows at the top of the stage and issue the next copy at once */
+#endif
 
 // Workspace rows.  A row holds one PAIR of fields for the 32 lanes of a warp: 32 x double2 = 512 B = four full
 // 128-byte lines; every workspace access of the kernel is one 128-bit load/store per lane of such a row.
@@ -72,6 +75,16 @@ __device__ __forceinline__ void tpp_st2(char *p, int row, double a, double b) {
 __device__ __forceinline__ void tpp_cp16(char *sdst, const char *gsrc) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+// L2 prefetch of this lane's 16 bytes of `n` consecutive rows (the warp's 32 lanes cover the rows' four lines each)
+#ifndef TPP_L2_PREFETCH
+#define TPP_L2_PREFETCH 1
+#endif
+__device__ __forceinline__ void tpp_l2_prefetch(const char *p, int row0, int n) {
+#if TPP_L2_PREFETCH
+#pragma unroll
+    for (int i = 0; i < n; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (row0 + i) * TPP_ROW_B));
+#endif
 }
 __device__ __forceinline__ void tpp_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tpp_cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -115,7 +128,20 @@ struct TppArgs {
     BatchArgs a;
     double *ws;   // [nwarps][N+1][TPP_NF][32]
     double *filt; // [nwarps][64][32]: 32 filter entries (phi, theta) per lane
+    unsigned long long *stats; // [8]: per sweep B, F, T: warp executions and active lanes; trips; warps
 };
+#ifndef TPP_STATS
+#define TPP_STATS 0
+#endif
+__device__ __forceinline__ void tpp_stat(const TppArgs &T, int i) {
+#if TPP_STATS
+    const unsigned m = __activemask();
+    if ((threadIdx.x & 31) == __ffs(m) - 1) {
+        atomicAdd(T.stats + 2 * i, 1ull);
+        atomicAdd(T.stats + 2 * i + 1, (unsigned long long)__popc(m));
+    }
+#endif
+}
 
 // Residual norms of an evaluated point (sweep T -> convergence tests of the same trip).
 struct TppNorms {
@@ -297,6 +323,12 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
         // the stage's rows are read from the staging buffer where they are needed; the copy of the next stage is
         // issued right after the last of them (TPP_BWD_PREFETCH), in front of the Riccati algebra
         const double2 x01 = tpp_sld(sb, R_X01), x2l0 = tpp_sld(sb, R_X2L0), l12 = tpp_sld(sb, R_L12), u2 = tpp_sld(sb, R_U);
+#if TPP_BWD_EAGER
+        const double2 s2 = tpp_sld(sb, R_S), yd2 = tpp_sld(sb, R_YD), vl2 = tpp_sld(sb, R_VL), vu2 = tpp_sld(sb, R_VU);
+        tpp_consume(x01, x2l0, l12, u2);
+        tpp_consume(s2, yd2, vl2, vu2);
+#endif
+        if (k > 1) tpp_l2_prefetch(p - 2 * TPP_STAGE_B + co * TPP_ROW_B, 0, R_ITER);
 #define TPP_BWD_PREFETCH()                                                                                   \
     do {                                                                                                     \
         if (k > 0) {                                                                                         \
@@ -308,10 +340,15 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
         const double X[3] = {x01.x, x01.y, x2l0.x};
         double lam[3] = {0, 0, 0};
         if (k >= 1) { lam[0] = x2l0.y; lam[1] = l12.x; lam[2] = l12.y; }
+#if TPP_BWD_EAGER
+        TPP_BWD_PREFETCH();
+#endif
         if (k == N) {
             // terminal stage: no cost, no controls
+#if !TPP_BWD_EAGER
             tpp_consume(x01, x2l0, l12, u2);
             TPP_BWD_PREFETCH();
+#endif
             q00 = dw; q01 = 0; q02 = 0; q11 = dw; q12 = 0; q22 = dw;
             if (mode == BM_LSQ) { v0 = 0; v1 = 0; v2 = 0; }
             else { v0 = lam[0]; v1 = lam[1]; v2 = lam[2]; }
@@ -321,10 +358,12 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
             tpp_ref(P, goal, p, r, ub);
             TppLin q;
             tpp_lin<true>(P, r, ub, X, U, ln, df, q);
+#if !TPP_BWD_EAGER
             const double2 s2 = tpp_sld(sb, R_S), yd2 = tpp_sld(sb, R_YD), vl2 = tpp_sld(sb, R_VL), vu2 = tpp_sld(sb, R_VU);
             tpp_consume(x01, x2l0, l12, u2);
             tpp_consume(s2, yd2, vl2, vu2);
             TPP_BWD_PREFETCH();
+#endif
             const double c0 = Xn[0] - q.F0, c1 = Xn[1] - q.F1, c2 = Xn[2] - q.F2;
             double rx0, rx1, rx2, ru[2], Dsig[2], rs[2], rd[2], rc[3];
             if (mode == BM_LSQ) {
@@ -499,6 +538,12 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
         tpp_consume(pv1_, u2, s2, vl2);
         tpp_consume(vu2, xn01, xn2, xn2);
         if (k < N) tpp_forward_stage(sb, p + TPP_STAGE_B, co, k + 1 < N);
+        if (k + 2 <= N) {
+            tpp_l2_prefetch(p + 2 * TPP_STAGE_B, R_K, 9);
+            tpp_l2_prefetch(p + 2 * TPP_STAGE_B + co * TPP_ROW_B, R_U, 2);
+            tpp_l2_prefetch(p + 2 * TPP_STAGE_B + co * TPP_ROW_B, R_VL, 2);
+            if (k + 3 <= N) tpp_l2_prefetch(p + 3 * TPP_STAGE_B + co * TPP_ROW_B, R_X01, 2);
+        }
         double l0 = 0, l1 = 0, l2 = 0;
         if (!isfinite(y0) || !isfinite(y1) || !isfinite(y2)) bad = 1;
         if (k >= 1) {
@@ -607,6 +652,10 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
         tpp_consume(s2, yd2, vl2, vu2);
         tpp_consume(dx01, dx2l0, dl12, du2);
         if (k > 0) tpp_trial_stage(sb, p - TPP_STAGE_B, co, srow);
+        if (k > 1) {
+            tpp_l2_prefetch(p - 2 * TPP_STAGE_B + co * TPP_ROW_B, 0, R_ITER);
+            tpp_l2_prefetch(p - 2 * TPP_STAGE_B, srow, 4);
+        }
         double X[3] = {x01.x, x01.y, x2l0.x};
         double lam[3] = {0, 0, 0};
         if (k >= 1) {
@@ -859,10 +908,10 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L, co
 #ifndef TPP_SYNC
 #define TPP_SYNC 1
 #endif
-#if TPP_SYNC
+#if TPP_SYNC == 1
 #define TPP_BLOCK_SYNC() __syncthreads()
 #else
-#define TPP_BLOCK_SYNC() __syncwarp()
+#define TPP_BLOCK_SYNC() __syncwarp() /* TPP_SYNC == 2: the CTA only meets once per trip (at the exit test) */
 #endif
 #define TPP_SMEM_BYTES ((size_t)(TPP_THREADS / 32) * TPP_STAGE_SMEM + (size_t)TPP_THREADS * TPP_LANE_STRIDE * sizeof(double))
 
@@ -961,6 +1010,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
         TPP_BLOCK_SYNC();
         if (tpp_opaque(L.phase) == PH_B) {
             TppBwd r;
+            tpp_stat(T, 0);
             tpp_backward(P, A, wb, sb, cur, L, r);
             const int bmode = L.bmode;
             if (bmode == BM_LSQ) {
@@ -994,6 +1044,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
         TPP_BLOCK_SYNC();
         if (tpp_opaque(L.phase) == PH_F) {
             TppFwd f;
+            tpp_stat(T, 1);
             tpp_forward(P, A, wb, sb, cur, L, f);
             const int bmode = L.bmode;
             if (bmode == BM_LSQ) {
@@ -1032,6 +1083,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
         TPP_BLOCK_SYNC();
         if (tpp_opaque(L.phase) == PH_T) {
             TppTrial t;
+            tpp_stat(T, 2);
             tpp_trial(P, A, wb, sb, cur, L, t);
             const int tm = L.tmode;
             bool accepted = false;
@@ -1137,5 +1189,6 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             L.moved = 0;
         }
         cur ^= 1;
+        tpp_stat(T, 3);
     }
 }

@@ -24,4 +24,5 @@ for _ in range(nrep):
     o = S.solve_batch(x0, xr, **kw)
     print("kernel ms %.3f -> %.0f solves/s, iters %.2f, conv %.4f" % (S.last_kernel_ms(), B / S.last_kernel_ms() * 1e3, o["iters"].mean(),
           np.isin(o["status"], (0, 1)).mean()), flush=True)
+print("lane kernel stats", S.lane_kernel_stats())
 S.close()
