@@ -394,9 +394,9 @@ def main():
                 traffic = json.load(f).get(f"{kname}_{args.variant}_{B}")
         except Exception:
             pass
-        # streamed workspace of the lane-per-problem kernel: 896 B per stage and sweep triple
+        # streamed workspace of the lane-per-problem kernel: 44 rows x 16 B = 704 B per stage and sweep triple
         trips = iters.astype(np.float64) + 1.0 + ls.astype(np.float64)
-        ws_bytes = float(trips.sum()) * (N + 1) * 896.0 if lane else None
+        ws_bytes = float(trips.sum()) * (N + 1) * 704.0 if lane else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,

@@ -13,11 +13,18 @@
 // row (fully coalesced, compile-time field offsets from one per-stage pointer, L1 bypassed), and a stage record is
 // one contiguous block whose next-needed rows are prefetched into L2 one stage ahead.  Each interior-point
 // iteration is three streaming sweeps over the stages:
-//     B  backward  k = N..0   read iterate, re-linearise, condense, Riccati recursion        -> K, kf, P, pv
-//     F  forward   k = 0..N   read K, kf, P, pv (+ iterate), roll the step out              -> dX, dU, dlam,
+//     B  backward  k = N..0   read iterate, re-linearise, condense, Riccati recursion        -> K, kf
+//     F  forward   k = 0..N   read K, kf (+ iterate), roll the step out                      -> dX, dU,
 //                             fraction-to-the-boundary step sizes, directional derivative
-//     T  trial     k = N..0   read iterate + step, write curr + alpha*step into the OTHER iterate buffer, and
-//                             evaluate that point: filter quantities (theta, phi) and all KKT residual norms
+//     T  trial     k = N..0   read iterate + step, recover the multiplier step from the stationarity rows of the
+//                             Newton system (costate recursion, below), write curr + alpha*step into the OTHER
+//                             iterate buffer, and evaluate that point: filter quantities (theta, phi) and all KKT
+//                             residual norms
+// The cost-to-go matrices P_k, p_k of the Riccati recursion never leave the registers of sweep B.  The textbook
+// forward pass needs them for the multiplier step, dlam_k = -(p_k + P_k dx_k); here sweep T, which walks the
+// horizon backwards anyway, gets the same quantity from the state rows of the very system being solved,
+//     lam_k + dlam_k = A_k' (lam_{k+1} + dlam_{k+1}) - g_k - (Hxx_k + delta_w) dx_k - Hxu_k du_k,
+// at the price of one more sin/cos pair per stage — 12 of 56 workspace rows per stage and iteration less traffic.
 // The trial point is written speculatively; if the line search accepts it (99 % of first trials) it simply is the
 // next iterate and the lane already holds its convergence norms, so there is no separate "accept" or "evaluate"
 // sweep.  The two iterate buffers swap roles every trip for the whole warp (so that every row access stays one
@@ -47,16 +54,15 @@ enum {
     R_X01 = 0, R_X2L0 = 1, R_L12 = 2, R_U = 3, R_S = 4, R_YD = 5, R_VL = 6, R_VU = 7, // iterate: (X0,X1) (X2,lam0) (lam1,lam2) U S yd vL vU
     R_ITER = 8,                                                                      // rows per iterate buffer; two buffers: rows 0-7, 8-15
     R_K = 16,    // (K00,K01) (K02,K10) (K11,K12) (kf0,kf1)
-    R_P = 20,    // (P00,P01) (P02,P11) (P12,P22) (pv0,pv1) (pv2,-)
-    R_STEP = 25, // Newton step: (dX0,dX1) (dX2,dlam0) (dlam1,dlam2) (dU0,dU1)
-    R_SSTEP = 29, // second-order-correction step, same layout
-    R_CS = 33,   // second-order-correction right-hand sides: (cs0,cs1) (cs2,-) (ds0,ds1)
-    R_REF = 36,  // per-stage references (trajectory tracking only): (r0,r1) (r2,-) (ub0,ub1)
-    TPP_NR = 39
+    R_STEP = 20, // Newton step: (dX0,dX1) (dX2,-) (dU0,dU1)
+    R_SSTEP = 23, // second-order-correction step, same layout
+    R_CS = 26,   // second-order-correction right-hand sides: (cs0,cs1) (cs2,-) (ds0,ds1)
+    R_REF = 29,  // per-stage references (trajectory tracking only): (r0,r1) (r2,-) (ub0,ub1)
+    TPP_NR = 32
 };
 #define TPP_ROW_B 512
 #define TPP_STAGE_B (TPP_NR * TPP_ROW_B)
-#define TPP_STAGE_SLOTS 15                       /* staging rows per warp: the forward sweep needs 15 */
+#define TPP_STAGE_SLOTS 11                       /* staging rows per warp: the trial sweep needs 11 */
 #define TPP_STAGE_SMEM (TPP_STAGE_SLOTS * TPP_ROW_B) /* bytes of shared-memory staging per warp */
 
 enum { PH_LOAD = 0, PH_B = 1, PH_F = 2, PH_T = 3, PH_BACKTRACK = 4, PH_FIN = 6, PH_DONE = 7 };
@@ -160,6 +166,7 @@ struct TppLane {
     int status, iter, ls_extra, n_resto, acceptable_count, ntrial, soc_count, ring;
     unsigned fmask;
     int keep, soc_first, moved;
+    double ymax_f;                                 // LSQ mode: largest slack-multiplier estimate seen by sweep F
 };
 #define TPP_LANE_STRIDE (((sizeof(TppLane) + 7) / 8) | 1) /* in doubles, odd */
 
@@ -395,7 +402,7 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
                 rc[0] = c0; rc[1] = c1; rc[2] = c2;
                 if (mode == BM_SOC) {
                     // defects of the last trial point curr + at*step
-                    const double2 d01 = tpp_ld2(p, srow), d2 = tpp_ld2(p, srow + 1), du2 = tpp_ld2(p, srow + 3);
+                    const double2 d01 = tpp_ld2(p, srow), d2 = tpp_ld2(p, srow + 1), du2 = tpp_ld2(p, srow + 2);
                     double2 dsp = make_double2(rd[0], rd[1]), cs01 = make_double2(rc[0], rc[1]), cs2 = make_double2(rc[2], 0.0);
                     if (!sfirst) { dsp = tpp_ld2(p, R_CS + 2); cs01 = tpp_ld2(p, R_CS); cs2 = tpp_ld2(p, R_CS + 1); }
                     const double du[2] = {du2.x, du2.y}, rdp[2] = {dsp.x, dsp.y}, base[3] = {cs01.x, cs01.y, cs2.x};
@@ -473,10 +480,6 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
             v1 = gx1 + u01 * k0 + u11 * k1;
             v2 = gx2 + u02 * k0 + u12 * k1;
         }
-        if (k >= 1) {
-            tpp_st2(p, R_P, q00, q01); tpp_st2(p, R_P + 1, q02, q11); tpp_st2(p, R_P + 2, q12, q22);
-            tpp_st2(p, R_P + 3, v0, v1); tpp_st2(p, R_P + 4, v2, 0.0);
-        }
         Xn[0] = X[0]; Xn[1] = X[1]; Xn[2] = X[2];
         ln[0] = lam[0]; ln[1] = lam[1]; ln[2] = lam[2];
     }
@@ -489,24 +492,25 @@ struct TppFwd {
     int bad;
 };
 
-// staging of the forward sweep: slots 0-8 = factor rows of stage k, 9-12 = U, S, vL, vU of stage k,
-// 13-14 = (X0,X1) (X2,lam0) of stage k+1
+// staging of the forward sweep: slots 0-3 = K, kf rows of stage k, 4-7 = U, S, vL, vU of stage k,
+// 8-9 = (X0,X1) (X2,lam0) of stage k+1
 __device__ __forceinline__ void tpp_forward_stage(char *sb, const char *p, int co, bool has_next) {
 #pragma unroll
-    for (int i = 0; i < 9; i++) tpp_cp16(sb + i * TPP_ROW_B, p + (R_K + i) * TPP_ROW_B);
+    for (int i = 0; i < 4; i++) tpp_cp16(sb + i * TPP_ROW_B, p + (R_K + i) * TPP_ROW_B);
     const char *pc = p + co * TPP_ROW_B;
-    tpp_cp16(sb + 9 * TPP_ROW_B, pc + R_U * TPP_ROW_B);
-    tpp_cp16(sb + 10 * TPP_ROW_B, pc + R_S * TPP_ROW_B);
-    tpp_cp16(sb + 11 * TPP_ROW_B, pc + R_VL * TPP_ROW_B);
-    tpp_cp16(sb + 12 * TPP_ROW_B, pc + R_VU * TPP_ROW_B);
+    tpp_cp16(sb + 4 * TPP_ROW_B, pc + R_U * TPP_ROW_B);
+    tpp_cp16(sb + 5 * TPP_ROW_B, pc + R_S * TPP_ROW_B);
+    tpp_cp16(sb + 6 * TPP_ROW_B, pc + R_VL * TPP_ROW_B);
+    tpp_cp16(sb + 7 * TPP_ROW_B, pc + R_VU * TPP_ROW_B);
     if (has_next) {
-        tpp_cp16(sb + 13 * TPP_ROW_B, pc + TPP_STAGE_B + R_X01 * TPP_ROW_B);
-        tpp_cp16(sb + 14 * TPP_ROW_B, pc + TPP_STAGE_B + R_X2L0 * TPP_ROW_B);
+        tpp_cp16(sb + 8 * TPP_ROW_B, pc + TPP_STAGE_B + R_X01 * TPP_ROW_B);
+        tpp_cp16(sb + 9 * TPP_ROW_B, pc + TPP_STAGE_B + R_X2L0 * TPP_ROW_B);
     }
     tpp_cp_commit();
 }
 
 // ---- sweep F: forward roll-out of the step; step sizes and directional derivative ----------------------------------
+// (the multiplier step is recovered by sweep T; in LSQ mode ymax covers the slack-multiplier estimate only)
 __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A, char *wb, char *sb, int cur,
                                             const TppLane &L, TppFwd &o) {
     const int N = P.N;
@@ -530,34 +534,24 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
         char *p = wb + (size_t)k * TPP_STAGE_B;
         tpp_cp_wait();
         const double2 k0_ = tpp_sld(sb, 0), k1_ = tpp_sld(sb, 1), k2_ = tpp_sld(sb, 2), kf_ = tpp_sld(sb, 3);
-        const double2 p0_ = tpp_sld(sb, 4), p1_ = tpp_sld(sb, 5), p2_ = tpp_sld(sb, 6), pv0_ = tpp_sld(sb, 7);
-        const double2 pv1_ = tpp_sld(sb, 8), u2 = tpp_sld(sb, 9), s2 = tpp_sld(sb, 10), vl2 = tpp_sld(sb, 11);
-        const double2 vu2 = tpp_sld(sb, 12), xn01 = tpp_sld(sb, 13), xn2 = tpp_sld(sb, 14);
+        const double2 u2 = tpp_sld(sb, 4), s2 = tpp_sld(sb, 5), vl2 = tpp_sld(sb, 6), vu2 = tpp_sld(sb, 7);
+        const double2 xn01 = tpp_sld(sb, 8), xn2 = tpp_sld(sb, 9);
         tpp_consume(k0_, k1_, k2_, kf_);
-        tpp_consume(p0_, p1_, p2_, pv0_);
-        tpp_consume(pv1_, u2, s2, vl2);
-        tpp_consume(vu2, xn01, xn2, xn2);
+        tpp_consume(u2, s2, vl2, vu2);
+        tpp_consume(xn01, xn2, xn2, xn2);
         if (k < N) tpp_forward_stage(sb, p + TPP_STAGE_B, co, k + 1 < N);
         if (k + 2 <= N) {
-            tpp_l2_prefetch(p + 2 * TPP_STAGE_B, R_K, 9);
+            tpp_l2_prefetch(p + 2 * TPP_STAGE_B, R_K, 4);
             tpp_l2_prefetch(p + 2 * TPP_STAGE_B + co * TPP_ROW_B, R_U, 2);
             tpp_l2_prefetch(p + 2 * TPP_STAGE_B + co * TPP_ROW_B, R_VL, 2);
             if (k + 3 <= N) tpp_l2_prefetch(p + 3 * TPP_STAGE_B + co * TPP_ROW_B, R_X01, 2);
         }
-        double l0 = 0, l1 = 0, l2 = 0;
         if (!isfinite(y0) || !isfinite(y1) || !isfinite(y2)) bad = 1;
-        if (k >= 1) {
-            l0 = -(pv0_.x + p0_.x * y0 + p0_.y * y1 + p1_.x * y2);
-            l1 = -(pv0_.y + p0_.y * y0 + p1_.y * y1 + p2_.x * y2);
-            l2 = -(pv1_.x + p1_.x * y0 + p2_.x * y1 + p2_.y * y2);
-            if (!isfinite(l0) || !isfinite(l1) || !isfinite(l2)) bad = 1;
-            if (mode == BM_LSQ) ymax = fmax(ymax, fmax(fabs(l0), fmax(fabs(l1), fabs(l2))));
-        }
-        tpp_st2(p, orow, y0, y1); tpp_st2(p, orow + 1, y2, l0); tpp_st2(p, orow + 2, l1, l2);
+        tpp_st2(p, orow, y0, y1); tpp_st2(p, orow + 1, y2, 0.0);
         if (k < N) {
             const double du0 = kf_.x + k0_.x * y0 + k0_.y * y1 + k1_.x * y2;
             const double du1 = kf_.y + k1_.y * y0 + k2_.x * y1 + k2_.y * y2;
-            tpp_st2(p, orow + 3, du0, du1);
+            tpp_st2(p, orow + 2, du0, du1);
             if (!isfinite(du0) || !isfinite(du1)) bad = 1;
             const double du[2] = {du0, du1};
             const double U[2] = {u2.x, u2.y}, Sv[2] = {s2.x, s2.y}, vLv[2] = {vl2.x, vl2.y}, vUv[2] = {vu2.x, vu2.y};
@@ -606,23 +600,67 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
 }
 
 struct TppTrial {
-    double th, phi;
+    double th, phi, ymax;
+    int bad;
     TppNorms n;
 };
 
-// staging of the trial sweep: slots 0-7 = current iterate of stage k, 8-11 = step rows of stage k
+// staging of the trial sweep: slots 0-7 = current iterate of stage k, 8-10 = step rows of stage k
 __device__ __forceinline__ void tpp_trial_stage(char *sb, const char *p, int co, int srow) {
 #pragma unroll
     for (int i = 0; i < R_ITER; i++) tpp_cp16(sb + i * TPP_ROW_B, p + (co + i) * TPP_ROW_B);
 #pragma unroll
-    for (int i = 0; i < 4; i++) tpp_cp16(sb + (R_ITER + i) * TPP_ROW_B, p + (srow + i) * TPP_ROW_B);
+    for (int i = 0; i < 3; i++) tpp_cp16(sb + (R_ITER + i) * TPP_ROW_B, p + (srow + i) * TPP_ROW_B);
     tpp_cp_commit();
+}
+
+// State rows of the Newton system at stage k (1 <= k < N), linearised at the current iterate:
+//     Lam_k = A_k' Lam_{k+1} - g_k - (Hxx_k + dw) dx_k - Hxu_k du_k,      Lam = lam + dlam (full-step multipliers).
+// lo = multipliers of the defect of stage k+1 at the current iterate (they weight the second derivatives of F),
+// useW = 0 for the least-squares multiplier estimate (W = 0, dw = 1, unscaled objective: pass df = 1).
+__device__ __forceinline__ void tpp_costate(const KParams &P, const double r[3], const double X[3], const double U[2],
+                                            const double lo[3], const double Ln[3], const double dX[3],
+                                            const double dU[2], double df, double dw, bool useW, double Lk[3]) {
+    const double dt = P.dt, th = X[2], v = U[0], w = U[1];
+    double a13, a23, htt, htv, htw = 0;
+    if (P.integrator == B200MPC_EULER) {
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        a13 = -dt * v * sn; a23 = dt * v * cs;
+        htt = dt * v * (lo[0] * cs + lo[1] * sn);
+        htv = dt * (lo[0] * sn - lo[1] * cs);
+    } else {
+        double s0, c0, sm, cm, se, ce;
+        tpp_trig(th, 0.5 * dt * w, s0, c0, sm, cm, se, ce);
+        const double h = dt / 6.0;
+        const double C = c0 + 4.0 * cm + ce, S = s0 + 4.0 * sm + se;
+        const double C1 = 2.0 * cm + ce, S1 = 2.0 * sm + se;
+        a13 = -h * v * S; a23 = h * v * C;
+        htt = h * v * (lo[0] * C + lo[1] * S);
+        htv = h * (lo[0] * S - lo[1] * C);
+        htw = h * dt * v * (lo[0] * C1 + lo[1] * S1);
+    }
+    const double g0 = df * 2.0 * P.Q[0] * (X[0] - r[0]);
+    const double g1 = df * 2.0 * P.Q[1] * (X[1] - r[1]);
+    const double g2 = df * 2.0 * P.Q[2] * (X[2] - r[2]);
+    double hxx = dw, hyy = dw, hth = dw;
+    if (useW) {
+        hxx += df * 2.0 * P.Q[0];
+        hyy += df * 2.0 * P.Q[1];
+        hth += df * 2.0 * P.Q[2] + htt;
+    } else {
+        htv = 0; htw = 0;
+    }
+    Lk[0] = Ln[0] - g0 - hxx * dX[0];
+    Lk[1] = Ln[1] - g1 - hyy * dX[1];
+    Lk[2] = Ln[2] + a13 * Ln[0] + a23 * Ln[1] - g2 - hth * dX[2] - htv * dU[0] - htw * dU[1];
 }
 
 // ---- sweep T: write curr + alpha*step into the other iterate buffer and evaluate that point -------------------------
 // tmode EVAL:        new = current (after the restoration stand-in).
 // tmode LSQ:         new = current with the least-squares multiplier estimate (scaled by df; or zeros) for lam, yd.
 // tmode STEP(_SOC):  new = current + alpha*(dX,dU,dS,dlam,dyd) and bound multipliers + a_z*(dvL,dvU), clamped.
+// The multiplier step dlam is not stored by the other sweeps: it comes from the costate recursion (tpp_costate).
 __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, char *wb, char *sb, int cur,
                                           const TppLane &L, TppTrial &o) {
     const int N = P.N;
@@ -635,47 +673,69 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
     const int srow = soc0 ? R_SSTEP : R_STEP;
     const double ikap = 1.0 / KAPPA_SIGMA;
     double Xn[3] = {0, 0, 0}, ln[3] = {0, 0, 0};
-    double th = 0, slog = 0, pi = 0, di = 0, sy = 0, sz = 0, pmin = 1e300, pmax = -1e300, fs = 0;
+    double lo[3] = {0, 0, 0}, Lam[3] = {0, 0, 0}; // multipliers of stage k+1: at the current iterate / after a full step
+    double th = 0, slog = 0, pi = 0, di = 0, sy = 0, sz = 0, pmin = 1e300, pmax = -1e300, fs = 0, ymax = 0;
+    int bad = 0;
     tpp_trial_stage(sb, wb + (size_t)N * TPP_STAGE_B, co, srow);
 #pragma unroll 1
     for (int k = N; k >= 0; --k) {
         const int mode = tpp_opaque(tmode0);
         const bool step = (mode >= TM_STEP), soc = (mode == TM_STEP_SOC);
+        const bool lsq = (mode == TM_LSQ) && keep0;
         char *p = wb + (size_t)k * TPP_STAGE_B;
         char *pw = p + no * TPP_ROW_B;
         tpp_cp_wait();
         const double2 x01 = tpp_sld(sb, R_X01), x2l0 = tpp_sld(sb, R_X2L0), l12 = tpp_sld(sb, R_L12), u2 = tpp_sld(sb, R_U);
         const double2 s2 = tpp_sld(sb, R_S), yd2 = tpp_sld(sb, R_YD), vl2 = tpp_sld(sb, R_VL), vu2 = tpp_sld(sb, R_VU);
-        const double2 dx01 = tpp_sld(sb, R_ITER), dx2l0 = tpp_sld(sb, R_ITER + 1), dl12 = tpp_sld(sb, R_ITER + 2),
-                      du2 = tpp_sld(sb, R_ITER + 3);
+        const double2 dx01 = tpp_sld(sb, R_ITER), dx2 = tpp_sld(sb, R_ITER + 1), du2 = tpp_sld(sb, R_ITER + 2);
         tpp_consume(x01, x2l0, l12, u2);
         tpp_consume(s2, yd2, vl2, vu2);
-        tpp_consume(dx01, dx2l0, dl12, du2);
+        tpp_consume(dx01, dx2, du2, du2);
         if (k > 0) tpp_trial_stage(sb, p - TPP_STAGE_B, co, srow);
         if (k > 1) {
             tpp_l2_prefetch(p - 2 * TPP_STAGE_B + co * TPP_ROW_B, 0, R_ITER);
-            tpp_l2_prefetch(p - 2 * TPP_STAGE_B, srow, 4);
+            tpp_l2_prefetch(p - 2 * TPP_STAGE_B, srow, 3);
         }
+        double r[3], ub[2];
+        tpp_ref(P, goal, p, r, ub);
         double X[3] = {x01.x, x01.y, x2l0.x};
         double lam[3] = {0, 0, 0};
+        const double duv[2] = {du2.x, du2.y};
         if (k >= 1) {
             lam[0] = x2l0.y; lam[1] = l12.x; lam[2] = l12.y;
-            const double dX[3] = {dx01.x, dx01.y, dx2l0.x}, dL[3] = {dx2l0.y, dl12.x, dl12.y};
-            if (step) {
+            const double lcur[3] = {lam[0], lam[1], lam[2]};
+            const double dX[3] = {dx01.x, dx01.y, dx2.x};
+            if (step || lsq) {
+                const double dwk = lsq ? 1.0 : dw;
+                double Lk[3];
+                if (k == N) {
+                    // terminal stage: no cost, no controls
+                    Lk[0] = -dwk * dX[0]; Lk[1] = -dwk * dX[1]; Lk[2] = -dwk * dX[2];
+                } else {
+                    const double Uc[2] = {u2.x, u2.y};
+                    tpp_costate(P, r, X, Uc, lo, Lam, dX, duv, lsq ? 1.0 : df, dwk, !lsq, Lk);
+                }
+                Lam[0] = Lk[0]; Lam[1] = Lk[1]; Lam[2] = Lk[2];
+                if (!isfinite(Lk[0]) || !isfinite(Lk[1]) || !isfinite(Lk[2])) bad = 1;
+                if (step) {
 #pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    X[i] += alpha * dX[i];
-                    lam[i] += alpha * dL[i];
+                    for (int i = 0; i < 3; i++) {
+                        X[i] += alpha * dX[i];
+                        lam[i] += alpha * (Lk[i] - lam[i]);
+                    }
+                } else {
+                    ymax = fmax(ymax, fmax(fabs(Lk[0]), fmax(fabs(Lk[1]), fabs(Lk[2]))));
+#pragma unroll
+                    for (int i = 0; i < 3; i++) lam[i] = df * Lk[i];
                 }
             } else if (mode == TM_LSQ) {
-#pragma unroll
-                for (int i = 0; i < 3; i++) lam[i] = keep0 ? df * dL[i] : 0.0;
+                lam[0] = lam[1] = lam[2] = 0.0;
             }
+            lo[0] = lcur[0]; lo[1] = lcur[1]; lo[2] = lcur[2];
         }
         tpp_st2(pw, R_X01, X[0], X[1]); tpp_st2(pw, R_X2L0, X[2], lam[0]); tpp_st2(pw, R_L12, lam[1], lam[2]);
         if (k < N) {
             double U[2] = {u2.x, u2.y}, S[2] = {s2.x, s2.y}, yd[2] = {yd2.x, yd2.y}, vL[2] = {vl2.x, vl2.y}, vU[2] = {vu2.x, vu2.y};
-            const double duv[2] = {du2.x, du2.y};
             double rdv[2] = {U[0] - S[0], U[1] - S[1]};
             if (soc) {
                 const double2 d2 = tpp_ld2(p, R_CS + 2);
@@ -705,8 +765,6 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
             }
             tpp_st2(pw, R_U, U[0], U[1]); tpp_st2(pw, R_S, S[0], S[1]); tpp_st2(pw, R_YD, yd[0], yd[1]);
             tpp_st2(pw, R_VL, vL[0], vL[1]); tpp_st2(pw, R_VU, vU[0], vU[1]);
-            double r[3], ub[2];
-            tpp_ref(P, goal, p, r, ub);
             TppLin q;
             tpp_lin<false>(P, r, ub, X, U, ln, df, q);
             const double c[3] = {Xn[0] - q.F0, Xn[1] - q.F1, Xn[2] - q.F2};
@@ -755,6 +813,7 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
     }
     o.th = th;
     o.phi = df * fs - mu * slog;
+    o.ymax = ymax; o.bad = bad;
     o.n.theta = th; o.n.prim_inf = pi; o.n.dual_inf = di; o.n.sum_y = sy; o.n.sum_z = sz;
     o.n.pmin = pmin; o.n.pmax = pmax; o.n.f = fs; o.n.slog = slog;
 }
@@ -1048,6 +1107,8 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             tpp_forward(P, A, wb, sb, cur, L, f);
             const int bmode = L.bmode;
             if (bmode == BM_LSQ) {
+                // the estimate is kept if its largest entry is <= 1e3; sweep T adds the defect multipliers
+                L.ymax_f = f.ymax;
                 L.keep = (L.df * f.ymax <= 1e3) ? 1 : 0;
                 L.tmode = TM_LSQ;
                 L.phase = PH_T;
@@ -1087,8 +1148,15 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             tpp_trial(P, A, wb, sb, cur, L, t);
             const int tm = L.tmode;
             bool accepted = false;
-            if (tm == TM_EVAL || tm == TM_LSQ) {
+            if (tm == TM_EVAL) {
                 accepted = true;
+            } else if (tm == TM_LSQ) {
+                // discard the estimate (and write zeros in the next trip) if a defect multiplier exceeds the limit
+                if (L.keep && !(L.df * t.ymax <= 1e3)) L.keep = 0;
+                else accepted = true;
+            } else if (t.bad) {
+                L.status = B200MPC_ERROR_IN_STEP_COMPUTATION;
+                L.phase = PH_FIN;
             } else {
                 const bool soc = (tm == TM_STEP_SOC);
                 if (soc || L.ntrial++ > 0) L.ls_extra++;
