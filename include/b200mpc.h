@@ -119,7 +119,11 @@ void b200mpc_destroy(b200mpc_handle *h);
 const char *b200mpc_last_error(const b200mpc_handle *h);
 
 /* Host-buffer solve: copies inputs host->device, runs the solve kernel, copies results back, blocks until done.
- * Any of cost_out / iters_out / ls_out may be NULL. */
+ * Any of cost_out / iters_out / ls_out may be NULL.
+ * Large batches (>= 131072 problems on the lane-per-problem kernel) whose buffers are page-locked are STREAMED: the
+ * inputs are copied in chunks on a copy stream while the persistent kernel already solves the first chunks, and each
+ * chunk of results is copied out as soon as its last problem has finished (the kernel raises a per-chunk flag in
+ * host memory).  Pageable buffers take the plain copy-in / solve / copy-out sequence.  Results are identical. */
 int b200mpc_solve_batch(b200mpc_handle *h, int B, const double *x0, const double *xref, const double *uref,
                         const double *obs_x, const double *obs_y, int obs_stride, const double *u_init,
                         double *X_out, double *U_out, double *cost_out, int32_t *status_out, int32_t *iters_out,
@@ -152,6 +156,8 @@ int b200mpc_eval_batch(b200mpc_handle *h, int B, const double *x0, const double 
 int b200mpc_set_kernel(b200mpc_handle *h, int kind);
 /* B200MPC_KERNEL_WARP / _LANE: the kernel the most recent solve used. */
 int b200mpc_last_kernel_kind(const b200mpc_handle *h);
+/* Number of chunks the most recent host-buffer solve was streamed in (0 = plain copy-in / solve / copy-out). */
+int b200mpc_last_solve_chunks(const b200mpc_handle *h);
 
 /* Diagnostics of the lane-per-problem kernel, cumulative over the handle's life: out[2i], out[2i+1] = warp-level
  * executions and active lanes of sweep i (0 backward, 1 forward, 2 trial) and of the trips (i = 3).  Counted only

@@ -72,6 +72,8 @@ def lib():
         L.b200mpc_set_kernel.restype = C.c_int
         L.b200mpc_last_kernel_kind.argtypes = [vp]
         L.b200mpc_last_kernel_kind.restype = C.c_int
+        L.b200mpc_last_solve_chunks.argtypes = [vp]
+        L.b200mpc_last_solve_chunks.restype = C.c_int
         L.b200mpc_lane_kernel_stats.argtypes = [vp, C.POINTER(C.c_ulonglong * 8)]
         L.b200mpc_lane_kernel_stats.restype = C.c_int
         L.b200mpc_sizeof_params.restype = C.c_int
@@ -144,6 +146,11 @@ class Solver:
     @property
     def last_kernel_kind(self):
         return int(self._L.b200mpc_last_kernel_kind(self._h))
+
+    @property
+    def last_solve_chunks(self):
+        """Chunks the most recent host-buffer solve was streamed in (0 = plain copy-in / solve / copy-out)."""
+        return int(self._L.b200mpc_last_solve_chunks(self._h))
 
     def lane_kernel_stats(self):
         """Cumulative sweep statistics of the lane kernel (TPP_STATS builds): dict sweep -> (executions, mean lanes)."""

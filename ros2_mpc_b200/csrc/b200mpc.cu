@@ -28,6 +28,7 @@
 
 #include <mutex>
 #include <string>
+#include <thread>
 
 #define FULL 0xffffffffu
 #ifndef B200MPC_MIN_CTAS
@@ -1173,8 +1174,19 @@ struct b200mpc_handle {
     int tpp_ctas;
     double *d_ws, *d_filt;
     unsigned long long *d_stats;
+    // streamed host-buffer solves: copy-in / copy-out streams, device words (avail, done[chunks]) and host-mapped
+    // words (flags[chunks], marks[chunks])
+    cudaStream_t cstream, ostream;
+    cudaEvent_t ev_sync;
+    unsigned int *d_sync;
+    unsigned int *h_sync, *h_sync_dev;
+    int last_streamed;
     std::string err;
 };
+#define B200MPC_MAX_CHUNKS 64
+#ifndef B200MPC_STREAM_MIN_BATCH
+#define B200MPC_STREAM_MIN_BATCH 131072 /* host-buffer solves from this size on are streamed in chunks */
+#endif
 
 static int set_err(b200mpc_handle *h, int code, const std::string &msg) {
     if (h) h->err = msg;
@@ -1252,6 +1264,11 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     h->d_ws = nullptr;
     h->d_filt = nullptr;
     h->d_stats = nullptr;
+    h->cstream = h->ostream = nullptr;
+    h->ev_sync = nullptr;
+    h->d_sync = nullptr;
+    h->h_sync = h->h_sync_dev = nullptr;
+    h->last_streamed = 0;
     if (const char *ek = getenv("B200MPC_KERNEL")) {
         if (!strcmp(ek, "warp")) h->kernel_kind = B200MPC_KERNEL_WARP;
         else if (!strcmp(ek, "lane")) h->kernel_kind = B200MPC_KERNEL_LANE;
@@ -1306,6 +1323,13 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail(cudaGetErrorString(e));
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail(cudaGetErrorString(e));
     if ((e = cudaMalloc(&h->d_counter, sizeof(unsigned int))) != cudaSuccess) return fail(cudaGetErrorString(e));
+    if ((e = cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cudaGetErrorString(e));
+    if ((e = cudaStreamCreateWithFlags(&h->ostream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cudaGetErrorString(e));
+    if ((e = cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming)) != cudaSuccess) return fail(cudaGetErrorString(e));
+    if ((e = cudaMalloc(&h->d_sync, (1 + B200MPC_MAX_CHUNKS) * sizeof(unsigned int))) != cudaSuccess) return fail(cudaGetErrorString(e));
+    if ((e = cudaHostAlloc(&h->h_sync, 2 * B200MPC_MAX_CHUNKS * sizeof(unsigned int), cudaHostAllocMapped)) != cudaSuccess)
+        return fail(cudaGetErrorString(e));
+    if ((e = cudaHostGetDevicePointer(&h->h_sync_dev, h->h_sync, 0)) != cudaSuccess) return fail(cudaGetErrorString(e));
     return h;
 }
 
@@ -1318,6 +1342,11 @@ extern "C" void b200mpc_destroy(b200mpc_handle *h) {
     if (h->d_filt) cudaFree(h->d_filt);
     if (h->d_stats) cudaFree(h->d_stats);
     cudaFree(h->d_counter);
+    if (h->cstream) { cudaStreamSynchronize(h->cstream); cudaStreamDestroy(h->cstream); }
+    if (h->ostream) { cudaStreamSynchronize(h->ostream); cudaStreamDestroy(h->ostream); }
+    if (h->ev_sync) cudaEventDestroy(h->ev_sync);
+    if (h->d_sync) cudaFree(h->d_sync);
+    if (h->h_sync) cudaFreeHost(h->h_sync);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
@@ -1396,6 +1425,8 @@ extern "C" int b200mpc_set_kernel(b200mpc_handle *h, int kind) {
 
 extern "C" int b200mpc_last_kernel_kind(const b200mpc_handle *h) { return h ? h->last_kind : B200MPC_E_ARG; }
 
+extern "C" int b200mpc_last_solve_chunks(const b200mpc_handle *h) { return h ? h->last_streamed : B200MPC_E_ARG; }
+
 // Diagnostics of the lane-per-problem kernel (only counted in builds with -DTPP_STATS=1): cumulative
 // {executions, active lanes} of the sweeps B, F, T and of the trips; zeros otherwise.
 extern "C" int b200mpc_lane_kernel_stats(b200mpc_handle *h, unsigned long long out[8]) {
@@ -1408,7 +1439,13 @@ extern "C" int b200mpc_lane_kernel_stats(b200mpc_handle *h, unsigned long long o
 }
 
 // Lane-per-problem kernel: persistent grid, one workspace stripe per warp (allocated on first use).
-static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stream) {
+struct StreamWords {
+    const unsigned *avail;
+    unsigned *done, *flags;
+    int chunk;
+};
+
+static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stream, const StreamWords *sw = nullptr) {
     const int N = h->prm.N;
     const size_t nwarps = (size_t)h->tpp_ctas * (TPP_THREADS / 32);
     if (!h->d_ws) {
@@ -1428,6 +1465,8 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t 
     if (grid < 1) grid = 1;
     TppArgs t;
     t.a = a; t.ws = h->d_ws; t.filt = h->d_filt; t.stats = h->d_stats;
+    t.avail = sw ? sw->avail : nullptr; t.done = sw ? sw->done : nullptr; t.flags = sw ? sw->flags : nullptr;
+    t.chunk = sw ? sw->chunk : 1;
     CU_TRY(h, cudaEventRecord(h->ev0, stream));
     mpc_solve_tpp_kernel<<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
     CU_TRY(h, cudaGetLastError());
@@ -1437,12 +1476,17 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t 
     return 0;
 }
 
-static int launch_solve(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stream) {
-    // Kernel choice: the lane-per-problem kernel needs enough problems to fill the machine with lanes; below that
-    // (and whenever the obstacle cost is active) the warp-per-problem kernel is used.
+// Kernel choice: the lane-per-problem kernel needs enough problems to fill the machine with lanes; below that
+// (and whenever the obstacle cost is active) the warp-per-problem kernel is used.
+static int choose_kernel(const b200mpc_handle *h, int B) {
     int kind = h->kernel_kind;
     if (h->prm.obs_form != B200MPC_OBS_NONE) kind = B200MPC_KERNEL_WARP;
-    else if (kind == B200MPC_KERNEL_AUTO) kind = (a.B >= B200MPC_LANE_KERNEL_MIN_BATCH) ? B200MPC_KERNEL_LANE : B200MPC_KERNEL_WARP;
+    else if (kind == B200MPC_KERNEL_AUTO) kind = (B >= B200MPC_LANE_KERNEL_MIN_BATCH) ? B200MPC_KERNEL_LANE : B200MPC_KERNEL_WARP;
+    return kind;
+}
+
+static int launch_solve(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stream) {
+    const int kind = choose_kernel(h, a.B);
     if (kind == B200MPC_KERNEL_LANE) return launch_solve_tpp(h, a, stream);
     h->last_kind = B200MPC_KERNEL_WARP;
     CU_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), stream));
@@ -1493,6 +1537,13 @@ static int ensure_buf(b200mpc_handle *h, size_t bytes) {
 
 static size_t al256(size_t n) { return (n + 255) & ~(size_t)255; }
 
+// page-locked (cudaHostAlloc / cudaHostRegister) host memory?  Only then do asynchronous copies overlap the kernel.
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 extern "C" int b200mpc_solve_batch(b200mpc_handle *h, int B, const double *x0, const double *xref, const double *uref,
                                    const double *obs_x, const double *obs_y, int obs_stride, const double *u_init,
                                    double *X_out, double *U_out, double *cost_out, int32_t *status_out,
@@ -1523,6 +1574,74 @@ extern "C" int b200mpc_solve_batch(b200mpc_handle *h, int B, const double *x0, c
     double *d_X = (double *)take(sz_X), *d_U = (double *)take(sz_U), *d_c = (double *)take(sz_c);
     int *d_st = (int *)take(sz_i), *d_it = (int *)take(sz_i), *d_ls = (int *)take(sz_i);
     cudaStream_t s = h->stream;
+    h->last_streamed = 0;
+    if (choose_kernel(h, B) == B200MPC_KERNEL_LANE && B >= B200MPC_STREAM_MIN_BATCH && !getenv("B200MPC_NO_STREAMING") &&
+        is_pinned(x0) && is_pinned(X_out) && is_pinned(U_out)) {
+        // ---- streamed solve: inputs arrive and results leave in chunks while the persistent kernel runs ----
+        // copy stream:   [chunk c inputs H2D][avail := end of chunk c] ...          (the kernel waits for `avail`)
+        // kernel:        finishes problems in roughly ascending order; the lane completing chunk c raises flags[c]
+        // this thread:   polls flags[c] in host memory and enqueues the chunk's D2H copies on the output stream
+        int nchunks = B / 32768;
+        if (nchunks > B200MPC_MAX_CHUNKS) nchunks = B200MPC_MAX_CHUNKS;
+        if (nchunks < 2) nchunks = 2;
+        int chunk = (B + nchunks - 1) / nchunks;
+        chunk = (chunk + 255) & ~255;
+        nchunks = (B + chunk - 1) / chunk;
+        volatile unsigned int *flags = h->h_sync;
+        unsigned int *marks = h->h_sync + B200MPC_MAX_CHUNKS;
+        for (int c = 0; c < nchunks; c++) {
+            flags[c] = 0;
+            const long long end = (long long)(c + 1) * chunk;
+            marks[c] = (unsigned)(end < B ? end : B);
+        }
+        CU_TRY(h, cudaMemsetAsync(h->d_sync, 0, (1 + B200MPC_MAX_CHUNKS) * sizeof(unsigned int), s));
+        CU_TRY(h, cudaEventRecord(h->ev_sync, s));
+        CU_TRY(h, cudaStreamWaitEvent(h->cstream, h->ev_sync, 0));
+        CU_TRY(h, cudaStreamWaitEvent(h->ostream, h->ev_sync, 0)); // earlier work on the staging buffer is complete
+        const size_t w_ref = traj ? 3 * N : 3;
+        for (int c = 0; c < nchunks; c++) {
+            const size_t b0 = (size_t)c * chunk, n = marks[c] - b0;
+            cudaStream_t cs = h->cstream;
+            CU_TRY(h, cudaMemcpyAsync(d_x0 + b0 * 3, x0 + b0 * 3, n * 3 * 8, cudaMemcpyHostToDevice, cs));
+            CU_TRY(h, cudaMemcpyAsync(d_xref + b0 * w_ref, xref + b0 * w_ref, n * w_ref * 8, cudaMemcpyHostToDevice, cs));
+            if (traj) CU_TRY(h, cudaMemcpyAsync(d_uref + b0 * 2 * N, uref + b0 * 2 * N, n * 2 * N * 8, cudaMemcpyHostToDevice, cs));
+            if (u_init) CU_TRY(h, cudaMemcpyAsync(d_ui + b0 * 2 * N, u_init + b0 * 2 * N, n * 2 * N * 8, cudaMemcpyHostToDevice, cs));
+            CU_TRY(h, cudaMemcpyAsync(h->d_sync, marks + c, sizeof(unsigned int), cudaMemcpyHostToDevice, cs));
+        }
+        BatchArgs a;
+        a.B = B; a.obs_stride = obs_stride;
+        a.x0 = d_x0; a.xref = d_xref; a.uref = d_uref; a.ox = d_ox; a.oy = d_oy; a.u_init = d_ui;
+        a.X = d_X; a.U = d_U; a.cost = d_c; a.status = d_st; a.iters = d_it; a.ls = d_ls;
+        a.counter = h->d_counter;
+        StreamWords sw;
+        sw.avail = h->d_sync; sw.done = h->d_sync + 1; sw.flags = h->h_sync_dev; sw.chunk = chunk;
+        rc = launch_solve_tpp(h, a, s, &sw);
+        if (rc) return rc;
+        for (int c = 0; c < nchunks; c++) {
+            unsigned spins = 0;
+            while (!flags[c]) {
+                if ((++spins & 0x3ff) == 0) {
+                    const cudaError_t q = cudaStreamQuery(s);
+                    if (q == cudaSuccess) break; // kernel finished: every chunk is complete
+                    if (q != cudaErrorNotReady) return set_err(h, B200MPC_E_CUDA, std::string("solve kernel: ") + cudaGetErrorString(q));
+                    std::this_thread::yield();
+                }
+            }
+            const size_t b0 = (size_t)c * chunk, n = marks[c] - b0;
+            cudaStream_t os = h->ostream;
+            CU_TRY(h, cudaMemcpyAsync(X_out + b0 * 3 * (N + 1), d_X + b0 * 3 * (N + 1), n * 3 * (N + 1) * 8, cudaMemcpyDeviceToHost, os));
+            CU_TRY(h, cudaMemcpyAsync(U_out + b0 * 2 * N, d_U + b0 * 2 * N, n * 2 * N * 8, cudaMemcpyDeviceToHost, os));
+            if (cost_out) CU_TRY(h, cudaMemcpyAsync(cost_out + b0, d_c + b0, n * 8, cudaMemcpyDeviceToHost, os));
+            CU_TRY(h, cudaMemcpyAsync(status_out + b0, d_st + b0, n * 4, cudaMemcpyDeviceToHost, os));
+            if (iters_out) CU_TRY(h, cudaMemcpyAsync(iters_out + b0, d_it + b0, n * 4, cudaMemcpyDeviceToHost, os));
+            if (ls_out) CU_TRY(h, cudaMemcpyAsync(ls_out + b0, d_ls + b0, n * 4, cudaMemcpyDeviceToHost, os));
+        }
+        CU_TRY(h, cudaStreamSynchronize(s));
+        CU_TRY(h, cudaStreamSynchronize(h->cstream));
+        CU_TRY(h, cudaStreamSynchronize(h->ostream));
+        h->last_streamed = nchunks;
+        return 0;
+    }
     CU_TRY(h, cudaMemcpyAsync(d_x0, x0, nb * 3 * 8, cudaMemcpyHostToDevice, s));
     CU_TRY(h, cudaMemcpyAsync(d_xref, xref, nb * (traj ? 3 * N : 3) * 8, cudaMemcpyHostToDevice, s));
     if (traj) CU_TRY(h, cudaMemcpyAsync(d_uref, uref, nb * 2 * N * 8, cudaMemcpyHostToDevice, s));

@@ -135,6 +135,12 @@ struct TppArgs {
     double *ws;   // [nwarps][N+1][TPP_NF][32]
     double *filt; // [nwarps][64][32]: 32 filter entries (phi, theta) per lane
     unsigned long long *stats; // [8]: per sweep B, F, T: warp executions and active lanes; trips; warps
+    // streamed host-buffer solves (b200mpc_solve_batch): the inputs arrive chunk by chunk while the kernel runs and
+    // the results leave chunk by chunk.  All three are NULL for device-buffer solves.
+    const unsigned *avail;     // number of leading problems whose inputs are on the device (written by the copy stream)
+    unsigned *done;            // [chunks] finished problems per chunk
+    unsigned *flags;           // [chunks] host-mapped: set to 1 when the chunk's results are complete in device memory
+    int chunk;                 // problems per chunk
 };
 #ifndef TPP_STATS
 #define TPP_STATS 0
@@ -1002,10 +1008,16 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             } else {
                 newb = b;
                 L.b = b;
+                if (T.avail) {
+                    // streamed inputs: wait until the copy stream has delivered this problem (only ever at the start
+                    // of a batch: the copies run 20x faster than the problems are consumed)
+                    while (*reinterpret_cast<const volatile unsigned *>(T.avail) <= (unsigned)b) __nanosleep(500);
+                    __threadfence();
+                }
                 L.goal[0] = L.goal[1] = L.goal[2] = 0;
                 if (P.ref_kind == B200MPC_REF_GOAL) {
                     const double *xr = A.xref + 3 * (size_t)b;
-                    L.goal[0] = xr[0]; L.goal[1] = xr[1]; L.goal[2] = xr[2];
+                    L.goal[0] = __ldcg(xr); L.goal[1] = __ldcg(xr + 1); L.goal[2] = __ldcg(xr + 2);
                 }
                 L.status = B200MPC_MAXITER_EXCEEDED;
                 L.iter = 0; L.ls_extra = 0; L.n_resto = 0; L.acceptable_count = 0; L.ntrial = 0; L.soc_count = 0;
@@ -1024,7 +1036,8 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
         for (unsigned m = __ballot_sync(FULL, newb >= 0); m; m &= m - 1) {
             const int j = __ffs(m) - 1;                      // slot (lane) that receives the problem
             const size_t b = (size_t)__shfl_sync(FULL, newb, j);
-            const double x00 = A.x0[3 * b], x01 = A.x0[3 * b + 1], x02 = A.x0[3 * b + 2];
+            // inputs bypass L1 (a line may straddle two chunks of a streamed batch)
+            const double x00 = __ldcg(A.x0 + 3 * b), x01 = __ldcg(A.x0 + 3 * b + 1), x02 = __ldcg(A.x0 + 3 * b + 2);
             const double2 *ui = A.u_init ? reinterpret_cast<const double2 *>(A.u_init + b * 2 * N) : nullptr;
             for (int k = lane; k <= N; k += 32) {
                 char *p = wbase + (size_t)k * TPP_STAGE_B + j * 16;
@@ -1034,7 +1047,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 tpp_st2(pc, R_L12, 0.0, 0.0);
                 if (k < N) {
                     double2 u = make_double2(0.0, 0.0);
-                    if (ui) u = ui[k];
+                    if (ui) u = __ldcg(ui + k);
                     const double uv[2] = {u.x, u.y};
                     double sv[2];
 #pragma unroll
@@ -1053,7 +1066,8 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                     if (P.ref_kind == B200MPC_REF_TRAJ) {
                         const double *xr = A.xref + b * 3 * N + 3 * k;
                         const double *ur = A.uref + b * 2 * N + 2 * k;
-                        tpp_st2(p, R_REF, xr[0], xr[1]); tpp_st2(p, R_REF + 1, xr[2], 0.0); tpp_st2(p, R_REF + 2, ur[0], ur[1]);
+                        tpp_st2(p, R_REF, __ldcg(xr), __ldcg(xr + 1)); tpp_st2(p, R_REF + 1, __ldcg(xr + 2), 0.0);
+                        tpp_st2(p, R_REF + 2, __ldcg(ur), __ldcg(ur + 1));
                     }
                 }
             }
@@ -1238,6 +1252,21 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 if (A.iters) A.iters[b] = L.iter;
                 if (A.ls) A.ls[b] = L.ls_extra;
                 L.phase = PH_LOAD;
+            }
+            if (T.done && __any_sync(FULL, fin)) {
+                // streamed results: the lane that completes a chunk raises the chunk's flag in host memory; the host
+                // then copies the chunk out while the kernel keeps running
+                __threadfence(); // every lane: its share of the cooperative result stores
+                __syncwarp();
+                if (fin) {
+                    const int c = L.b / T.chunk;
+                    const unsigned n_in = (unsigned)min(T.chunk, A.B - c * T.chunk);
+                    if (atomicAdd(T.done + c, 1u) + 1u == n_in) {
+                        __threadfence_system();
+                        *reinterpret_cast<volatile unsigned *>(T.flags + c) = 1u;
+                        __threadfence_system();
+                    }
+                }
             }
             // the iterate stays where it is but the warp's buffers swap: copy it across (rejected trial point,
             // inertia-correction retry)

@@ -429,3 +429,41 @@ def test_lane_kernel_horizon_sweep(env, N):
     ref = O.solve_batch(O.variant_params("B", env["y"], N=N, **over), w["x0"], w["goal"])
     _assert_parity(out, ref, need_frac=0.9)
     S.close()
+
+
+@pytest.mark.parametrize("variant", ["B", "C"])
+def test_streamed_host_solve_matches_plain(env, variant):
+    """Page-locked host buffers: the batch is streamed (chunked H2D while the kernel runs, per-chunk D2H on
+    completion flags).  Every problem must come out bit-identical to the plain copy-in / solve / copy-out path,
+    including a ragged last chunk."""
+    import torch
+    shim, synth = env["shim"], env["synth"]
+    w = synth.robots_on_map(B=4096, seed=5)
+    rep, B = 33, 33 * 4096 - 77
+    N = env["y"]["N"]
+    x0 = np.tile(w["x0"], (rep, 1))[:B]
+    xr = np.tile(w["goal"], (rep, 1))[:B]
+    kw = {}
+    if variant == "C":
+        pxf, puf = synth.straight_reference(w["x0"], w["goal"], N)
+        xr = np.tile(pxf, (rep, 1))[:B]
+        kw["uref"] = np.tile(puf, (rep, 1))[:B]
+    ui = synth.warm_start_seeds(rep, N, [-0.05, -0.2], [0.15, 0.2], first_seed=11)
+    kw["u_init"] = np.repeat(ui, 4096, axis=0)[:B]
+    S = shim.Solver(env["make"](variant, env["y"]))
+    plain = S.solve_batch(x0, xr, **kw)
+    assert S.last_kernel_kind == shim.KERNEL_LANE and S.last_solve_chunks == 0
+
+    def pin(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+    out = dict(X=pin(np.zeros((B, N + 1, 3))), U=pin(np.zeros((B, N, 2))), cost=pin(np.zeros(B)),
+               status=pin(np.full(B, 99, np.int32)), iters=pin(np.zeros(B, np.int32)), ls=pin(np.zeros(B, np.int32)))
+    for rnd in range(2):  # twice: the flags and counters must reset between calls
+        for v in out.values():
+            v[...] = 7
+        st = S.solve_batch(pin(x0), pin(xr), out=out, **{k: pin(v) for k, v in kw.items()})
+        assert S.last_solve_chunks >= 2
+        for k in ("status", "iters", "ls", "cost", "X", "U"):
+            assert np.array_equal(st[k], plain[k]), (k, rnd)
+    S.close()
