@@ -15,6 +15,10 @@
  *   b200mpc_eval_batch    <- the NLP functions CasADi evaluates inside opti.solve():
  *                            rk4 :136-148, euler_integration (tracking) :132-137, define_cost_function :104-127,
  *                            define_obstacles_cost_function (mpc_point_stabilization.py:46-53)
+ *   b200mpc_obstacles_batch[_device]  <- get_obstacles   ros2_mpc/scripts/point_follower_local_planner.py:88-118
+ *                            with utils.convert_laser_scan_to_occupancy_grid (ros2_mpc/utils/utils.py:5-43),
+ *                            convert_to_map_coordinates (:114-124), rotate_coordinates (:145-152): the producer of the
+ *                            obstacles_x / obstacles_y arguments of perform_mpc, batched over robots
  *   b200mpc_destroy       <- garbage collection of the Mpc / Opti object
  *
  * Conventions: plain pointers and sizes only; no C++ exceptions cross the boundary; functions return 0 on
@@ -149,6 +153,27 @@ int b200mpc_eval_batch(b200mpc_handle *h, int B, const double *x0, const double 
                        const double *obs_x, const double *obs_y, int obs_stride, const double *X,
                        const double *U, const double *lam, double obj_scale, double *f_out, double *c_out,
                        double *grad_out, double *stage_out);
+
+/* Obstacle-list construction for B robots (get_obstacles of the reference, see the header comment).
+ *   scan      [B][n_beams]  laser ranges (NaN / +-inf allowed, handled as the reference does)
+ *   beam_cos, beam_sin [n_beams]  cos / sin of the beam angles i*(angle_max-angle_min)/n_beams + angle_min — a property
+ *             of the lidar, computed once by the caller exactly as utils.py:18-20 does (this keeps the cell indices
+ *             bit-exact with the reference; the device only multiplies, adds and divides)
+ *   pos [B][2], yaw [B]     robot pose (pos, ori[2])
+ *   size, resolution        params.yaml costmap_size and resolution (the local grid spans 2*size metres)
+ *   obs_x, obs_y [B][slots] obstacle points in world coordinates: the occupied cells in np.where order of the
+ *             180-degree-rotated grid, padded with the first one; all 100.0 when the scan marks no cell
+ *   count [B] (may be NULL) number of occupied cells; count > slots means the list was truncated (the reference
+ *             raises ValueError in that case — the Python mirror offers both behaviours)
+ * The _device variant takes device pointers and enqueues on `stream` without synchronising, so that scan -> obstacle
+ * list -> solve can run back to back on the device. */
+int b200mpc_obstacles_batch(b200mpc_handle *h, int B, int n_beams, const double *scan, const double *beam_cos,
+                            const double *beam_sin, const double *pos, const double *yaw, double size, double resolution,
+                            int slots, double *obs_x, double *obs_y, int32_t *count);
+int b200mpc_obstacles_batch_device(b200mpc_handle *h, int B, int n_beams, const double *scan, const double *beam_cos,
+                                   const double *beam_sin, const double *pos, const double *yaw, double size,
+                                   double resolution, int slots, double *obs_x, double *obs_y, int32_t *count,
+                                   void *stream);
 
 /* Forces one of the two solve kernels (default B200MPC_KERNEL_AUTO; the environment variable B200MPC_KERNEL=warp|lane
  * sets the default of new handles).  Both kernels run the same algorithm; results agree to rounding.  The

@@ -76,6 +76,12 @@ def lib():
         L.b200mpc_last_solve_chunks.restype = C.c_int
         L.b200mpc_lane_kernel_stats.argtypes = [vp, C.POINTER(C.c_ulonglong * 8)]
         L.b200mpc_lane_kernel_stats.restype = C.c_int
+        L.b200mpc_obstacles_batch.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, dp, dp, C.c_double, C.c_double, C.c_int,
+                                              dp, dp, ip]
+        L.b200mpc_obstacles_batch.restype = C.c_int
+        L.b200mpc_obstacles_batch_device.argtypes = [vp, C.c_int, C.c_int] + [vp] * 5 + [C.c_double, C.c_double, C.c_int] + \
+                                                     [vp] * 3 + [vp]
+        L.b200mpc_obstacles_batch_device.restype = C.c_int
         L.b200mpc_sizeof_params.restype = C.c_int
         if L.b200mpc_sizeof_params() != C.sizeof(Params):
             raise RuntimeError("b200mpc_params layout mismatch between _shim.Params and libb200mpc.so")
@@ -193,6 +199,28 @@ class Solver:
                                          _ip(out["status"]), _ip(out["iters"]), _ip(out["ls"]))
         self._check(rc)
         return out
+
+    def obstacles_batch(self, scan, beam_cos, beam_sin, pos, yaw, size, resolution, slots):
+        """Obstacle lists for B robots (host buffers).  scan (B,n); beam_cos/beam_sin (n,); pos (B,2); yaw (B,).
+        Returns obs_x, obs_y (B,slots) float64 and the raw occupied-cell count (B,) int32."""
+        scan = _f64(scan)
+        B, n = scan.shape
+        bc, bs = _f64(beam_cos, (n,)), _f64(beam_sin, (n,))
+        pos, yaw = _f64(pos, (B, 2)), _f64(yaw, (B,))
+        ox, oy, cnt = np.empty((B, slots)), np.empty((B, slots)), np.empty(B, np.int32)
+        rc = self._L.b200mpc_obstacles_batch(self._h, B, n, _dp(scan), _dp(bc), _dp(bs), _dp(pos), _dp(yaw), float(size),
+                                             float(resolution), int(slots), _dp(ox), _dp(oy), _ip(cnt))
+        self._check(rc)
+        return ox, oy, cnt
+
+    def obstacles_batch_device(self, B, n_beams, scan, beam_cos, beam_sin, pos, yaw, size, resolution, slots, obs_x, obs_y,
+                               count, stream=0):
+        """Device-buffer variant: raw device addresses (int, 0 = NULL for count); asynchronous on `stream`."""
+        v = lambda a: C.c_void_p(int(a) if a else None)  # noqa: E731
+        rc = self._L.b200mpc_obstacles_batch_device(self._h, int(B), int(n_beams), v(scan), v(beam_cos), v(beam_sin), v(pos),
+                                                    v(yaw), float(size), float(resolution), int(slots), v(obs_x), v(obs_y),
+                                                    v(count), v(stream))
+        self._check(rc)
 
     def solve_batch_device(self, B, x0, xref, uref, obs_x, obs_y, obs_stride, u_init, X, U, cost, status, iters, ls,
                            stream=0):

@@ -1145,6 +1145,7 @@ __global__ void __launch_bounds__(128) mpc_eval_kernel(const KParams P, const Ev
 }
 
 #include "tpp_kernel.cuh"
+#include "obstacles_kernel.cuh"
 
 // =============================================================================================================
 // Host side: C ABI
@@ -1724,6 +1725,90 @@ extern "C" int b200mpc_eval_batch(b200mpc_handle *h, int B, const double *x0, co
     if (c_out) CU_TRY(h, cudaMemcpyAsync(c_out, d_c, nb * 3 * N * 8, cudaMemcpyDeviceToHost, s));
     if (grad_out) CU_TRY(h, cudaMemcpyAsync(grad_out, d_g, nb * 5 * N * 8, cudaMemcpyDeviceToHost, s));
     if (stage_out) CU_TRY(h, cudaMemcpyAsync(stage_out, d_s, nb * (N + 1) * 36 * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ---- obstacle-list construction (get_obstacles, scripts/point_follower_local_planner.py:88-118) -------------------
+static int launch_obstacles(b200mpc_handle *h, int B, int n_beams, const double *scan, const double *bcos,
+                            const double *bsin, const double *pos, const double *yaw, double size, double resolution,
+                            int slots, double *ox, double *oy, int32_t *count, cudaStream_t stream) {
+    ObsBuildArgs a;
+    const double map_size = size * 2.0; // the caller passes costmap_size; the grid spans 2*size (reference :89)
+    a.B = B; a.n = n_beams; a.slots = slots;
+    a.nc = (int)(map_size / resolution); // int(map_size / cell_size), utils.py:13
+    if (a.nc < 1 || a.nc > 256) return set_err(h, B200MPC_E_ARG, "grid side int(2*size/resolution) out of range [1,256]");
+    a.nwords = (a.nc * a.nc + 31) / 32;
+    a.scan = scan; a.bcos = bcos; a.bsin = bsin; a.pos = pos; a.yaw = yaw;
+    a.half = map_size / 2; a.res = resolution; a.origin = (double)(a.nc / 2) * resolution;
+    a.ox = ox; a.oy = oy; a.count = count;
+    const size_t per_warp = (((size_t)a.nwords * 4 + (size_t)slots * 16) + 15) & ~(size_t)15;
+    const size_t smem = per_warp * OBS_WARPS + 16;
+    if (smem > 200 * 1024) return set_err(h, B200MPC_E_ARG, "grid / slots too large for the shared-memory staging");
+    if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(obstacles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (B + OBS_WARPS - 1) / OBS_WARPS;
+    const int cap = h->sm_count * 8; // grid-stride above 8 CTAs per SM
+    if (grid > cap) grid = cap;
+    CU_TRY(h, cudaEventRecord(h->ev0, stream));
+    obstacles_kernel<<<grid, OBS_WARPS * 32, smem, stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->ev1, stream));
+    h->launches++;
+    return 0;
+}
+
+static int check_obstacle_args(b200mpc_handle *h, int B, int n_beams, const void *scan, const void *bcos, const void *bsin,
+                               const void *pos, const void *yaw, double size, double resolution, int slots,
+                               const void *ox, const void *oy) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || n_beams < 1) return set_err(h, B200MPC_E_ARG, "B < 0 or n_beams < 1");
+    if (slots < 1 || slots > B200MPC_MAX_M) return set_err(h, B200MPC_E_ARG, "slots out of range [1,1024]");
+    if (!(size > 0) || !(resolution > 0)) return set_err(h, B200MPC_E_ARG, "size and resolution must be > 0");
+    if (B > 0 && (!scan || !bcos || !bsin || !pos || !yaw || !ox || !oy)) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    return 0;
+}
+
+extern "C" int b200mpc_obstacles_batch_device(b200mpc_handle *h, int B, int n_beams, const double *scan,
+                                              const double *beam_cos, const double *beam_sin, const double *pos,
+                                              const double *yaw, double size, double resolution, int slots,
+                                              double *obs_x, double *obs_y, int32_t *count, void *stream) {
+    int rc = check_obstacle_args(h, B, n_beams, scan, beam_cos, beam_sin, pos, yaw, size, resolution, slots, obs_x, obs_y);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    CU_TRY(h, cudaSetDevice(h->device));
+    return launch_obstacles(h, B, n_beams, scan, beam_cos, beam_sin, pos, yaw, size, resolution, slots, obs_x, obs_y, count,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int b200mpc_obstacles_batch(b200mpc_handle *h, int B, int n_beams, const double *scan, const double *beam_cos,
+                                       const double *beam_sin, const double *pos, const double *yaw, double size,
+                                       double resolution, int slots, double *obs_x, double *obs_y, int32_t *count) {
+    int rc = check_obstacle_args(h, B, n_beams, scan, beam_cos, beam_sin, pos, yaw, size, resolution, slots, obs_x, obs_y);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t nb = (size_t)B;
+    const size_t sz_scan = al256(nb * n_beams * 8), sz_tab = al256((size_t)n_beams * 8), sz_pos = al256(nb * 2 * 8);
+    const size_t sz_yaw = al256(nb * 8), sz_o = al256(nb * slots * 8), sz_c = al256(nb * 4);
+    rc = ensure_buf(h, sz_scan + 2 * sz_tab + sz_pos + sz_yaw + 2 * sz_o + sz_c);
+    if (rc) return rc;
+    char *p = h->d_buf;
+    auto take = [&](size_t n) { char *r = p; p += n; return r; };
+    double *d_scan = (double *)take(sz_scan), *d_c = (double *)take(sz_tab), *d_s = (double *)take(sz_tab);
+    double *d_pos = (double *)take(sz_pos), *d_yaw = (double *)take(sz_yaw);
+    double *d_ox = (double *)take(sz_o), *d_oy = (double *)take(sz_o);
+    int *d_cnt = (int *)take(sz_c);
+    cudaStream_t s = h->stream;
+    CU_TRY(h, cudaMemcpyAsync(d_scan, scan, nb * n_beams * 8, cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaMemcpyAsync(d_c, beam_cos, (size_t)n_beams * 8, cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaMemcpyAsync(d_s, beam_sin, (size_t)n_beams * 8, cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaMemcpyAsync(d_pos, pos, nb * 2 * 8, cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaMemcpyAsync(d_yaw, yaw, nb * 8, cudaMemcpyHostToDevice, s));
+    rc = launch_obstacles(h, B, n_beams, d_scan, d_c, d_s, d_pos, d_yaw, size, resolution, slots, d_ox, d_oy, d_cnt, s);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(obs_x, d_ox, nb * slots * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaMemcpyAsync(obs_y, d_oy, nb * slots * 8, cudaMemcpyDeviceToHost, s));
+    if (count) CU_TRY(h, cudaMemcpyAsync(count, d_cnt, nb * 4, cudaMemcpyDeviceToHost, s));
     CU_TRY(h, cudaStreamSynchronize(s));
     return 0;
 }

@@ -1,0 +1,131 @@
+// obstacles_kernel.cuh — batched obstacle-list construction: laser scan -> local occupancy grid -> fixed-length list
+// of obstacle points in world coordinates (the obstacles_x / obstacles_y parameters of the MPC).
+//
+// Replaces, for a batch of robots, the producer that runs right before every solve in the reference:
+//   get_obstacles                          ros2_mpc/scripts/point_follower_local_planner.py:88-118
+//   convert_laser_scan_to_occupancy_grid   ros2_mpc/utils/utils.py:5-43
+//   convert_to_map_coordinates             ros2_mpc/utils/utils.py:114-124
+//   rotate_coordinates                     ros2_mpc/utils/utils.py:145-152
+//
+// One warp per robot.  The occupancy grid (num_cells x num_cells, 80 x 80 for params.yaml) is a bit set in shared
+// memory, stored directly in the order np.where() walks the 180-degree-rotated grid (np.rot90(k=2): rotated
+// row-major position q = num_cells^2 - 1 - (y*num_cells + x)), so "the first `slots` obstacle cells" are the first
+// `slots` set bits.  Ranks come from per-lane popcounts and a warp prefix sum; the list is assembled in shared
+// memory and written out with coalesced stores.  HBM-bound: 8*n_beams bytes in, 16*slots + 4 bytes out per robot.
+//
+// Cell indexing is bit-exact with the reference: the beam direction table cos/sin(i*(max-min)/n + min) is computed
+// once on the host (it is a property of the lidar, not of the robot), and every device operation that feeds an index
+// is a single correctly-rounded IEEE operation (__dmul_rn / __dadd_rn / __ddiv_rn: no FMA contraction).  The quirks
+// of the reference are kept: the rotation-by-0.0 matrix product turns +-inf coordinates into NaN, NaN becomes 0,
+// int() truncates toward zero, more than `slots` cells are truncated (the raw count is returned so that a caller
+// can raise like the reference does), no cell at all yields the sentinel 100.0.
+#pragma once
+
+struct ObsBuildArgs {
+    int B, n, nc, slots, nwords;
+    const double *scan;      // [B][n]
+    const double *bcos, *bsin; // [n] beam direction table
+    const double *pos;       // [B][2]
+    const double *yaw;       // [B]
+    double half, res, origin; // map_size/2, resolution, (nc/2)*resolution
+    double *ox, *oy;         // [B][slots]
+    int *count;              // [B] raw number of occupied cells
+};
+
+#define OBS_WARPS 8
+
+__device__ __forceinline__ double obs_fix(double v) { return (v != v) ? 0.0 : v; }
+
+__global__ void __launch_bounds__(OBS_WARPS * 32) obstacles_kernel(const ObsBuildArgs a) {
+    extern __shared__ __align__(16) unsigned char obs_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t per_warp = (size_t)a.nwords * 4 + (size_t)a.slots * 16;
+    unsigned *bits = reinterpret_cast<unsigned *>(obs_smem + wid * ((per_warp + 15) & ~(size_t)15));
+    double *sx = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(bits) + (((size_t)a.nwords * 4 + 15) & ~(size_t)15));
+    double *sy = sx + a.slots;
+    const int wpl = (a.nwords + 31) / 32; // words per lane (contiguous, so that lane order = bit order)
+    const int nbits = a.nc * a.nc;
+    for (int b = blockIdx.x * OBS_WARPS + wid; b < a.B; b += gridDim.x * OBS_WARPS) {
+        for (int w = lane; w < a.nwords; w += 32) bits[w] = 0u;
+        const double *sc = a.scan + (size_t)b * a.n;
+        // ---- pass 1: largest finite coordinate per axis (the reference replaces +-inf by it) ----
+        double mx = -INFINITY, my = -INFINITY;
+        int anyinf = 0;
+        for (int i = lane; i < a.n; i += 32) {
+            const double r = sc[i];
+            const double x = __dmul_rn(r, a.bcos[i]), y = __dmul_rn(r, a.bsin[i]);
+            // rotate_coordinates(., 0.0): [[1, -0], [0, 1]] @ [x; y]
+            const double xr = obs_fix(__dadd_rn(x, __dmul_rn(-0.0, y)));
+            const double yr = obs_fix(__dadd_rn(__dmul_rn(0.0, x), y));
+            if (isinf(xr)) anyinf = 1; else mx = fmax(mx, xr);
+            if (isinf(yr)) anyinf = 1; else my = fmax(my, yr);
+        }
+        anyinf = __any_sync(FULL, anyinf);
+        if (anyinf) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+                my = fmax(my, __shfl_xor_sync(FULL, my, o));
+            }
+        }
+        __syncwarp();
+        // ---- pass 2: cell indices, occupancy bits in rotated np.where order ----
+        for (int i = lane; i < a.n; i += 32) {
+            const double r = sc[i];
+            const double x = __dmul_rn(r, a.bcos[i]), y = __dmul_rn(r, a.bsin[i]);
+            double xr = obs_fix(__dadd_rn(x, __dmul_rn(-0.0, y)));
+            double yr = obs_fix(__dadd_rn(__dmul_rn(0.0, x), y));
+            if (isinf(xr)) xr = mx;
+            if (isinf(yr)) yr = my;
+            const double tx = trunc(__ddiv_rn(__dadd_rn(xr, a.half), a.res));
+            const double ty = trunc(__ddiv_rn(__dadd_rn(yr, a.half), a.res));
+            if (tx >= 0.0 && tx < (double)a.nc && ty >= 0.0 && ty < (double)a.nc) {
+                const int q = nbits - 1 - ((int)ty * a.nc + (int)tx);
+                atomicOr(bits + (q >> 5), 1u << (q & 31));
+            }
+        }
+        __syncwarp();
+        // ---- ranks: per-lane popcount over a contiguous word range, exclusive warp prefix sum ----
+        const int w0 = lane * wpl;
+        int mine = 0;
+        for (int t = 0; t < wpl; t++)
+            if (w0 + t < a.nwords) mine += __popc(bits[w0 + t]);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        int rank = incl - mine;
+        // ---- world coordinates of the first `slots` cells ----
+        double sn, cs;
+        sincos(a.yaw[b], &sn, &cs);
+        const double px = a.pos[2 * (size_t)b], py = a.pos[2 * (size_t)b + 1];
+        for (int t = 0; t < wpl && rank < a.slots; t++) {
+            if (w0 + t >= a.nwords) break;
+            unsigned m = bits[w0 + t];
+            while (m && rank < a.slots) {
+                const int q = ((w0 + t) << 5) + (__ffs(m) - 1);
+                m &= m - 1;
+                const int i = q / a.nc, j = q - i * a.nc;
+                // convert_to_map_coordinates: x = -i*res + origin, y = -j*res + origin
+                const double cx = __dadd_rn(__dmul_rn(-(double)i, a.res), a.origin);
+                const double cy = __dadd_rn(__dmul_rn(-(double)j, a.res), a.origin);
+                sx[rank] = __dadd_rn(__dadd_rn(__dmul_rn(cs, cx), __dmul_rn(-sn, cy)), px);
+                sy[rank] = __dadd_rn(__dadd_rn(__dmul_rn(sn, cx), __dmul_rn(cs, cy)), py);
+                rank++;
+            }
+        }
+        __syncwarp();
+        // ---- padding (first obstacle, or the sentinel 100.0) and coalesced stores ----
+        const double fx = total ? sx[0] : 100.0, fy = total ? sy[0] : 100.0;
+        double *gx = a.ox + (size_t)b * a.slots, *gy = a.oy + (size_t)b * a.slots;
+        for (int s = lane; s < a.slots; s += 32) {
+            gx[s] = (s < total) ? sx[s] : fx;
+            gy[s] = (s < total) ? sy[s] : fy;
+        }
+        if (lane == 0 && a.count) a.count[b] = total;
+        __syncwarp();
+    }
+}

@@ -176,14 +176,46 @@ struct TppLane {
 };
 #define TPP_LANE_STRIDE (((sizeof(TppLane) + 7) / 8) | 1) /* in doubles, odd */
 
+// sin and cos of one angle: three-constant Cody-Waite reduction by pi/2 (exact products through FMA) and the
+// fdlibm kernel polynomials on [-pi/4, pi/4]; < 1.5 ulp for |x| <= 1e5 (headings are a few radians), the library
+// routine beyond.  Half the instructions of sincos(), whose argument reduction for huge arguments the solver never needs.
+__device__ __forceinline__ void tpp_sincos_core(double x, double &sn, double &cs) {
+    const double kf = rint(x * 6.36619772367581382433e-01);
+    double r = fma(-kf, 1.5707963267948966e+00, x);
+    r = fma(-kf, 6.1232339957367574e-17, r);
+    r = fma(-kf, 8.4784276603688985e-32, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double s = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const int q = (int)kf;
+    const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;
+    sn = (q & 2) ? -a : a;
+    cs = ((q + 1) & 2) ? -b : b;
+}
+__device__ __noinline__ void tpp_sincos_far(double x, double *sn, double *cs) { sincos(x, sn, cs); }
+__device__ __forceinline__ void tpp_sincos(double x, double &sn, double &cs) {
+    if (fabs(x) <= 1e5) tpp_sincos_core(x, sn, cs); // (NaN takes the library routine)
+    else tpp_sincos_far(x, &sn, &cs);
+}
 // sin/cos of th and hw: one out-of-line copy shared by all sweeps (instruction-cache footprint)
 struct TppSC { double s0, c0, sh, ch; };
 __device__ __noinline__ TppSC tpp_sincos2(double th, double hw) {
     TppSC r;
-    sincos(th, &r.s0, &r.c0);
-    sincos(hw, &r.sh, &r.ch);
+    tpp_sincos(th, r.s0, r.c0);
+    tpp_sincos(hw, r.sh, r.ch);
     return r;
 }
+__device__ __noinline__ void tpp_sincos1(double th, double *sn, double *cs) { tpp_sincos(th, *sn, *cs); }
 // sin/cos of th, th + hw, th + 2 hw (RK4 stage angles) from two sincos evaluations
 __device__ __forceinline__ void tpp_trig(double th, double hw, double &s0, double &c0, double &sm, double &cm,
                                          double &se, double &ce) {
@@ -213,7 +245,7 @@ __device__ __forceinline__ void tpp_lin(const KParams &P, const double r[3], con
     o.htw = 0; o.hvw = 0; o.hww = 0;
     if (P.integrator == B200MPC_EULER) {
         double sn, cs;
-        sincos(th, &sn, &cs);
+        tpp_sincos1(th, &sn, &cs);
         o.F0 = X[0] + dt * v * cs;
         o.F1 = X[1] + dt * v * sn;
         o.a13 = -dt * v * sn; o.a23 = dt * v * cs;
@@ -266,7 +298,7 @@ __device__ __noinline__ void tpp_dyn(const KParams &P, const double X[3], const 
     const double dt = P.dt, th = X[2], v = U[0], w = U[1];
     if (P.integrator == B200MPC_EULER) {
         double sn, cs;
-        sincos(th, &sn, &cs);
+        tpp_sincos1(th, &sn, &cs);
         F[0] = X[0] + dt * v * cs;
         F[1] = X[1] + dt * v * sn;
     } else {
@@ -631,7 +663,7 @@ __device__ __forceinline__ void tpp_costate(const KParams &P, const double r[3],
     double a13, a23, htt, htv, htw = 0;
     if (P.integrator == B200MPC_EULER) {
         double sn, cs;
-        sincos(th, &sn, &cs);
+        tpp_sincos1(th, &sn, &cs);
         a13 = -dt * v * sn; a23 = dt * v * cs;
         htt = dt * v * (lo[0] * cs + lo[1] * sn);
         htv = dt * (lo[0] * sn - lo[1] * cs);

@@ -102,3 +102,54 @@ def get_obstacles(scan, angles, size, resolution, pos, yaw, slots, overflow="tru
         obs_x[b, :len(wx)] = wx
         obs_y[b, :len(wy)] = wy
     return obs_x, obs_y, count
+
+
+# ---- CUDA path (libb200mpc.so: b200mpc_obstacles_batch) --------------------------------------------------------------
+def beam_table(n_beams, angles):
+    """cos / sin of the beam angles exactly as utils.py:18-20 forms them (a property of the lidar, computed once on
+    the host so that the device's cell indices are bit-exact with the reference)."""
+    amin, amax = float(angles[0]), float(angles[1])
+    beam = np.arange(n_beams) * (amax - amin) / n_beams + amin
+    return np.cos(beam), np.sin(beam)
+
+
+_SOLVERS = {}
+
+
+def _default_solver(device=0):
+    """The obstacle builder does not depend on the MPC variant; any handle on the device will do."""
+    if device not in _SOLVERS:
+        from . import _shim, load_params, make_params  # noqa: PLC0415
+        _SOLVERS[device] = _shim.Solver(make_params("B", load_params()), device=device)
+    return _SOLVERS[device]
+
+
+def get_obstacles_batch_gpu(scan, angles, size, resolution, pos, yaw, slots, overflow="truncate", solver=None):
+    """Batched get_obstacles on the GPU; same arguments and results as `get_obstacles` above (the numpy mirror)."""
+    scan = np.atleast_2d(np.asarray(scan, dtype=np.float64))
+    B, n = scan.shape
+    angles = np.asarray(angles, dtype=np.float64)
+    if angles.ndim != 1:
+        if not np.all(angles == angles[0]):
+            raise ValueError("the GPU path takes one (angle_min, angle_max) pair for the whole batch (one lidar model)")
+        angles = angles[0]
+    bc, bs = beam_table(n, angles)
+    pos = np.ascontiguousarray(np.broadcast_to(np.asarray(pos, dtype=np.float64), (B, 2)))
+    yaw = np.ascontiguousarray(np.broadcast_to(np.asarray(yaw, dtype=np.float64), (B,)))
+    S = solver or _default_solver()
+    ox, oy, cnt = S.obstacles_batch(scan, bc, bs, pos, yaw, size, resolution, slots)
+    if overflow == "raise" and (cnt > slots).any():
+        k = int(cnt[np.argmax(cnt > slots)])
+        raise ValueError(f"could not broadcast input array from shape ({k},) into shape ({slots},)")
+    return ox, oy, cnt.astype(np.int64)
+
+
+def get_obstacles_gpu(scan_data, angles, size, resolution, pos, ori, obstacles_x, obstacles_y, solver=None):
+    """Drop-in for get_obstacles(scan_data, angles, size, resolution, pos, ori, obstacles_x, obstacles_y)
+    (scripts/point_follower_local_planner.py:88-118): one robot, ori = (roll, pitch, yaw), obstacles_x / obstacles_y
+    only give the number of slots.  Raises ValueError when the scan marks more cells than there are slots, as the
+    reference does; returns the 100.0 sentinel arrays when it marks none."""
+    slots = int(np.size(obstacles_x))
+    ox, oy, _ = get_obstacles_batch_gpu(np.asarray(scan_data)[None], angles, size, resolution, np.asarray(pos)[None, :2],
+                                        np.asarray([ori[2]]), slots, overflow="raise", solver=solver)
+    return ox[0].reshape(np.shape(obstacles_x)), oy[0].reshape(np.shape(obstacles_y))

@@ -467,3 +467,53 @@ def test_streamed_host_solve_matches_plain(env, variant):
         for k in ("status", "iters", "ls", "cost", "X", "U"):
             assert np.array_equal(st[k], plain[k]), (k, rnd)
     S.close()
+
+
+# ---- obstacle-list construction on the GPU ----------------------------------------------------
+def test_gpu_obstacles_match_reference_golden(env):
+    """Cell indexing bit-exact, coordinates <= 1e-12, against the outputs of the reference's own numba helpers
+    (tests/golden/obstacles_golden.npz), including NaN / inf beams, the empty scan and the overflow case."""
+    from ros2_mpc_b200 import obstacles as ob
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "obstacles_golden.npz"))
+    S = g["scans"].shape[0]
+    groups = {}
+    for i in range(S):  # one lidar geometry per call
+        groups.setdefault(tuple(g["angles"][i]), []).append(i)
+    for ang, idx in groups.items():
+        idx = np.array(idx)
+        ox, oy, cnt = ob.get_obstacles_batch_gpu(g["scans"][idx], np.array(ang), 2.0, 0.05, g["pos"][idx], g["yaw"][idx], 160)
+        assert np.array_equal(cnt, g["count"][idx])
+        assert np.allclose(ox, g["obs_x"][idx], rtol=0, atol=1e-12)
+        assert np.allclose(oy, g["obs_y"][idx], rtol=0, atol=1e-12)
+    none = np.where(g["count"] == 0)[0]
+    assert len(none) >= 1
+    over = np.where(g["count"] > 160)[0]
+    with pytest.raises(ValueError):
+        ob.get_obstacles_gpu(g["scans"][over[0]], g["angles"][over[0]], 2.0, 0.05, g["pos"][over[0]],
+                             (0.0, 0.0, g["yaw"][over[0]]), np.ones(160), np.ones(160))
+    i = none[0]
+    x, y = ob.get_obstacles_gpu(g["scans"][i], g["angles"][i], 2.0, 0.05, g["pos"][i], (0.0, 0.0, g["yaw"][i]),
+                                np.ones(160), np.ones(160))
+    assert np.all(x == 100.0) and np.all(y == 100.0)
+
+
+def test_gpu_obstacles_match_numpy_mirror_on_map_scans(env, robots):
+    """4096 ray-cast scans of map_carto + random NaN / inf / out-of-range beams: identical cells (the occupied-cell
+    set is recovered from the coordinates), identical counts, coordinates to 1e-12; other grid sizes and slot counts."""
+    from ros2_mpc_b200 import obstacles as ob
+    w = env["synth"].robots_on_map(B=4096, seed=0)
+    scan = w["scan"].copy()
+    rng = np.random.default_rng(5)
+    m = rng.random(scan.shape)
+    scan[m < 0.02] = np.inf
+    scan[(m >= 0.02) & (m < 0.03)] = np.nan
+    scan[(m >= 0.03) & (m < 0.04)] = -np.inf
+    scan[(m >= 0.04) & (m < 0.05)] *= -1.0
+    scan[7] = np.inf
+    scan[8] = 3.5
+    for size, res, slots in ((2.0, 0.05, 160), (2.0, 0.05, 40), (1.5, 0.1, 64), (3.0, 0.025, 1024)):
+        rx, ry, rc = ob.get_obstacles(scan, w["angles"], size, res, w["x0"][:, :2], w["x0"][:, 2], slots)
+        gx, gy, gc = ob.get_obstacles_batch_gpu(scan, w["angles"], size, res, w["x0"][:, :2], w["x0"][:, 2], slots)
+        assert np.array_equal(gc, rc), (size, res, slots)
+        assert np.max(np.abs(gx - rx)) <= 1e-12 and np.max(np.abs(gy - ry)) <= 1e-12, (size, res, slots)
+    assert (rc > slots).any() or slots == 1024
