@@ -205,6 +205,53 @@ def single_solve_latency(variant, params, wl, device, n=300):
             "what": "one cold-start solve per call through the C ABI (host buffers, batch of 1) vs oracle/mpc_oracle.c on one core"}
 
 
+def obstacle_builder_line(solver, torch, dev, params, robots=4096, tile=64, reps=5):
+    """Secondary kernel: batched get_obstacles, scan -> obstacle list, HBM-bound.  Device-resident
+    scans of `robots` map poses tiled `tile` times; CUDA events on the launch stream; next to the numpy mirror on the host."""
+    from ros2_mpc_b200 import obstacles as ob, synth  # noqa: PLC0415
+    w = synth.robots_on_map(B=robots, seed=0, params=params)
+    n = w["scan"].shape[1]
+    slots = 160
+    B = robots * tile
+    bc, bs = ob.beam_table(n, w["angles"])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    scan = t(np.tile(w["scan"], (tile, 1)))
+    pos = t(np.tile(w["x0"][:, :2], (tile, 1)))
+    yaw = t(np.tile(w["x0"][:, 2], tile))
+    dbc, dbs = t(bc), t(bs)
+    ox = torch.empty((B, slots), dtype=torch.float64, device=dev)
+    oy = torch.empty((B, slots), dtype=torch.float64, device=dev)
+    cnt = torch.empty(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def run():
+        solver.obstacles_batch_device(B, n, scan.data_ptr(), dbc.data_ptr(), dbs.data_ptr(), pos.data_ptr(), yaw.data_ptr(),
+                                      params["costmap_size"], params["resolution"], slots, ox.data_ptr(), oy.data_ptr(),
+                                      cnt.data_ptr(), stream=stream.cuda_stream)
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    t0 = time.perf_counter()
+    rx, ry, rc = ob.get_obstacles(w["scan"], w["angles"], params["costmap_size"], params["resolution"], w["x0"][:, :2],
+                                  w["x0"][:, 2], slots)
+    cpu_s = time.perf_counter() - t0
+    same = bool(np.array_equal(cnt[:robots].cpu().numpy(), rc) and np.max(np.abs(ox[:robots].cpu().numpy() - rx)) <= 1e-12)
+    bytes_per_robot = 8 * n + 16 * slots + 4 + 24
+    return {"kernel": "obstacles_kernel", "robots_per_launch": B, "ms_per_launch": ms, "robots_per_s": B / (ms * 1e-3),
+            "bound": "hbm", "algorithmic_bytes_per_robot": bytes_per_robot,
+            "achieved_gbs": bytes_per_robot * B / (ms * 1e-3) / 1e9,
+            "l2": f"{bytes_per_robot * B / 1e6:.0f} MB per launch exceed the 126 MB L2",
+            "cpu_numpy_mirror_robots_per_s": robots / cpu_s, "matches_cpu_mirror": same}
+
+
 def run_reference(args, params):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -426,6 +473,11 @@ def main():
         }
         if latency is not None:
             line["latency"] = latency
+        if world == 1:
+            ob_line = obstacle_builder_line(solver, torch, dev, params)
+            ob_line["peak_gbs"] = hbm_peak
+            ob_line["frac"] = ob_line["achieved_gbs"] / hbm_peak
+            line["obstacle_builder"] = ob_line
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_baseline(args.variant, params, wl)
             line["cpu_baseline"] = cb

@@ -36,6 +36,15 @@ struct ObsBuildArgs {
 
 __device__ __forceinline__ double obs_fix(double v) { return (v != v) ? 0.0 : v; }
 
+// trunc(v / res), the reference's int(x_indices[i] / cell_size) (utils.py:39), without paying for an IEEE division per
+// beam: q = v * (1/res) is within 4.5e-16 |q| of the correctly rounded quotient, so the two can only truncate
+// differently when q lies that close to an integer — only then is the division carried out.  Bit-exact.
+__device__ __forceinline__ double obs_cell(double v, double res, double inv_res) {
+    const double q = v * inv_res;
+    if (fabs(q - rint(q)) <= 1e-15 * fabs(q)) return trunc(__ddiv_rn(v, res));
+    return trunc(q);
+}
+
 __global__ void __launch_bounds__(OBS_WARPS * 32) obstacles_kernel(const ObsBuildArgs a) {
     extern __shared__ __align__(16) unsigned char obs_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -45,43 +54,59 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) obstacles_kernel(const ObsBuil
     double *sy = sx + a.slots;
     const int wpl = (a.nwords + 31) / 32; // words per lane (contiguous, so that lane order = bit order)
     const int nbits = a.nc * a.nc;
+    const double inv_res = 1.0 / a.res, fnc = (double)a.nc;
     for (int b = blockIdx.x * OBS_WARPS + wid; b < a.B; b += gridDim.x * OBS_WARPS) {
         for (int w = lane; w < a.nwords; w += 32) bits[w] = 0u;
+        __syncwarp();
         const double *sc = a.scan + (size_t)b * a.n;
-        // ---- pass 1: largest finite coordinate per axis (the reference replaces +-inf by it) ----
-        double mx = -INFINITY, my = -INFINITY;
+        // ---- cell indices, occupancy bits in rotated np.where order ----
+        // (an infinite coordinate would have to be replaced by the scan's largest finite one, utils.py:30-31: that
+        //  needs a second pass, taken only if one shows up — the rotation-by-0.0 product turns the infinities of
+        //  infinite ranges into NaN, so with the reference's call it never does)
         int anyinf = 0;
         for (int i = lane; i < a.n; i += 32) {
-            const double r = sc[i];
+            const double r = __ldcs(sc + i);
             const double x = __dmul_rn(r, a.bcos[i]), y = __dmul_rn(r, a.bsin[i]);
             // rotate_coordinates(., 0.0): [[1, -0], [0, 1]] @ [x; y]
             const double xr = obs_fix(__dadd_rn(x, __dmul_rn(-0.0, y)));
             const double yr = obs_fix(__dadd_rn(__dmul_rn(0.0, x), y));
-            if (isinf(xr)) anyinf = 1; else mx = fmax(mx, xr);
-            if (isinf(yr)) anyinf = 1; else my = fmax(my, yr);
+            if (isinf(xr) || isinf(yr)) { anyinf = 1; continue; }
+            const double tx = obs_cell(__dadd_rn(xr, a.half), a.res, inv_res);
+            const double ty = obs_cell(__dadd_rn(yr, a.half), a.res, inv_res);
+            if (tx >= 0.0 && tx < fnc && ty >= 0.0 && ty < fnc) {
+                const int q = nbits - 1 - ((int)ty * a.nc + (int)tx);
+                atomicOr(bits + (q >> 5), 1u << (q & 31));
+            }
         }
-        anyinf = __any_sync(FULL, anyinf);
-        if (anyinf) {
+        if (__any_sync(FULL, anyinf)) {
+            double mx = -INFINITY, my = -INFINITY;
+            for (int i = lane; i < a.n; i += 32) {
+                const double r = sc[i];
+                const double x = __dmul_rn(r, a.bcos[i]), y = __dmul_rn(r, a.bsin[i]);
+                const double xr = obs_fix(__dadd_rn(x, __dmul_rn(-0.0, y)));
+                const double yr = obs_fix(__dadd_rn(__dmul_rn(0.0, x), y));
+                if (!isinf(xr)) mx = fmax(mx, xr);
+                if (!isinf(yr)) my = fmax(my, yr);
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
                 my = fmax(my, __shfl_xor_sync(FULL, my, o));
             }
-        }
-        __syncwarp();
-        // ---- pass 2: cell indices, occupancy bits in rotated np.where order ----
-        for (int i = lane; i < a.n; i += 32) {
-            const double r = sc[i];
-            const double x = __dmul_rn(r, a.bcos[i]), y = __dmul_rn(r, a.bsin[i]);
-            double xr = obs_fix(__dadd_rn(x, __dmul_rn(-0.0, y)));
-            double yr = obs_fix(__dadd_rn(__dmul_rn(0.0, x), y));
-            if (isinf(xr)) xr = mx;
-            if (isinf(yr)) yr = my;
-            const double tx = trunc(__ddiv_rn(__dadd_rn(xr, a.half), a.res));
-            const double ty = trunc(__ddiv_rn(__dadd_rn(yr, a.half), a.res));
-            if (tx >= 0.0 && tx < (double)a.nc && ty >= 0.0 && ty < (double)a.nc) {
-                const int q = nbits - 1 - ((int)ty * a.nc + (int)tx);
-                atomicOr(bits + (q >> 5), 1u << (q & 31));
+            for (int i = lane; i < a.n; i += 32) {
+                const double r = sc[i];
+                const double x = __dmul_rn(r, a.bcos[i]), y = __dmul_rn(r, a.bsin[i]);
+                double xr = obs_fix(__dadd_rn(x, __dmul_rn(-0.0, y)));
+                double yr = obs_fix(__dadd_rn(__dmul_rn(0.0, x), y));
+                if (!isinf(xr) && !isinf(yr)) continue; // already marked
+                if (isinf(xr)) xr = mx;
+                if (isinf(yr)) yr = my;
+                const double tx = trunc(__ddiv_rn(__dadd_rn(xr, a.half), a.res));
+                const double ty = trunc(__ddiv_rn(__dadd_rn(yr, a.half), a.res));
+                if (tx >= 0.0 && tx < fnc && ty >= 0.0 && ty < fnc) {
+                    const int q = nbits - 1 - ((int)ty * a.nc + (int)tx);
+                    atomicOr(bits + (q >> 5), 1u << (q & 31));
+                }
             }
         }
         __syncwarp();
@@ -99,31 +124,33 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) obstacles_kernel(const ObsBuil
         const int total = __shfl_sync(FULL, incl, 31);
         int rank = incl - mine;
         // ---- world coordinates of the first `slots` cells ----
-        double sn, cs;
-        sincos(a.yaw[b], &sn, &cs);
-        const double px = a.pos[2 * (size_t)b], py = a.pos[2 * (size_t)b + 1];
-        for (int t = 0; t < wpl && rank < a.slots; t++) {
-            if (w0 + t >= a.nwords) break;
-            unsigned m = bits[w0 + t];
-            while (m && rank < a.slots) {
-                const int q = ((w0 + t) << 5) + (__ffs(m) - 1);
-                m &= m - 1;
-                const int i = q / a.nc, j = q - i * a.nc;
-                // convert_to_map_coordinates: x = -i*res + origin, y = -j*res + origin
-                const double cx = __dadd_rn(__dmul_rn(-(double)i, a.res), a.origin);
-                const double cy = __dadd_rn(__dmul_rn(-(double)j, a.res), a.origin);
-                sx[rank] = __dadd_rn(__dadd_rn(__dmul_rn(cs, cx), __dmul_rn(-sn, cy)), px);
-                sy[rank] = __dadd_rn(__dadd_rn(__dmul_rn(sn, cx), __dmul_rn(cs, cy)), py);
-                rank++;
+        if (mine > 0 && rank < a.slots) {
+            double sn, cs;
+            sincos(a.yaw[b], &sn, &cs);
+            const double px = a.pos[2 * (size_t)b], py = a.pos[2 * (size_t)b + 1];
+            for (int t = 0; t < wpl && rank < a.slots; t++) {
+                if (w0 + t >= a.nwords) break;
+                unsigned m = bits[w0 + t];
+                while (m && rank < a.slots) {
+                    const int q = ((w0 + t) << 5) + (__ffs(m) - 1);
+                    m &= m - 1;
+                    const int i = q / a.nc, j = q - i * a.nc;
+                    // convert_to_map_coordinates: x = -i*res + origin, y = -j*res + origin
+                    const double cx = __dadd_rn(__dmul_rn(-(double)i, a.res), a.origin);
+                    const double cy = __dadd_rn(__dmul_rn(-(double)j, a.res), a.origin);
+                    sx[rank] = __dadd_rn(__dadd_rn(__dmul_rn(cs, cx), __dmul_rn(-sn, cy)), px);
+                    sy[rank] = __dadd_rn(__dadd_rn(__dmul_rn(sn, cx), __dmul_rn(cs, cy)), py);
+                    rank++;
+                }
             }
         }
         __syncwarp();
-        // ---- padding (first obstacle, or the sentinel 100.0) and coalesced stores ----
+        // ---- padding (first obstacle, or the sentinel 100.0) and coalesced streaming stores ----
         const double fx = total ? sx[0] : 100.0, fy = total ? sy[0] : 100.0;
         double *gx = a.ox + (size_t)b * a.slots, *gy = a.oy + (size_t)b * a.slots;
         for (int s = lane; s < a.slots; s += 32) {
-            gx[s] = (s < total) ? sx[s] : fx;
-            gy[s] = (s < total) ? sy[s] : fy;
+            __stcs(gx + s, (s < total) ? sx[s] : fx);
+            __stcs(gy + s, (s < total) ? sy[s] : fy);
         }
         if (lane == 0 && a.count) a.count[b] = total;
         __syncwarp();
