@@ -19,6 +19,10 @@
  *                            with utils.convert_laser_scan_to_occupancy_grid (ros2_mpc/utils/utils.py:5-43),
  *                            convert_to_map_coordinates (:114-124), rotate_coordinates (:145-152): the producer of the
  *                            obstacles_x / obstacles_y arguments of perform_mpc, batched over robots
+ *   b200mpc_goals_batch[_device]    <- get_goal_for_mpc   ros2_mpc/scripts/point_follower_local_planner.py:16-30
+ *                            (the final_state argument of perform_mpc, variants A / B), batched over robots
+ *   b200mpc_reftraj_batch[_device]  <- get_reference_trajectory   ros2_mpc/scripts/path_follower_local_planner.py:27-73
+ *                            (the pf / puf arguments of perform_mpc, variant C), batched over robots
  *   b200mpc_destroy       <- garbage collection of the Mpc / Opti object
  *
  * Conventions: plain pointers and sizes only; no C++ exceptions cross the boundary; functions return 0 on
@@ -174,6 +178,32 @@ int b200mpc_obstacles_batch_device(b200mpc_handle *h, int B, int n_beams, const 
                                    const double *beam_sin, const double *pos, const double *yaw, double size,
                                    double resolution, int slots, double *obs_x, double *obs_y, int32_t *count,
                                    void *stream);
+
+/* Look-ahead goals for B robots (get_goal_for_mpc).  path_xy [K][2] and path_heading [K] shared by the batch, or
+ * [B][K][2] / [B][K] with per_robot_paths != 0; goal [B][5] (x, y, -, -, yaw: the reference reads goal[0], goal[1],
+ * goal[4]); pos [B][2].  goal_out [B][3] = the final goal (yaw mod 2 pi) when it is nearer than `lookahead`, else the
+ * first path point farther than `lookahead` (the nearest one if there is none) with its heading mod 2 pi.
+ * index_out [B] (may be NULL): the chosen path index, -1 for the final goal.  Bit-exact with the reference. */
+int b200mpc_goals_batch(b200mpc_handle *h, int B, int K, const double *path_xy, const double *path_heading,
+                        int per_robot_paths, const double *goal, const double *pos, double lookahead, double *goal_out,
+                        int32_t *index_out);
+int b200mpc_goals_batch_device(b200mpc_handle *h, int B, int K, const double *path_xy, const double *path_heading,
+                               int per_robot_paths, const double *goal, const double *pos, double lookahead,
+                               double *goal_out, int32_t *index_out, void *stream);
+
+/* Tracking references for B robots (get_reference_trajectory; N = the handle's horizon).  path_xy [K][2],
+ * path_heading [K], path_velocity [K], path_omega [n_omega] (n_omega = K-1 as get_headings returns it, or K) shared or
+ * per robot; x0 [B][3]; goal [B][3] (the reference tiles goal[:3] when the robot is within 0.5 m of the path end).
+ * pxf_out [B][3N] and puf_out [B][2N] are the P_X[3:] / P_U parameters (xref / uref of b200mpc_solve_batch);
+ * index_out [B] (may be NULL) the nearest path index.  Every array is padded with its last element, as the reference
+ * does.  Bit-exact with the reference. */
+int b200mpc_reftraj_batch(b200mpc_handle *h, int B, int K, const double *path_xy, const double *path_heading,
+                          const double *path_velocity, const double *path_omega, int n_omega, int per_robot_paths,
+                          const double *x0, const double *goal, double *pxf_out, double *puf_out, int32_t *index_out);
+int b200mpc_reftraj_batch_device(b200mpc_handle *h, int B, int K, const double *path_xy, const double *path_heading,
+                                 const double *path_velocity, const double *path_omega, int n_omega, int per_robot_paths,
+                                 const double *x0, const double *goal, double *pxf_out, double *puf_out,
+                                 int32_t *index_out, void *stream);
 
 /* Forces one of the two solve kernels (default B200MPC_KERNEL_AUTO; the environment variable B200MPC_KERNEL=warp|lane
  * sets the default of new handles).  Both kernels run the same algorithm; results agree to rounding.  The

@@ -82,6 +82,14 @@ def lib():
         L.b200mpc_obstacles_batch_device.argtypes = [vp, C.c_int, C.c_int] + [vp] * 5 + [C.c_double, C.c_double, C.c_int] + \
                                                      [vp] * 3 + [vp]
         L.b200mpc_obstacles_batch_device.restype = C.c_int
+        L.b200mpc_goals_batch.argtypes = [vp, C.c_int, C.c_int, dp, dp, C.c_int, dp, dp, C.c_double, dp, ip]
+        L.b200mpc_goals_batch.restype = C.c_int
+        L.b200mpc_goals_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_double, vp, vp, vp]
+        L.b200mpc_goals_batch_device.restype = C.c_int
+        L.b200mpc_reftraj_batch.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, dp, C.c_int, C.c_int, dp, dp, dp, dp, ip]
+        L.b200mpc_reftraj_batch.restype = C.c_int
+        L.b200mpc_reftraj_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
+        L.b200mpc_reftraj_batch_device.restype = C.c_int
         L.b200mpc_sizeof_params.restype = C.c_int
         if L.b200mpc_sizeof_params() != C.sizeof(Params):
             raise RuntimeError("b200mpc_params layout mismatch between _shim.Params and libb200mpc.so")
@@ -221,6 +229,37 @@ class Solver:
                                                     v(yaw), float(size), float(resolution), int(slots), v(obs_x), v(obs_y),
                                                     v(count), v(stream))
         self._check(rc)
+
+    def goals_batch(self, path_xy, path_heading, goal, pos, lookahead):
+        """Look-ahead goals (get_goal_for_mpc) for B robots.  path_xy (K,2)|(B,K,2); path_heading (K,)|(B,K);
+        goal (B,5); pos (B,2).  Returns goal_pose (B,3) and the chosen path index (B,) (-1 = final goal)."""
+        path_xy, goal, pos = _f64(path_xy), _f64(goal), _f64(pos)
+        B = goal.shape[0]
+        per = 1 if path_xy.ndim == 3 else 0
+        K = path_xy.shape[-2]
+        path_heading = _f64(path_heading, (B, K) if per else (K,))
+        pos = np.ascontiguousarray(pos[:, :2])
+        out, idx = np.empty((B, 3)), np.empty(B, np.int32)
+        self._check(self._L.b200mpc_goals_batch(self._h, B, K, _dp(path_xy), _dp(path_heading), per, _dp(goal), _dp(pos),
+                                                float(lookahead), _dp(out), _ip(idx)))
+        return out, idx
+
+    def reftraj_batch(self, path_xy, path_heading, path_velocity, path_omega, x0, goal):
+        """Tracking references (get_reference_trajectory) for B robots.  Returns pxf (B,3N), puf (B,2N), nearest (B,)."""
+        path_xy, x0 = _f64(path_xy), _f64(x0)
+        B = x0.shape[0]
+        per = 1 if path_xy.ndim == 3 else 0
+        K = path_xy.shape[-2]
+        path_omega = _f64(path_omega)
+        n_om = path_omega.shape[-1]
+        path_heading = _f64(path_heading, (B, K) if per else (K,))
+        path_velocity = _f64(path_velocity, (B, K) if per else (K,))
+        goal = np.ascontiguousarray(_f64(goal)[:, :3])
+        N = self.params.N
+        pxf, puf, idx = np.empty((B, 3 * N)), np.empty((B, 2 * N)), np.empty(B, np.int32)
+        self._check(self._L.b200mpc_reftraj_batch(self._h, B, K, _dp(path_xy), _dp(path_heading), _dp(path_velocity),
+                                                  _dp(path_omega), n_om, per, _dp(x0), _dp(goal), _dp(pxf), _dp(puf), _ip(idx)))
+        return pxf, puf, idx
 
     def solve_batch_device(self, B, x0, xref, uref, obs_x, obs_y, obs_stride, u_init, X, U, cost, status, iters, ls,
                            stream=0):

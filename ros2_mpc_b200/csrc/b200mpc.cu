@@ -1159,6 +1159,7 @@ __global__ void __launch_bounds__(128) mpc_eval_kernel(const KParams P, const Ev
 
 #include "tpp_kernel.cuh"
 #include "obstacles_kernel.cuh"
+#include "refgen_kernel.cuh"
 
 // =============================================================================================================
 // Host side: C ABI
@@ -1871,5 +1872,132 @@ extern "C" int b200mpc_obstacles_batch(b200mpc_handle *h, int B, int n_beams, co
     CU_TRY(h, cudaMemcpyAsync(obs_y, d_oy, nb * slots * 8, cudaMemcpyDeviceToHost, s));
     if (count) CU_TRY(h, cudaMemcpyAsync(count, d_cnt, nb * 4, cudaMemcpyDeviceToHost, s));
     CU_TRY(h, cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ---- reference producers (get_goal_for_mpc / get_reference_trajectory) ---------------------------------------------
+static int refgen_grid(const b200mpc_handle *h, int B) {
+    int grid = (B + REFGEN_WARPS - 1) / REFGEN_WARPS;
+    const int cap = h->sm_count * 8;
+    return grid > cap ? cap : (grid < 1 ? 1 : grid);
+}
+
+extern "C" int b200mpc_goals_batch_device(b200mpc_handle *h, int B, int K, const double *path_xy, const double *path_heading,
+                                          int per_robot_paths, const double *goal, const double *pos, double lookahead,
+                                          double *goal_out, int32_t *index_out, void *stream) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || K < 1) return set_err(h, B200MPC_E_ARG, "B < 0 or K < 1");
+    if (B == 0) return 0;
+    if (!path_xy || !path_heading || !goal || !pos || !goal_out) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    RefGenArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.K = K; a.N = h->prm.N; a.Ko = K;
+    a.path_stride = per_robot_paths ? K : 0;
+    a.path_xy = path_xy; a.heading = path_heading;
+    a.goal = goal; a.goal_stride = 5; a.pos = pos; a.pos_stride = 2; a.lookahead = lookahead;
+    a.out_goal = goal_out; a.nearest = index_out;
+    goals_kernel<<<refgen_grid(h, B), REFGEN_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+extern "C" int b200mpc_reftraj_batch_device(b200mpc_handle *h, int B, int K, const double *path_xy,
+                                            const double *path_heading, const double *path_velocity,
+                                            const double *path_omega, int n_omega, int per_robot_paths, const double *x0,
+                                            const double *goal, double *pxf_out, double *puf_out, int32_t *index_out,
+                                            void *stream) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || K < 1 || n_omega < 1 || n_omega > K) return set_err(h, B200MPC_E_ARG, "B < 0, K < 1 or n_omega outside [1,K]");
+    if (B == 0) return 0;
+    if (!path_xy || !path_heading || !path_velocity || !path_omega || !x0 || !goal || !pxf_out || !puf_out)
+        return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    RefGenArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.K = K; a.N = h->prm.N; a.Ko = n_omega;
+    a.path_stride = per_robot_paths ? K : 0;
+    a.path_xy = path_xy; a.heading = path_heading; a.velocity = path_velocity; a.omega = path_omega;
+    a.goal = goal; a.goal_stride = 3; a.pos = x0; a.pos_stride = 3;
+    a.pxf = pxf_out; a.puf = puf_out; a.nearest = index_out;
+    reftraj_kernel<<<refgen_grid(h, B), REFGEN_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+// host-buffer variants: stage through the handle's device buffer, blocking
+struct HostStage {
+    b200mpc_handle *h;
+    char *p;
+    size_t used;
+};
+static size_t stage_size(size_t n) { return al256(n); }
+template <class T>
+static T *stage_in(HostStage &st, const T *src, size_t count, cudaError_t &e) {
+    T *d = (T *)(st.p + st.used);
+    st.used += stage_size(count * sizeof(T));
+    if (src && e == cudaSuccess) e = cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, st.h->stream);
+    return d;
+}
+
+extern "C" int b200mpc_goals_batch(b200mpc_handle *h, int B, int K, const double *path_xy, const double *path_heading,
+                                   int per_robot_paths, const double *goal, const double *pos, double lookahead,
+                                   double *goal_out, int32_t *index_out) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || K < 1) return set_err(h, B200MPC_E_ARG, "B < 0 or K < 1");
+    if (B == 0) return 0;
+    if (!path_xy || !path_heading || !goal || !pos || !goal_out) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t nb = (size_t)B, np = per_robot_paths ? nb * K : (size_t)K;
+    int rc = ensure_buf(h, stage_size(np * 16) + stage_size(np * 8) + stage_size(nb * 40) + stage_size(nb * 16) +
+                               stage_size(nb * 24) + stage_size(nb * 4));
+    if (rc) return rc;
+    HostStage st{h, h->d_buf, 0};
+    cudaError_t e = cudaSuccess;
+    double *d_xy = stage_in(st, path_xy, np * 2, e), *d_h = stage_in(st, path_heading, np, e);
+    double *d_g = stage_in(st, goal, nb * 5, e), *d_p = stage_in(st, pos, nb * 2, e);
+    double *d_o = stage_in<double>(st, nullptr, nb * 3, e);
+    int32_t *d_i = stage_in<int32_t>(st, nullptr, nb, e);
+    CU_TRY(h, e);
+    rc = b200mpc_goals_batch_device(h, B, K, d_xy, d_h, per_robot_paths, d_g, d_p, lookahead, d_o, d_i, h->stream);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(goal_out, d_o, nb * 24, cudaMemcpyDeviceToHost, h->stream));
+    if (index_out) CU_TRY(h, cudaMemcpyAsync(index_out, d_i, nb * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int b200mpc_reftraj_batch(b200mpc_handle *h, int B, int K, const double *path_xy, const double *path_heading,
+                                     const double *path_velocity, const double *path_omega, int n_omega,
+                                     int per_robot_paths, const double *x0, const double *goal, double *pxf_out,
+                                     double *puf_out, int32_t *index_out) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || K < 1 || n_omega < 1 || n_omega > K) return set_err(h, B200MPC_E_ARG, "B < 0, K < 1 or n_omega outside [1,K]");
+    if (B == 0) return 0;
+    if (!path_xy || !path_heading || !path_velocity || !path_omega || !x0 || !goal || !pxf_out || !puf_out)
+        return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int N = h->prm.N;
+    const size_t nb = (size_t)B, np = per_robot_paths ? nb * K : (size_t)K, nw = per_robot_paths ? nb * n_omega : (size_t)n_omega;
+    int rc = ensure_buf(h, stage_size(np * 16) + 2 * stage_size(np * 8) + stage_size(nw * 8) + 2 * stage_size(nb * 24) +
+                               stage_size(nb * 3 * N * 8) + stage_size(nb * 2 * N * 8) + stage_size(nb * 4));
+    if (rc) return rc;
+    HostStage st{h, h->d_buf, 0};
+    cudaError_t e = cudaSuccess;
+    double *d_xy = stage_in(st, path_xy, np * 2, e), *d_h = stage_in(st, path_heading, np, e);
+    double *d_v = stage_in(st, path_velocity, np, e), *d_w = stage_in(st, path_omega, nw, e);
+    double *d_x0 = stage_in(st, x0, nb * 3, e), *d_g = stage_in(st, goal, nb * 3, e);
+    double *d_pxf = stage_in<double>(st, nullptr, nb * 3 * N, e), *d_puf = stage_in<double>(st, nullptr, nb * 2 * N, e);
+    int32_t *d_i = stage_in<int32_t>(st, nullptr, nb, e);
+    CU_TRY(h, e);
+    rc = b200mpc_reftraj_batch_device(h, B, K, d_xy, d_h, d_v, d_w, n_omega, per_robot_paths, d_x0, d_g, d_pxf, d_puf, d_i,
+                                      h->stream);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(pxf_out, d_pxf, nb * 3 * N * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(puf_out, d_puf, nb * 2 * N * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (index_out) CU_TRY(h, cudaMemcpyAsync(index_out, d_i, nb * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -517,3 +517,44 @@ def test_gpu_obstacles_match_numpy_mirror_on_map_scans(env, robots):
         assert np.array_equal(gc, rc), (size, res, slots)
         assert np.max(np.abs(gx - rx)) <= 1e-12 and np.max(np.abs(gy - ry)) <= 1e-12, (size, res, slots)
     assert (rc > slots).any() or slots == 1024
+
+
+# ---- reference producers on the GPU -----------------------------------------------------------
+def test_gpu_reference_producers_match_reference_golden(env):
+    """get_goal_for_mpc and get_reference_trajectory: bit-exact against outputs of the reference's own functions
+    (tests/golden/refgen_golden.npz: straight, curved, shorter-than-horizon and long paths; robots on path points, near
+    the path end, on the odometry raster, far away), shared and per-robot paths, and through the one-robot drop-ins."""
+    from ros2_mpc_b200 import references as rf, MpcTracking
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "refgen_golden.npz"))
+    mpc = MpcTracking()
+    for pi in range(int(g["n_paths"])):
+        pxy, head, vel, om = (g[f"path{pi}_{k}"] for k in ("xy", "heading", "velocity", "omega"))
+        pos, goal = g[f"path{pi}_pos"], g[f"path{pi}_goal"]
+        h2, v2, o2 = rf.get_headings(pxy, 0.2)
+        assert np.array_equal(h2, head) and np.array_equal(v2, vel) and np.array_equal(o2, om)
+        gp, idx = rf.get_goals_batch(pxy, head, goal, pos, 0.5)
+        assert np.array_equal(gp, g[f"path{pi}_goal_pose"]), pi
+        assert (idx >= -1).all() and (idx < len(pxy)).all()
+        pxf, puf, near = rf.get_reference_trajectories_batch(pos, goal, pxy, head, vel, om, mpc._solver)
+        assert np.array_equal(pxf, g[f"path{pi}_pxf"]), pi
+        assert np.array_equal(puf, g[f"path{pi}_puf"]), pi
+        # per-robot copies of the path give the same answers
+        R = pos.shape[0]
+        gp2, _ = rf.get_goals_batch(np.tile(pxy, (R, 1, 1)), np.tile(head, (R, 1)), goal, pos, 0.5)
+        assert np.array_equal(gp2, gp)
+        pxf2, puf2, _ = mpc._solver.reftraj_batch(np.tile(pxy, (R, 1, 1)), np.tile(head, (R, 1)), np.tile(vel, (R, 1)),
+                                                  np.tile(om, (R, 1)), pos, goal)
+        assert np.array_equal(pxf2, pxf) and np.array_equal(puf2, puf)
+        # one-robot drop-ins with the reference's signatures and shapes
+        one = rf.get_goal_for_mpc(pxy, head.reshape(-1, 1), goal[3], pos[3], 0.5)
+        assert one.shape == (3,) and np.array_equal(one, gp[3])
+        a, b = rf.get_reference_trajectory(pos[5], goal[5], pxy, head, vel, om, mpc)
+        assert a.shape == (90, 1) and b.shape == (60, 1)
+        assert np.array_equal(a.ravel(), pxf[5]) and np.array_equal(b.ravel(), puf[5])
+    # the produced references feed the tracking solve directly (smooth path 0, a robot standing on the path)
+    p0 = np.array([g["path0_xy"][10, 0], g["path0_xy"][10, 1], g["path0_heading"][10]])
+    a, b = rf.get_reference_trajectory(p0, g["path0_goal"][0], g["path0_xy"], g["path0_heading"], g["path0_velocity"],
+                                       g["path0_omega"], mpc)
+    x_opt, u = mpc.perform_mpc(np.zeros((2, mpc.N)), p0, a, b)
+    assert x_opt.shape == (3, mpc.N + 1) and np.all(np.isfinite(u))
+    mpc.close()
