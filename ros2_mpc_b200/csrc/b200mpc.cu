@@ -480,6 +480,237 @@ __device__ __forceinline__ bool kkt_solve(const KParams &P, Stg (&s)[J], const d
     return true;
 }
 
+// ---- K4, lane-parallel form (default) ------------------------------------------------------------------------------
+// kkt_solve above lets the lane that owns stage k do the whole 3x3 / 3x2 block algebra of the stage while the other
+// 31 lanes execute the same instructions on garbage: ~380 warp instructions per stage on the serial critical path
+// (65 % of all instructions of a solve, profiles/r1_warp_b1_*).  Here the stage data are first written to shared
+// memory by their owners (stage-parallel), and the serial recursion then spreads the block algebra of ONE stage over
+// the lanes of the warp, one matrix entry per lane, in the generic form
+//     z = (x, u),  G = [A B] (3x5),  M = H + G' P G,  m = h + G'(P d + p),
+//     P' = Mxx - Mxu Muu^-1 Mux,  p' = mx - Mxu Muu^-1 mu,  K = -Muu^-1 Mux,  kf = -Muu^-1 mu:
+//   step A  lanes 0-14: T = P G (entry (i,c));              lanes 15-17: w = P d + p
+//   step B  lanes 0-14: M (15 symmetric pairs (a,c));        lanes 15-19: m (entry a)
+//   step C  all lanes:  2x2 inverse of Muu (inertia test: Muu positive definite)
+//   step E  lanes 0-5: P' pairs; 6-8: p'; 9-14: K; 15-16: kf   -> shared memory (forward sweep, multiplier step)
+// Values move between the steps with warp shuffles whose source lanes come from a per-lane role table; the structural
+// entries of G (0, 1, dt) are read from three constant slots of the stage record, so every lane runs the same dense
+// formulas.  ~90 warp instructions and ~300 cycles per stage.  The forward sweep needs no communication at all:
+// every lane rolls the whole step out redundantly from the gains in shared memory and keeps the entries of its own
+// stages.  The terminal stage is the same step with P = 0 coming in and Muu = I.
+#define KKT_REC 50          /* doubles per stage: 32 record + 18 results */
+#define KR_ZERO 0
+#define KR_ONE 1
+#define KR_DT 2
+#define KR_G 3              /* a13 a23 b11 b12 b21 b22 */
+#define KR_H 9              /* 15 symmetric pairs */
+#define KR_h 24             /* 5 */
+#define KR_D 29             /* 3: d = -rc */
+#define KR_OUT 32           /* K[2][3] kf[2] P'[6] p'[3] */
+
+struct KktRoles {
+    unsigned a_off;  // record offsets of the three step-A operands (G[0..2][c] or d), one byte each
+    unsigned a_src;  // source lanes (previous stage's step E) of P[i][0..2] and p[i]
+    unsigned b_src;  // source lanes of T[0..2][c] (or w), byte 3: record offset of H[a][c] / h[a]
+    unsigned b_off;  // record offsets of G[0..2][a], byte 3: result offset (0xff = none)
+    unsigned e_src;  // source lanes of Mxu[a][0], Mxu[a][1], Mxu[b][0], Mxu[b][1]
+    unsigned e_misc; // byte 0: source lane of m[a]; byte 1: role (0 P' diag, 1 P' off-diag, 2 p', 3 K row 0, 4 K row 1,
+                     //          5 kf0, 6 kf1, 7 none); byte 2: 1 if the lane adds p[i] in step A
+};
+
+__device__ __forceinline__ unsigned kkt_g_off(int j, int c) {
+    // record offset of G[j][c], G = [A B], A = I + a e1 e3' + b e2 e3', B = [[b11,b12],[b21,b22],[0,dt]]
+    if (c < 2) return (j == c) ? KR_ONE : KR_ZERO;
+    if (c == 2) return (j == 0) ? KR_G + 0 : (j == 1) ? KR_G + 1 : KR_ONE;
+    if (c == 3) return (j == 0) ? KR_G + 2 : (j == 1) ? KR_G + 4 : KR_ZERO;
+    return (j == 0) ? KR_G + 3 : (j == 1) ? KR_G + 5 : KR_DT;
+}
+__device__ __forceinline__ int kkt_sym3(int i, int j) { // lane holding P'[i][j]
+    if (i > j) { const int t = i; i = j; j = t; }
+    return (i == 0) ? j : (i == 1) ? 2 + j : 5;
+}
+__device__ __forceinline__ void kkt_pair(int e, int &a, int &c) { // the 15 symmetric pairs of M
+    const int pa[15] = {0, 0, 0, 1, 1, 2, 0, 0, 1, 1, 2, 2, 3, 3, 4};
+    const int pc[15] = {0, 1, 2, 1, 2, 2, 3, 4, 3, 4, 3, 4, 3, 4, 4};
+    a = pa[e]; c = pc[e];
+}
+
+__device__ __forceinline__ KktRoles kkt_roles(int lane) {
+    KktRoles r;
+    // step A
+    int i = 0;
+    unsigned addp = 0;
+    if (lane < 15) {
+        i = lane / 5;
+        const int c = lane % 5;
+        r.a_off = kkt_g_off(0, c) | (kkt_g_off(1, c) << 8) | (kkt_g_off(2, c) << 16);
+    } else {
+        i = (lane < 18) ? lane - 15 : 0;
+        addp = (lane < 18) ? 1u : 0u;
+        r.a_off = (KR_D + 0) | ((KR_D + 1) << 8) | ((KR_D + 2) << 16);
+    }
+    r.a_src = (unsigned)kkt_sym3(i, 0) | ((unsigned)kkt_sym3(i, 1) << 8) | ((unsigned)kkt_sym3(i, 2) << 16) | ((unsigned)(6 + i) << 24);
+    // step B
+    unsigned out = 0xff;
+    if (lane < 15) {
+        int a, c;
+        kkt_pair(lane, a, c);
+        r.b_src = (unsigned)(0 + c) | ((unsigned)(5 + c) << 8) | ((unsigned)(10 + c) << 16) | ((unsigned)(KR_H + lane) << 24);
+        r.b_off = kkt_g_off(0, a) | (kkt_g_off(1, a) << 8) | (kkt_g_off(2, a) << 16);
+    } else {
+        const int a = (lane < 20) ? lane - 15 : 0;
+        r.b_src = 15u | (16u << 8) | (17u << 16) | ((unsigned)(KR_h + a) << 24);
+        r.b_off = kkt_g_off(0, a) | (kkt_g_off(1, a) << 8) | (kkt_g_off(2, a) << 16);
+    }
+    // step E
+    int ea = 0, eb = 0, role = 7;
+    if (lane < 6) { kkt_pair(lane, ea, eb); role = (ea == eb) ? 0 : 1; out = 8 + lane; }
+    else if (lane < 9) { ea = eb = lane - 6; role = 2; out = 14 + (lane - 6); }
+    else if (lane < 15) { ea = eb = (lane - 9) % 3; role = 3 + (lane - 9) / 3; out = lane - 9; }
+    else if (lane < 17) { role = 5 + (lane - 15); out = 6 + (lane - 15); }
+    r.e_src = (unsigned)(6 + 2 * ea) | ((unsigned)(7 + 2 * ea) << 8) | ((unsigned)(6 + 2 * eb) << 16) | ((unsigned)(7 + 2 * eb) << 24);
+    r.e_misc = (unsigned)(15 + ea) | ((unsigned)role << 8) | (addp << 16);
+    r.b_off |= out << 24;
+    return r;
+}
+
+template <int J>
+__device__ __forceinline__ bool kkt_solve_lp(const KParams &P, Stg (&s)[J], const double (&rc)[J][3],
+                                             const double (&rd)[J][2], bool useW, double dw, Step (&o)[J], int lane,
+                                             double *rec, const KktRoles &R) {
+    const int N = P.N;
+    const double dt = P.dt;
+    // ---- stage records (stage-parallel) ----
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int k = lane * J + j;
+        if (k > N) continue;
+        const Stg &t = s[j];
+        double *q = rec + (size_t)k * KKT_REC;
+        const bool dyn = k < N;
+        q[KR_ZERO] = 0.0; q[KR_ONE] = 1.0; q[KR_DT] = dt;
+        q[KR_G + 0] = dyn ? t.a13 : 0.0; q[KR_G + 1] = dyn ? t.a23 : 0.0;
+        q[KR_G + 2] = dyn ? t.b11 : 0.0; q[KR_G + 3] = dyn ? t.b12 : 0.0;
+        q[KR_G + 4] = dyn ? t.b21 : 0.0; q[KR_G + 5] = dyn ? t.b22 : 0.0;
+                q[KR_H + 0] = (useW ? t.hxx : 0.0) + dw; q[KR_H + 1] = (useW ? t.hxy : 0.0); q[KR_H + 2] = 0.0;
+        q[KR_H + 3] = (useW ? t.hyy : 0.0) + dw; q[KR_H + 4] = 0.0; q[KR_H + 5] = (useW ? t.htt : 0.0) + dw;
+        q[KR_H + 6] = 0.0; q[KR_H + 7] = 0.0; q[KR_H + 8] = 0.0; q[KR_H + 9] = 0.0;
+        q[KR_H + 10] = dyn ? (useW ? t.htv : 0.0) : 0.0; q[KR_H + 11] = dyn ? (useW ? t.htw : 0.0) : 0.0;
+        q[KR_H + 12] = dyn ? ((useW ? t.hvv : 0.0) + dw + t.Dsig[0]) : 1.0;
+        q[KR_H + 13] = dyn ? (useW ? t.hvw : 0.0) : 0.0;
+        q[KR_H + 14] = dyn ? ((useW ? t.hww : 0.0) + dw + t.Dsig[1]) : 1.0;
+        const bool hasx = k >= 1;
+        q[KR_h + 0] = hasx ? t.rx[0] : 0.0; q[KR_h + 1] = hasx ? t.rx[1] : 0.0; q[KR_h + 2] = hasx ? t.rx[2] : 0.0;
+        q[KR_h + 3] = dyn ? (t.ru[0] + t.Dsig[0] * rd[j][0] + t.rs[0]) : 0.0;
+        q[KR_h + 4] = dyn ? (t.ru[1] + t.Dsig[1] * rd[j][1] + t.rs[1]) : 0.0;
+        q[KR_D + 0] = dyn ? -rc[j][0] : 0.0; q[KR_D + 1] = dyn ? -rc[j][1] : 0.0; q[KR_D + 2] = dyn ? -rc[j][2] : 0.0;
+    }
+    __syncwarp();
+    // ---- backward recursion: one stage per step, one matrix entry per lane ----
+    const int a0 = R.a_off & 0xff, a1 = (R.a_off >> 8) & 0xff, a2 = (R.a_off >> 16) & 0xff;
+    const int sp0 = R.a_src & 0xff, sp1 = (R.a_src >> 8) & 0xff, sp2 = (R.a_src >> 16) & 0xff, spv = R.a_src >> 24;
+    const int bs0 = R.b_src & 0xff, bs1 = (R.b_src >> 8) & 0xff, bs2 = (R.b_src >> 16) & 0xff, bh = R.b_src >> 24;
+    const int b0 = R.b_off & 0xff, b1 = (R.b_off >> 8) & 0xff, b2 = (R.b_off >> 16) & 0xff, outo = R.b_off >> 24;
+    const int eu0 = R.e_src & 0xff, eu1 = (R.e_src >> 8) & 0xff, eu2 = (R.e_src >> 16) & 0xff, eu3 = R.e_src >> 24;
+    const int em = R.e_misc & 0xff, role = (R.e_misc >> 8) & 0xff;
+    const bool addp = (R.e_misc >> 16) & 1;
+    // role flags for the branch-free step E (a divergent if/else chain here would serialise seven paths)
+    const bool isP = role <= 1, isp = role == 2, iskf = role >= 5, row0 = (role == 3 || role == 5);
+    double res = 0.0; // this lane's step-E result of the previous stage (P = 0, p = 0 enter the terminal stage)
+    // operands that do not depend on the recursion are fetched one stage ahead
+    const double *q = rec + (size_t)N * KKT_REC;
+    double ga0 = q[a0], ga1 = q[a1], ga2 = q[a2], gb0 = q[b0], gb1 = q[b1], gb2 = q[b2], hb = q[bh];
+#pragma unroll 1
+    for (int k = N; k >= 0; --k) {
+        const double ca0 = ga0, ca1 = ga1, ca2 = ga2, cb0 = gb0, cb1 = gb1, cb2 = gb2, ch = hb;
+        if (k > 0) {
+            const double *qn = rec + (size_t)(k - 1) * KKT_REC;
+            ga0 = qn[a0]; ga1 = qn[a1]; ga2 = qn[a2]; gb0 = qn[b0]; gb1 = qn[b1]; gb2 = qn[b2]; hb = qn[bh];
+        }
+        // step A
+        const double p0 = __shfl_sync(FULL, res, sp0), p1 = __shfl_sync(FULL, res, sp1), p2 = __shfl_sync(FULL, res, sp2);
+        const double pv = __shfl_sync(FULL, res, spv);
+        const double tA = (p0 * ca0 + p1 * ca1) + (p2 * ca2 + (addp ? pv : 0.0)); // (tree form: shorter dependent chain)
+        // step B
+        const double t0 = __shfl_sync(FULL, tA, bs0), t1 = __shfl_sync(FULL, tA, bs1), t2 = __shfl_sync(FULL, tA, bs2);
+        const double mB = (ch + cb0 * t0) + (cb1 * t1 + cb2 * t2);
+        // step C: Muu and mu to every lane
+        const double r00 = __shfl_sync(FULL, mB, 12), r01 = __shfl_sync(FULL, mB, 13), r11 = __shfl_sync(FULL, mB, 14);
+        const double m3 = __shfl_sync(FULL, mB, 18), m4 = __shfl_sync(FULL, mB, 19);
+        const double ua0 = __shfl_sync(FULL, mB, eu0), ua1 = __shfl_sync(FULL, mB, eu1);
+        const double ub0 = __shfl_sync(FULL, mB, eu2), ub1 = __shfl_sync(FULL, mB, eu3);
+        const double ma = __shfl_sync(FULL, mB, em);
+        const double det = r00 * r11 - r01 * r01;
+        if (!(r00 > 0.0) || !(det > 0.0)) return false; // warp-uniform: every lane holds the same Muu
+        const double idet = fast_rcp(det);
+        // step E, one formula for every role:  r = base + idet * ((x.y) + (z.w)) / 2  with the adjugate -adj(Muu) in
+        // place of -Muu^-1, so that the products run while the reciprocal of det is still in flight:
+        //   P'[a][b] = M[a][b] + (Mxu[a].K[.][b] + Mxu[b].K[.][a]) / 2      p'[a] = m[a] + Mxu[a].kf
+        //   K[c][a]  = -Muu^-1[c].Mxu[a]                                     kf[c] = -Muu^-1[c].mu
+        const double n00 = -r11, n01 = r01, n11 = -r00; // -adj(Muu)
+        const double K0a = n00 * ua0 + n01 * ua1, K1a = n01 * ua0 + n11 * ua1;
+        const double K0b = n00 * ub0 + n01 * ub1, K1b = n01 * ub0 + n11 * ub1;
+        const double kf0 = n00 * m3 + n01 * m4, kf1 = n01 * m3 + n11 * m4;
+        const double base = isP ? mB : (isp ? ma : 0.0);
+        const double x0 = iskf ? m3 : ua0, x1 = iskf ? m4 : ua1;
+        const double y0 = isP ? K0b : (isp ? kf0 : (row0 ? n00 : n01));
+        const double y1 = isP ? K1b : (isp ? kf1 : (row0 ? n01 : n11));
+        const double z0 = isP ? ub0 : x0, z1 = isP ? ub1 : x1;
+        const double w0 = isP ? K0a : y0, w1 = isP ? K1a : y1;
+        const double r = base + (0.5 * idet) * ((x0 * y0 + x1 * y1) + (z0 * w0 + z1 * w1));
+        res = r;
+        if (outo != 0xff) rec[(size_t)k * KKT_REC + KR_OUT + outo] = r;
+    }
+    __syncwarp();
+    // ---- forward roll-out: every lane computes the whole step, keeps the entries of its own stages ----
+    {
+        double y0 = 0, y1 = 0, y2 = 0;
+        for (int k = 0; k <= N; ++k) {
+            const double *q = rec + (size_t)k * KKT_REC;
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+                if (k == lane * J + j) { o[j].dX[0] = y0; o[j].dX[1] = y1; o[j].dX[2] = y2; }
+            if (k < N) {
+                const double *g = q + KR_OUT;
+                const double du0 = g[6] + g[0] * y0 + g[1] * y1 + g[2] * y2;
+                const double du1 = g[7] + g[3] * y0 + g[4] * y1 + g[5] * y2;
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    if (k == lane * J + j) { o[j].dU[0] = du0; o[j].dU[1] = du1; }
+                const double n0 = y0 + q[KR_G + 0] * y2 + q[KR_G + 2] * du0 + q[KR_G + 3] * du1 + q[KR_D + 0];
+                const double n1 = y1 + q[KR_G + 1] * y2 + q[KR_G + 4] * du0 + q[KR_G + 5] * du1 + q[KR_D + 1];
+                const double n2 = y2 + dt * du1 + q[KR_D + 2];
+                y0 = n0; y1 = n1; y2 = n2;
+            }
+        }
+    }
+    // ---- multiplier and slack steps (stage-parallel) ----
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int k = lane * J + j;
+        Stg &t = s[j];
+        const bool act = (k <= N), dyn = (k < N);
+        const double *g = rec + (size_t)(act ? k : 0) * KKT_REC + KR_OUT;
+        const double a0_ = o[j].dX[0], a1_ = o[j].dX[1], a2_ = o[j].dX[2];
+        // P' pairs at g[8..13] = (0,0) (0,1) (0,2) (1,1) (1,2) (2,2), p' at g[14..16]
+        const double l0 = -(g[14] + g[8] * a0_ + g[9] * a1_ + g[10] * a2_);
+        const double l1 = -(g[15] + g[9] * a0_ + g[11] * a1_ + g[12] * a2_);
+        const double l2 = -(g[16] + g[10] * a0_ + g[12] * a1_ + g[13] * a2_);
+        const bool hasl = act && (k >= 1);
+        o[j].dlam[0] = hasl ? l0 : 0.0; o[j].dlam[1] = hasl ? l1 : 0.0; o[j].dlam[2] = hasl ? l2 : 0.0;
+        if (!act) { o[j].dX[0] = o[j].dX[1] = o[j].dX[2] = 0; }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const double ds = dyn ? (o[j].dU[i] + rd[j][i]) : 0.0;
+            o[j].dS[i] = ds;
+            o[j].dyd[i] = dyn ? (t.Dsig[i] * ds + t.rs[i]) : 0.0;
+            if (!dyn) o[j].dU[i] = 0;
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
 // fraction-to-the-boundary step for the slacks
 template <int J>
 __device__ __forceinline__ double frac_to_bound(const KParams &P, const Stg (&s)[J], const Step (&o)[J], double tau,
@@ -577,8 +808,15 @@ __device__ __forceinline__ void filter_add(double phi, double theta, double &fph
 }
 
 // ---- the per-problem solve ----------------------------------------------------------------------------------
+#ifndef B200MPC_KKT_SERIAL
+#define KKT_SOLVE(P, s, rc, rd, useW, dw, o, lane) kkt_solve_lp<J>(P, s, rc, rd, useW, dw, o, lane, rec, roles)
+#else
+#define KKT_SOLVE(P, s, rc, rd, useW, dw, o, lane) kkt_solve<J>(P, s, rc, rd, useW, dw, o, lane)
+#endif
+
 template <int J>
-__device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane, double *sox, double *soy) {
+__device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane, double *sox, double *soy, double *rec,
+                          const KktRoles &roles) {
     const int N = P.N;
     Stg s[J];
     Step st[J], soc[J];
@@ -696,7 +934,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                 rd[j][i] = 0;
             }
         }
-        const bool ok = kkt_solve<J>(P, s, rc, rd, false, 1.0, st, lane);
+        const bool ok = KKT_SOLVE(P, s, rc, rd, false, 1.0, st, lane);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
 #pragma unroll
@@ -834,7 +1072,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                         s[j].Dsig[i] = s[j].vL[i] / sl + s[j].vU[i] / su + dw;
                     }
                 }
-                if (kkt_solve<J>(P, s, rc, rd, true, dw, st, lane)) { solved = true; break; }
+                if (KKT_SOLVE(P, s, rc, rd, true, dw, st, lane)) { solved = true; break; }
                 if (dw == 0.0) dw = (dw_last == 0.0) ? DW_INIT : fmax(DW_MIN, dw_last * DW_DEC);
                 else dw = (dw_last == 0.0 || 1e5 * dw_last < dw) ? dw * DW_INC_FIRST : dw * DW_INC;
                 if (dw > DW_MAX) break;
@@ -920,7 +1158,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                             for (int i = 0; i < 2; i++)
                                 dsoc[j][i] = dyn ? (alpha_soc * dsoc[j][i] + (s[j].Ut[i] - s[j].St[i])) : 0.0;
                         }
-                        if (!kkt_solve<J>(P, s, csoc, dsoc, true, dw, soc, lane)) break;
+                        if (!KKT_SOLVE(P, s, csoc, dsoc, true, dw, soc, lane)) break;
                         alpha_soc = frac_to_bound<J>(P, s, soc, tau, lane);
                         double phi_s;
                         trial_eval<J>(P, sox, soy, s, soc, alpha_soc, mu, df, lane, th_trial, phi_s);
@@ -1068,13 +1306,16 @@ __global__ void __launch_bounds__(128, B200MPC_MIN_CTAS) mpc_solve_kernel(const 
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int Mpad = (P.M + 3) & ~3;
-    double *sox = smem + (size_t)wid * 2 * Mpad, *soy = sox + Mpad;
+    // per warp: the problem's obstacle lists (2*Mpad doubles) and the stage records of the KKT solve
+    const size_t per_warp = 2 * (size_t)Mpad + (size_t)(P.N + 1) * KKT_REC;
+    double *sox = smem + (size_t)wid * per_warp, *soy = sox + Mpad, *rec = soy + Mpad;
+    const KktRoles roles = kkt_roles(lane);
     for (;;) {
         int b = 0;
         if (lane == 0) b = (int)atomicAdd(A.counter, 1u);
         b = __shfl_sync(FULL, b, 0);
         if (b >= A.B) break;
-        solve_one<J>(P, A, b, lane, sox, soy);
+        solve_one<J>(P, A, b, lane, sox, soy, rec, roles);
     }
 }
 
@@ -1312,7 +1553,13 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     k.mu_floor = fmin(p->tol, 1e-4) / (K_EPS + 1.0);
     h->J = (p->N + 1 + 31) / 32;
     const int Mpad = (k.M + 3) & ~3;
-    h->smem_bytes = (size_t)4 * 2 * Mpad * sizeof(double);
+    // per warp: obstacle lists + the stage records of the lane-parallel KKT solve (KKT_REC doubles per stage)
+    h->smem_bytes = (size_t)4 * (2 * (size_t)Mpad + (size_t)(p->N + 1) * KKT_REC) * sizeof(double);
+    if (h->smem_bytes > 227 * 1024) {
+        set_err(nullptr, B200MPC_E_ARG, "N and M too large for the shared-memory staging of the warp kernel");
+        delete h;
+        return nullptr;
+    }
     auto fail = [&](const std::string &m) -> b200mpc_handle * {
         set_err(nullptr, B200MPC_E_CUDA, m);
         delete h;
