@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--robots", type=int, default=4096)
     ap.add_argument("--seeds", type=int, default=256, help="warm-start seeds per robot per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the 300 single solves (profiling runs)")
     ap.add_argument("--ref-sample", type=int, default=0, help="problems per step of the reference arm (0 = auto)")
     return ap.parse_args()
 
@@ -361,7 +362,7 @@ def main():
         return float(t.item())
 
     fp64_peak = solver.measure_fp64_peak() if rank == 0 else 0.0
-    latency = single_solve_latency(args.variant, params, wl, local_rank) if (rank == 0 and world == 1) else None
+    latency = single_solve_latency(args.variant, params, wl, local_rank) if (rank == 0 and world == 1 and not args.no_latency) else None
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -473,7 +474,7 @@ def main():
         }
         if latency is not None:
             line["latency"] = latency
-        if world == 1:
+        if world == 1 and not args.no_latency:
             ob_line = obstacle_builder_line(solver, torch, dev, params)
             ob_line["peak_gbs"] = hbm_peak
             ob_line["frac"] = ob_line["achieved_gbs"] / hbm_peak

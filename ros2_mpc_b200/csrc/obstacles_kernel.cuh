@@ -48,13 +48,13 @@ __device__ __forceinline__ double obs_cell(double v, double res, double inv_res)
 __global__ void __launch_bounds__(OBS_WARPS * 32) obstacles_kernel(const ObsBuildArgs a) {
     extern __shared__ __align__(16) unsigned char obs_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const size_t per_warp = (size_t)a.nwords * 4 + (size_t)a.slots * 16;
-    unsigned *bits = reinterpret_cast<unsigned *>(obs_smem + wid * ((per_warp + 15) & ~(size_t)15));
-    double *sx = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(bits) + (((size_t)a.nwords * 4 + 15) & ~(size_t)15));
-    double *sy = sx + a.slots;
+    const size_t per_warp = ((size_t)a.nwords * 4 + (size_t)a.slots * 4 + 15) & ~(size_t)15;
+    unsigned *bits = reinterpret_cast<unsigned *>(obs_smem + wid * per_warp);
+    int *qlist = reinterpret_cast<int *>(bits + a.nwords); // positions of the first `slots` set bits, in order
     const int wpl = (a.nwords + 31) / 32; // words per lane (contiguous, so that lane order = bit order)
     const int nbits = a.nc * a.nc;
     const double inv_res = 1.0 / a.res, fnc = (double)a.nc;
+    const unsigned magic = (unsigned)((0x100000000ull + (unsigned)a.nc - 1) / (unsigned)a.nc); // q / nc = umulhi(q, magic), q < 2^16
     for (int b = blockIdx.x * OBS_WARPS + wid; b < a.B; b += gridDim.x * OBS_WARPS) {
         for (int w = lane; w < a.nwords; w += 32) bits[w] = 0u;
         __syncwarp();
@@ -64,18 +64,27 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) obstacles_kernel(const ObsBuil
         //  needs a second pass, taken only if one shows up — the rotation-by-0.0 product turns the infinities of
         //  infinite ranges into NaN, so with the reference's call it never does)
         int anyinf = 0;
-        for (int i = lane; i < a.n; i += 32) {
-            const double r = __ldcs(sc + i);
-            const double x = __dmul_rn(r, a.bcos[i]), y = __dmul_rn(r, a.bsin[i]);
-            // rotate_coordinates(., 0.0): [[1, -0], [0, 1]] @ [x; y]
-            const double xr = obs_fix(__dadd_rn(x, __dmul_rn(-0.0, y)));
-            const double yr = obs_fix(__dadd_rn(__dmul_rn(0.0, x), y));
-            if (isinf(xr) || isinf(yr)) { anyinf = 1; continue; }
-            const double tx = obs_cell(__dadd_rn(xr, a.half), a.res, inv_res);
-            const double ty = obs_cell(__dadd_rn(yr, a.half), a.res, inv_res);
-            if (tx >= 0.0 && tx < fnc && ty >= 0.0 && ty < fnc) {
-                const int q = nbits - 1 - ((int)ty * a.nc + (int)tx);
-                atomicOr(bits + (q >> 5), 1u << (q & 31));
+        // four beams per lane in flight (the ranges are the only HBM reads of the kernel)
+        for (int i0 = lane; i0 < a.n; i0 += 128) {
+            double r4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) r4[u] = (i0 + 32 * u < a.n) ? __ldcs(sc + i0 + 32 * u) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + 32 * u;
+                if (i >= a.n) break;
+                const double r = r4[u];
+                const double x = __dmul_rn(r, a.bcos[i]), y = __dmul_rn(r, a.bsin[i]);
+                // rotate_coordinates(., 0.0): [[1, -0], [0, 1]] @ [x; y]
+                const double xr = obs_fix(__dadd_rn(x, __dmul_rn(-0.0, y)));
+                const double yr = obs_fix(__dadd_rn(__dmul_rn(0.0, x), y));
+                if (isinf(xr) || isinf(yr)) { anyinf = 1; continue; }
+                const double tx = obs_cell(__dadd_rn(xr, a.half), a.res, inv_res);
+                const double ty = obs_cell(__dadd_rn(yr, a.half), a.res, inv_res);
+                if (tx >= 0.0 && tx < fnc && ty >= 0.0 && ty < fnc) {
+                    const int q = nbits - 1 - ((int)ty * a.nc + (int)tx);
+                    atomicOr(bits + (q >> 5), 1u << (q & 31));
+                }
             }
         }
         if (__any_sync(FULL, anyinf)) {
@@ -123,34 +132,43 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) obstacles_kernel(const ObsBuil
         }
         const int total = __shfl_sync(FULL, incl, 31);
         int rank = incl - mine;
-        // ---- world coordinates of the first `slots` cells ----
-        if (mine > 0 && rank < a.slots) {
-            double sn, cs;
-            sincos(a.yaw[b], &sn, &cs);
-            const double px = a.pos[2 * (size_t)b], py = a.pos[2 * (size_t)b + 1];
-            for (int t = 0; t < wpl && rank < a.slots; t++) {
-                if (w0 + t >= a.nwords) break;
-                unsigned m = bits[w0 + t];
-                while (m && rank < a.slots) {
-                    const int q = ((w0 + t) << 5) + (__ffs(m) - 1);
-                    m &= m - 1;
-                    const int i = q / a.nc, j = q - i * a.nc;
-                    // convert_to_map_coordinates: x = -i*res + origin, y = -j*res + origin
-                    const double cx = __dadd_rn(__dmul_rn(-(double)i, a.res), a.origin);
-                    const double cy = __dadd_rn(__dmul_rn(-(double)j, a.res), a.origin);
-                    sx[rank] = __dadd_rn(__dadd_rn(__dmul_rn(cs, cx), __dmul_rn(-sn, cy)), px);
-                    sy[rank] = __dadd_rn(__dadd_rn(__dmul_rn(sn, cx), __dmul_rn(cs, cy)), py);
-                    rank++;
-                }
+        // ---- positions of the first `slots` set bits, in order (cheap per-lane loop: the bits of a wall cluster in a
+        //      few lanes' words) ----
+        for (int t = 0; t < wpl && rank < a.slots; t++) {
+            if (w0 + t >= a.nwords) break;
+            unsigned m = bits[w0 + t];
+            while (m && rank < a.slots) {
+                qlist[rank++] = ((w0 + t) << 5) + (__ffs(m) - 1);
+                m &= m - 1;
             }
         }
         __syncwarp();
-        // ---- padding (first obstacle, or the sentinel 100.0) and coalesced streaming stores ----
-        const double fx = total ? sx[0] : 100.0, fy = total ? sy[0] : 100.0;
+        // ---- world coordinates, one slot per lane (balanced), padding, coalesced streaming stores ----
+        const int nout = min(total, a.slots);
+        double sn = 0.0, cs = 1.0, px = 0.0, py = 0.0;
+        if (nout > 0) {
+            sincos(a.yaw[b], &sn, &cs);
+            px = a.pos[2 * (size_t)b]; py = a.pos[2 * (size_t)b + 1];
+        }
         double *gx = a.ox + (size_t)b * a.slots, *gy = a.oy + (size_t)b * a.slots;
-        for (int s = lane; s < a.slots; s += 32) {
-            __stcs(gx + s, (s < total) ? sx[s] : fx);
-            __stcs(gy + s, (s < total) ? sy[s] : fy);
+        double fx = 100.0, fy = 100.0; // sentinel of the "No obstacles" branch
+        for (int s0 = 0; s0 < a.slots; s0 += 32) {
+            const int sl = s0 + lane;
+            double wx = 0.0, wy = 0.0;
+            if (sl < nout) {
+                const int q = qlist[sl];
+                const int i = (int)__umulhi((unsigned)q, magic), j = q - i * a.nc;
+                // convert_to_map_coordinates: x = -i*res + origin, y = -j*res + origin
+                const double cx = __dadd_rn(__dmul_rn(-(double)i, a.res), a.origin);
+                const double cy = __dadd_rn(__dmul_rn(-(double)j, a.res), a.origin);
+                wx = __dadd_rn(__dadd_rn(__dmul_rn(cs, cx), __dmul_rn(-sn, cy)), px);
+                wy = __dadd_rn(__dadd_rn(__dmul_rn(sn, cx), __dmul_rn(cs, cy)), py);
+            }
+            if (s0 == 0 && nout > 0) { fx = __shfl_sync(FULL, wx, 0); fy = __shfl_sync(FULL, wy, 0); } // padding: first obstacle
+            if (sl < a.slots) {
+                __stcs(gx + sl, (sl < nout) ? wx : fx);
+                __stcs(gy + sl, (sl < nout) ? wy : fy);
+            }
         }
         if (lane == 0 && a.count) a.count[b] = total;
         __syncwarp();

@@ -1,0 +1,52 @@
+"""GPU box: throughput of the configurations BASELINE.json names besides the bench line (config 4 = bench.py).
+
+  config 1  single solve (latency: tools/dev_latency.py / bench.py "latency")
+  config 3  4096 random poses / goals on map_carto, variants A (obstacle cost active) and B, warp kernel
+  config 5  horizon sweep N = 10 / 25 / 50 / 100, halved control box, 160 distinct obstacle points, variant-A cost form,
+            4096 problems each (max_iter 300 as in the parity test)
+Prints one JSON line per case: kernel time from CUDA events (b200mpc_last_kernel_ms), converged fraction, iterations.
+"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from ros2_mpc_b200 import _shim, synth, load_params, make_params
+
+y = load_params()
+w = synth.robots_on_map(B=4096, seed=0)
+
+
+def run(name, p, x0, xr, reps=3, **kw):
+    S = _shim.Solver(p)
+    S.solve_batch(x0, xr, **kw)
+    ms, t = [], []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        o = S.solve_batch(x0, xr, **kw)
+        t.append(time.perf_counter() - t0)
+        ms.append(S.last_kernel_ms())
+    conv = np.isin(o["status"], (0, 1))
+    B = x0.shape[0]
+    print(json.dumps({"case": name, "problems": B, "kernel": "lane" if S.last_kernel_kind == _shim.KERNEL_LANE else "warp",
+                      "kernel_ms": float(np.median(ms)), "e2e_ms": float(np.median(t) * 1e3),
+                      "converged_fraction": float(conv.mean()),
+                      "converged_solves_per_s": float(conv.sum() / (np.median(ms) * 1e-3)),
+                      "iters_mean": float(o["iters"].mean()), "iters_max": int(o["iters"].max()),
+                      "status_counts": {int(k): int(v) for k, v in zip(*np.unique(o["status"], return_counts=True))}}), flush=True)
+    S.close()
+
+
+run("config3 variant B, 4096 problems", make_params("B", y), w["x0"], w["goal"])
+run("config3 variant A, 4096 problems", make_params("A", y), w["x0"], w["goal"], obs_x=w["obs_x"], obs_y=w["obs_y"])
+pxf, puf = synth.straight_reference(w["x0"], w["goal"], y["N"])
+run("config3 variant C (tracking), 4096 problems", make_params("C", y), w["x0"], pxf, uref=puf)
+ox, oy = synth.dense_obstacle_field(w["x0"], seed=2, r_in=0.6)
+for N in (10, 25, 50, 100):
+    p = make_params("A", y, N=N, u_lo=[-0.025, -0.1], u_hi=[0.075, 0.1], max_iter=300)
+    run(f"config5 N={N}, dense obstacle field, tightened bounds, 4096 problems", p, w["x0"], w["goal"], obs_x=ox, obs_y=oy)
+# large batches of the three variants through the automatic kernel choice
+for var, rep in (("B", 64), ("C", 64)):
+    x0 = np.tile(w["x0"], (rep, 1))
+    if var == "C":
+        run(f"variant C, {4096 * rep} problems", make_params("C", y), x0, np.tile(pxf, (rep, 1)), uref=np.tile(puf, (rep, 1)), reps=2)
+    else:
+        run(f"variant B, {4096 * rep} problems", make_params("B", y), x0, np.tile(w["goal"], (rep, 1)), reps=2)
