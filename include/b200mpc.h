@@ -23,6 +23,9 @@
  *                            (the final_state argument of perform_mpc, variants A / B), batched over robots
  *   b200mpc_reftraj_batch[_device]  <- get_reference_trajectory   ros2_mpc/scripts/path_follower_local_planner.py:27-73
  *                            (the pf / puf arguments of perform_mpc, variant C), batched over robots
+ *   b200mpc_control_step_device     <- the node loop after the solve   ros2_mpc/scripts/point_follower_local_planner.py:196-231
+ *                            (acceleration limiter, goal-reached logic), the next measured state (:172 with the rounding
+ *                            of ros2_mpc/core/ros_topics.py:66-80) and a simulated plant step, for a fleet on the device
  *   b200mpc_destroy       <- garbage collection of the Mpc / Opti object
  *
  * Conventions: plain pointers and sizes only; no C++ exceptions cross the boundary; functions return 0 on
@@ -187,9 +190,10 @@ int b200mpc_obstacles_batch_device(b200mpc_handle *h, int B, int n_beams, const 
 int b200mpc_goals_batch(b200mpc_handle *h, int B, int K, const double *path_xy, const double *path_heading,
                         int per_robot_paths, const double *goal, const double *pos, double lookahead, double *goal_out,
                         int32_t *index_out);
+/* (device variant: pos has `pos_stride` doubles per robot, so the measured states x0 [B][3] can be passed directly) */
 int b200mpc_goals_batch_device(b200mpc_handle *h, int B, int K, const double *path_xy, const double *path_heading,
-                               int per_robot_paths, const double *goal, const double *pos, double lookahead,
-                               double *goal_out, int32_t *index_out, void *stream);
+                               int per_robot_paths, const double *goal, const double *pos, int pos_stride,
+                               double lookahead, double *goal_out, int32_t *index_out, void *stream);
 
 /* Tracking references for B robots (get_reference_trajectory; N = the handle's horizon).  path_xy [K][2],
  * path_heading [K], path_velocity [K], path_omega [n_omega] (n_omega = K-1 as get_headings returns it, or K) shared or
@@ -204,6 +208,20 @@ int b200mpc_reftraj_batch_device(b200mpc_handle *h, int B, int K, const double *
                                  const double *path_velocity, const double *path_omega, int n_omega, int per_robot_paths,
                                  const double *x0, const double *goal, double *pxf_out, double *puf_out,
                                  int32_t *index_out, void *stream);
+
+/* One control step of a fleet after its solve, entirely on the device (all pointers are device pointers; asynchronous
+ * on `stream`).  Per robot, as the node loop does (scripts/point_follower_local_planner.py:196-231):
+ *   u = U_sol[b][0];  GOAL_FLAG set -> command (0,0);  |u - u_last| > accel_limit -> command u_last + accel_limit (both
+ *   components, as the reference) else u;  u_last = u;  then with the measured position x0[b] the solve started from:
+ *   farther than goal_threshold from goal[b][0:2] -> GOAL_FLAG = 0, else (first time) command (0,0), GOAL_FLAG = 1.
+ * A failed solve (status not 0 / 1; status may be NULL) commands (0,0) — the node would raise.
+ * Then state[b] (true pose) advances by one RK4 step of the unicycle under the command, x0[b] becomes the next
+ * measurement (pose rounded to two decimals when `quantise`, yaw % 2 pi), cmd_out[b] the executed command, and u_next
+ * (may be NULL) the plan shifted by one stage for a warm start.  N and dt are the handle's. */
+int b200mpc_control_step_device(b200mpc_handle *h, int B, const double *U_sol, const int32_t *status, double *state,
+                                double *x0, double *u_last, const double *goal, int goal_stride, int32_t *goal_flag,
+                                double goal_threshold, double accel_limit, int quantise, double *cmd_out, double *u_next,
+                                void *stream);
 
 /* Forces one of the two solve kernels (default B200MPC_KERNEL_AUTO; the environment variable B200MPC_KERNEL=warp|lane
  * sets the default of new handles).  Both kernels run the same algorithm; results agree to rounding.  The

@@ -84,12 +84,15 @@ def lib():
         L.b200mpc_obstacles_batch_device.restype = C.c_int
         L.b200mpc_goals_batch.argtypes = [vp, C.c_int, C.c_int, dp, dp, C.c_int, dp, dp, C.c_double, dp, ip]
         L.b200mpc_goals_batch.restype = C.c_int
-        L.b200mpc_goals_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_double, vp, vp, vp]
+        L.b200mpc_goals_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, C.c_double, vp, vp, vp]
         L.b200mpc_goals_batch_device.restype = C.c_int
         L.b200mpc_reftraj_batch.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, dp, C.c_int, C.c_int, dp, dp, dp, dp, ip]
         L.b200mpc_reftraj_batch.restype = C.c_int
         L.b200mpc_reftraj_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
         L.b200mpc_reftraj_batch_device.restype = C.c_int
+        L.b200mpc_control_step_device.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_double, C.c_double,
+                                                  C.c_int, vp, vp, vp]
+        L.b200mpc_control_step_device.restype = C.c_int
         L.b200mpc_sizeof_params.restype = C.c_int
         if L.b200mpc_sizeof_params() != C.sizeof(Params):
             raise RuntimeError("b200mpc_params layout mismatch between _shim.Params and libb200mpc.so")
@@ -260,6 +263,22 @@ class Solver:
         self._check(self._L.b200mpc_reftraj_batch(self._h, B, K, _dp(path_xy), _dp(path_heading), _dp(path_velocity),
                                                   _dp(path_omega), n_om, per, _dp(x0), _dp(goal), _dp(pxf), _dp(puf), _ip(idx)))
         return pxf, puf, idx
+
+    def goals_batch_device(self, B, K, path_xy, path_heading, per_robot_paths, goal, pos, pos_stride, lookahead, goal_out,
+                           index_out=0, stream=0):
+        v = lambda a: C.c_void_p(int(a) if a else None)  # noqa: E731
+        self._check(self._L.b200mpc_goals_batch_device(self._h, int(B), int(K), v(path_xy), v(path_heading),
+                                                       int(per_robot_paths), v(goal), v(pos), int(pos_stride),
+                                                       float(lookahead), v(goal_out), v(index_out), v(stream)))
+
+    def control_step_device(self, B, U_sol, status, state, x0, u_last, goal, goal_stride, goal_flag, goal_threshold,
+                            accel_limit, quantise, cmd_out, u_next=0, stream=0):
+        """Limiter / goal logic / plant step / next measurement for a fleet (raw device addresses)."""
+        v = lambda a: C.c_void_p(int(a) if a else None)  # noqa: E731
+        self._check(self._L.b200mpc_control_step_device(self._h, int(B), v(U_sol), v(status), v(state), v(x0), v(u_last),
+                                                        v(goal), int(goal_stride), v(goal_flag), float(goal_threshold),
+                                                        float(accel_limit), int(bool(quantise)), v(cmd_out), v(u_next),
+                                                        v(stream)))
 
     def solve_batch_device(self, B, x0, xref, uref, obs_x, obs_y, obs_stride, u_init, X, U, cost, status, iters, ls,
                            stream=0):

@@ -1401,6 +1401,7 @@ __global__ void __launch_bounds__(128) mpc_eval_kernel(const KParams P, const Ev
 #include "tpp_kernel.cuh"
 #include "obstacles_kernel.cuh"
 #include "refgen_kernel.cuh"
+#include "control_kernel.cuh"
 
 // =============================================================================================================
 // Host side: C ABI
@@ -2130,10 +2131,10 @@ static int refgen_grid(const b200mpc_handle *h, int B) {
 }
 
 extern "C" int b200mpc_goals_batch_device(b200mpc_handle *h, int B, int K, const double *path_xy, const double *path_heading,
-                                          int per_robot_paths, const double *goal, const double *pos, double lookahead,
-                                          double *goal_out, int32_t *index_out, void *stream) {
+                                          int per_robot_paths, const double *goal, const double *pos, int pos_stride,
+                                          double lookahead, double *goal_out, int32_t *index_out, void *stream) {
     if (!h) return B200MPC_E_ARG;
-    if (B < 0 || K < 1) return set_err(h, B200MPC_E_ARG, "B < 0 or K < 1");
+    if (B < 0 || K < 1 || pos_stride < 2) return set_err(h, B200MPC_E_ARG, "B < 0, K < 1 or pos_stride < 2");
     if (B == 0) return 0;
     if (!path_xy || !path_heading || !goal || !pos || !goal_out) return set_err(h, B200MPC_E_ARG, "NULL argument");
     CU_TRY(h, cudaSetDevice(h->device));
@@ -2142,7 +2143,7 @@ extern "C" int b200mpc_goals_batch_device(b200mpc_handle *h, int B, int K, const
     a.B = B; a.K = K; a.N = h->prm.N; a.Ko = K;
     a.path_stride = per_robot_paths ? K : 0;
     a.path_xy = path_xy; a.heading = path_heading;
-    a.goal = goal; a.goal_stride = 5; a.pos = pos; a.pos_stride = 2; a.lookahead = lookahead;
+    a.goal = goal; a.goal_stride = 5; a.pos = pos; a.pos_stride = pos_stride; a.lookahead = lookahead;
     a.out_goal = goal_out; a.nearest = index_out;
     goals_kernel<<<refgen_grid(h, B), REFGEN_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     CU_TRY(h, cudaGetLastError());
@@ -2208,7 +2209,7 @@ extern "C" int b200mpc_goals_batch(b200mpc_handle *h, int B, int K, const double
     double *d_o = stage_in<double>(st, nullptr, nb * 3, e);
     int32_t *d_i = stage_in<int32_t>(st, nullptr, nb, e);
     CU_TRY(h, e);
-    rc = b200mpc_goals_batch_device(h, B, K, d_xy, d_h, per_robot_paths, d_g, d_p, lookahead, d_o, d_i, h->stream);
+    rc = b200mpc_goals_batch_device(h, B, K, d_xy, d_h, per_robot_paths, d_g, d_p, 2, lookahead, d_o, d_i, h->stream);
     if (rc) return rc;
     CU_TRY(h, cudaMemcpyAsync(goal_out, d_o, nb * 24, cudaMemcpyDeviceToHost, h->stream));
     if (index_out) CU_TRY(h, cudaMemcpyAsync(index_out, d_i, nb * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -2246,5 +2247,25 @@ extern "C" int b200mpc_reftraj_batch(b200mpc_handle *h, int B, int K, const doub
     CU_TRY(h, cudaMemcpyAsync(puf_out, d_puf, nb * 2 * N * 8, cudaMemcpyDeviceToHost, h->stream));
     if (index_out) CU_TRY(h, cudaMemcpyAsync(index_out, d_i, nb * 4, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- after the solve: limiter, goal logic, plant step, next measurement (scripts/point_follower_local_planner.py:196-231)
+extern "C" int b200mpc_control_step_device(b200mpc_handle *h, int B, const double *U_sol, const int32_t *status,
+                                           double *state, double *x0, double *u_last, const double *goal, int goal_stride,
+                                           int32_t *goal_flag, double goal_threshold, double accel_limit, int quantise,
+                                           double *cmd_out, double *u_next, void *stream) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || goal_stride < 2) return set_err(h, B200MPC_E_ARG, "B < 0 or goal_stride < 2");
+    if (B == 0) return 0;
+    if (!U_sol || !state || !x0 || !u_last || !goal || !goal_flag || !cmd_out) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    ControlArgs a;
+    a.B = B; a.N = h->prm.N; a.U = U_sol; a.status = status; a.state = state; a.x0 = x0; a.u_last = u_last;
+    a.goal = goal; a.goal_stride = goal_stride; a.goal_flag = goal_flag; a.goal_threshold = goal_threshold;
+    a.accel_limit = accel_limit; a.dt = h->prm.dt; a.quantise = quantise; a.cmd = cmd_out; a.u_next = u_next;
+    control_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    h->launches++;
     return 0;
 }

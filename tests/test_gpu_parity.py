@@ -558,3 +558,71 @@ def test_gpu_reference_producers_match_reference_golden(env):
     x_opt, u = mpc.perform_mpc(np.zeros((2, mpc.N)), p0, a, b)
     assert x_opt.shape == (3, mpc.N + 1) and np.all(np.isfinite(u))
     mpc.close()
+
+
+# ---- device-side closed loop ------------------------------------------------------------------------
+@pytest.mark.parametrize("warm", [False, True])
+def test_fleet_closed_loop_matches_host_loop(env, warm):
+    """96 robots, 70 control steps, all on the device (goals -> solve -> limiter / goal logic / plant / next
+    measurement) against the node loop written out with numpy on the host (the reference's expressions,
+    scripts/point_follower_local_planner.py:172-231, around the same host-buffer solve).  Commands, flags and
+    the quantised measurements must agree exactly; some robots reach their goal, some are still under way."""
+    import torch  # noqa: F401
+    from ros2_mpc_b200 import references as rf
+    from ros2_mpc_b200.fleet import FleetPointStabilization
+    y, shim = env["y"], env["shim"]
+    rng = np.random.default_rng(42)
+    B, T, N = 96, 70, y["N"]
+    t = np.linspace(0, 1, 60)
+    path = np.stack([1.6 * t, 0.4 * np.sin(2.5 * t)], axis=1)
+    head, _, _ = rf.get_headings(path, y["dt"])
+    start = np.c_[rng.normal(0, 0.15, B), rng.normal(0, 0.15, B), rng.uniform(-0.6, 0.6, B)]
+    start[::3, :2] += path[35] + 0.0  # a third of the fleet starts far along the path and arrives within the run
+    goal = np.tile(np.r_[path[-1], 0.0, 0.0, head[-1]], (B, 1))
+    goal[:, :2] += rng.normal(0, 0.02, (B, 2))
+    fleet = FleetPointStabilization(start, goal, path, head, params=y, warm_start=warm, quantise=True)
+    fleet.step(T)
+    dev = fleet.snapshot()
+    fleet.close()
+
+    # the same loop on the host
+    S = shim.Solver(env["make"]("B", y))
+    state = start.copy()
+    x0 = np.round(state, 2); x0[:, 2] = x0[:, 2] % (2 * np.pi)
+    u_last = np.zeros((B, 2)); flag = np.zeros(B, dtype=bool); cmd = np.zeros((B, 2)); u_init = None
+    for step in range(T):
+        goal_mpc, _ = rf.get_goals_batch(path, head, goal, x0[:, :2], y["look_ahead_distance"], solver=S)
+        out = S.solve_batch(x0, goal_mpc, u_init=u_init)
+        ok = np.isin(out["status"], (0, 1))
+        for b in range(B):
+            u = out["U"][b, 0] if ok[b] else np.zeros(2)
+            if flag[b]:
+                cmd[b] = 0.0
+            elif np.linalg.norm(u - u_last[b]) > 0.03:
+                cmd[b] = u_last[b] + 0.03
+                u_last[b] = u
+            else:
+                cmd[b] = u
+                u_last[b] = u
+            if np.linalg.norm(x0[b, 0:2] - goal[b, 0:2]) > y["goal_threshold"]:
+                flag[b] = False
+            elif not flag[b]:
+                cmd[b] = 0.0
+                flag[b] = True
+        th, v, w_ = state[:, 2].copy(), cmd[:, 0], cmd[:, 1]
+        tm, te = th + 0.5 * y["dt"] * w_, th + y["dt"] * w_
+        state[:, 0] += y["dt"] / 6.0 * v * (np.cos(th) + 4 * np.cos(tm) + np.cos(te))
+        state[:, 1] += y["dt"] / 6.0 * v * (np.sin(th) + 4 * np.sin(tm) + np.sin(te))
+        state[:, 2] = te
+        x0 = np.round(state, 2); x0[:, 2] = x0[:, 2] % (2 * np.pi)
+        if warm:
+            u_init = np.concatenate([out["U"][:, 1:], out["U"][:, -1:]], axis=1)
+            u_init[~ok] = 0.0
+    S.close()
+    assert np.array_equal(dev["goal_flag"].astype(bool), flag)
+    assert flag.any() and not flag.all()
+    assert np.array_equal(dev["cmd"], cmd)
+    assert np.array_equal(dev["u_last"], u_last)
+    assert np.array_equal(dev["x0"], x0)
+    assert np.max(np.abs(dev["state"] - state)) <= 1e-9
+    assert np.isin(dev["status"], (0, 1)).all()
