@@ -626,3 +626,38 @@ def test_fleet_closed_loop_matches_host_loop(env, warm):
     assert np.array_equal(dev["x0"], x0)
     assert np.max(np.abs(dev["state"] - state)) <= 1e-9
     assert np.isin(dev["status"], (0, 1)).all()
+
+
+def test_gpu_producers_edge_cases(env):
+    """Empty batches, one-point paths, beam counts that are not multiples of the warp size, a single robot."""
+    from ros2_mpc_b200 import obstacles as ob, references as rf
+    S = env["shim"].Solver(env["make"]("C", env["y"]))
+    N = env["y"]["N"]
+    # empty batches are accepted and do nothing
+    ox, oy, cnt = S.obstacles_batch(np.zeros((0, 360)), np.ones(360), np.zeros(360), np.zeros((0, 2)), np.zeros(0), 2.0, 0.05, 160)
+    assert ox.shape == (0, 160) and cnt.shape == (0,)
+    gp, idx = S.goals_batch(np.zeros((4, 2)), np.zeros(4), np.zeros((0, 5)), np.zeros((0, 2)), 0.5)
+    assert gp.shape == (0, 3)
+    # one-point path: every robot gets that point (or the final goal when it is near)
+    pxy, head = np.array([[1.0, 2.0]]), np.array([7.5])
+    goal = np.array([[1.0, 2.0, 0, 0, -1.0], [5.0, 5.0, 0, 0, 9.0]])
+    pos = np.array([[1.2, 2.1], [0.0, 0.0]])
+    gp, idx = S.goals_batch(pxy, head, goal, pos, 0.5)
+    assert np.array_equal(gp[0], [1.0, 2.0, (-1.0) % (2 * np.pi)]) and idx[0] == -1
+    assert np.array_equal(gp[1], [1.0, 2.0, 7.5 % (2 * np.pi)]) and idx[1] == 0
+    pxf, puf, near = S.reftraj_batch(pxy, head, np.array([0.3]), np.array([0.1]), np.array([[4.0, 4.0, 0.0]]), goal[:1, :3])
+    assert np.array_equal(pxf[0], np.tile([1.0, 2.0, 7.5], N)) and np.array_equal(puf[0], np.tile([0.3, 0.1], N)) and near[0] == 0
+    # beam counts 1, 33, 100, 361, 719 against the numpy mirror (random ranges incl. NaN / inf), one robot and many
+    rng = np.random.default_rng(3)
+    for n in (1, 33, 100, 361, 719):
+        for B in (1, 37):
+            scan = np.round(rng.uniform(0.1, 3.0, (B, n)), 2)
+            scan[rng.random((B, n)) < 0.05] = np.inf
+            scan[rng.random((B, n)) < 0.03] = np.nan
+            ang = np.array([-1.0, 5.0])
+            pos, yaw = rng.uniform(-3, 3, (B, 2)), rng.uniform(-3, 3, B)
+            rx, ry, rc = ob.get_obstacles(scan, ang, 2.0, 0.05, pos, yaw, 160)
+            gx, gy, gc = ob.get_obstacles_batch_gpu(scan, ang, 2.0, 0.05, pos, yaw, 160, solver=S)
+            assert np.array_equal(gc, rc), (n, B)
+            assert np.max(np.abs(gx - rx)) <= 1e-12 and np.max(np.abs(gy - ry)) <= 1e-12, (n, B)
+    S.close()
