@@ -2052,7 +2052,7 @@ static int launch_obstacles(b200mpc_handle *h, int B, int n_beams, const double 
     a.scan = scan; a.bcos = bcos; a.bsin = bsin; a.pos = pos; a.yaw = yaw;
     a.half = map_size / 2; a.res = resolution; a.origin = (double)(a.nc / 2) * resolution;
     a.ox = ox; a.oy = oy; a.count = count;
-    const size_t per_warp = (((size_t)a.nwords * 4 + (size_t)slots * 4) + 15) & ~(size_t)15;
+    const size_t per_warp = (((size_t)a.nwords * 8 + (size_t)slots * 4) + 15) & ~(size_t)15;
     const size_t smem = per_warp * OBS_WARPS + 16;
     if (smem > 200 * 1024) return set_err(h, B200MPC_E_ARG, "grid / slots too large for the shared-memory staging");
     if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(obstacles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -44,13 +44,24 @@ __device__ __forceinline__ double obs_cell(double v, double res, double inv_res)
     if (fabs(q - rint(q)) <= 1e-15 * fabs(q)) return trunc(__ddiv_rn(v, res));
     return trunc(q);
 }
+// the same as a cell number: truncation toward zero is the conversion's rounding mode, the conversion saturates, and
+// one unsigned compare then tests 0 <= idx < num_cells ((-0.05, 0) -> cell 0, as int() does)
+__device__ __forceinline__ int obs_cell_i(double v, double res, double inv_res) {
+    const double q = v * inv_res;
+    int iq = __double2int_rz(q);
+    // distance of q from the integers on either side of it (rint() costs ~20 instructions on this architecture)
+    const double f = fabs(q - (double)iq), tol = 1e-15 * fabs(q);
+    if (f <= tol || f >= 1.0 - tol) iq = __double2int_rz(__ddiv_rn(v, res));
+    return iq;
+}
 
 __global__ void __launch_bounds__(OBS_WARPS * 32) obstacles_kernel(const ObsBuildArgs a) {
     extern __shared__ __align__(16) unsigned char obs_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const size_t per_warp = ((size_t)a.nwords * 4 + (size_t)a.slots * 4 + 15) & ~(size_t)15;
+    const size_t per_warp = ((size_t)a.nwords * 8 + (size_t)a.slots * 4 + 15) & ~(size_t)15;
     unsigned *bits = reinterpret_cast<unsigned *>(obs_smem + wid * per_warp);
-    int *qlist = reinterpret_cast<int *>(bits + a.nwords); // positions of the first `slots` set bits, in order
+    int *wpre = reinterpret_cast<int *>(bits + a.nwords);  // set bits in front of each word
+    int *qlist = wpre + a.nwords;                          // positions of the first `slots` set bits, in order
     const int wpl = (a.nwords + 31) / 32; // words per lane (contiguous, so that lane order = bit order)
     const int nbits = a.nc * a.nc;
     const double inv_res = 1.0 / a.res, fnc = (double)a.nc;
@@ -74,15 +85,20 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) obstacles_kernel(const ObsBuil
                 const int i = i0 + 32 * u;
                 if (i >= a.n) break;
                 const double r = r4[u];
-                const double x = __dmul_rn(r, a.bcos[i]), y = __dmul_rn(r, a.bsin[i]);
-                // rotate_coordinates(., 0.0): [[1, -0], [0, 1]] @ [x; y]
-                const double xr = obs_fix(__dadd_rn(x, __dmul_rn(-0.0, y)));
-                const double yr = obs_fix(__dadd_rn(__dmul_rn(0.0, x), y));
-                if (isinf(xr) || isinf(yr)) { anyinf = 1; continue; }
-                const double tx = obs_cell(__dadd_rn(xr, a.half), a.res, inv_res);
-                const double ty = obs_cell(__dadd_rn(yr, a.half), a.res, inv_res);
-                if (tx >= 0.0 && tx < fnc && ty >= 0.0 && ty < fnc) {
-                    const int q = nbits - 1 - ((int)ty * a.nc + (int)tx);
+                double xr, yr;
+                if (fabs(r) < 1.0e300) {
+                    // finite range: the rotation by 0.0 ([[1, -0], [0, 1]] @ [x; y]) returns x and y unchanged
+                    xr = __dmul_rn(r, a.bcos[i]); yr = __dmul_rn(r, a.bsin[i]);
+                } else {
+                    const double x = __dmul_rn(r, a.bcos[i]), y = __dmul_rn(r, a.bsin[i]);
+                    xr = obs_fix(__dadd_rn(x, __dmul_rn(-0.0, y)));
+                    yr = obs_fix(__dadd_rn(__dmul_rn(0.0, x), y));
+                    if (isinf(xr) || isinf(yr)) { anyinf = 1; continue; }
+                }
+                const unsigned ix = (unsigned)obs_cell_i(__dadd_rn(xr, a.half), a.res, inv_res);
+                const unsigned iy = (unsigned)obs_cell_i(__dadd_rn(yr, a.half), a.res, inv_res);
+                if (ix < (unsigned)a.nc && iy < (unsigned)a.nc) {
+                    const int q = nbits - 1 - (int)(iy * a.nc + ix);
                     atomicOr(bits + (q >> 5), 1u << (q & 31));
                 }
             }
@@ -119,7 +135,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) obstacles_kernel(const ObsBuil
             }
         }
         __syncwarp();
-        // ---- ranks: per-lane popcount over a contiguous word range, exclusive warp prefix sum ----
+        // ---- ranks: per-lane popcount over a contiguous word range, exclusive warp prefix sum; per-word prefix to
+        //      shared memory ----
         const int w0 = lane * wpl;
         int mine = 0;
         for (int t = 0; t < wpl; t++)
@@ -131,14 +148,19 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) obstacles_kernel(const ObsBuil
             if (lane >= o) incl += v;
         }
         const int total = __shfl_sync(FULL, incl, 31);
-        int rank = incl - mine;
-        // ---- positions of the first `slots` set bits, in order (cheap per-lane loop: the bits of a wall cluster in a
-        //      few lanes' words) ----
-        for (int t = 0; t < wpl && rank < a.slots; t++) {
-            if (w0 + t >= a.nwords) break;
-            unsigned m = bits[w0 + t];
+        {
+            int run = incl - mine;
+            for (int t = 0; t < wpl; t++)
+                if (w0 + t < a.nwords) { wpre[w0 + t] = run; run += __popc(bits[w0 + t]); }
+        }
+        __syncwarp();
+        // ---- positions of the first `slots` set bits, in order; the words are dealt round-robin so that the bits of
+        //      a wall (consecutive words) spread over the lanes ----
+        for (int w = lane; w < a.nwords; w += 32) {
+            int rank = wpre[w];
+            unsigned m = bits[w];
             while (m && rank < a.slots) {
-                qlist[rank++] = ((w0 + t) << 5) + (__ffs(m) - 1);
+                qlist[rank++] = (w << 5) + (__ffs(m) - 1);
                 m &= m - 1;
             }
         }
