@@ -109,6 +109,19 @@ __device__ __forceinline__ bool cmp_le(double lhs, double rhs, double bas) {
     return lhs - rhs <= 10.0 * DBL_EPS * fabs(bas);
 }
 
+// Reciprocal to within 1 ulp: hardware seed (MUFU.RCP64H) + two Newton steps, five dependent instructions instead of
+// the ~25 of an IEEE division — it sits on the serial critical path of the Riccati recursion.  det is finite, normal
+// and > 0 whenever the result is used (otherwise the factorisation is rejected).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
 // ---- K3: obstacle sum at one predicted position ---------------------------------------------------------
 // ox/oy are the problem's obstacle list staged in shared memory (all lanes read the same address: broadcast).
 template <bool DERIV>
@@ -122,7 +135,7 @@ __device__ __forceinline__ void obstacle_sum(const KParams &P, const double *__r
         for (int j = 0; j < P.M; j++) {
             double dx = x - sox[j], dy = y - soy[j];
             double s = (dx * dx + dy * dy) * ir2;
-            double is = 1.0 / s;
+            double is = fast_rcp(s); // s = 0 (robot on an obstacle point) gives NaN instead of inf: invalid number either way
             double q = c * is;
             double e = exp(q);
             v += e;
@@ -321,19 +334,6 @@ __device__ __forceinline__ double stage_value(const KParams &P, const double *so
             dst[2] = __shfl_down_sync(FULL, s[0].field[2], 1);                             \
         }                                                                                  \
     } while (0)
-
-// Reciprocal to within 1 ulp: hardware seed (MUFU.RCP64H) + two Newton steps, five dependent instructions instead of
-// the ~25 of an IEEE division — it sits on the serial critical path of the Riccati recursion.  det is finite, normal
-// and > 0 whenever the result is used (otherwise the factorisation is rejected).
-__device__ __forceinline__ double fast_rcp(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    return y;
-}
 
 // ---- K4: Riccati solve of the condensed stage-wise KKT system --------------------------------------------
 // Solves (IPOPT augmented system with ds, dyd eliminated stage-locally):
