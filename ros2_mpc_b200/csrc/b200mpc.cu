@@ -37,6 +37,9 @@
 #ifndef B200MPC_TPP_MIN_CTAS
 #define B200MPC_TPP_MIN_CTAS 1
 #endif
+#ifndef B200MPC_LANE_FUSED_DEFAULT
+#define B200MPC_LANE_FUSED_DEFAULT 0
+#endif
 
 // ---- IPOPT defaults (Waechter & Biegler 2006; IPOPT option documentation) -------------------------------
 #define K_EPS 10.0
@@ -131,7 +134,7 @@ __device__ __forceinline__ void obstacle_sum(const KParams &P, const double *__r
     const double ir2 = P.inv_r2, c = P.obs_c;
     double v = 0, ax = 0, ay = 0, bxx = 0, bxy = 0, byy = 0;
     if (P.obs_form == B200MPC_OBS_EXPLOG) {
-#pragma unroll 2
+#pragma unroll 4
         for (int j = 0; j < P.M; j++) {
             double dx = x - sox[j], dy = y - soy[j];
             double s = (dx * dx + dy * dy) * ir2;
@@ -152,7 +155,7 @@ __device__ __forceinline__ void obstacle_sum(const KParams &P, const double *__r
             }
         }
     } else {
-#pragma unroll 2
+#pragma unroll 4
         for (int j = 0; j < P.M; j++) {
             double dx = x - sox[j], dy = y - soy[j];
             double s = (dx * dx + dy * dy) * ir2;
@@ -1399,6 +1402,7 @@ __global__ void __launch_bounds__(128) mpc_eval_kernel(const KParams P, const Ev
 }
 
 #include "tpp_kernel.cuh"
+#include "tpp_fused.cuh"
 #include "obstacles_kernel.cuh"
 #include "refgen_kernel.cuh"
 #include "control_kernel.cuh"
@@ -1429,6 +1433,7 @@ struct b200mpc_handle {
     int kernel_kind;   // B200MPC_KERNEL_AUTO / _WARP / _LANE
     int last_kind;     // kernel used by the most recent solve
     int tpp_ctas;
+    int lane_fused;    // 1: two-sweep lane kernel (tpp_fused.cuh), 0: three-sweep lane kernel (tpp_kernel.cuh)
     double *d_ws, *d_filt;
     unsigned long long *d_stats;
     // streamed host-buffer solves: copy-in / copy-out streams, device words (avail, done[chunks]) and host-mapped
@@ -1584,6 +1589,10 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     const size_t tpp_smem = TPP_SMEM_BYTES;
     if ((e = cudaFuncSetAttribute(mpc_solve_tpp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tpp_smem)) != cudaSuccess)
         return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
+    if ((e = cudaFuncSetAttribute(mpc_solve_tppf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tpp_smem)) != cudaSuccess)
+        return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
+    h->lane_fused = B200MPC_LANE_FUSED_DEFAULT;
+    if (const char *ef = getenv("B200MPC_LANE_FUSED")) h->lane_fused = (ef[0] == '1');
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tblocks, mpc_solve_tpp_kernel, TPP_THREADS, tpp_smem)) != cudaSuccess)
         return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
     if (tblocks < 1) tblocks = 1;
@@ -1741,7 +1750,8 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t 
     t.avail = sw ? sw->avail : nullptr; t.done = sw ? sw->done : nullptr; t.flags = sw ? sw->flags : nullptr;
     t.chunk = sw ? sw->chunk : 1;
     CU_TRY(h, cudaEventRecord(h->ev0, stream));
-    mpc_solve_tpp_kernel<<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
+    if (h->lane_fused) mpc_solve_tppf_kernel<<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
+    else mpc_solve_tpp_kernel<<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev1, stream));
     h->launches++;

@@ -44,6 +44,14 @@
 // distances), sin/cos of the RK4 mid- and end-point angles come from the angle-addition formulas, and the
 // least-squares multiplier estimate is computed for the unscaled objective and scaled afterwards (it is linear).
 #pragma once
+// experiment knobs: fix the integrator / reference kind at compile time (dead code leaves the sweeps' loop bodies)
+#ifdef TPP_FORCE_RK4_GOAL
+#define TPP_IS_EULER(P) false
+#define TPP_IS_GOAL(P) true
+#else
+#define TPP_IS_EULER(P) ((P).integrator == B200MPC_EULER)
+#define TPP_IS_GOAL(P) ((P).ref_kind == B200MPC_REF_GOAL)
+#endif
 #ifndef TPP_BWD_EAGER
 #define TPP_BWD_EAGER 1 /* backward sweep: read all staged rows at the top of the stage and issue the next copy at once */
 #endif
@@ -58,7 +66,8 @@ enum {
     R_SSTEP = 23, // second-order-correction step, same layout
     R_CS = 26,   // second-order-correction right-hand sides: (cs0,cs1) (cs2,-) (ds0,ds1)
     R_REF = 29,  // per-stage references (trajectory tracking only): (r0,r1) (r2,-) (ub0,ub1)
-    TPP_NR = 32
+    R_KB = 32,   // two-sweep kernel (tpp_fused.cuh) only: (kfb0,kfb1), barrier-parameter coefficient of the gain kf
+    TPP_NR = 33
 };
 #define TPP_ROW_B 512
 #define TPP_STAGE_B (TPP_NR * TPP_ROW_B)
@@ -173,6 +182,7 @@ struct TppLane {
     unsigned fmask;
     int keep, soc_first, moved;
     double ymax_f;                                 // LSQ mode: largest slack-multiplier estimate seen by sweep F
+    double dw_b;                                   // two-sweep kernel: delta_w of the factorisation in progress
 };
 #define TPP_LANE_STRIDE (((sizeof(TppLane) + 7) / 8) | 1) /* in doubles, odd */
 
@@ -243,7 +253,7 @@ __device__ __forceinline__ void tpp_lin(const KParams &P, const double r[3], con
     const double dt = P.dt, th = X[2], v = U[0], w = U[1];
     o.b12 = 0; o.b22 = 0;
     o.htw = 0; o.hvw = 0; o.hww = 0;
-    if (P.integrator == B200MPC_EULER) {
+    if (TPP_IS_EULER(P)) {
         double sn, cs;
         tpp_sincos1(th, &sn, &cs);
         o.F0 = X[0] + dt * v * cs;
@@ -296,7 +306,7 @@ __device__ __forceinline__ void tpp_lin(const KParams &P, const double r[3], con
 // value of the integration step only (second-order-correction defects, restoration roll-out: rare paths)
 __device__ __noinline__ void tpp_dyn(const KParams &P, const double X[3], const double U[2], double F[3]) {
     const double dt = P.dt, th = X[2], v = U[0], w = U[1];
-    if (P.integrator == B200MPC_EULER) {
+    if (TPP_IS_EULER(P)) {
         double sn, cs;
         tpp_sincos1(th, &sn, &cs);
         F[0] = X[0] + dt * v * cs;
@@ -313,7 +323,7 @@ __device__ __noinline__ void tpp_dyn(const KParams &P, const double X[3], const 
 
 // per-stage references: the goal (registers) or the tracking reference rows of the stage
 __device__ __forceinline__ void tpp_ref(const KParams &P, const double goal[3], const char *p, double r[3], double ub[2]) {
-    if (P.ref_kind == B200MPC_REF_GOAL) {
+    if (TPP_IS_GOAL(P)) {
         r[0] = goal[0]; r[1] = goal[1]; r[2] = goal[2];
         ub[0] = 0; ub[1] = 0;
     } else {
@@ -661,7 +671,7 @@ __device__ __forceinline__ void tpp_costate(const KParams &P, const double r[3],
                                             const double dU[2], double df, double dw, bool useW, double Lk[3]) {
     const double dt = P.dt, th = X[2], v = U[0], w = U[1];
     double a13, a23, htt, htv, htw = 0;
-    if (P.integrator == B200MPC_EULER) {
+    if (TPP_IS_EULER(P)) {
         double sn, cs;
         tpp_sincos1(th, &sn, &cs);
         a13 = -dt * v * sn; a23 = dt * v * cs;

@@ -661,3 +661,34 @@ def test_gpu_producers_edge_cases(env):
             assert np.array_equal(gc, rc), (n, B)
             assert np.max(np.abs(gx - rx)) <= 1e-12 and np.max(np.abs(gy - ry)) <= 1e-12, (n, B)
     S.close()
+
+
+@pytest.mark.parametrize("variant", ["B", "C"])
+def test_two_sweep_lane_kernel_matches_oracle(env, robots, variant, monkeypatch):
+    """The experimental two-sweep lane kernel (csrc/tpp_fused.cuh, B200MPC_LANE_FUSED=1: trial sweep fused with the
+    next iteration's Riccati sweep) solves the same problems to the same optima in the same number of iterations."""
+    O, shim, synth = env["O"], env["shim"], env["synth"]
+    monkeypatch.setenv("B200MPC_LANE_FUSED", "1")
+    S = shim.Solver(env["make"](variant, env["y"]))
+    monkeypatch.delenv("B200MPC_LANE_FUSED")
+    S.set_kernel(shim.KERNEL_LANE)
+    po = O.variant_params(variant, env["y"])
+    w = robots
+    N = env["y"]["N"]
+    xr, kw = w["goal"], {}
+    if variant == "C":
+        pxf, puf = synth.straight_reference(w["x0"], w["goal"], N)
+        xr, kw = pxf, dict(uref=puf)
+    B = w["x0"].shape[0]
+    ui = synth.warm_start_seeds(B, N, [-0.05, -0.2], [0.15, 0.2], first_seed=31)
+    for u_init in (None, ui):
+        out = S.solve_batch(w["x0"], xr, u_init=u_init, **kw)
+        ref = O.solve_batch(po, w["x0"], xr, u_init=None if u_init is None else u_init.reshape(B, -1), **kw)
+        _assert_parity(out, ref, need_frac=1.0)
+        assert (out["iters"] == ref["iters"]).mean() >= 0.99
+    # ragged: fewer problems than lanes of one warp, and a batch that leaves lanes idle at the end
+    for nb in (1, 33):
+        out = S.solve_batch(w["x0"][:nb], xr[:nb], **{k: v[:nb] for k, v in kw.items()})
+        ref = O.solve_batch(po, w["x0"][:nb], xr[:nb], **{k: v[:nb] for k, v in kw.items()})
+        _assert_parity(out, ref, need_frac=1.0)
+    S.close()
