@@ -692,3 +692,21 @@ def test_two_sweep_lane_kernel_matches_oracle(env, robots, variant, monkeypatch)
         ref = O.solve_batch(po, w["x0"][:nb], xr[:nb], **{k: v[:nb] for k, v in kw.items()})
         _assert_parity(out, ref, need_frac=1.0)
     S.close()
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 33, 127])
+def test_extreme_horizons_both_kernels(env, N):
+    """Shortest horizons (one to three stages), one stage more than a warp, and the longest supported one."""
+    O, shim = env["O"], env["shim"]
+    w = env["synth"].robots_on_map(B=64 if N < 100 else 16, seed=9)
+    p = env["make"]("B", env["y"], N=N)
+    po = O.variant_params("B", env["y"], N=N)
+    S = shim.Solver(p)
+    ref = O.solve_batch(po, w["x0"], w["goal"])
+    for kind in (shim.KERNEL_WARP, shim.KERNEL_LANE):
+        S.set_kernel(kind)
+        out = S.solve_batch(w["x0"], w["goal"])
+        assert S.last_kernel_kind == kind
+        _assert_parity(out, ref, need_frac=0.9)
+        assert out["X"].shape == (w["x0"].shape[0], N + 1, 3)
+    S.close()
