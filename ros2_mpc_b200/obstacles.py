@@ -1,12 +1,17 @@
 """Obstacle-list construction: laser scan -> local occupancy grid -> fixed-length obstacle point list.
 
-Host-side (numpy, batched over robots) mirror of the reference's input producer for the solve:
+Product path (bottom of this file): `get_obstacles_gpu` / `get_obstacles_batch_gpu` -> libb200mpc.so
+(b200mpc_obstacles_batch, csrc/obstacles_kernel.cuh).  It needs a CUDA device and fails loudly without one; it never
+calls the numpy functions below.
+
+The numpy functions (top of this file) are a batched, line-by-line mirror of the reference's producer
   get_obstacles                          scripts/point_follower_local_planner.py:88-118
   convert_laser_scan_to_occupancy_grid   utils/utils.py:5-43
   convert_to_map_coordinates             utils/utils.py:114-124
   rotate_coordinates                     utils/utils.py:145-152
-Cell indices are bit-exact with the reference's numba helpers (tests/test_obstacles.py runs both on seeded
-scans, including NaN / +-inf beams and the truncation-toward-zero cases).  Quirks kept on purpose:
+used for two things only: building the synthetic workloads (synth.py: ray-cast scans -> obstacle lists, on machines
+without a GPU as well) and as the second checker of the kernel in the tests.  They are bit-exact in the cell indices
+against the reference's own numba helpers (tests/golden/obstacles_golden.npz).  Quirks kept on purpose:
   * beam angle i*(max-min)/n + min (the last beam stops one step short of angle_max);
   * the rotation-by-0.0 matrix product turns +-inf coordinates into NaN (0*inf), NaN becomes 0, so an
     infinite-range beam marks the robot's own cell (40,40);
