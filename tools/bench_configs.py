@@ -50,3 +50,31 @@ for var, rep in (("B", 64), ("C", 64)):
         run(f"variant C, {4096 * rep} problems", make_params("C", y), x0, np.tile(pxf, (rep, 1)), uref=np.tile(puf, (rep, 1)), reps=2)
     else:
         run(f"variant B, {4096 * rep} problems", make_params("B", y), x0, np.tile(w["goal"], (rep, 1)), reps=2)
+
+# closed loop on the device (fleet.py: goals -> solve -> limiter / goal logic / plant / next measurement), no host round trips
+import torch
+from ros2_mpc_b200 import references as rf
+from ros2_mpc_b200.fleet import FleetPointStabilization
+for Bf, steps in ((4096, 20), (262144, 5)):
+    rng = np.random.default_rng(1)
+    tt = np.linspace(0, 1, 60)
+    path = np.stack([1.6 * tt, 0.4 * np.sin(2.5 * tt)], axis=1)
+    head, _, _ = rf.get_headings(path, y["dt"])
+    start = np.c_[rng.normal(0, 0.3, Bf), rng.normal(0, 0.3, Bf), rng.uniform(-0.6, 0.6, Bf)]
+    goal = np.tile(np.r_[path[-1], 0.0, 0.0, head[-1]], (Bf, 1))
+    fl = FleetPointStabilization(start, goal, path, head, params=y, warm_start=False, quantise=True)
+    fl.step(2)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fl.step(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    snap = fl.snapshot()
+    print(json.dumps({"case": f"closed loop on the device, {Bf} robots x {steps} control steps (cold start each step, as the reference)",
+                      "robots": Bf, "control_steps": steps, "ms_per_control_step": ms / steps,
+                      "robot_steps_per_s": Bf * steps / (ms * 1e-3),
+                      "solve_success_fraction_last_step": float(np.isin(snap["status"], (0, 1)).mean()),
+                      "iters_mean_last_step": float(snap["iters"].mean())}), flush=True)
+    fl.close()
