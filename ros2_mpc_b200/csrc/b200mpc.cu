@@ -1433,6 +1433,7 @@ struct b200mpc_handle {
     int kernel_kind;   // B200MPC_KERNEL_AUTO / _WARP / _LANE
     int last_kind;     // kernel used by the most recent solve
     int tpp_ctas;
+    int lane_spec;     // template instance of the lane kernels (TPP_SPEC_*)
     int lane_fused;    // 1: two-sweep lane kernel (tpp_fused.cuh), 0: three-sweep lane kernel (tpp_kernel.cuh)
     double *d_ws, *d_filt;
     unsigned long long *d_stats;
@@ -1587,13 +1588,22 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     h->ctas = blocks * h->sm_count; // persistent grid: a multiple of the SM count (148 on B200)
     int tblocks = 0;
     const size_t tpp_smem = TPP_SMEM_BYTES;
-    if ((e = cudaFuncSetAttribute(mpc_solve_tpp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tpp_smem)) != cudaSuccess)
-        return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
-    if ((e = cudaFuncSetAttribute(mpc_solve_tppf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tpp_smem)) != cudaSuccess)
-        return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
+    // lane kernels: one instance per problem family (tpp_kernel.cuh: TPP_SPEC_*)
+    h->lane_spec = TPP_SPEC_GENERIC;
+    if (p->integrator == B200MPC_RK4 && p->ref_kind == B200MPC_REF_GOAL) h->lane_spec = TPP_SPEC_RK4_GOAL;
+    if (p->integrator == B200MPC_EULER && p->ref_kind == B200MPC_REF_TRAJ) h->lane_spec = TPP_SPEC_EULER_TRAJ;
+    if (getenv("B200MPC_LANE_GENERIC")) h->lane_spec = TPP_SPEC_GENERIC;
+    {
+        const void *fns[6] = {(const void *)mpc_solve_tpp_kernel<0>, (const void *)mpc_solve_tpp_kernel<1>,
+                              (const void *)mpc_solve_tpp_kernel<2>, (const void *)mpc_solve_tppf_kernel<0>,
+                              (const void *)mpc_solve_tppf_kernel<1>, (const void *)mpc_solve_tppf_kernel<2>};
+        for (int i = 0; i < 6; i++)
+            if ((e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tpp_smem)) != cudaSuccess)
+                return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
+    }
     h->lane_fused = B200MPC_LANE_FUSED_DEFAULT;
     if (const char *ef = getenv("B200MPC_LANE_FUSED")) h->lane_fused = (ef[0] == '1');
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tblocks, mpc_solve_tpp_kernel, TPP_THREADS, tpp_smem)) != cudaSuccess)
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tblocks, mpc_solve_tpp_kernel<0>, TPP_THREADS, tpp_smem)) != cudaSuccess)
         return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
     if (tblocks < 1) tblocks = 1;
     h->tpp_ctas = tblocks * h->sm_count;
@@ -1750,8 +1760,16 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t 
     t.avail = sw ? sw->avail : nullptr; t.done = sw ? sw->done : nullptr; t.flags = sw ? sw->flags : nullptr;
     t.chunk = sw ? sw->chunk : 1;
     CU_TRY(h, cudaEventRecord(h->ev0, stream));
-    if (h->lane_fused) mpc_solve_tppf_kernel<<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
-    else mpc_solve_tpp_kernel<<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
+    const int spec = h->lane_spec;
+    if (h->lane_fused) {
+        if (spec == TPP_SPEC_RK4_GOAL) mpc_solve_tppf_kernel<TPP_SPEC_RK4_GOAL><<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
+        else if (spec == TPP_SPEC_EULER_TRAJ) mpc_solve_tppf_kernel<TPP_SPEC_EULER_TRAJ><<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
+        else mpc_solve_tppf_kernel<TPP_SPEC_GENERIC><<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
+    } else {
+        if (spec == TPP_SPEC_RK4_GOAL) mpc_solve_tpp_kernel<TPP_SPEC_RK4_GOAL><<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
+        else if (spec == TPP_SPEC_EULER_TRAJ) mpc_solve_tpp_kernel<TPP_SPEC_EULER_TRAJ><<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
+        else mpc_solve_tpp_kernel<TPP_SPEC_GENERIC><<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
+    }
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev1, stream));
     h->launches++;

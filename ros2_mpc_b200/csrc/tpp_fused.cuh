@@ -41,6 +41,7 @@ __device__ __forceinline__ void tppf_forward_stage(char *sb, const char *p, int 
     tpp_cp_commit();
 }
 
+template <int SPEC>
 __device__ __forceinline__ void tppf_forward(const KParams &P, char *wb, char *sb, int buf, const TppLane &L, TppFwd &o) {
     const int N = P.N;
     const double dt = P.dt, mu = L.mu, tau = fmax(TAU_MIN, 1.0 - L.mu), df = L.df;
@@ -88,10 +89,10 @@ __device__ __forceinline__ void tppf_forward(const KParams &P, char *wb, char *s
             const double U[2] = {u2.x, u2.y}, Sv[2] = {s2.x, s2.y}, vLv[2] = {vl2.x, vl2.y}, vUv[2] = {vu2.x, vu2.y};
             const double Xn[3] = {xn01.x, xn01.y, xn2.x};
             double r[3], ub[2];
-            tpp_ref(P, goal, p, r, ub);
+            tpp_ref<SPEC>(P, goal, p, r, ub);
             const double ln0[3] = {0, 0, 0};
             TppLin q;
-            tpp_lin<false>(P, r, ub, X, U, ln0, df, q);
+            tpp_lin<false, SPEC>(P, r, ub, X, U, ln0, df, q);
             double rc0, rc1, rc2, rdv[2] = {U[0] - Sv[0], U[1] - Sv[1]};
             if (mode == BM_LSQ) {
                 rc0 = rc1 = rc2 = 0;
@@ -142,6 +143,7 @@ __device__ __forceinline__ void tppf_stage(char *sb, const char *p, int co, int 
 // T-part (tmode): INIT / EVAL / HOLD  new = current;  LSQ  new = current with the multiplier estimate;
 //                 STEP(_SOC)  new = current + alpha*step, multiplier step from the costate recursion.
 // B-part (bmode): NEWTON / SOC / LSQ as tpp_backward, on the new point, right-hand side split in (1, mu) parts.
+template <int SPEC>
 __device__ __forceinline__ void tppf_trial_backward(const KParams &P, char *wb, char *sb, int cur, const TppLane &L, double dwb,
                                                     TppTrial &o, TppBwd &ob) {
     const int N = P.N;
@@ -188,7 +190,7 @@ __device__ __forceinline__ void tppf_trial_backward(const KParams &P, char *wb, 
             tpp_l2_prefetch(p - 2 * TPP_STAGE_B, srow, 3);
         }
         double r[3], ub[2];
-        tpp_ref(P, goal, p, r, ub);
+        tpp_ref<SPEC>(P, goal, p, r, ub);
         // ================= T-part: the new iterate of stage k =================
         const double Xc[3] = {x01.x, x01.y, x2l0.x}; // current iterate (the second-order correction needs it below)
         double X[3] = {Xc[0], Xc[1], Xc[2]};
@@ -205,7 +207,7 @@ __device__ __forceinline__ void tppf_trial_backward(const KParams &P, char *wb, 
                     Lk[0] = -dwk * dX[0]; Lk[1] = -dwk * dX[1]; Lk[2] = -dwk * dX[2];
                 } else {
                     const double Uc[2] = {u2.x, u2.y};
-                    tpp_costate(P, r, X, Uc, lo, Lam, dX, duv, lsq ? 1.0 : df, dwk, !lsq, Lk);
+                    tpp_costate<SPEC>(P, r, X, Uc, lo, Lam, dX, duv, lsq ? 1.0 : df, dwk, !lsq, Lk);
                 }
                 Lam[0] = Lk[0]; Lam[1] = Lk[1]; Lam[2] = Lk[2];
                 chk = fma(0.0, (Lk[0] + Lk[1]) + Lk[2], chk); // 0*inf = NaN and NaN sticks: one test after the sweep
@@ -273,7 +275,7 @@ __device__ __forceinline__ void tppf_trial_backward(const KParams &P, char *wb, 
             tpp_st2(pw, R_U, U[0], U[1]); tpp_st2(pw, R_S, S[0], S[1]); tpp_st2(pw, R_YD, yd[0], yd[1]);
             tpp_st2(pw, R_VL, vL[0], vL[1]); tpp_st2(pw, R_VU, vU[0], vU[1]);
             TppLin q;
-            tpp_lin<true>(P, r, ub, X, U, ln, df, q);
+            tpp_lin<true, SPEC>(P, r, ub, X, U, ln, df, q);
             const double c[3] = {Xn[0] - q.F0, Xn[1] - q.F1, Xn[2] - q.F2};
             fs += q.f;
 #pragma unroll
@@ -345,7 +347,7 @@ __device__ __forceinline__ void tppf_trial_backward(const KParams &P, char *wb, 
                         St[i] = Sc[i] + at * (dub_[i] + rdp[i]);
                         rd[i] = at * rdp[i] + (Ut[i] - St[i]);
                     }
-                    tpp_dyn(P, Xt, Ut, Ft);
+                    tpp_dyn<SPEC>(P, Xt, Ut, Ft);
 #pragma unroll
                     for (int i = 0; i < 3; i++) rc[i] = at * base[i] + (Xtn[i] - Ft[i]);
                     tpp_st2(p, R_CS, rc[0], rc[1]); tpp_st2(p, R_CS + 1, rc[2], 0.0); tpp_st2(p, R_CS + 2, rd[0], rd[1]);
@@ -433,6 +435,7 @@ __device__ __forceinline__ bool tppf_iterate_top(const KParams &P, TppLane &L, c
     return true;
 }
 
+template <int SPEC>
 __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_tppf_kernel(const KParams P, const TppArgs T) {
     extern __shared__ __align__(16) char tpp_smem[];
     const BatchArgs &A = T.a;
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                     __threadfence();
                 }
                 L.goal[0] = L.goal[1] = L.goal[2] = 0;
-                if (P.ref_kind == B200MPC_REF_GOAL) {
+                if (TPP_IS_GOAL(P)) {
                     const double *xr = A.xref + 3 * (size_t)b;
                     L.goal[0] = __ldcg(xr); L.goal[1] = __ldcg(xr + 1); L.goal[2] = __ldcg(xr + 2);
                 }
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                     }
                     tpp_st2(pc, R_U, uv[0], uv[1]); tpp_st2(pc, R_S, sv[0], sv[1]); tpp_st2(pc, R_YD, 0.0, 0.0);
                     tpp_st2(pc, R_VL, 1.0, 1.0); tpp_st2(pc, R_VU, 1.0, 1.0);
-                    if (P.ref_kind == B200MPC_REF_TRAJ) {
+                    if (!TPP_IS_GOAL(P)) {
                         const double *xr = A.xref + b * 3 * N + 3 * k;
                         const double *ur = A.uref + b * 2 * N + 2 * k;
                         tpp_st2(p, R_REF, __ldcg(xr), __ldcg(xr + 1)); tpp_st2(p, R_REF + 1, __ldcg(xr + 2), 0.0);
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             tpp_stat(T, 2);
             const int bm = L.bmode;
             const double dwb = (bm == BM_SOC) ? L.dw : L.dw_b;
-            tppf_trial_backward(P, wb, sb, cur, L, dwb, t, r);
+            tppf_trial_backward<SPEC>(P, wb, sb, cur, L, dwb, t, r);
             const int tm = L.tmode;
             bool use_b = false; // the point of this sweep is the (new) current iterate: the B-part's output counts
             if (tm == TMF_INIT || tm == TMF_HOLD) {
@@ -622,7 +625,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
         if (tpp_opaque(L.phase) == PHF_F) {
             TppFwd f;
             tpp_stat(T, 1);
-            tppf_forward(P, wb, sb, 1 - cur, L, f);
+            tppf_forward<SPEC>(P, wb, sb, 1 - cur, L, f);
             const int bmode = L.bmode;
             L.phase = PHF_TB;
             L.dw_b = 0.0;
@@ -666,7 +669,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             L.dw_b = 0.0;
             if (L.alpha < L.a_min) {
                 // buffer `cur` holds the current iterate (a HOLD sweep only copied it); the restored point goes to 1 - cur
-                tpp_restore(P, wb, fl, cur, L);
+                tpp_restore<SPEC>(P, wb, fl, cur, L);
                 if (L.phase == PH_FIN) L.phase = PHF_FIN;
                 else { L.tmode = TMF_EVAL; L.phase = PHF_TB; }
             } else {

@@ -44,14 +44,14 @@
 // distances), sin/cos of the RK4 mid- and end-point angles come from the angle-addition formulas, and the
 // least-squares multiplier estimate is computed for the unscaled objective and scaled afterwards (it is linear).
 #pragma once
-// experiment knobs: fix the integrator / reference kind at compile time (dead code leaves the sweeps' loop bodies)
-#ifdef TPP_FORCE_RK4_GOAL
-#define TPP_IS_EULER(P) false
-#define TPP_IS_GOAL(P) true
-#else
-#define TPP_IS_EULER(P) ((P).integrator == B200MPC_EULER)
-#define TPP_IS_GOAL(P) ((P).ref_kind == B200MPC_REF_GOAL)
-#endif
+// The lane kernels are instantiated per problem family (template parameter SPEC), so that the integrator and the kind of
+// reference are compile-time constants and the other family's code leaves the sweeps' loop bodies (instruction cache):
+//   SPEC 0  generic (run-time switches)   SPEC 1  RK4 + fixed goal (variants A, B)   SPEC 2  Euler + trajectory (variant C)
+#define TPP_SPEC_GENERIC 0
+#define TPP_SPEC_RK4_GOAL 1
+#define TPP_SPEC_EULER_TRAJ 2
+#define TPP_IS_EULER(P) (SPEC == TPP_SPEC_RK4_GOAL ? false : (SPEC == TPP_SPEC_EULER_TRAJ ? true : ((P).integrator == B200MPC_EULER)))
+#define TPP_IS_GOAL(P) (SPEC == TPP_SPEC_RK4_GOAL ? true : (SPEC == TPP_SPEC_EULER_TRAJ ? false : ((P).ref_kind == B200MPC_REF_GOAL)))
 #ifndef TPP_BWD_EAGER
 #define TPP_BWD_EAGER 1 /* backward sweep: read all staged rows at the top of the stage and issue the next copy at once */
 #endif
@@ -247,7 +247,7 @@ struct TppLin {
 
 // K1+K2 of a stage with controls (k < N): integration step, Jacobian entries, stage cost and its gradient; with
 // HESS also the Lagrangian Hessian block (ln = multiplier of the defect X_{k+1} - F(X_k, U_k)).
-template <bool HESS>
+template <bool HESS, int SPEC>
 __device__ __forceinline__ void tpp_lin(const KParams &P, const double r[3], const double ub[2], const double X[3],
                                         const double U[2], const double ln[3], double df, TppLin &o) {
     const double dt = P.dt, th = X[2], v = U[0], w = U[1];
@@ -304,6 +304,7 @@ __device__ __forceinline__ void tpp_lin(const KParams &P, const double r[3], con
 }
 
 // value of the integration step only (second-order-correction defects, restoration roll-out: rare paths)
+template <int SPEC>
 __device__ __noinline__ void tpp_dyn(const KParams &P, const double X[3], const double U[2], double F[3]) {
     const double dt = P.dt, th = X[2], v = U[0], w = U[1];
     if (TPP_IS_EULER(P)) {
@@ -322,6 +323,7 @@ __device__ __noinline__ void tpp_dyn(const KParams &P, const double X[3], const 
 }
 
 // per-stage references: the goal (registers) or the tracking reference rows of the stage
+template <int SPEC>
 __device__ __forceinline__ void tpp_ref(const KParams &P, const double goal[3], const char *p, double r[3], double ub[2]) {
     if (TPP_IS_GOAL(P)) {
         r[0] = goal[0]; r[1] = goal[1]; r[2] = goal[2];
@@ -347,6 +349,7 @@ struct TppBwd {
 //               unscaled objective (L.df is 1); also returns the largest gradient entry (objective scaling), the
 //               objective and the invalid-number flag of the starting point.
 // o.ok = 0 when a condensed Quu block is not positive definite (wrong inertia).
+template <int SPEC>
 __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &A, char *wb, char *sb, int cur,
                                              const TppLane &L, TppBwd &o) {
     const int N = P.N;
@@ -410,9 +413,9 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
         } else {
             const double U[2] = {u2.x, u2.y};
             double r[3], ub[2];
-            tpp_ref(P, goal, p, r, ub);
+            tpp_ref<SPEC>(P, goal, p, r, ub);
             TppLin q;
-            tpp_lin<true>(P, r, ub, X, U, ln, df, q);
+            tpp_lin<true, SPEC>(P, r, ub, X, U, ln, df, q);
 #if !TPP_BWD_EAGER
             const double2 s2 = tpp_sld(sb, R_S), yd2 = tpp_sld(sb, R_YD), vl2 = tpp_sld(sb, R_VL), vu2 = tpp_sld(sb, R_VU);
             tpp_consume(x01, x2l0, l12, u2);
@@ -465,7 +468,7 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
                         St[i] = S[i] + at * (du[i] + rdp[i]);
                         rd[i] = at * rdp[i] + (Ut[i] - St[i]);
                     }
-                    tpp_dyn(P, Xt, Ut, Ft);
+                    tpp_dyn<SPEC>(P, Xt, Ut, Ft);
 #pragma unroll
                     for (int i = 0; i < 3; i++) {
                         rc[i] = at * base[i] + (Xtn[i] - Ft[i]);
@@ -559,6 +562,7 @@ __device__ __forceinline__ void tpp_forward_stage(char *sb, const char *p, int c
 
 // ---- sweep F: forward roll-out of the step; step sizes and directional derivative ----------------------------------
 // (the multiplier step is recovered by sweep T; in LSQ mode ymax covers the slack-multiplier estimate only)
+template <int SPEC>
 __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A, char *wb, char *sb, int cur,
                                             const TppLane &L, TppFwd &o) {
     const int N = P.N;
@@ -605,10 +609,10 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
             const double U[2] = {u2.x, u2.y}, Sv[2] = {s2.x, s2.y}, vLv[2] = {vl2.x, vl2.y}, vUv[2] = {vu2.x, vu2.y};
             const double Xn[3] = {xn01.x, xn01.y, xn2.x};
             double r[3], ub[2];
-            tpp_ref(P, goal, p, r, ub);
+            tpp_ref<SPEC>(P, goal, p, r, ub);
             const double ln0[3] = {0, 0, 0};
             TppLin q;
-            tpp_lin<false>(P, r, ub, X, U, ln0, df, q);
+            tpp_lin<false, SPEC>(P, r, ub, X, U, ln0, df, q);
             double rc0, rc1, rc2, rdv[2] = {U[0] - Sv[0], U[1] - Sv[1]};
             if (mode == BM_LSQ) {
                 rc0 = rc1 = rc2 = 0;
@@ -666,6 +670,7 @@ __device__ __forceinline__ void tpp_trial_stage(char *sb, const char *p, int co,
 //     Lam_k = A_k' Lam_{k+1} - g_k - (Hxx_k + dw) dx_k - Hxu_k du_k,      Lam = lam + dlam (full-step multipliers).
 // lo = multipliers of the defect of stage k+1 at the current iterate (they weight the second derivatives of F),
 // useW = 0 for the least-squares multiplier estimate (W = 0, dw = 1, unscaled objective: pass df = 1).
+template <int SPEC>
 __device__ __forceinline__ void tpp_costate(const KParams &P, const double r[3], const double X[3], const double U[2],
                                             const double lo[3], const double Ln[3], const double dX[3],
                                             const double dU[2], double df, double dw, bool useW, double Lk[3]) {
@@ -709,6 +714,7 @@ __device__ __forceinline__ void tpp_costate(const KParams &P, const double r[3],
 // tmode LSQ:         new = current with the least-squares multiplier estimate (scaled by df; or zeros) for lam, yd.
 // tmode STEP(_SOC):  new = current + alpha*(dX,dU,dS,dlam,dyd) and bound multipliers + a_z*(dvL,dvU), clamped.
 // The multiplier step dlam is not stored by the other sweeps: it comes from the costate recursion (tpp_costate).
+template <int SPEC>
 __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, char *wb, char *sb, int cur,
                                           const TppLane &L, TppTrial &o) {
     const int N = P.N;
@@ -745,7 +751,7 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
             tpp_l2_prefetch(p - 2 * TPP_STAGE_B, srow, 3);
         }
         double r[3], ub[2];
-        tpp_ref(P, goal, p, r, ub);
+        tpp_ref<SPEC>(P, goal, p, r, ub);
         double X[3] = {x01.x, x01.y, x2l0.x};
         double lam[3] = {0, 0, 0};
         const double duv[2] = {du2.x, du2.y};
@@ -761,7 +767,7 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
                     Lk[0] = -dwk * dX[0]; Lk[1] = -dwk * dX[1]; Lk[2] = -dwk * dX[2];
                 } else {
                     const double Uc[2] = {u2.x, u2.y};
-                    tpp_costate(P, r, X, Uc, lo, Lam, dX, duv, lsq ? 1.0 : df, dwk, !lsq, Lk);
+                    tpp_costate<SPEC>(P, r, X, Uc, lo, Lam, dX, duv, lsq ? 1.0 : df, dwk, !lsq, Lk);
                 }
                 Lam[0] = Lk[0]; Lam[1] = Lk[1]; Lam[2] = Lk[2];
                 if (!isfinite(Lk[0]) || !isfinite(Lk[1]) || !isfinite(Lk[2])) bad = 1;
@@ -814,7 +820,7 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
             tpp_st2(pw, R_U, U[0], U[1]); tpp_st2(pw, R_S, S[0], S[1]); tpp_st2(pw, R_YD, yd[0], yd[1]);
             tpp_st2(pw, R_VL, vL[0], vL[1]); tpp_st2(pw, R_VU, vU[0], vU[1]);
             TppLin q;
-            tpp_lin<false>(P, r, ub, X, U, ln, df, q);
+            tpp_lin<false, SPEC>(P, r, ub, X, U, ln, df, q);
             const double c[3] = {Xn[0] - q.F0, Xn[1] - q.F1, Xn[2] - q.F2};
             fs += q.f;
 #pragma unroll
@@ -920,6 +926,7 @@ __device__ __forceinline__ bool tpp_ls_acceptable(const TppLane &L, const double
 
 // Line search gave up on the Newton direction (alpha < alpha_min): restoration stand-in of the warp kernel — roll
 // the controls out (closed-form feasible point), restart the multipliers.  Writes the other iterate buffer.
+template <int SPEC>
 __device__ __forceinline__ void tpp_restore(const KParams &P, char *wb, double *fl, int cur, TppLane &L) {
     const int N = P.N;
     if (L.theta <= 1e-10 || L.n_resto >= MAX_RESTO) { L.status = B200MPC_RESTORATION_FAILED; L.phase = PH_FIN; return; }
@@ -950,7 +957,7 @@ __device__ __forceinline__ void tpp_restore(const KParams &P, char *wb, double *
             tpp_st2(pw, R_VL, reset ? 1.0 : a.x, reset ? 1.0 : a.y);
             tpp_st2(pw, R_VU, reset ? 1.0 : b.x, reset ? 1.0 : b.y);
             double F[3];
-            tpp_dyn(P, y, U, F);
+            tpp_dyn<SPEC>(P, y, U, F);
             y[0] = F[0]; y[1] = F[1]; y[2] = F[2];
         }
     }
@@ -1022,6 +1029,7 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L, co
 #endif
 #define TPP_SMEM_BYTES ((size_t)(TPP_THREADS / 32) * TPP_STAGE_SMEM + (size_t)TPP_THREADS * TPP_LANE_STRIDE * sizeof(double))
 
+template <int SPEC>
 __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kernel(const KParams P, const TppArgs T) {
     extern __shared__ __align__(16) char tpp_smem[];
     const BatchArgs &A = T.a;
@@ -1057,7 +1065,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                     __threadfence();
                 }
                 L.goal[0] = L.goal[1] = L.goal[2] = 0;
-                if (P.ref_kind == B200MPC_REF_GOAL) {
+                if (TPP_IS_GOAL(P)) {
                     const double *xr = A.xref + 3 * (size_t)b;
                     L.goal[0] = __ldcg(xr); L.goal[1] = __ldcg(xr + 1); L.goal[2] = __ldcg(xr + 2);
                 }
@@ -1105,7 +1113,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                     }
                     tpp_st2(pc, R_U, uv[0], uv[1]); tpp_st2(pc, R_S, sv[0], sv[1]); tpp_st2(pc, R_YD, 0.0, 0.0);
                     tpp_st2(pc, R_VL, 1.0, 1.0); tpp_st2(pc, R_VU, 1.0, 1.0);
-                    if (P.ref_kind == B200MPC_REF_TRAJ) {
+                    if (!TPP_IS_GOAL(P)) {
                         const double *xr = A.xref + b * 3 * N + 3 * k;
                         const double *ur = A.uref + b * 2 * N + 2 * k;
                         tpp_st2(p, R_REF, __ldcg(xr), __ldcg(xr + 1)); tpp_st2(p, R_REF + 1, __ldcg(xr + 2), 0.0);
@@ -1126,7 +1134,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
         if (tpp_opaque(L.phase) == PH_B) {
             TppBwd r;
             tpp_stat(T, 0);
-            tpp_backward(P, A, wb, sb, cur, L, r);
+            tpp_backward<SPEC>(P, A, wb, sb, cur, L, r);
             const int bmode = L.bmode;
             if (bmode == BM_LSQ) {
                 // objective scaling from the gradient at the starting point; invalid-number check
@@ -1160,7 +1168,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
         if (tpp_opaque(L.phase) == PH_F) {
             TppFwd f;
             tpp_stat(T, 1);
-            tpp_forward(P, A, wb, sb, cur, L, f);
+            tpp_forward<SPEC>(P, A, wb, sb, cur, L, f);
             const int bmode = L.bmode;
             if (bmode == BM_LSQ) {
                 // the estimate is kept if its largest entry is <= 1e3; sweep T adds the defect multipliers
@@ -1201,7 +1209,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
         if (tpp_opaque(L.phase) == PH_T) {
             TppTrial t;
             tpp_stat(T, 2);
-            tpp_trial(P, A, wb, sb, cur, L, t);
+            tpp_trial<SPEC>(P, A, wb, sb, cur, L, t);
             const int tm = L.tmode;
             bool accepted = false;
             if (tm == TM_EVAL) {
@@ -1256,7 +1264,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
         if (tpp_opaque(L.phase) == PH_BACKTRACK) {
             L.alpha *= 0.5;
             if (L.alpha < L.a_min) {
-                tpp_restore(P, wb, fl, cur, L);
+                tpp_restore<SPEC>(P, wb, fl, cur, L);
             } else {
                 L.tmode = TM_STEP;
                 L.phase = PH_T;

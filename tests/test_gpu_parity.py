@@ -710,3 +710,30 @@ def test_extreme_horizons_both_kernels(env, N):
         _assert_parity(out, ref, need_frac=0.9)
         assert out["X"].shape == (w["x0"].shape[0], N + 1, 3)
     S.close()
+
+
+def test_lane_kernel_instances(env, robots, monkeypatch):
+    """The lane kernels exist once per problem family (RK4 + goal, Euler + trajectory) and once with run-time switches.
+    The generic instance must agree with the specialised ones, and it alone serves the mixed families (here the
+    tracking cost on RK4 dynamics, and the goal cost on Euler dynamics)."""
+    O, shim, synth = env["O"], env["shim"], env["synth"]
+    y, w = env["y"], robots
+    N = y["N"]
+    pxf, puf = synth.straight_reference(w["x0"], w["goal"], N)
+    for variant, over in (("B", {}), ("C", {}), ("C", dict(integrator=shim.RK4)), ("B", dict(integrator=shim.EULER))):
+        xr, kw = (w["goal"], {}) if variant == "B" else (pxf, dict(uref=puf))
+        po = O.variant_params(variant, y, **over)
+        ref = O.solve_batch(po, w["x0"], xr, **kw)
+        outs = []
+        for generic in (False, True):
+            if generic:
+                monkeypatch.setenv("B200MPC_LANE_GENERIC", "1")
+            S = shim.Solver(env["make"](variant, y, **over))
+            monkeypatch.delenv("B200MPC_LANE_GENERIC", raising=False)
+            S.set_kernel(shim.KERNEL_LANE)
+            out = S.solve_batch(w["x0"], xr, **kw)
+            S.close()
+            _assert_parity(out, ref, need_frac=0.95)
+            outs.append(out)
+        assert np.array_equal(outs[0]["status"], outs[1]["status"]) and np.array_equal(outs[0]["iters"], outs[1]["iters"])
+        assert np.max(np.abs(outs[0]["U"] - outs[1]["U"])) <= 1e-9
