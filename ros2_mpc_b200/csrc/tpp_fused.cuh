@@ -19,6 +19,14 @@
 // Trip = blocks L(oad), TB, F.  Everything else (workspace layout, staging, lane state, filter, restoration stand-in,
 // result stores) is shared with tpp_kernel.cuh; the algorithm and its decisions are unchanged.
 #pragma once
+#ifndef TPPF_L2_PREFETCH
+#define TPPF_L2_PREFETCH 0 /* the two-sweep kernel is instruction-fetch bound: the L2 prefetches cost more than they hide */
+#endif
+__device__ __forceinline__ void tppf_l2_prefetch(const char *p, int row0, int n) {
+#if TPPF_L2_PREFETCH
+    tpp_l2_prefetch(p, row0, n);
+#endif
+}
 
 // workspace row R_KB = (kfb0, kfb1): barrier-parameter coefficient of the feed-forward gain (tpp_kernel.cuh)
 enum { PHF_LOAD = 0, PHF_TB = 1, PHF_F = 2, PHF_BACKTRACK = 4, PHF_FIN = 6, PHF_DONE = 7 };
@@ -71,11 +79,11 @@ __device__ __forceinline__ void tppf_forward(const KParams &P, char *wb, char *s
         tpp_consume(vu2, xn01, xn2, xn2);
         if (k < N) tppf_forward_stage(sb, p + TPP_STAGE_B, co, k + 1 < N);
         if (k + 2 <= N) {
-            tpp_l2_prefetch(p + 2 * TPP_STAGE_B, R_K, 4);
-            tpp_l2_prefetch(p + 2 * TPP_STAGE_B, R_KB, 1);
-            tpp_l2_prefetch(p + 2 * TPP_STAGE_B + co * TPP_ROW_B, R_U, 2);
-            tpp_l2_prefetch(p + 2 * TPP_STAGE_B + co * TPP_ROW_B, R_VL, 2);
-            if (k + 3 <= N) tpp_l2_prefetch(p + 3 * TPP_STAGE_B + co * TPP_ROW_B, R_X01, 2);
+            tppf_l2_prefetch(p + 2 * TPP_STAGE_B, R_K, 4);
+            tppf_l2_prefetch(p + 2 * TPP_STAGE_B, R_KB, 1);
+            tppf_l2_prefetch(p + 2 * TPP_STAGE_B + co * TPP_ROW_B, R_U, 2);
+            tppf_l2_prefetch(p + 2 * TPP_STAGE_B + co * TPP_ROW_B, R_VL, 2);
+            if (k + 3 <= N) tppf_l2_prefetch(p + 3 * TPP_STAGE_B + co * TPP_ROW_B, R_X01, 2);
         }
         if (!isfinite(y0) || !isfinite(y1) || !isfinite(y2)) bad = 1;
         tpp_st2(p, orow, y0, y1); tpp_st2(p, orow + 1, y2, 0.0);
@@ -186,8 +194,8 @@ __device__ __forceinline__ void tppf_trial_backward(const KParams &P, char *wb, 
         tpp_consume(dx01, dx2, du2, du2);
         if (k > 0) tppf_stage(sb, p - TPP_STAGE_B, co, srow);
         if (k > 1) {
-            tpp_l2_prefetch(p - 2 * TPP_STAGE_B + co * TPP_ROW_B, 0, R_ITER);
-            tpp_l2_prefetch(p - 2 * TPP_STAGE_B, srow, 3);
+            tppf_l2_prefetch(p - 2 * TPP_STAGE_B + co * TPP_ROW_B, 0, R_ITER);
+            tppf_l2_prefetch(p - 2 * TPP_STAGE_B, srow, 3);
         }
         double r[3], ub[2];
         tpp_ref<SPEC>(P, goal, p, r, ub);
