@@ -1577,11 +1577,16 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(cudaGetErrorString(e));
     h->sm_count = prop.multiProcessorCount;
     int blocks = 0;
+    // The dynamic shared-memory limit is an attribute of the kernel, shared by every handle of the process: it is
+    // raised to the device's opt-in maximum once (a later handle with a smaller need must not lower it under an
+    // earlier handle's launches); occupancy is computed for this handle's own size.
+    const size_t smem_cap = prop.sharedMemPerBlockOptin;
+    if (h->smem_bytes > smem_cap) return fail("N and M too large for the shared memory of this device");
     switch (h->J) {
-        case 1: e = configure_kernels<1>(h->smem_bytes); if (e == cudaSuccess) e = occupancy<1>(&blocks, h->smem_bytes); break;
-        case 2: e = configure_kernels<2>(h->smem_bytes); if (e == cudaSuccess) e = occupancy<2>(&blocks, h->smem_bytes); break;
-        case 3: e = configure_kernels<3>(h->smem_bytes); if (e == cudaSuccess) e = occupancy<3>(&blocks, h->smem_bytes); break;
-        default: e = configure_kernels<4>(h->smem_bytes); if (e == cudaSuccess) e = occupancy<4>(&blocks, h->smem_bytes); break;
+        case 1: e = configure_kernels<1>(smem_cap); if (e == cudaSuccess) e = occupancy<1>(&blocks, h->smem_bytes); break;
+        case 2: e = configure_kernels<2>(smem_cap); if (e == cudaSuccess) e = occupancy<2>(&blocks, h->smem_bytes); break;
+        case 3: e = configure_kernels<3>(smem_cap); if (e == cudaSuccess) e = occupancy<3>(&blocks, h->smem_bytes); break;
+        default: e = configure_kernels<4>(smem_cap); if (e == cudaSuccess) e = occupancy<4>(&blocks, h->smem_bytes); break;
     }
     if (e != cudaSuccess) return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
     if (blocks < 1) blocks = 1;
@@ -2083,7 +2088,7 @@ static int launch_obstacles(b200mpc_handle *h, int B, int n_beams, const double 
     const size_t per_warp = (((size_t)a.nwords * 8 + (size_t)slots * 4) + 15) & ~(size_t)15;
     const size_t smem = per_warp * OBS_WARPS + 16;
     if (smem > 200 * 1024) return set_err(h, B200MPC_E_ARG, "grid / slots too large for the shared-memory staging");
-    if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(obstacles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(obstacles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int grid = (B + OBS_WARPS - 1) / OBS_WARPS;
     const int cap = h->sm_count * 8; // grid-stride above 8 CTAs per SM
     if (grid > cap) grid = cap;

@@ -737,3 +737,67 @@ def test_lane_kernel_instances(env, robots, monkeypatch):
             outs.append(out)
         assert np.array_equal(outs[0]["status"], outs[1]["status"]) and np.array_equal(outs[0]["iters"], outs[1]["iters"])
         assert np.max(np.abs(outs[0]["U"] - outs[1]["U"])) <= 1e-9
+
+
+def test_closed_loop_with_obstacles_variant_a(env):
+    """Config 2 with the obstacle cost active (variant A): every control step runs scan (ray-cast of map_carto) ->
+    obstacle list (GPU, first 160 cells) -> look-ahead goal (GPU) -> solve (GPU) -> plant.  Each step's solve is checked
+    against the oracle on identical inputs, and the robot must keep its distance from the occupied cells.  (Whether it
+    approaches the goal is the reference's business: variant A weighs the x error with 5e-5 against obstacle terms of
+    order one, and the oracle steers exactly the same way.)"""
+    O, synth = env["O"], env["synth"]
+    from ros2_mpc_b200 import MpcPointStabilization, obstacles as ob, references as rf
+    y = env["y"]
+    m = synth.load_map()
+    clr = synth.clearance(m)
+    start = np.array([-2.965, 2.315, 0.3])
+    goal5 = np.array([-1.9, 2.9, 0.0, 0.0, 0.5])
+    path = np.linspace(start[:2], goal5[:2], 40)
+    head, _, _ = rf.get_headings(path, y["dt"])
+    mpc = MpcPointStabilization()
+    po = O.variant_params("A", y)
+    N = mpc.N
+    x = start.copy()
+    d0 = np.linalg.norm(x[:2] - goal5[:2])
+    worst_u, min_clear, n_cmp = 0.0, 1e9, 0
+    for step in range(45):
+        scan, angles = synth.raycast(m, x[None, :2], x[None, 2:3].ravel())
+        ox, oy, cnt = ob.get_obstacles_batch_gpu(scan, angles, y["costmap_size"], y["resolution"], x[None, :2], x[None, 2], 160)
+        rx, ry, rc = ob.get_obstacles(scan, angles, y["costmap_size"], y["resolution"], x[None, :2], x[None, 2], 160)
+        assert np.array_equal(cnt, rc) and np.max(np.abs(ox - rx)) <= 1e-12 and np.max(np.abs(oy - ry)) <= 1e-12
+        gm = rf.get_goal_for_mpc(path, head.reshape(-1, 1), goal5, x, y["look_ahead_distance"])
+        x0 = np.array([x[0], x[1], x[2] % (2 * np.pi)])
+        x_opt, u_opt = mpc.perform_mpc(np.zeros((2, N)), x0, gm, ox[0], oy[0])
+        ro = O.solve(po, x0, gm, obs_x=ox[0], obs_y=oy[0])
+        if ro["status"] == 0 and abs(ro["cost"] - mpc.last_cost) <= 1e-5 * abs(ro["cost"]):  # same local optimum
+            worst_u = max(worst_u, float(np.max(np.abs(u_opt - ro["U"]))))
+            n_cmp += 1
+        u = u_opt[:, 0]
+        th = x[2]
+        tm, te = th + 0.5 * y["dt"] * u[1], th + y["dt"] * u[1]
+        x[0] += y["dt"] / 6 * u[0] * (np.cos(th) + 4 * np.cos(tm) + np.cos(te))
+        x[1] += y["dt"] / 6 * u[0] * (np.sin(th) + 4 * np.sin(tm) + np.sin(te))
+        x[2] = te
+        r, c = synth.world_to_cell(m, x[:2])
+        min_clear = min(min_clear, float(clr[r, c]))
+    mpc.close()
+    assert n_cmp >= 40 and worst_u <= U_ATOL
+    assert np.isfinite(x).all() and np.linalg.norm(x[:2] - start[:2]) > 0.1 and d0 > 0
+    assert min_clear > 0.2
+
+
+def test_handles_with_different_shared_memory_needs_coexist(env, robots):
+    """The warp kernel's dynamic shared-memory limit is a per-kernel attribute shared by all handles of the process: a
+    handle created later with a smaller need (no obstacle lists) must not break the launches of an earlier one."""
+    shim, w = env["shim"], robots
+    Sa = shim.Solver(env["make"]("A", env["y"]))          # obstacle lists in shared memory: > 48 KB
+    Sb = shim.Solver(env["make"]("B", env["y"]))          # created afterwards, needs less
+    Sn = shim.Solver(env["make"]("B", env["y"], N=5))     # and a tiny one
+    k = 32
+    for _ in range(2):
+        a = Sa.solve_batch(w["x0"][:k], w["goal"][:k], obs_x=w["obs_x"][:k], obs_y=w["obs_y"][:k])
+        b = Sb.solve_batch(w["x0"][:k], w["goal"][:k])
+        n = Sn.solve_batch(w["x0"][:k], w["goal"][:k])
+        assert np.isin(b["status"], (0, 1)).all() and np.isin(n["status"], (0, 1)).all() and a["X"].shape == (k, 31, 3)
+    for S in (Sa, Sb, Sn):
+        S.close()
