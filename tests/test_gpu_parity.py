@@ -801,3 +801,29 @@ def test_handles_with_different_shared_memory_needs_coexist(env, robots):
         assert np.isin(b["status"], (0, 1)).all() and np.isin(n["status"], (0, 1)).all() and a["X"].shape == (k, 31, 3)
     for S in (Sa, Sb, Sn):
         S.close()
+
+
+def test_handle_lifecycle_releases_device_memory(env, robots):
+    """Creating, using (lane kernel: ~0.9 GB workspace; streamed and zero-copy host paths) and destroying handles
+    repeatedly must give the device memory back."""
+    import torch
+    shim, w = env["shim"], robots
+    x0, goal = np.tile(w["x0"], (48, 1)), np.tile(w["goal"], (48, 1))   # 18 432 problems -> lane kernel
+
+    def cycle():
+        S = shim.Solver(env["make"]("B", env["y"]))
+        o = S.solve_batch(x0, goal)
+        assert S.last_kernel_kind == shim.KERNEL_LANE and np.isin(o["status"], (0, 1)).all()
+        S.solve_batch(w["x0"][:1], w["goal"][:1])
+        S.obstacles_batch(w["scan"][:8], *__import__("ros2_mpc_b200.obstacles", fromlist=["beam_table"]).beam_table(360, w["angles"]),
+                          w["x0"][:8, :2], w["x0"][:8, 2], 2.0, 0.05, 160)
+        S.close()
+
+    cycle()
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(6):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 * 1024 * 1024, (free0, free1)
