@@ -827,3 +827,39 @@ def test_handle_lifecycle_releases_device_memory(env, robots):
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 64 * 1024 * 1024, (free0, free1)
+
+
+def test_c_abi_argument_errors(env):
+    """Bad arguments come back as negative codes with a message — never a crash, never an exception across the ABI."""
+    import ctypes as C
+    shim = env["shim"]
+    L = shim.lib()
+    p = env["make"]("B", env["y"])
+    for field, val in (("N", 0), ("N", 500), ("dt", 0.0)):
+        q = env["make"]("B", env["y"])
+        setattr(q, field, val)
+        assert not L.b200mpc_create(C.byref(q), 0)
+        assert len(L.b200mpc_last_error(None)) > 0
+    assert not L.b200mpc_create(C.byref(p), 99) and b"device" in L.b200mpc_last_error(None)
+    S = shim.Solver(p)
+    h = S._h
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    x = np.zeros((4, 3)); X = np.zeros((4, 31, 3)); U = np.zeros((4, 30, 2)); st = np.zeros(4, np.int32)
+    P = lambda a: a.ctypes.data_as(dp)
+    E_ARG = -1
+    assert L.b200mpc_solve_batch(h, -1, P(x), P(x), None, None, None, 0, None, P(X), P(U), None, st.ctypes.data_as(ip), None, None) == E_ARG
+    assert L.b200mpc_solve_batch(h, 4, None, P(x), None, None, None, 0, None, P(X), P(U), None, st.ctypes.data_as(ip), None, None) == E_ARG
+    assert L.b200mpc_solve_batch(h, 4, P(x), P(x), None, None, None, 0, None, None, P(U), None, st.ctypes.data_as(ip), None, None) == E_ARG
+    assert b"NULL" in L.b200mpc_last_error(h)
+    assert L.b200mpc_solve_batch(None, 4, P(x), P(x), None, None, None, 0, None, P(X), P(U), None, st.ctypes.data_as(ip), None, None) == E_ARG
+    assert L.b200mpc_set_kernel(h, 7) == E_ARG
+    sc = np.ones((2, 8)); t = np.ones(8); ox = np.zeros((2, 160)); cnt = np.zeros(2, np.int32)
+    assert L.b200mpc_obstacles_batch(h, 2, 8, P(sc), P(t), P(t), P(x), P(x), 2.0, 0.05, 0, P(ox), P(ox), cnt.ctypes.data_as(ip)) == E_ARG
+    assert L.b200mpc_obstacles_batch(h, 2, 8, P(sc), P(t), P(t), P(x), P(x), 2.0, 0.0, 160, P(ox), P(ox), cnt.ctypes.data_as(ip)) == E_ARG
+    assert L.b200mpc_obstacles_batch(h, 2, 8, P(sc), P(t), P(t), P(x), P(x), 500.0, 0.05, 160, P(ox), P(ox), cnt.ctypes.data_as(ip)) == E_ARG
+    assert L.b200mpc_goals_batch(h, 2, 0, P(x), P(x), 0, P(x), P(x), 0.5, P(x), None) == E_ARG
+    assert L.b200mpc_reftraj_batch(h, 2, 4, P(x), P(x), P(x), P(x), 9, 0, P(x), P(x), P(X), P(U), None) == E_ARG
+    # the handle is still usable afterwards
+    o = S.solve_batch(np.zeros((1, 3)), np.array([[0.5, 0.2, 0.0]]))
+    assert o["status"][0] == 0
+    S.close()
