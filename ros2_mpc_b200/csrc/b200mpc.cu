@@ -224,7 +224,7 @@ __device__ __forceinline__ void dyn_value(const KParams &P, const double X[3], c
 // act: stage exists (k <= N); dyn: stage has controls and a successor (k < N); obs: obstacle sum on this stage.
 __device__ __forceinline__ double stage_full(const KParams &P, const double *sox, const double *soy, Stg &s,
                                              const double Xn[3], const double ln[3], double df, bool act,
-                                             bool dyn, bool obs) {
+                                             bool dyn, bool obs, const double *oc = nullptr) {
     double fval = 0;
     s.a13 = s.a23 = s.b11 = s.b12 = s.b21 = s.b22 = 0;
     s.hxx = s.hxy = s.hyy = s.htt = s.htv = s.htw = s.hvv = s.hvw = s.hww = 0;
@@ -287,7 +287,8 @@ __device__ __forceinline__ double stage_full(const KParams &P, const double *sox
     }
     if (obs && act) {
         double ov, gx, gy, oxx, oxy, oyy;
-        obstacle_sum<true>(P, sox, soy, s.X[0], s.X[1], ov, gx, gy, oxx, oxy, oyy);
+        if (oc) { ov = oc[0]; gx = oc[1]; gy = oc[2]; oxx = oc[3]; oxy = oc[4]; oyy = oc[5]; }
+        else obstacle_sum<true>(P, sox, soy, s.X[0], s.X[1], ov, gx, gy, oxx, oxy, oyy);
         fval += ov;
         s.g[0] += df * gx;
         s.g[1] += df * gy;
@@ -733,8 +734,8 @@ __device__ __forceinline__ double frac_to_bound(const KParams &P, const Stg (&s)
 }
 
 // trial point curr + alpha*step: theta (1-norm) and barrier objective, both warp-uniform
-template <int J>
-__device__ __forceinline__ void trial_eval(const KParams &P, const double *sox, const double *soy, Stg (&s)[J],
+template <int J, bool OBS>
+__device__ __forceinline__ void trial_eval(const KParams &P, const double *sox, const double *soy, double *ocs, Stg (&s)[J],
                                            const Step (&o)[J], double alpha, double mu, double df, int lane,
                                            double &th_t, double &phi_t) {
 #pragma unroll
@@ -753,11 +754,20 @@ __device__ __forceinline__ void trial_eval(const KParams &P, const double *sox, 
     for (int j = 0; j < J; ++j) {
         const int k = lane * J + j;
         const bool act = (k <= P.N), dyn = (k < P.N);
-        const bool obs = P.obs_form != B200MPC_OBS_NONE && k >= P.obs_k0 && k <= P.obs_k1;
+        const bool obs = OBS && P.obs_form != B200MPC_OBS_NONE && k >= P.obs_k0 && k <= P.obs_k1;
         Stg &t = s[j];
         double Xn[3];
         NEXT3(Xn, Xt, j);
-        const double fv = stage_value(P, sox, soy, t.Xt, t.Ut, t.r, t.ub, Xn, t.ct, act, dyn, obs);
+        double fv = stage_value(P, sox, soy, t.Xt, t.Ut, t.r, t.ub, Xn, t.ct, act, dyn, false);
+        if (obs && act) {
+            // value and derivatives: the accepted trial point is the next iterate, and its linearisation then takes
+            // the sums from this per-stage cache in shared memory instead of walking the obstacle list again
+            double ov, gx, gy, oxx, oxy, oyy;
+            obstacle_sum<true>(P, sox, soy, t.Xt[0], t.Xt[1], ov, gx, gy, oxx, oxy, oyy);
+            double *oc = ocs + 6 * k;
+            oc[0] = ov; oc[1] = gx; oc[2] = gy; oc[3] = oxx; oc[4] = oxy; oc[5] = oyy;
+            fv += ov;
+        }
         double bar = 0, thl = 0;
         if (dyn) {
             thl = fabs(t.ct[0]) + fabs(t.ct[1]) + fabs(t.ct[2]) + fabs(t.Ut[0] - t.St[0]) + fabs(t.Ut[1] - t.St[1]);
@@ -817,7 +827,9 @@ __device__ __forceinline__ void filter_add(double phi, double theta, double &fph
 #define KKT_SOLVE(P, s, rc, rd, useW, dw, o, lane) kkt_solve<J>(P, s, rc, rd, useW, dw, o, lane)
 #endif
 
-template <int J>
+// OBS: the kernel instance carries the obstacle cost (variant A; B with its gauss cost enabled).  The instance without
+// it has no obstacle loops at all — they would cost the obstacle-free variants registers (spills) for nothing.
+template <int J, bool OBS>
 __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane, double *sox, double *soy, double *rec,
                           const KktRoles &roles) {
     const int N = P.N;
@@ -827,7 +839,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
 
     // ---- load the problem (coalesced: consecutive lanes read consecutive stages) ----
     const double x00 = A.x0[3 * (size_t)b], x01 = A.x0[3 * (size_t)b + 1], x02 = A.x0[3 * (size_t)b + 2];
-    if (P.obs_form != B200MPC_OBS_NONE) {
+    if (OBS && P.obs_form != B200MPC_OBS_NONE) {
         const double *gx = A.ox + (size_t)A.obs_stride * b, *gy = A.oy + (size_t)A.obs_stride * b;
         for (int i = lane; i < P.M; i += 32) { sox[i] = gx[i]; soy[i] = gy[i]; }
     }
@@ -876,6 +888,8 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
     double df = 1.0;
     double fcur = 0;
 
+    bool oc_valid = false; // ocs holds the obstacle sums of the current iterate (it was the accepted trial point)
+    double *ocs = rec + (size_t)(N + 1) * KKT_REC; // per stage: value, gradient (2), Hessian (3) of the obstacle sum
     // full evaluation of the current point; returns the objective value (unscaled, warp-uniform)
     auto eval_point = [&](double dfv) -> double {
         double Xn0[3], ln0[3];
@@ -884,11 +898,12 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
         for (int j = 0; j < J; ++j) {
             const int k = lane * J + j;
             const bool act = (k <= N), dyn = (k < N);
-            const bool obs = P.obs_form != B200MPC_OBS_NONE && k >= P.obs_k0 && k <= P.obs_k1;
+            const bool obs = OBS && P.obs_form != B200MPC_OBS_NONE && k >= P.obs_k0 && k <= P.obs_k1;
             NEXT3(Xn0, X, j);
             NEXT3(ln0, lam, j);
-            fl += stage_full(P, sox, soy, s[j], Xn0, ln0, dfv, act, dyn, obs);
+            fl += stage_full(P, sox, soy, s[j], Xn0, ln0, dfv, act, dyn, obs, (oc_valid && k <= N) ? ocs + 6 * k : nullptr);
         }
+        oc_valid = false;
         return wsum(fl);
     };
 
@@ -1136,7 +1151,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
             int ntrial = 0;
             while (!acc) {
                 double th_t, phi_t;
-                trial_eval<J>(P, sox, soy, s, st, alpha, mu, df, lane, th_t, phi_t);
+                trial_eval<J, OBS>(P, sox, soy, ocs, s, st, alpha, mu, df, lane, th_t, phi_t);
                 if (ntrial++ > 0) ls_extra++;
                 if (ls_acceptable(ref, alpha, phi_t, th_t, fphi, ftheta, fvalid, fa)) { acc = 1; alpha_acc = alpha; break; }
                 if (ntrial == 1 && P.max_soc > 0 && isfinite(th_t) && th_t >= theta) {
@@ -1164,7 +1179,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                         if (!KKT_SOLVE(P, s, csoc, dsoc, true, dw, soc, lane)) break;
                         alpha_soc = frac_to_bound<J>(P, s, soc, tau, lane);
                         double phi_s;
-                        trial_eval<J>(P, sox, soy, s, soc, alpha_soc, mu, df, lane, th_trial, phi_s);
+                        trial_eval<J, OBS>(P, sox, soy, ocs, s, soc, alpha_soc, mu, df, lane, th_trial, phi_s);
                         ls_extra++;
                         if (ls_acceptable(ref, alpha, phi_s, th_trial, fphi, ftheta, fvalid, fa)) { acc = 2; alpha_acc = alpha_soc; }
                         else count++;
@@ -1245,7 +1260,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                 if (k >= 1 && k <= N) {
 #pragma unroll
                     for (int i = 0; i < 3; i++) {
-                        t.X[i] += alpha_acc * q.dX[i];
+                        t.X[i] = t.Xt[i]; // = X + alpha_acc*dX, the point the last trial evaluation (and ocs) belongs to
                         t.lam[i] += alpha_acc * q.dlam[i];
                     }
                 }
@@ -1264,6 +1279,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                 }
             }
             iter++;
+            oc_valid = OBS && (P.obs_form != B200MPC_OBS_NONE);
         }
     }
 
@@ -1276,7 +1292,7 @@ finish:
         for (int j = 0; j < J; ++j) {
             const int k = lane * J + j;
             const bool act = (k <= N), dyn = (k < N);
-            const bool obs = P.obs_form != B200MPC_OBS_NONE && k >= P.obs_k0 && k <= P.obs_k1;
+            const bool obs = OBS && P.obs_form != B200MPC_OBS_NONE && k >= P.obs_k0 && k <= P.obs_k1;
             double Xn[3], ct[3];
             NEXT3(Xn, X, j);
             fl += stage_value(P, sox, soy, s[j].X, s[j].U, s[j].r, s[j].ub, Xn, ct, act, dyn, obs);
@@ -1304,13 +1320,13 @@ finish:
     __syncwarp();
 }
 
-template <int J>
+template <int J, bool OBS>
 __global__ void __launch_bounds__(128, B200MPC_MIN_CTAS) mpc_solve_kernel(const KParams P, const BatchArgs A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int Mpad = (P.M + 3) & ~3;
     // per warp: the problem's obstacle lists (2*Mpad doubles) and the stage records of the KKT solve
-    const size_t per_warp = 2 * (size_t)Mpad + (size_t)(P.N + 1) * KKT_REC;
+    const size_t per_warp = 2 * (size_t)Mpad + (size_t)(P.N + 1) * (KKT_REC + 6);
     double *sox = smem + (size_t)wid * per_warp, *soy = sox + Mpad, *rec = soy + Mpad;
     const KktRoles roles = kkt_roles(lane);
     for (;;) {
@@ -1318,7 +1334,7 @@ __global__ void __launch_bounds__(128, B200MPC_MIN_CTAS) mpc_solve_kernel(const 
         if (lane == 0) b = (int)atomicAdd(A.counter, 1u);
         b = __shfl_sync(FULL, b, 0);
         if (b >= A.B) break;
-        solve_one<J>(P, A, b, lane, sox, soy, rec, roles);
+        solve_one<J, OBS>(P, A, b, lane, sox, soy, rec, roles);
     }
 }
 
@@ -1490,14 +1506,16 @@ extern "C" const char *b200mpc_last_error(const b200mpc_handle *h) {
 
 template <int J>
 static cudaError_t configure_kernels(size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(mpc_solve_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mpc_solve_kernel<J, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mpc_solve_kernel<J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(mpc_eval_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 template <int J>
 static cudaError_t occupancy(int *blocks, size_t smem) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, mpc_solve_kernel<J>, 128, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, mpc_solve_kernel<J, true>, 128, smem);
 }
 
 extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
@@ -1561,7 +1579,7 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     h->J = (p->N + 1 + 31) / 32;
     const int Mpad = (k.M + 3) & ~3;
     // per warp: obstacle lists + the stage records of the lane-parallel KKT solve (KKT_REC doubles per stage)
-    h->smem_bytes = (size_t)4 * (2 * (size_t)Mpad + (size_t)(p->N + 1) * KKT_REC) * sizeof(double);
+    h->smem_bytes = (size_t)4 * (2 * (size_t)Mpad + (size_t)(p->N + 1) * (KKT_REC + 6)) * sizeof(double);
     if (h->smem_bytes > 227 * 1024) {
         set_err(nullptr, B200MPC_E_ARG, "N and M too large for the shared-memory staging of the warp kernel");
         delete h;
@@ -1802,10 +1820,16 @@ static int launch_solve(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stre
     if (grid < 1) grid = 1;
     CU_TRY(h, cudaEventRecord(h->ev0, stream));
     switch (h->J) {
-        case 1: mpc_solve_kernel<1><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a); break;
-        case 2: mpc_solve_kernel<2><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a); break;
-        case 3: mpc_solve_kernel<3><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a); break;
-        default: mpc_solve_kernel<4><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a); break;
+#define LAUNCH_WARP(JJ)                                                                                    \
+    do {                                                                                                    \
+        if (h->prm.obs_form != B200MPC_OBS_NONE) mpc_solve_kernel<JJ, true><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a); \
+        else mpc_solve_kernel<JJ, false><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a);                  \
+    } while (0)
+        case 1: LAUNCH_WARP(1); break;
+        case 2: LAUNCH_WARP(2); break;
+        case 3: LAUNCH_WARP(3); break;
+        default: LAUNCH_WARP(4); break;
+#undef LAUNCH_WARP
     }
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev1, stream));
