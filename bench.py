@@ -201,7 +201,26 @@ def single_solve_latency(variant, params, wl, device, n=300):
         tc.append(time.perf_counter() - t)
     S.close()
     q = lambda a, f: float(np.quantile(np.asarray(a), f) * 1e3)  # noqa: E731
-    return {"unit": "ms", "gpu_p50": q(tg, 0.5), "gpu_p99": q(tg, 0.99), "gpu_solves": len(tg),
+    # config 1: the reference's own default call — x0 = (0,0,0), goal = (10,10,0), u0 = zeros, sentinel
+    # obstacles (100.0 x 160) — for the standalone script's class (variant A) and the planner node's (variant B)
+    from ros2_mpc_b200 import make_params  # noqa: PLC0415
+    config1 = {}
+    for var in ("A", "B"):
+        Sv = _shim.Solver(make_params(var, params), device=device)
+        pv = O.variant_params(var, params)
+        x0, goal = np.zeros((1, 3)), np.array([[10.0, 10.0, 0.0]])
+        kw = dict(obs_x=np.full(wl["p"].M, 100.0), obs_y=np.full(wl["p"].M, 100.0)) if var == "A" else {}
+        Sv.solve_batch(x0, goal, **kw)
+        t1, t2 = [], []
+        for _ in range(50):
+            t = time.perf_counter(); og = Sv.solve_batch(x0, goal, **kw); t1.append(time.perf_counter() - t)
+        for _ in range(20):
+            t = time.perf_counter(); oc = O.solve(pv, x0[0], goal[0], **kw); t2.append(time.perf_counter() - t)
+        Sv.close()
+        config1[var] = {"gpu_p50": q(t1, 0.5), "cpu_oracle_p50": q(t2, 0.5), "iters": int(og["iters"][0]),
+                        "status": int(og["status"][0]), "cost": float(og["cost"][0]),
+                        "cost_rel_diff_vs_oracle": float(abs(og["cost"][0] - oc["cost"]) / abs(oc["cost"]))}
+    return {"unit": "ms", "config1": config1, "gpu_p50": q(tg, 0.5), "gpu_p99": q(tg, 0.99), "gpu_solves": len(tg),
             "cpu_oracle_p50": q(tc, 0.5), "cpu_oracle_p99": q(tc, 0.99), "cpu_solves": len(tc),
             "what": "one cold-start solve per call through the C ABI (host buffers, batch of 1) vs oracle/mpc_oracle.c on one core"}
 
