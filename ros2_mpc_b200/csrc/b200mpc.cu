@@ -1556,6 +1556,9 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     h->last_streamed = 0;
     h->h_small = h->h_small_dev = nullptr;
     h->small_cap = 0;
+    h->stream = nullptr;
+    h->ev0 = h->ev1 = nullptr;
+    h->d_counter = nullptr;
     if (const char *ek = getenv("B200MPC_KERNEL")) {
         if (!strcmp(ek, "warp")) h->kernel_kind = B200MPC_KERNEL_WARP;
         else if (!strcmp(ek, "lane")) h->kernel_kind = B200MPC_KERNEL_LANE;
@@ -1582,12 +1585,12 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     h->smem_bytes = (size_t)4 * (2 * (size_t)Mpad + (size_t)(p->N + 1) * (KKT_REC + 6)) * sizeof(double);
     if (h->smem_bytes > 227 * 1024) {
         set_err(nullptr, B200MPC_E_ARG, "N and M too large for the shared-memory staging of the warp kernel");
-        delete h;
+        b200mpc_destroy(h);
         return nullptr;
     }
     auto fail = [&](const std::string &m) -> b200mpc_handle * {
         set_err(nullptr, B200MPC_E_CUDA, m);
-        delete h;
+        b200mpc_destroy(h); // releases whatever has been created so far
         return nullptr;
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
@@ -1650,21 +1653,21 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
 extern "C" void b200mpc_destroy(b200mpc_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->d_buf) cudaFree(h->d_buf);
     if (h->d_ws) cudaFree(h->d_ws);
     if (h->d_filt) cudaFree(h->d_filt);
     if (h->d_stats) cudaFree(h->d_stats);
-    cudaFree(h->d_counter);
+    if (h->d_counter) cudaFree(h->d_counter);
     if (h->cstream) { cudaStreamSynchronize(h->cstream); cudaStreamDestroy(h->cstream); }
     if (h->ostream) { cudaStreamSynchronize(h->ostream); cudaStreamDestroy(h->ostream); }
     if (h->ev_sync) cudaEventDestroy(h->ev_sync);
     if (h->d_sync) cudaFree(h->d_sync);
     if (h->h_sync) cudaFreeHost(h->h_sync);
     if (h->h_small) cudaFreeHost(h->h_small);
-    cudaEventDestroy(h->ev0);
-    cudaEventDestroy(h->ev1);
-    cudaStreamDestroy(h->stream);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
