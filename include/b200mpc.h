@@ -85,7 +85,7 @@ extern "C" {
 #define B200MPC_KERNEL_AUTO 0 /* by batch size: lane-per-problem from B200MPC_LANE_KERNEL_MIN_BATCH problems on */
 #define B200MPC_KERNEL_WARP 1 /* one warp per problem, horizon in registers: small batches, single-solve latency */
 #define B200MPC_KERNEL_LANE 2 /* one lane per problem, horizon streamed through an HBM workspace: large batches */
-#define B200MPC_LANE_KERNEL_MIN_BATCH 16384
+#define B200MPC_LANE_KERNEL_MIN_BATCH 30720 /* measured crossover: a lane-kernel launch lasts >= ~20 ms (60-70 trips), the warp kernel solves 1.4 M problems/s */
 
 /* library error codes */
 #define B200MPC_E_ARG (-1)

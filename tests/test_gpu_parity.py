@@ -340,7 +340,7 @@ def test_closed_loop_config2(env):
 
 @pytest.mark.parametrize("variant", ["B", "C"])
 def test_lane_kernel_matches_oracle(env, robots, variant):
-    """The lane-per-problem kernel (forced; normally chosen from 16384 problems on) against the oracle on the
+    """The lane-per-problem kernel (forced; normally chosen from 30720 problems on) against the oracle on the
     config-3 problems, cold start and with random warm-start seeds."""
     O, shim, synth = env["O"], env["shim"], env["synth"]
     xr, kw = _inputs(env, variant, robots)
@@ -377,7 +377,9 @@ def test_lane_kernel_agrees_with_warp_kernel(env):
     S.set_kernel(shim.KERNEL_AUTO)
     S.solve_batch(w["x0"][:100], w["goal"][:100])
     assert S.last_kernel_kind == shim.KERNEL_WARP
-    big = 5
+    mid, big = 5, 8  # 20 480 problems: still the warp kernel; 32 768: the lane kernel
+    S.solve_batch(np.tile(w["x0"], (mid, 1)), np.tile(w["goal"], (mid, 1)))
+    assert S.last_kernel_kind == shim.KERNEL_WARP
     S.solve_batch(np.tile(w["x0"], (big, 1)), np.tile(w["goal"], (big, 1)))
     assert S.last_kernel_kind == shim.KERNEL_LANE
     S.close()
@@ -808,7 +810,7 @@ def test_handle_lifecycle_releases_device_memory(env, robots):
     repeatedly must give the device memory back."""
     import torch
     shim, w = env["shim"], robots
-    x0, goal = np.tile(w["x0"], (48, 1)), np.tile(w["goal"], (48, 1))   # 18 432 problems -> lane kernel
+    x0, goal = np.tile(w["x0"], (96, 1)), np.tile(w["goal"], (96, 1))   # 36 864 problems -> lane kernel
 
     def cycle():
         S = shim.Solver(env["make"]("B", env["y"]))
