@@ -113,3 +113,21 @@ def test_bench_flop_model(params, built):
     assert bench.algorithmic_flops(a, it, ls)[0] == pytest.approx(548 * 30 + 34 * 31 * 160 + 20 * (210 + 31 * 160))
     inb, outb = bench.io_bytes_per_solve(a, True)
     assert inb == 8 * (3 + 3 + 2 * 30 + 2 * 160)
+
+
+def test_gpu_only_helpers_fail_loudly_without_a_device(built):
+    """The producers around the solve have no CPU fallback either: without a CUDA device the drop-ins raise, they do
+    not quietly run the numpy mirror."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from ros2_mpc_b200 import obstacles as ob, references as rf
+    ob._SOLVERS.clear()
+    scan = np.full(360, 1.0)
+    with pytest.raises(RuntimeError, match="no CUDA device|CPU fallback"):
+        ob.get_obstacles_gpu(scan, np.array([0.0, 6.28]), 2.0, 0.05, np.zeros(2), np.zeros(3), np.ones(160), np.ones(160))
+    with pytest.raises(RuntimeError, match="no CUDA device|CPU fallback"):
+        rf.get_goal_for_mpc(np.zeros((4, 2)), np.zeros(4), np.zeros(5), np.zeros(2))
+    # the numpy mirror itself (workload generation, checker) of course runs
+    ox, oy, cnt = ob.get_obstacles(scan, np.array([0.0, 6.28]), 2.0, 0.05, np.zeros((1, 2)), np.zeros(1), 160)
+    assert ox.shape == (1, 160) and cnt[0] > 0
