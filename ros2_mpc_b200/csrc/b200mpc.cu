@@ -73,6 +73,7 @@ struct KParams {
     int N, M, integrator, ref_kind, obs_form, obs_k0, obs_k1, max_iter, acceptable_iter, max_soc;
     double dt, Q[3], R[2], kappa, obs_c, obs_r, u_lo[2], u_hi[2], tol, acceptable_tol, mu_init;
     double sL[2], sU[2], inv_r2, mu_floor;
+    int kkt_scan; // warp kernel, N + 1 <= 32: parallel-in-time Riccati recursion (kkt_backward_scan)
 };
 
 struct BatchArgs {
@@ -577,7 +578,208 @@ __device__ __forceinline__ KktRoles kkt_roles(int lane) {
     return r;
 }
 
-template <int J>
+
+// ---- K4, parallel-in-time form of the backward recursion (single-solve latency; N + 1 <= 32) --------------------------
+// The serial recursion costs ~700 cycles per stage on its critical path (dependent FP64 operations at 11.5 cycles each,
+// profiles/r1_warp_b1_*).  Here the cost-to-go of EVERY stage comes out of a five-level suffix scan over the lanes
+// (Saerkkae & Garcia-Fernandez, "Temporal parallelization of dynamic programming and linear quadratic control", 2021):
+// lane k holds the conditional value function of the stages k..j-1,
+//     V(x_k, x_j) = max_lam  x_k'J x_k / 2 - x_k'eta - lam'C lam / 2 - lam'(x_j - A x_k - b),
+// one stage is  A = A_k - B R^-1 S',  b = d_k - B R^-1 r_u,  C = B R^-1 B',  eta = -(r_x - S R^-1 r_u),
+// J = Hxx - S R^-1 S'  (R = Huu + Sigma + delta_w, S = Hxu), and two adjacent ranges combine associatively as
+//     M = (I + C1 J2)^-1,  A = A2 M A1,  b = A2 M (b1 + C1 eta2) + b2,  C = A2 M C1 A2' + C2,
+//     eta = A1' M'(eta2 - J2 b1) + eta1,  J = A1' M' J2 A1 + J1.
+// After the scan lane k holds (P_k, p_k) = (J, -eta) of the range k..N; the gains, the inertia test (Quu_k positive
+// definite) and P'_k then follow from P_{k+1} with the formulas of the serial recursion, all stages at once.
+// Algebraically this is the same block elimination in another order, so the decisions coincide with the serial form;
+// the values differ at rounding level.  Out of line, operands and results in shared memory: the scan needs ~150
+// registers of its own, which the solver's per-stage state would otherwise be spilled for.
+#define SCAN_NF 27 /* A[9] b[3] C[6] eta[3] J[6] */
+__device__ __noinline__ int kkt_backward_scan(double *rec, double *el, int N, double dt, int lane) {
+    const int k = lane;
+    const bool act = k <= N, dyn = k < N;
+    const double *q = rec + (size_t)(act ? k : 0) * KKT_REC;
+    double A[9], b[3], C[6], e[3], Jm[6];
+    if (dyn) {
+        const double a13 = q[KR_G + 0], a23 = q[KR_G + 1], b11 = q[KR_G + 2], b12 = q[KR_G + 3], b21 = q[KR_G + 4], b22 = q[KR_G + 5];
+        const double R00 = q[KR_H + 12], R01 = q[KR_H + 13], R11 = q[KR_H + 14], htv = q[KR_H + 10], htw = q[KR_H + 11];
+        const double idet = fast_rcp(R00 * R11 - R01 * R01);
+        const double i00 = R11 * idet, i01 = -R01 * idet, i11 = R00 * idet;
+        // B R^-1 (3x2)
+        const double g00 = b11 * i00 + b12 * i01, g01 = b11 * i01 + b12 * i11;
+        const double g10 = b21 * i00 + b22 * i01, g11 = b21 * i01 + b22 * i11;
+        const double g20 = dt * i01, g21 = dt * i11;
+        const double ru0 = q[KR_h + 3], ru1 = q[KR_h + 4];
+        // A~ = A - B R^-1 S', S = e3 (htv, htw)
+        A[0] = 1; A[1] = 0; A[2] = a13 - (g00 * htv + g01 * htw);
+        A[3] = 0; A[4] = 1; A[5] = a23 - (g10 * htv + g11 * htw);
+        A[6] = 0; A[7] = 0; A[8] = 1.0 - (g20 * htv + g21 * htw);
+        b[0] = q[KR_D + 0] - (g00 * ru0 + g01 * ru1);
+        b[1] = q[KR_D + 1] - (g10 * ru0 + g11 * ru1);
+        b[2] = q[KR_D + 2] - (g20 * ru0 + g21 * ru1);
+        C[0] = g00 * b11 + g01 * b12; C[1] = g00 * b21 + g01 * b22; C[2] = g01 * dt;
+        C[3] = g10 * b21 + g11 * b22; C[4] = g11 * dt; C[5] = g21 * dt;
+        const double s0 = htv * i00 + htw * i01, s1 = htv * i01 + htw * i11;
+        Jm[0] = q[KR_H + 0]; Jm[1] = q[KR_H + 1]; Jm[2] = q[KR_H + 2]; Jm[3] = q[KR_H + 3]; Jm[4] = q[KR_H + 4];
+        Jm[5] = q[KR_H + 5] - (s0 * htv + s1 * htw);
+        e[0] = -q[KR_h + 0]; e[1] = -q[KR_h + 1]; e[2] = -(q[KR_h + 2] - (s0 * ru0 + s1 * ru1));
+    } else {
+        // terminal stage (and idle lanes): A = 0, b = 0, C = 0, eta = -r_x, J = Hxx
+#pragma unroll
+        for (int i = 0; i < 9; i++) A[i] = 0;
+        b[0] = b[1] = b[2] = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { C[i] = 0; Jm[i] = q[KR_H + i]; }
+        e[0] = -q[KR_h + 0]; e[1] = -q[KR_h + 1]; e[2] = -q[KR_h + 2];
+    }
+#pragma unroll 1
+    for (int lvl = 1; lvl <= N; lvl <<= 1) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 9; i++) el[i * 32 + lane] = A[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { el[(9 + i) * 32 + lane] = b[i]; el[(18 + i) * 32 + lane] = e[i]; }
+#pragma unroll
+        for (int i = 0; i < 6; i++) { el[(12 + i) * 32 + lane] = C[i]; el[(21 + i) * 32 + lane] = Jm[i]; }
+        __syncwarp();
+        const int pj = lane + lvl;
+        if (pj <= N) {
+            double A2[9], b2[3], C2[6], e2[3], J2[6];
+#pragma unroll
+            for (int i = 0; i < 9; i++) A2[i] = el[i * 32 + pj];
+#pragma unroll
+            for (int i = 0; i < 3; i++) { b2[i] = el[(9 + i) * 32 + pj]; e2[i] = el[(18 + i) * 32 + pj]; }
+#pragma unroll
+            for (int i = 0; i < 6; i++) { C2[i] = el[(12 + i) * 32 + pj]; J2[i] = el[(21 + i) * 32 + pj]; }
+            // symmetric 3x3 stored as (00,01,02,11,12,22)
+#define SYM(M_, i_, j_) M_[(i_) <= (j_) ? ((i_) == 0 ? (j_) : (i_) == 1 ? 2 + (j_) : 5) : ((j_) == 0 ? (i_) : (j_) == 1 ? 2 + (i_) : 5)]
+            double T[9];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+                    T[3 * i + j] = (i == j ? 1.0 : 0.0) + SYM(C, i, 0) * SYM(J2, 0, j) + SYM(C, i, 1) * SYM(J2, 1, j) + SYM(C, i, 2) * SYM(J2, 2, j);
+            // M = T^-1 (adjugate)
+            const double c00 = T[4] * T[8] - T[5] * T[7], c01 = T[5] * T[6] - T[3] * T[8], c02 = T[3] * T[7] - T[4] * T[6];
+            const double idt = fast_rcp(T[0] * c00 + T[1] * c01 + T[2] * c02);
+            double M[9];
+            M[0] = c00 * idt; M[3] = c01 * idt; M[6] = c02 * idt;
+            M[1] = (T[2] * T[7] - T[1] * T[8]) * idt; M[4] = (T[0] * T[8] - T[2] * T[6]) * idt; M[7] = (T[1] * T[6] - T[0] * T[7]) * idt;
+            M[2] = (T[1] * T[5] - T[2] * T[4]) * idt; M[5] = (T[2] * T[3] - T[0] * T[5]) * idt; M[8] = (T[0] * T[4] - T[1] * T[3]) * idt;
+            double MA[9], An[9], MC[9], X[9], MtJ[9], Y[9];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    MA[3 * i + j] = M[3 * i] * A[j] + M[3 * i + 1] * A[3 + j] + M[3 * i + 2] * A[6 + j];
+                    MC[3 * i + j] = M[3 * i] * SYM(C, 0, j) + M[3 * i + 1] * SYM(C, 1, j) + M[3 * i + 2] * SYM(C, 2, j);
+                    MtJ[3 * i + j] = M[i] * SYM(J2, 0, j) + M[3 + i] * SYM(J2, 1, j) + M[6 + i] * SYM(J2, 2, j);
+                }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    An[3 * i + j] = A2[3 * i] * MA[j] + A2[3 * i + 1] * MA[3 + j] + A2[3 * i + 2] * MA[6 + j];
+                    X[3 * i + j] = A2[3 * i] * MC[j] + A2[3 * i + 1] * MC[3 + j] + A2[3 * i + 2] * MC[6 + j];
+                    Y[3 * i + j] = MtJ[3 * i] * A[j] + MtJ[3 * i + 1] * A[3 + j] + MtJ[3 * i + 2] * A[6 + j];
+                }
+            // vectors
+            double v[3], w[3], Mv[3], Mw[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                v[i] = b[i] + SYM(C, i, 0) * e2[0] + SYM(C, i, 1) * e2[1] + SYM(C, i, 2) * e2[2];
+                w[i] = e2[i] - (SYM(J2, i, 0) * b[0] + SYM(J2, i, 1) * b[1] + SYM(J2, i, 2) * b[2]);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                Mv[i] = M[3 * i] * v[0] + M[3 * i + 1] * v[1] + M[3 * i + 2] * v[2];
+                Mw[i] = M[i] * w[0] + M[3 + i] * w[1] + M[6 + i] * w[2];
+            }
+            double bn[3], en[3], Cn[6], Jn[6];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                bn[i] = A2[3 * i] * Mv[0] + A2[3 * i + 1] * Mv[1] + A2[3 * i + 2] * Mv[2] + b2[i];
+                en[i] = A[i] * Mw[0] + A[3 + i] * Mw[1] + A[6 + i] * Mw[2] + e[i];
+            }
+            {
+                int t = 0;
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = i; j < 3; j++, t++) {
+                        Cn[t] = X[3 * i] * A2[3 * j] + X[3 * i + 1] * A2[3 * j + 1] + X[3 * i + 2] * A2[3 * j + 2] + C2[t];
+                        Jn[t] = A[i] * Y[j] + A[3 + i] * Y[3 + j] + A[6 + i] * Y[6 + j] + Jm[t];
+                    }
+            }
+#undef SYM
+#pragma unroll
+            for (int i = 0; i < 9; i++) A[i] = An[i];
+#pragma unroll
+            for (int i = 0; i < 3; i++) { b[i] = bn[i]; e[i] = en[i]; }
+#pragma unroll
+            for (int i = 0; i < 6; i++) { C[i] = Cn[i]; Jm[i] = Jn[i]; }
+        }
+    }
+    // ---- (P_k, p_k) = (J, -eta) of the range k..N; every stage takes its successor's ----
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 6; i++) el[i * 32 + lane] = Jm[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) el[(6 + i) * 32 + lane] = -e[i];
+    __syncwarp();
+    int ok = 1;
+    if (act) {
+        double *g = rec + (size_t)k * KKT_REC + KR_OUT;
+        if (!dyn) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) g[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) g[8 + i] = q[KR_H + i];
+            g[14] = q[KR_h + 0]; g[15] = q[KR_h + 1]; g[16] = q[KR_h + 2];
+        } else {
+            const int n = lane + 1;
+            const double q00 = el[0 * 32 + n], q01 = el[1 * 32 + n], q02 = el[2 * 32 + n], q11 = el[3 * 32 + n], q12 = el[4 * 32 + n],
+                         q22 = el[5 * 32 + n], v0 = el[6 * 32 + n], v1 = el[7 * 32 + n], v2 = el[8 * 32 + n];
+            const double a = q[KR_G + 0], bb = q[KR_G + 1], b11 = q[KR_G + 2], b12 = q[KR_G + 3], b21 = q[KR_G + 4], b22 = q[KR_G + 5];
+            const double d0 = q[KR_D + 0], d1 = q[KR_D + 1], d2 = q[KR_D + 2];
+            const double w0 = q00 * d0 + q01 * d1 + q02 * d2 + v0;
+            const double w1 = q01 * d0 + q11 * d1 + q12 * d2 + v1;
+            const double w2 = q02 * d0 + q12 * d1 + q22 * d2 + v2;
+            const double t0 = q02 + a * q00 + bb * q01, t1 = q12 + a * q01 + bb * q11, t2 = q22 + a * q02 + bb * q12;
+            const double x00 = q[KR_H + 0] + q00, x01 = q[KR_H + 1] + q01, x11 = q[KR_H + 3] + q11;
+            const double x02 = t0, x12 = t1, x22 = q[KR_H + 5] + t2 + a * t0 + bb * t1;
+            const double e0 = b11 * q00 + b21 * q01, e1 = b11 * q01 + b21 * q11;
+            const double f0 = b12 * q00 + b22 * q01 + dt * q02, f1 = b12 * q01 + b22 * q11 + dt * q12, f2 = b12 * q02 + b22 * q12 + dt * q22;
+            const double u00 = e0, u01 = e1, u02 = q[KR_H + 10] + b11 * t0 + b21 * t1;
+            const double u10 = f0, u11 = f1, u12 = q[KR_H + 11] + b12 * t0 + b22 * t1 + dt * t2;
+            const double r00 = q[KR_H + 12] + b11 * e0 + b21 * e1;
+            const double r01 = q[KR_H + 13] + b11 * f0 + b21 * f1;
+            const double r11 = q[KR_H + 14] + b12 * f0 + b22 * f1 + dt * f2;
+            const double gx0 = q[KR_h + 0] + w0, gx1 = q[KR_h + 1] + w1, gx2 = q[KR_h + 2] + a * w0 + bb * w1 + w2;
+            const double gu0 = q[KR_h + 3] + b11 * w0 + b21 * w1, gu1 = q[KR_h + 4] + b12 * w0 + b22 * w1 + dt * w2;
+            const double det = r00 * r11 - r01 * r01;
+            if (!(r00 > 0.0) || !(det > 0.0)) ok = 0;
+            const double idet = fast_rcp(det);
+            const double i00 = r11 * idet, i01 = -r01 * idet, i11 = r00 * idet;
+            const double K00 = -(i00 * u00 + i01 * u10), K01 = -(i00 * u01 + i01 * u11), K02 = -(i00 * u02 + i01 * u12);
+            const double K10 = -(i01 * u00 + i11 * u10), K11 = -(i01 * u01 + i11 * u11), K12 = -(i01 * u02 + i11 * u12);
+            const double k0 = -(i00 * gu0 + i01 * gu1), k1 = -(i01 * gu0 + i11 * gu1);
+            g[0] = K00; g[1] = K01; g[2] = K02; g[3] = K10; g[4] = K11; g[5] = K12; g[6] = k0; g[7] = k1;
+            g[8] = x00 + u00 * K00 + u10 * K10;
+            g[9] = x01 + 0.5 * ((u00 * K01 + u10 * K11) + (u01 * K00 + u11 * K10));
+            g[10] = x02 + 0.5 * ((u00 * K02 + u10 * K12) + (u02 * K00 + u12 * K10));
+            g[11] = x11 + u01 * K01 + u11 * K11;
+            g[12] = x12 + 0.5 * ((u01 * K02 + u11 * K12) + (u02 * K01 + u12 * K11));
+            g[13] = x22 + u02 * K02 + u12 * K12;
+            g[14] = gx0 + u00 * k0 + u10 * k1;
+            g[15] = gx1 + u01 * k0 + u11 * k1;
+            g[16] = gx2 + u02 * k0 + u12 * k1;
+        }
+    }
+    return __all_sync(FULL, ok);
+}
+
+template <int J, bool SCAN>
 __device__ __forceinline__ bool kkt_solve_lp(const KParams &P, Stg (&s)[J], const double (&rc)[J][3],
                                              const double (&rd)[J][2], bool useW, double dw, Step (&o)[J], int lane,
                                              double *rec, const KktRoles &R) {
@@ -610,6 +812,10 @@ __device__ __forceinline__ bool kkt_solve_lp(const KParams &P, Stg (&s)[J], cons
         q[KR_D + 0] = dyn ? -rc[j][0] : 0.0; q[KR_D + 1] = dyn ? -rc[j][1] : 0.0; q[KR_D + 2] = dyn ? -rc[j][2] : 0.0;
     }
     __syncwarp();
+    if (SCAN && J == 1) {
+        // parallel-in-time form: all cost-to-go matrices from a suffix scan over the lanes (kkt_backward_scan)
+        if (!kkt_backward_scan(rec, rec + (size_t)(N + 1) * (KKT_REC + 6), N, dt, lane)) return false;
+    } else {
     // ---- backward recursion: one stage per step, one matrix entry per lane ----
     const int a0 = R.a_off & 0xff, a1 = (R.a_off >> 8) & 0xff, a2 = (R.a_off >> 16) & 0xff;
     const int sp0 = R.a_src & 0xff, sp1 = (R.a_src >> 8) & 0xff, sp2 = (R.a_src >> 16) & 0xff, spv = R.a_src >> 24;
@@ -664,6 +870,7 @@ __device__ __forceinline__ bool kkt_solve_lp(const KParams &P, Stg (&s)[J], cons
         const double r = base + (0.5 * idet) * ((x0 * y0 + x1 * y1) + (z0 * w0 + z1 * w1));
         res = r;
         if (outo != 0xff) rec[(size_t)k * KKT_REC + KR_OUT + outo] = r;
+    }
     }
     __syncwarp();
     // ---- forward roll-out: every lane computes the whole step, keeps the entries of its own stages ----
@@ -822,14 +1029,16 @@ __device__ __forceinline__ void filter_add(double phi, double theta, double &fph
 
 // ---- the per-problem solve ----------------------------------------------------------------------------------
 #ifndef B200MPC_KKT_SERIAL
-#define KKT_SOLVE(P, s, rc, rd, useW, dw, o, lane) kkt_solve_lp<J>(P, s, rc, rd, useW, dw, o, lane, rec, roles)
+#define KKT_SOLVE(P, s, rc, rd, useW, dw, o, lane) kkt_solve_lp<J, SCAN>(P, s, rc, rd, useW, dw, o, lane, rec, roles)
 #else
 #define KKT_SOLVE(P, s, rc, rd, useW, dw, o, lane) kkt_solve<J>(P, s, rc, rd, useW, dw, o, lane)
 #endif
 
 // OBS: the kernel instance carries the obstacle cost (variant A; B with its gauss cost enabled).  The instance without
 // it has no obstacle loops at all — they would cost the obstacle-free variants registers (spills) for nothing.
-template <int J, bool OBS>
+// SCAN: the instance uses the parallel-in-time form of the Riccati recursion (J == 1 only).  A separate instance, so
+// that the out-of-line call does not cost the serial-form instance registers.
+template <int J, bool OBS, bool SCAN>
 __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane, double *sox, double *soy, double *rec,
                           const KktRoles &roles) {
     const int N = P.N;
@@ -1320,13 +1529,13 @@ finish:
     __syncwarp();
 }
 
-template <int J, bool OBS>
+template <int J, bool OBS, bool SCAN>
 __global__ void __launch_bounds__(128, B200MPC_MIN_CTAS) mpc_solve_kernel(const KParams P, const BatchArgs A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int Mpad = (P.M + 3) & ~3;
     // per warp: the problem's obstacle lists (2*Mpad doubles) and the stage records of the KKT solve
-    const size_t per_warp = 2 * (size_t)Mpad + (size_t)(P.N + 1) * (KKT_REC + 6);
+    const size_t per_warp = 2 * (size_t)Mpad + (size_t)(P.N + 1) * (KKT_REC + 6) + (J == 1 ? SCAN_NF * 32 : 0);
     double *sox = smem + (size_t)wid * per_warp, *soy = sox + Mpad, *rec = soy + Mpad;
     const KktRoles roles = kkt_roles(lane);
     for (;;) {
@@ -1334,7 +1543,7 @@ __global__ void __launch_bounds__(128, B200MPC_MIN_CTAS) mpc_solve_kernel(const 
         if (lane == 0) b = (int)atomicAdd(A.counter, 1u);
         b = __shfl_sync(FULL, b, 0);
         if (b >= A.B) break;
-        solve_one<J, OBS>(P, A, b, lane, sox, soy, rec, roles);
+        solve_one<J, OBS, SCAN>(P, A, b, lane, sox, soy, rec, roles);
     }
 }
 
@@ -1449,6 +1658,7 @@ struct b200mpc_handle {
     int kernel_kind;   // B200MPC_KERNEL_AUTO / _WARP / _LANE
     int last_kind;     // kernel used by the most recent solve
     int tpp_ctas;
+    int kkt_scan_mode; // warp kernel: -1 scan recursion for batches that leave warps idle, 0 never, 1 always
     int lane_spec;     // template instance of the lane kernels (TPP_SPEC_*)
     int lane_fused;    // 1: two-sweep lane kernel (tpp_fused.cuh), 0: three-sweep lane kernel (tpp_kernel.cuh)
     double *d_ws, *d_filt;
@@ -1506,16 +1716,22 @@ extern "C" const char *b200mpc_last_error(const b200mpc_handle *h) {
 
 template <int J>
 static cudaError_t configure_kernels(size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(mpc_solve_kernel<J, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mpc_solve_kernel<J, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(mpc_solve_kernel<J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(mpc_solve_kernel<J, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (J == 1) {
+        e = cudaFuncSetAttribute(mpc_solve_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(mpc_solve_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     return cudaFuncSetAttribute(mpc_eval_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 template <int J>
 static cudaError_t occupancy(int *blocks, size_t smem) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, mpc_solve_kernel<J, true>, 128, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, mpc_solve_kernel<J, true, false>, 128, smem);
 }
 
 extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
@@ -1579,10 +1795,14 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     }
     k.inv_r2 = 1.0 / (p->obs_r * p->obs_r);
     k.mu_floor = fmin(p->tol, 1e-4) / (K_EPS + 1.0);
+    // parallel-in-time Riccati recursion: -1 = by batch size (launch_solve), 0 / 1 = forced (env B200MPC_KKT_SCAN)
+    h->kkt_scan_mode = -1;
+    if (const char *es = getenv("B200MPC_KKT_SCAN")) h->kkt_scan_mode = (es[0] == '1') ? 1 : 0;
+    k.kkt_scan = 0;
     h->J = (p->N + 1 + 31) / 32;
     const int Mpad = (k.M + 3) & ~3;
     // per warp: obstacle lists + the stage records of the lane-parallel KKT solve (KKT_REC doubles per stage)
-    h->smem_bytes = (size_t)4 * (2 * (size_t)Mpad + (size_t)(p->N + 1) * (KKT_REC + 6)) * sizeof(double);
+    h->smem_bytes = (size_t)4 * (2 * (size_t)Mpad + (size_t)(p->N + 1) * (KKT_REC + 6) + (h->J == 1 ? SCAN_NF * 32 : 0)) * sizeof(double);
     if (h->smem_bytes > 227 * 1024) {
         set_err(nullptr, B200MPC_E_ARG, "N and M too large for the shared-memory staging of the warp kernel");
         b200mpc_destroy(h);
@@ -1821,17 +2041,22 @@ static int launch_solve(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stre
     const int need = (a.B + 3) / 4;
     if (need < grid) grid = need;
     if (grid < 1) grid = 1;
+    // The scan form of the Riccati recursion shortens the critical path of ONE solve (-27 % latency) but does more
+    // total work: it is used while the batch leaves warps of the persistent grid idle, i.e. when latency is what
+    // the caller sees; a batch that fills the machine keeps the lane-parallel serial form (+17 % solves/s there).
+    const bool scan = (h->kkt_scan_mode >= 0) ? (h->kkt_scan_mode == 1) : (a.B <= h->ctas * 4);
+    h->kp.kkt_scan = scan ? 1 : 0;
     CU_TRY(h, cudaEventRecord(h->ev0, stream));
     switch (h->J) {
-#define LAUNCH_WARP(JJ)                                                                                    \
+#define LAUNCH_WARP(JJ, SC)                                                                                \
     do {                                                                                                    \
-        if (h->prm.obs_form != B200MPC_OBS_NONE) mpc_solve_kernel<JJ, true><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a); \
-        else mpc_solve_kernel<JJ, false><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a);                  \
+        if (h->prm.obs_form != B200MPC_OBS_NONE) mpc_solve_kernel<JJ, true, SC><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a); \
+        else mpc_solve_kernel<JJ, false, SC><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a);              \
     } while (0)
-        case 1: LAUNCH_WARP(1); break;
-        case 2: LAUNCH_WARP(2); break;
-        case 3: LAUNCH_WARP(3); break;
-        default: LAUNCH_WARP(4); break;
+        case 1: if (scan) LAUNCH_WARP(1, true); else LAUNCH_WARP(1, false); break;
+        case 2: LAUNCH_WARP(2, false); break;
+        case 3: LAUNCH_WARP(3, false); break;
+        default: LAUNCH_WARP(4, false); break;
 #undef LAUNCH_WARP
     }
     CU_TRY(h, cudaGetLastError());

@@ -865,3 +865,34 @@ def test_c_abi_argument_errors(env):
     o = S.solve_batch(np.zeros((1, 3)), np.array([[0.5, 0.2, 0.0]]))
     assert o["status"][0] == 0
     S.close()
+
+
+def test_scan_recursion_matches_serial_recursion(env, robots, monkeypatch):
+    """Small batches run the warp kernel with the parallel-in-time (scan) form of the Riccati recursion, batches that
+    fill the machine with the serial lane-parallel form (B200MPC_KKT_SCAN=0/1 forces one).  Both against the oracle
+    and against each other: same status, same optimum; the scan's iterates differ at the 1e-9 level, so iteration
+    counts may differ on a few problems."""
+    O, shim = env["O"], env["shim"]
+    w = robots
+    po = O.variant_params("B", env["y"])
+    ref = O.solve_batch(po, w["x0"], w["goal"])
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B200MPC_KKT_SCAN", mode)
+        S = shim.Solver(env["make"]("B", env["y"]))
+        monkeypatch.delenv("B200MPC_KKT_SCAN")
+        S.set_kernel(shim.KERNEL_WARP)
+        outs[mode] = S.solve_batch(w["x0"], w["goal"])
+        S.close()
+        _assert_parity(outs[mode], ref, need_frac=1.0)
+    assert (outs["0"]["iters"] == ref["iters"]).all()
+    assert (outs["1"]["iters"] == ref["iters"]).mean() >= 0.99
+    assert np.max(np.abs(outs["0"]["U"] - outs["1"]["U"])) <= 1e-6
+    # horizons the scan does not cover (more than 32 stages) fall back to the serial form
+    monkeypatch.setenv("B200MPC_KKT_SCAN", "1")
+    S = shim.Solver(env["make"]("B", env["y"], N=50))
+    monkeypatch.delenv("B200MPC_KKT_SCAN")
+    o = S.solve_batch(w["x0"][:16], w["goal"][:16])
+    r = O.solve_batch(O.variant_params("B", env["y"], N=50), w["x0"][:16], w["goal"][:16])
+    _assert_parity(o, r, need_frac=1.0)
+    S.close()
