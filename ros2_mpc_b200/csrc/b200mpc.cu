@@ -113,6 +113,54 @@ __device__ __forceinline__ bool cmp_le(double lhs, double rhs, double bas) {
     return lhs - rhs <= 10.0 * DBL_EPS * fabs(bas);
 }
 
+// sin and cos of one angle: three-constant Cody-Waite reduction by pi/2 (exact products through FMA) and the
+// fdlibm kernel polynomials on [-pi/4, pi/4]; < 1.5 ulp for |x| <= 1e5 (headings are a few radians), the library
+// routine beyond.  Half the instructions of sincos(), whose argument reduction for huge arguments the solver never needs.
+__device__ __forceinline__ void tpp_sincos_core(double x, double &sn, double &cs) {
+    const double kf = rint(x * 6.36619772367581382433e-01);
+    double r = fma(-kf, 1.5707963267948966e+00, x);
+    r = fma(-kf, 6.1232339957367574e-17, r);
+    r = fma(-kf, 8.4784276603688985e-32, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double s = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const int q = (int)kf;
+    const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;
+    sn = (q & 2) ? -a : a;
+    cs = ((q + 1) & 2) ? -b : b;
+}
+
+// sin / cos of th, th + hw, th + 2 hw (the RK4 stage angles) from two branch-free evaluations and the angle-addition
+// formulas; the three library sincos() calls they replace each hide a slow-path branch, which keeps the compiler from
+// interleaving their (independent) polynomial chains.  Warp-uniform fallback for absurd arguments.
+__device__ __forceinline__ void rk4_trig(double th, double hw, double &s0, double &c0, double &sm, double &cm, double &se,
+                                         double &ce) {
+    if (__any_sync(FULL, !(fabs(th) <= 1e5) || !(fabs(hw) <= 1e5))) {
+        sincos(th, &s0, &c0);
+        sincos(th + hw, &sm, &cm);
+        sincos(th + 2.0 * hw, &se, &ce);
+        return;
+    }
+    double sh, ch;
+    tpp_sincos_core(th, s0, c0);
+    tpp_sincos_core(hw, sh, ch);
+    sm = s0 * ch + c0 * sh;
+    cm = c0 * ch - s0 * sh;
+    const double s2 = 2.0 * sh * ch, c2 = 1.0 - 2.0 * sh * sh;
+    se = s0 * c2 + c0 * s2;
+    ce = c0 * c2 - s0 * s2;
+}
+
 // Reciprocal to within 1 ulp: hardware seed (MUFU.RCP64H) + two Newton steps, five dependent instructions instead of
 // the ~25 of an IEEE division — it sits on the serial critical path of the Riccati recursion.  det is finite, normal
 // and > 0 whenever the result is used (otherwise the factorisation is rejected).
@@ -211,9 +259,7 @@ __device__ __forceinline__ void dyn_value(const KParams &P, const double X[3], c
         F[2] = th + dt * w;
     } else {
         double s0, c0, sm, cm, se, ce;
-        sincos(th, &s0, &c0);
-        sincos(th + 0.5 * dt * w, &sm, &cm);
-        sincos(th + dt * w, &se, &ce);
+        rk4_trig(th, 0.5 * dt * w, s0, c0, sm, cm, se, ce);
         const double h = dt / 6.0;
         F[0] = X[0] + h * v * (c0 + 4.0 * cm + ce);
         F[1] = X[1] + h * v * (s0 + 4.0 * sm + se);
@@ -246,9 +292,7 @@ __device__ __forceinline__ double stage_full(const KParams &P, const double *sox
             d2y[0] = -dt * v * sn; d2y[1] = dt * cs; d2y[2] = d2y[3] = d2y[4] = d2y[5] = 0;
         } else {
             double s0, c0, sm, cm, se, ce;
-            sincos(th, &s0, &c0);
-            sincos(th + 0.5 * dt * w, &sm, &cm);
-            sincos(th + dt * w, &se, &ce);
+            rk4_trig(th, 0.5 * dt * w, s0, c0, sm, cm, se, ce);
             const double h = dt / 6.0;
             const double C = c0 + 4.0 * cm + ce, S = s0 + 4.0 * sm + se;
             const double C1 = 2.0 * cm + ce, S1 = 2.0 * sm + se, C2 = cm + ce, S2 = sm + se;
@@ -978,8 +1022,11 @@ __device__ __forceinline__ void trial_eval(const KParams &P, const double *sox, 
         double bar = 0, thl = 0;
         if (dyn) {
             thl = fabs(t.ct[0]) + fabs(t.ct[1]) + fabs(t.ct[2]) + fabs(t.Ut[0] - t.St[0]) + fabs(t.Ut[1] - t.St[1]);
-            bar = -mu * (log(t.St[0] - P.sL[0]) + log(P.sU[0] - t.St[0]) + log(t.St[1] - P.sL[1]) +
-                         log(P.sU[1] - t.St[1]));
+            // one logarithm per stage (of the product of the four slack distances; a slack outside its bounds gives
+            // NaN like log(negative) would)
+            const double l0 = t.St[0] - P.sL[0], l1 = P.sU[0] - t.St[0], l2 = t.St[1] - P.sL[1], l3 = P.sU[1] - t.St[1];
+            const bool inside = (l0 > 0.0) && (l1 > 0.0) && (l2 > 0.0) && (l3 > 0.0);
+            bar = -mu * log(inside ? (l0 * l1) * (l2 * l3) : -1.0);
         }
         th += thl;
         ph += df * fv + bar;
@@ -1330,13 +1377,15 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                     const int k = lane * J + j;
                     const bool dyn = k < N;
                     if (dyn) {
+                        double prod = 1.0; // (the current iterate's slacks are strictly inside their bounds)
 #pragma unroll
                         for (int i = 0; i < 2; i++) {
                             const double sl = s[j].S[i] - P.sL[i], su = P.sU[i] - s[j].S[i];
-                            bar -= mu * (log(sl) + log(su));
+                            prod *= sl * su;
                             gb += (-mu / sl + mu / su) * st[j].dS[i];
                             gb += s[j].g[3 + i] * st[j].dU[i];
                         }
+                        bar -= mu * log(prod);
                     }
                     if (k >= 1 && k <= N) {
 #pragma unroll

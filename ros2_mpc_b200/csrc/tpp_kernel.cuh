@@ -186,32 +186,7 @@ struct TppLane {
 };
 #define TPP_LANE_STRIDE (((sizeof(TppLane) + 7) / 8) | 1) /* in doubles, odd */
 
-// sin and cos of one angle: three-constant Cody-Waite reduction by pi/2 (exact products through FMA) and the
-// fdlibm kernel polynomials on [-pi/4, pi/4]; < 1.5 ulp for |x| <= 1e5 (headings are a few radians), the library
-// routine beyond.  Half the instructions of sincos(), whose argument reduction for huge arguments the solver never needs.
-__device__ __forceinline__ void tpp_sincos_core(double x, double &sn, double &cs) {
-    const double kf = rint(x * 6.36619772367581382433e-01);
-    double r = fma(-kf, 1.5707963267948966e+00, x);
-    r = fma(-kf, 6.1232339957367574e-17, r);
-    r = fma(-kf, 8.4784276603688985e-32, r);
-    const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
-    const double s = fma(z * r, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
-    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
-    const int q = (int)kf;
-    const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;
-    sn = (q & 2) ? -a : a;
-    cs = ((q + 1) & 2) ? -b : b;
-}
+// (tpp_sincos_core: b200mpc.cu, shared with the warp kernel)
 __device__ __noinline__ void tpp_sincos_far(double x, double *sn, double *cs) { sincos(x, sn, cs); }
 __device__ __forceinline__ void tpp_sincos(double x, double &sn, double &cs) {
     if (fabs(x) <= 1e5) tpp_sincos_core(x, sn, cs); // (NaN takes the library routine)
