@@ -142,10 +142,11 @@ __device__ __forceinline__ void tpp_sincos_core(double x, double &sn, double &cs
 
 // sin / cos of th, th + hw, th + 2 hw (the RK4 stage angles) from two branch-free evaluations and the angle-addition
 // formulas; the three library sincos() calls they replace each hide a slow-path branch, which keeps the compiler from
-// interleaving their (independent) polynomial chains.  Warp-uniform fallback for absurd arguments.
+// interleaving their (independent) polynomial chains.  Library fallback for absurd arguments.
 __device__ __forceinline__ void rk4_trig(double th, double hw, double &s0, double &c0, double &sm, double &cm, double &se,
                                          double &ce) {
-    if (__any_sync(FULL, !(fabs(th) <= 1e5) || !(fabs(hw) <= 1e5))) {
+    // (per-lane test, no warp vote: the callers sit inside per-stage branches that not every lane takes)
+    if (!(fabs(th) <= 1e5) || !(fabs(hw) <= 1e5)) {
         sincos(th, &s0, &c0);
         sincos(th + hw, &sm, &cm);
         sincos(th + 2.0 * hw, &se, &ce);
