@@ -773,6 +773,8 @@ __device__ __noinline__ int kkt_backward_scan(double *rec, double *el, int N, do
     for (int i = 0; i < 3; i++) el[(6 + i) * 32 + lane] = -e[i];
     __syncwarp();
     int ok = 1;
+    // closed-loop map of the stage, y_{k+1} = Phi y_k + phi (identity for the terminal stage and idle lanes), and its gains
+    double Ph[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, ph[3] = {0, 0, 0}, Kr[6] = {0, 0, 0, 0, 0, 0}, kr[2] = {0, 0};
     if (act) {
         double *g = rec + (size_t)k * KKT_REC + KR_OUT;
         if (!dyn) {
@@ -810,6 +812,11 @@ __device__ __noinline__ int kkt_backward_scan(double *rec, double *el, int N, do
             const double K10 = -(i01 * u00 + i11 * u10), K11 = -(i01 * u01 + i11 * u11), K12 = -(i01 * u02 + i11 * u12);
             const double k0 = -(i00 * gu0 + i01 * gu1), k1 = -(i01 * gu0 + i11 * gu1);
             g[0] = K00; g[1] = K01; g[2] = K02; g[3] = K10; g[4] = K11; g[5] = K12; g[6] = k0; g[7] = k1;
+            Kr[0] = K00; Kr[1] = K01; Kr[2] = K02; Kr[3] = K10; Kr[4] = K11; Kr[5] = K12; kr[0] = k0; kr[1] = k1;
+            Ph[0] = 1.0 + b11 * K00 + b12 * K10; Ph[1] = b11 * K01 + b12 * K11; Ph[2] = a + b11 * K02 + b12 * K12;
+            Ph[3] = b21 * K00 + b22 * K10; Ph[4] = 1.0 + b21 * K01 + b22 * K11; Ph[5] = bb + b21 * K02 + b22 * K12;
+            Ph[6] = dt * K10; Ph[7] = dt * K11; Ph[8] = 1.0 + dt * K12;
+            ph[0] = b11 * k0 + b12 * k1 + d0; ph[1] = b21 * k0 + b22 * k1 + d1; ph[2] = dt * k1 + d2;
             g[8] = x00 + u00 * K00 + u10 * K10;
             g[9] = x01 + 0.5 * ((u00 * K01 + u10 * K11) + (u01 * K00 + u11 * K10));
             g[10] = x02 + 0.5 * ((u00 * K02 + u10 * K12) + (u02 * K00 + u12 * K10));
@@ -821,6 +828,48 @@ __device__ __noinline__ int kkt_backward_scan(double *rec, double *el, int N, do
             g[16] = gx2 + u02 * k0 + u12 * k1;
         }
     }
+    // ---- forward roll-out as an inclusive prefix scan of the affine maps: after it lane k maps y_0 to y_{k+1} ----
+#pragma unroll 1
+    for (int lvl = 1; lvl <= N; lvl <<= 1) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 9; i++) el[i * 32 + lane] = Ph[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) el[(9 + i) * 32 + lane] = ph[i];
+        __syncwarp();
+        const int pj = lane - lvl;
+        if (pj >= 0) {
+            double P1[9], p1[3], Pn[9], pn[3];
+#pragma unroll
+            for (int i = 0; i < 9; i++) P1[i] = el[i * 32 + pj];
+#pragma unroll
+            for (int i = 0; i < 3; i++) p1[i] = el[(9 + i) * 32 + pj];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+#pragma unroll
+                for (int j = 0; j < 3; j++) Pn[3 * i + j] = Ph[3 * i] * P1[j] + Ph[3 * i + 1] * P1[3 + j] + Ph[3 * i + 2] * P1[6 + j];
+                pn[i] = Ph[3 * i] * p1[0] + Ph[3 * i + 1] * p1[1] + Ph[3 * i + 2] * p1[2] + ph[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 9; i++) Ph[i] = Pn[i];
+#pragma unroll
+            for (int i = 0; i < 3; i++) ph[i] = pn[i];
+        }
+    }
+    // y_0 = 0, so y_{k+1} = phi of lane k: every stage takes its predecessor's, then du_k = kf_k + K_k y_k
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 3; i++) el[i * 32 + lane] = ph[i];
+    __syncwarp();
+    if (act) {
+        double y0 = 0, y1 = 0, y2 = 0;
+        if (lane >= 1) { y0 = el[0 * 32 + lane - 1]; y1 = el[1 * 32 + lane - 1]; y2 = el[2 * 32 + lane - 1]; }
+        // step entries of the stage -> rows 3-7 of the scan scratch (read back by kkt_solve_lp)
+        el[3 * 32 + lane] = y0; el[4 * 32 + lane] = y1; el[5 * 32 + lane] = y2;
+        el[6 * 32 + lane] = kr[0] + Kr[0] * y0 + Kr[1] * y1 + Kr[2] * y2;
+        el[7 * 32 + lane] = kr[1] + Kr[3] * y0 + Kr[4] * y1 + Kr[5] * y2;
+    }
+    __syncwarp();
     return __all_sync(FULL, ok);
 }
 
@@ -918,6 +967,15 @@ __device__ __forceinline__ bool kkt_solve_lp(const KParams &P, Stg (&s)[J], cons
     }
     }
     __syncwarp();
+    if (SCAN && J == 1) {
+        // (the scan routine has rolled the step out as a prefix scan of the closed-loop maps)
+        const int k = lane;
+        if (k <= N) {
+            const double *el = rec + (size_t)(N + 1) * (KKT_REC + 6);
+            o[0].dX[0] = el[3 * 32 + lane]; o[0].dX[1] = el[4 * 32 + lane]; o[0].dX[2] = el[5 * 32 + lane];
+            if (k < N) { o[0].dU[0] = el[6 * 32 + lane]; o[0].dU[1] = el[7 * 32 + lane]; }
+        }
+    } else
     // ---- forward roll-out: every lane computes the whole step, keeps the entries of its own stages ----
     {
         double y0 = 0, y1 = 0, y2 = 0;
