@@ -26,6 +26,15 @@
  *   b200mpc_control_step_device     <- the node loop after the solve   ros2_mpc/scripts/point_follower_local_planner.py:196-231
  *                            (acceleration limiter, goal-reached logic), the next measured state (:172 with the rounding
  *                            of ros2_mpc/core/ros_topics.py:66-80) and a simulated plant step, for a fleet on the device
+ *   b200mpc_dilate_batch[_device]        <- cv2.dilate(grid, np.ones((10, 10)), iterations=1).astype(np.uint8)
+ *                            ros2_mpc/core/local_costmap_publisher.py:34-35, ros2_mpc/core/global_costmap_publisher.py (same call)
+ *   b200mpc_inflate_batch[_device]       <- inflate_global / inflate_local   ros2_mpc/utils/costmap.py:5-41
+ *   b200mpc_local_costmap_batch[_device] <- the loop body of the local costmap publisher   ros2_mpc/core/local_costmap_publisher.py:29-35
+ *                            (convert_laser_scan_to_occupancy_grid with rotation = yaw, utils.py:5-43, then the dilation), fused
+ *   b200mpc_raycast_batch[_device]       the laser scanner of the simulated robots: scans of the shared static map
+ *                            (maps/map_carto.pgm with the pixel convention of ros2_mpc/core/map_server.py:14-20), the input
+ *                            LaserSubscriber.get_scan() delivers to get_obstacles (ros2_mpc/core/ros_topics.py:103)
+ *   b200mpc_headings_batch[_device]      <- get_headings   ros2_mpc/scripts/path_follower_local_planner.py:14-23
  *   b200mpc_destroy       <- garbage collection of the Mpc / Opti object
  *
  * Conventions: plain pointers and sizes only; no C++ exceptions cross the boundary; functions return 0 on
@@ -76,6 +85,7 @@ extern "C" {
 /* per-problem status: IPOPT ApplicationReturnStatus */
 #define B200MPC_SOLVE_SUCCEEDED 0
 #define B200MPC_SOLVED_TO_ACCEPTABLE_LEVEL 1
+#define B200MPC_SEARCH_DIRECTION_TOO_SMALL 3 /* tiny steps at the smallest barrier parameter: "solved to best possible numerical accuracy" (not a success for Opti) */
 #define B200MPC_MAXITER_EXCEEDED (-1)
 #define B200MPC_RESTORATION_FAILED (-2)
 #define B200MPC_ERROR_IN_STEP_COMPUTATION (-3)
@@ -222,6 +232,51 @@ int b200mpc_control_step_device(b200mpc_handle *h, int B, const double *U_sol, c
                                 double *x0, double *u_last, const double *goal, int goal_stride, int32_t *goal_flag,
                                 double goal_threshold, double accel_limit, int quantise, double *cmd_out, double *u_next,
                                 void *stream);
+
+/* ---- costmap inflation / dilation (the costmap publishers' image operations; the MPC itself does not read them) ----
+ * Dilation with a kh x kw box of ones, OpenCV's conventions for cv2.dilate(grid, np.ones((kh, kw))): anchor (kh/2, kw/2),
+ * the border never wins:  out[y][x] = max grid[y + i - kh/2][x + j - kw/2], 0 <= i < kh, 0 <= j < kw, inside the image,
+ * then the cast to uint8 (truncation; the grids hold 0 / 100).  grid [B][H][W] float64 -> out [B][H][W] uint8. */
+int b200mpc_dilate_batch(b200mpc_handle *h, int B, int H, int W, const double *grid, int kh, int kw, uint8_t *out);
+int b200mpc_dilate_batch_device(b200mpc_handle *h, int B, int H, int W, const double *grid, int kh, int kw, uint8_t *out,
+                                void *stream);
+/* inflate_global (utils/costmap.py:5-20): every cell whose value is exactly 0 and whose (2c+1)^2 window lies completely
+ * inside the grid stamps np.minimum(window, inflation_matrix).  grid, out [B][H][W] float64; inflation_matrix [2c+1][2c+1].
+ * inflate_local is the same on a cropped grid (the Python mirror computes the crop as the reference's slices do). */
+int b200mpc_inflate_batch(b200mpc_handle *h, int B, int H, int W, const double *grid, const double *inflation_matrix,
+                          int cells_inflation, double *out);
+int b200mpc_inflate_batch_device(b200mpc_handle *h, int B, int H, int W, const double *grid, const double *inflation_matrix,
+                                 int cells_inflation, double *out, void *stream);
+/* Local costmap images for B robots: scan -> occupancy grid rotated by yaw (utils.py:5-43 with rotation = orientation[2])
+ * -> dilation -> uint8 (0 / 100), out [B][nc][nc] with nc = int(2*size/resolution).  beam_cos / beam_sin as for
+ * b200mpc_obstacles_batch.  The float64 grid never exists in memory. */
+int b200mpc_local_costmap_batch(b200mpc_handle *h, int B, int n_beams, const double *scan, const double *beam_cos,
+                                const double *beam_sin, const double *yaw, double size, double resolution, int kh, int kw,
+                                uint8_t *out);
+int b200mpc_local_costmap_batch_device(b200mpc_handle *h, int B, int n_beams, const double *scan, const double *beam_cos,
+                                       const double *beam_sin, const double *yaw, double size, double resolution, int kh,
+                                       int kw, uint8_t *out, void *stream);
+
+/* ---- the simulated lidar: scans of a shared static occupancy map ----
+ * occ_bits [H][ceil(W/32)] uint32: bit (c & 31) of word c >> 5 in row r = cell (r, c) occupied; row 0 is the lowest y
+ * (core/map_server.py:20 flips the image), cell (r, c) covers [origin + c*res, origin + (c+1)*res) x [.. r ..].
+ * pose [B][pose_stride] = (x, y, yaw, ...).  Beam i points along yaw + (i*(angle_max-angle_min)/n_beams + angle_min) and is
+ * sampled at range_min + t*step, t = 0 .. round((range_max-range_min)/step); the first sample in an occupied cell is the
+ * range, range_max otherwise.  scan [B][n_beams].  The map bits are staged in shared memory once per thread block. */
+int b200mpc_raycast_batch(b200mpc_handle *h, int B, int n_beams, const uint32_t *occ_bits, int H, int W, double origin_x,
+                          double origin_y, double resolution, const double *pose, double angle_min, double angle_max,
+                          double range_min, double range_max, double step, double *scan);
+int b200mpc_raycast_batch_device(b200mpc_handle *h, int B, int n_beams, const uint32_t *occ_bits, int H, int W,
+                                 double origin_x, double origin_y, double resolution, const double *pose, int pose_stride,
+                                 double angle_min, double angle_max, double range_min, double range_max, double step,
+                                 double *scan, void *stream);
+
+/* get_headings for P paths of K >= 2 points (path_xy [P][K][2]): heading [P][K] = arctan2 of the segments, the last one
+ * repeated; velocity [P][K] = 2 * segment length / dt, the last one repeated; omega [P][K-1] = heading differences / 2. */
+int b200mpc_headings_batch(b200mpc_handle *h, int P, int K, const double *path_xy, double dt, double *heading,
+                           double *velocity, double *omega);
+int b200mpc_headings_batch_device(b200mpc_handle *h, int P, int K, const double *path_xy, double dt, double *heading,
+                                  double *velocity, double *omega, void *stream);
 
 /* Forces one of the two solve kernels (default B200MPC_KERNEL_AUTO; the environment variable B200MPC_KERNEL=warp|lane
  * sets the default of new handles).  Both kernels run the same algorithm; results agree to rounding.  The

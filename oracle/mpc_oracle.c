@@ -22,6 +22,7 @@
 #include <float.h>
 #include <math.h>
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -754,6 +755,10 @@ void orc_default_options(orc_params *p) {
 #define DW_DEC (1.0 / 3.0)
 #define MAX_FILTER 32
 #define OBJ_MAX_INC 5.0
+#define TINY_STEP_TOL (10.0 * DBL_EPSILON)
+#define TINY_STEP_Y_TOL 1e-2
+#define KAPPA_RESTO 0.9
+#define RESTO_T_MIN (1.0 / 1024.0)
 #define MAX_RESTO 20
 
 /* Filter: MAX_FILTER slots (phi, theta, valid).  A new entry evicts the entries it dominates and takes the
@@ -868,6 +873,7 @@ int orc_solve(const orc_params *p, const double *x0, const double *xref, const d
     memset(&stt, 0, sizeof(stt));
     int status = ORC_MAXITER_EXCEEDED;
     int iter = 0;
+    const int trace = getenv("ORC_TRACE") != NULL; /* debugging aid: one line per iteration on stderr */
 
     /* relaxed slack bounds (bound_relax_factor) */
     for (int i = 0; i < 2; i++) {
@@ -951,6 +957,7 @@ int orc_solve(const orc_params *p, const double *x0, const double *xref, const d
     double theta_max = -1, theta_min = -1;
     double dw_last = 0.0;
     int acceptable_count = 0;
+    int tiny_last = 0, tiny_flag = 0; /* BacktrackingLineSearch::tiny_step_last_iteration_, IpoptData::tiny_step_flag */
 
     for (;;) {
         /* ---- evaluate the current point ---- */
@@ -1009,6 +1016,10 @@ int orc_solve(const orc_params *p, const double *x0, const double *xref, const d
         double E0 = fmax(dual_inf / sd, fmax(prim_inf, compl0 / sc));
         stt.err = E0;
         stt.mu = mu;
+        if (trace)
+            fprintf(stderr, "it %4d f %.9e th %.3e du %.3e cm %.3e E0 %.3e mu %.1e dw_last %.1e resto %d lsx %d\n", iter,
+                    eval_f(&q, w->X, w->U), theta, dual_inf, compl0, E0, mu, dw_last, stt.n_resto, stt.ls_extra),
+            fprintf(stderr, "        df %.3e acc_count %d prim %.3e dual/df %.3e compl/df %.3e\n", df, acceptable_count, prim_inf, dual_inf / df, compl0 / df);
         if (!isfinite(E0)) { status = ORC_INVALID_NUMBER_DETECTED; break; }
 
         /* ---- convergence (OptimalityErrorConvergenceCheck) ---- */
@@ -1025,20 +1036,28 @@ int orc_solve(const orc_params *p, const double *x0, const double *xref, const d
         }
         if (iter >= p->max_iter) { status = ORC_MAXITER_EXCEEDED; break; }
 
-        /* ---- barrier parameter update (monotone, fast decrease allowed) ---- */
-        for (;;) {
-            double cm = 0;
-            for (int i = 0; i < n2; i++) {
-                double sl = w->S[i] - w->sL[i & 1], su = w->sU[i & 1] - w->S[i];
-                cm = fmax(cm, fmax(fabs(sl * w->vL[i] - mu), fabs(su * w->vU[i] - mu)));
+        /* ---- barrier parameter update (MonotoneMuUpdate::UpdateBarrierParameter, fast decrease allowed).
+         * A tiny step in two consecutive iterations forces a decrease of mu; when mu cannot decrease any more the
+         * problem is "solved to best possible numerical accuracy": Search_Direction_Becomes_Too_Small. ---- */
+        {
+            int tflag = tiny_flag, stop = 0;
+            tiny_flag = 0;
+            for (;;) {
+                double cm = 0;
+                for (int i = 0; i < n2; i++) {
+                    double sl = w->S[i] - w->sL[i & 1], su = w->sU[i & 1] - w->S[i];
+                    cm = fmax(cm, fmax(fabs(sl * w->vL[i] - mu), fabs(su * w->vU[i] - mu)));
+                }
+                double Emu = fmax(dual_inf / sd, fmax(prim_inf, cm / sc));
+                if (!(Emu <= K_EPS * mu) && !tflag) break;
+                double nm = fmax(fmin(K_MU * mu, pow(mu, TH_MU)), mu_floor);
+                if (nm == mu) { stop = tflag; break; }
+                mu = nm;
+                tau = fmax(TAU_MIN, 1.0 - mu);
+                filter_reset(&filt);
+                tflag = 0;
             }
-            double Emu = fmax(dual_inf / sd, fmax(prim_inf, cm / sc));
-            if (!(Emu <= K_EPS * mu)) break;
-            double nm = fmax(fmin(K_MU * mu, pow(mu, TH_MU)), mu_floor);
-            if (nm == mu) break;
-            mu = nm;
-            tau = fmax(TAU_MIN, 1.0 - mu);
-            filter_reset(&filt);
+            if (stop) { status = ORC_SEARCH_DIRECTION_TOO_SMALL; break; }
         }
 
         /* ---- search direction with inertia correction (PDPerturbationHandler, delta_x = delta_s) ---- */
@@ -1095,6 +1114,40 @@ int orc_solve(const orc_params *p, const double *x0, const double *xref, const d
         double alpha = a_max, alpha_acc = 0;
         const step_t *acc = NULL;
         int fa = 0, ntrial = 0;
+        /* BacktrackingLineSearch::DetectTinyStep: every primal component moves by less than tiny_step_tol = 10 eps
+         * (relative) and the point is nearly feasible -> the full step is taken without a line search. */
+        int tiny = 0;
+        {
+            /* |d_i| / (1 + |x_i|) <= tol, written without the division (the CUDA kernels use the same form) */
+            int big = 0;
+            double c2 = 0;
+            for (int i = 3; i < n3; i++)
+                if (!(fabs(w->main.dX[i]) <= TINY_STEP_TOL * (1.0 + fabs(w->X[i])))) big = 1;
+            for (int i = 0; i < n2; i++) {
+                if (!(fabs(w->main.dU[i]) <= TINY_STEP_TOL * (1.0 + fabs(w->U[i])))) big = 1;
+                if (!(fabs(w->main.dS[i]) <= TINY_STEP_TOL * (1.0 + fabs(w->S[i])))) big = 1;
+                c2 += w->rd[i] * w->rd[i];
+            }
+            for (int i = 3; i < n3; i++) c2 += w->rc[i] * w->rc[i];
+            tiny = !big && (sqrt(c2) <= 1e-4);
+        }
+        if (tiny) {
+            double th_t, phi_t;
+            trial_eval(w, &q, &w->main, alpha, mu, df, &th_t, &phi_t);
+            if (isfinite(th_t) && isfinite(phi_t)) {
+                (void)ls_acceptable(&ref, alpha, phi_t, th_t, &fa); /* only for the filter-augmentation rule */
+                acc = &w->main;
+                alpha_acc = alpha;
+                if (tiny_last) tiny_flag = 1;
+                double dy = 0;
+                for (int i = 3; i < n3; i++) dy = fmax(dy, fabs(w->main.dlam[i]));
+                for (int i = 0; i < n2; i++) dy = fmax(dy, fabs(w->main.dyd[i]));
+                tiny_last = dy < TINY_STEP_Y_TOL;
+            } else {
+                tiny = 0;
+            }
+        }
+        if (!tiny) { tiny_flag = 0; tiny_last = 0; }
         while (!acc) {
             double th_t, phi_t;
             trial_eval(w, &q, &w->main, alpha, mu, df, &th_t, &phi_t);
@@ -1132,8 +1185,29 @@ int orc_solve(const orc_params *p, const double *x0, const double *xref, const d
              * (strictly inside the bounds), rolls X out and restarts the multipliers. */
             if (theta <= 1e-10 || stt.n_resto >= MAX_RESTO) { status = ORC_RESTORATION_FAILED; break; }
             filter_add(&filt, ref.phi - GAMMA_PHI * theta, (1 - GAMMA_THETA) * theta);
-            for (int i = 0; i < n2; i++) w->U[i] = w->S[i];
-            rollout(p, x0, w->U, w->X);
+            /* restoration direction: towards the closed-form feasible point (U = S, X rolled out) */
+            for (int i = 0; i < n2; i++) { w->soc.dU[i] = w->S[i] - w->U[i]; w->soc.dS[i] = 0.0; }
+            rollout(p, x0, w->S, w->Xt);
+            for (int i = 0; i < n3; i++) w->soc.dX[i] = w->Xt[i] - w->X[i];
+            double t_acc = 0.0;
+            for (double t = 1.0; t >= RESTO_T_MIN; t *= 0.5) {
+                double th_r, phi_r;
+                trial_eval(w, &q, &w->soc, t, mu, df, &th_r, &phi_r);
+                if (trace) fprintf(stderr, "   resto t %.4g th %.4e (ref %.4e) phi %.6e (ref %.6e) filt %d\n", t, th_r, theta, phi_r, ref.phi, filter_acceptable(&filt, phi_r, th_r));
+                if (!isfinite(th_r) || !isfinite(phi_r)) continue;
+                if (!(th_r <= KAPPA_RESTO * theta)) continue;
+                if (phi_r > ref.phi) {
+                    double bas = 1.0;
+                    if (fabs(ref.phi) > 10.0) bas = log10(fabs(ref.phi));
+                    if (log10(phi_r - ref.phi) > OBJ_MAX_INC + bas) continue;
+                }
+                if (!filter_acceptable(&filt, phi_r, th_r)) continue;
+                t_acc = t;
+                break;
+            }
+            if (t_acc == 0.0) { status = ORC_RESTORATION_FAILED; break; }
+            for (int i = 3; i < n3; i++) w->X[i] += t_acc * w->soc.dX[i];
+            for (int i = 0; i < n2; i++) w->U[i] += t_acc * w->soc.dU[i];
             double zmax = 0;
             for (int i = 0; i < n2; i++) zmax = fmax(zmax, fmax(w->vL[i], w->vU[i]));
             if (zmax > 1e3)

@@ -18,7 +18,8 @@ REF_GOAL, REF_TRAJ = 0, 1
 KERNEL_AUTO, KERNEL_WARP, KERNEL_LANE = 0, 1, 2
 
 STATUS_NAMES = {
-    0: "Solve_Succeeded", 1: "Solved_To_Acceptable_Level", -1: "Maximum_Iterations_Exceeded",
+    0: "Solve_Succeeded", 1: "Solved_To_Acceptable_Level", 3: "Search_Direction_Becomes_Too_Small",
+    -1: "Maximum_Iterations_Exceeded",
     -2: "Restoration_Failed", -3: "Error_In_Step_Computation", -13: "Invalid_Number_Detected",
 }
 SUCCESS_STATUSES = (0, 1)  # CasADi's return_success(): Solve_Succeeded, Solved_To_Acceptable_Level
@@ -93,6 +94,24 @@ def lib():
         L.b200mpc_control_step_device.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_double, C.c_double,
                                                   C.c_int, vp, vp, vp]
         L.b200mpc_control_step_device.restype = C.c_int
+        u8p, u32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+        L.b200mpc_dilate_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int, u8p]
+        L.b200mpc_dilate_batch_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp]
+        L.b200mpc_inflate_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, dp]
+        L.b200mpc_inflate_batch_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
+        L.b200mpc_local_costmap_batch.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, C.c_int,
+                                                  C.c_int, u8p]
+        L.b200mpc_local_costmap_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_double, C.c_double,
+                                                         C.c_int, C.c_int, vp, vp]
+        L.b200mpc_raycast_batch.argtypes = [vp, C.c_int, C.c_int, u32p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                            dp] + [C.c_double] * 5 + [dp]
+        L.b200mpc_raycast_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_double, C.c_double,
+                                                   C.c_double, vp, C.c_int] + [C.c_double] * 5 + [vp, vp]
+        L.b200mpc_headings_batch.argtypes = [vp, C.c_int, C.c_int, dp, C.c_double, dp, dp, dp]
+        L.b200mpc_headings_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, C.c_double, vp, vp, vp, vp]
+        for fn in ("dilate", "inflate", "local_costmap", "raycast", "headings"):
+            getattr(L, f"b200mpc_{fn}_batch").restype = C.c_int
+            getattr(L, f"b200mpc_{fn}_batch_device").restype = C.c_int
         L.b200mpc_sizeof_params.restype = C.c_int
         if L.b200mpc_sizeof_params() != C.sizeof(Params):
             raise RuntimeError("b200mpc_params layout mismatch between _shim.Params and libb200mpc.so")
@@ -309,3 +328,71 @@ class Solver:
                                         _dp(X), _dp(U), _dp(lam), float(obj_scale), _dp(f), _dp(c), _dp(g), _dp(st))
         self._check(rc)
         return dict(f=f, c=c, grad=g, stages=st)
+
+    # ---- costmap inflation / dilation (csrc/costmap_kernel.cuh) ------------------------------------------------------
+    def dilate_batch(self, grids, kh=10, kw=10):
+        """cv2.dilate(grid, np.ones((kh, kw)), iterations=1).astype(np.uint8) for grids (B,H,W) float64 -> (B,H,W) uint8."""
+        g = _f64(grids)
+        B, H, W = g.shape
+        out = np.empty((B, H, W), np.uint8)
+        self._check(self._L.b200mpc_dilate_batch(self._h, B, H, W, _dp(g), int(kh), int(kw),
+                                                 out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def inflate_batch(self, grids, inflation_matrix, cells_inflation):
+        """inflate_global (utils/costmap.py:5-20) for grids (B,H,W) float64 -> (B,H,W) float64."""
+        g, m = _f64(grids), _f64(inflation_matrix)
+        B, H, W = g.shape
+        n = 2 * int(cells_inflation) + 1
+        if m.shape != (n, n):
+            raise ValueError(f"inflation_matrix must be ({n}, {n})")
+        out = np.empty((B, H, W))
+        self._check(self._L.b200mpc_inflate_batch(self._h, B, H, W, _dp(g), _dp(m), int(cells_inflation), _dp(out)))
+        return out
+
+    def local_costmap_batch(self, scan, beam_cos, beam_sin, yaw, size, resolution, kh=10, kw=10):
+        """scan -> occupancy grid (rotation = yaw) -> dilate -> uint8 image (local_costmap_publisher.py:29-35), (B,nc,nc)."""
+        scan = _f64(scan)
+        B, n = scan.shape
+        bc, bs, yaw = _f64(beam_cos, (n,)), _f64(beam_sin, (n,)), _f64(yaw, (B,))
+        nc = int(float(size) * 2 / float(resolution))
+        out = np.empty((B, nc, nc), np.uint8)
+        self._check(self._L.b200mpc_local_costmap_batch(self._h, B, n, _dp(scan), _dp(bc), _dp(bs), _dp(yaw), float(size),
+                                                        float(resolution), int(kh), int(kw),
+                                                        out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def device_call(self, name, *args):
+        """Generic caller of a *_device entry point: ints / floats are passed as such, device addresses as c_void_p
+        (wrap them in `DevPtr`)."""
+        conv = [C.c_void_p(int(a.addr) if a.addr else None) if isinstance(a, DevPtr) else a for a in args]
+        self._check(getattr(self._L, name)(self._h, *conv))
+
+    # ---- sensor model / path preprocessing (csrc/sensor_kernel.cuh) ---------------------------------------------------
+    def raycast_batch(self, occ_bits, H, W, origin, resolution, pose, angle_min=0.0, angle_max=6.28, range_min=0.12,
+                      range_max=3.5, step=0.01, n_beams=360):
+        """Laser scans (B,n_beams) of the shared occupancy map for poses (B,3).  occ_bits: (H, ceil(W/32)) uint32."""
+        pose = _f64(pose)
+        B = pose.shape[0]
+        occ_bits = np.ascontiguousarray(occ_bits, dtype=np.uint32)
+        scan = np.empty((B, n_beams))
+        self._check(self._L.b200mpc_raycast_batch(self._h, B, int(n_beams), occ_bits.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                  int(H), int(W), float(origin[0]), float(origin[1]), float(resolution),
+                                                  _dp(np.ascontiguousarray(pose[:, :3])), float(angle_min), float(angle_max),
+                                                  float(range_min), float(range_max), float(step), _dp(scan)))
+        return scan
+
+    def headings_batch(self, path_xy, dt):
+        """get_headings for P paths: path_xy (P,K,2) -> heading (P,K), velocity (P,K), omega (P,K-1)."""
+        path_xy = _f64(path_xy)
+        P, K, _ = path_xy.shape
+        h, v, w = np.empty((P, K)), np.empty((P, K)), np.empty((P, K - 1))
+        self._check(self._L.b200mpc_headings_batch(self._h, P, K, _dp(path_xy), float(dt), _dp(h), _dp(v), _dp(w)))
+        return h, v, w
+
+
+class DevPtr:
+    """A raw device address for Solver.device_call."""
+
+    def __init__(self, addr):
+        self.addr = int(addr) if addr else 0

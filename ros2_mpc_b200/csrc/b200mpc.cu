@@ -67,6 +67,10 @@
 #define DW_DEC (1.0 / 3.0)
 #define OBJ_MAX_INC 5.0
 #define MAX_RESTO 20
+#define KAPPA_RESTO 0.9
+#define RESTO_T_MIN (1.0 / 1024.0)
+#define TINY_STEP_TOL (10.0 * 2.220446049250313e-16)
+#define TINY_STEP_Y_TOL 1e-2
 #define DBL_EPS 2.220446049250313e-16
 
 struct KParams {
@@ -636,8 +640,9 @@ __device__ __forceinline__ KktRoles kkt_roles(int lane) {
 //     eta = A1' M'(eta2 - J2 b1) + eta1,  J = A1' M' J2 A1 + J1.
 // After the scan lane k holds (P_k, p_k) = (J, -eta) of the range k..N; the gains, the inertia test (Quu_k positive
 // definite) and P'_k then follow from P_{k+1} with the formulas of the serial recursion, all stages at once.
-// Algebraically this is the same block elimination in another order, so the decisions coincide with the serial form;
-// the values differ at rounding level.  Out of line, operands and results in shared memory: the scan needs ~150
+// Algebraically this is the same block elimination in another order WHEN every local block R_k is nonsingular; it is
+// only used when all R_k are safely positive definite (return value -1 otherwise: the caller then runs the serial
+// recursion, which needs only the condensed Quu_k to be positive definite).  The values differ at rounding level.  Out of line, operands and results in shared memory: the scan needs ~150
 // registers of its own, which the solver's per-stage state would otherwise be spilled for.
 #define SCAN_NF 27 /* A[9] b[3] C[6] eta[3] J[6] */
 __device__ __noinline__ int kkt_backward_scan(double *rec, double *el, int N, double dt, int lane) {
@@ -645,10 +650,15 @@ __device__ __noinline__ int kkt_backward_scan(double *rec, double *el, int N, do
     const bool act = k <= N, dyn = k < N;
     const double *q = rec + (size_t)(act ? k : 0) * KKT_REC;
     double A[9], b[3], C[6], e[3], Jm[6];
+    int r_ok = 1;
     if (dyn) {
         const double a13 = q[KR_G + 0], a23 = q[KR_G + 1], b11 = q[KR_G + 2], b12 = q[KR_G + 3], b21 = q[KR_G + 4], b22 = q[KR_G + 5];
         const double R00 = q[KR_H + 12], R01 = q[KR_H + 13], R11 = q[KR_H + 14], htv = q[KR_H + 10], htw = q[KR_H + 11];
-        const double idet = fast_rcp(R00 * R11 - R01 * R01);
+        const double Rdet = R00 * R11 - R01 * R01;
+        // the scan eliminates the controls of every stage LOCALLY, so it needs R_k itself to be safely positive definite
+        // (the serial recursion only needs the condensed Quu_k = R_k + B'PB): otherwise the caller takes the serial form
+        if (!(R00 > 0.0) || !(R11 > 0.0) || !(Rdet > 1e-8 * R00 * R11)) r_ok = 0;
+        const double idet = fast_rcp(Rdet);
         const double i00 = R11 * idet, i01 = -R01 * idet, i11 = R00 * idet;
         // B R^-1 (3x2)
         const double g00 = b11 * i00 + b12 * i01, g01 = b11 * i01 + b12 * i11;
@@ -677,6 +687,7 @@ __device__ __noinline__ int kkt_backward_scan(double *rec, double *el, int N, do
         for (int i = 0; i < 6; i++) { C[i] = 0; Jm[i] = q[KR_H + i]; }
         e[0] = -q[KR_h + 0]; e[1] = -q[KR_h + 1]; e[2] = -q[KR_h + 2];
     }
+    if (!__all_sync(FULL, r_ok)) return -1; // the scan does not apply to this system: the caller takes the serial recursion
 #pragma unroll 1
     for (int lvl = 1; lvl <= N; lvl <<= 1) {
         __syncwarp();
@@ -873,43 +884,9 @@ __device__ __noinline__ int kkt_backward_scan(double *rec, double *el, int N, do
     return __all_sync(FULL, ok);
 }
 
-template <int J, bool SCAN>
-__device__ __forceinline__ bool kkt_solve_lp(const KParams &P, Stg (&s)[J], const double (&rc)[J][3],
-                                             const double (&rd)[J][2], bool useW, double dw, Step (&o)[J], int lane,
-                                             double *rec, const KktRoles &R) {
-    const int N = P.N;
-    const double dt = P.dt;
-    // ---- stage records (stage-parallel) ----
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        const int k = lane * J + j;
-        if (k > N) continue;
-        const Stg &t = s[j];
-        double *q = rec + (size_t)k * KKT_REC;
-        const bool dyn = k < N;
-        q[KR_ZERO] = 0.0; q[KR_ONE] = 1.0; q[KR_DT] = dt;
-        q[KR_G + 0] = dyn ? t.a13 : 0.0; q[KR_G + 1] = dyn ? t.a23 : 0.0;
-        q[KR_G + 2] = dyn ? t.b11 : 0.0; q[KR_G + 3] = dyn ? t.b12 : 0.0;
-        q[KR_G + 4] = dyn ? t.b21 : 0.0; q[KR_G + 5] = dyn ? t.b22 : 0.0;
-                q[KR_H + 0] = (useW ? t.hxx : 0.0) + dw; q[KR_H + 1] = (useW ? t.hxy : 0.0); q[KR_H + 2] = 0.0;
-        q[KR_H + 3] = (useW ? t.hyy : 0.0) + dw; q[KR_H + 4] = 0.0; q[KR_H + 5] = (useW ? t.htt : 0.0) + dw;
-        q[KR_H + 6] = 0.0; q[KR_H + 7] = 0.0; q[KR_H + 8] = 0.0; q[KR_H + 9] = 0.0;
-        q[KR_H + 10] = dyn ? (useW ? t.htv : 0.0) : 0.0; q[KR_H + 11] = dyn ? (useW ? t.htw : 0.0) : 0.0;
-        q[KR_H + 12] = dyn ? ((useW ? t.hvv : 0.0) + dw + t.Dsig[0]) : 1.0;
-        q[KR_H + 13] = dyn ? (useW ? t.hvw : 0.0) : 0.0;
-        q[KR_H + 14] = dyn ? ((useW ? t.hww : 0.0) + dw + t.Dsig[1]) : 1.0;
-        const bool hasx = k >= 1;
-        q[KR_h + 0] = hasx ? t.rx[0] : 0.0; q[KR_h + 1] = hasx ? t.rx[1] : 0.0; q[KR_h + 2] = hasx ? t.rx[2] : 0.0;
-        q[KR_h + 3] = dyn ? (t.ru[0] + t.Dsig[0] * rd[j][0] + t.rs[0]) : 0.0;
-        q[KR_h + 4] = dyn ? (t.ru[1] + t.Dsig[1] * rd[j][1] + t.rs[1]) : 0.0;
-        q[KR_D + 0] = dyn ? -rc[j][0] : 0.0; q[KR_D + 1] = dyn ? -rc[j][1] : 0.0; q[KR_D + 2] = dyn ? -rc[j][2] : 0.0;
-    }
-    __syncwarp();
-    if (SCAN && J == 1) {
-        // parallel-in-time form: all cost-to-go matrices from a suffix scan over the lanes (kkt_backward_scan)
-        if (!kkt_backward_scan(rec, rec + (size_t)(N + 1) * (KKT_REC + 6), N, dt, lane)) return false;
-    } else {
+// Serial backward recursion of the lane-parallel form (steps A-E above): one stage per step, one matrix entry per lane.
+// Returns false when a condensed Muu block is not positive definite (wrong inertia).
+__device__ __forceinline__ bool kkt_backward_serial(double *rec, int N, const KktRoles &R) {
     // ---- backward recursion: one stage per step, one matrix entry per lane ----
     const int a0 = R.a_off & 0xff, a1 = (R.a_off >> 8) & 0xff, a2 = (R.a_off >> 16) & 0xff;
     const int sp0 = R.a_src & 0xff, sp1 = (R.a_src >> 8) & 0xff, sp2 = (R.a_src >> 16) & 0xff, spv = R.a_src >> 24;
@@ -965,9 +942,57 @@ __device__ __forceinline__ bool kkt_solve_lp(const KParams &P, Stg (&s)[J], cons
         res = r;
         if (outo != 0xff) rec[(size_t)k * KKT_REC + KR_OUT + outo] = r;
     }
+    return true;
+}
+// out-of-line copy for the scan instance (its fallback when the scan does not apply)
+__device__ __noinline__ bool kkt_backward_serial_ool(double *rec, int N, const KktRoles &R) { return kkt_backward_serial(rec, N, R); }
+
+template <int J, bool SCAN>
+__device__ __forceinline__ bool kkt_solve_lp(const KParams &P, Stg (&s)[J], const double (&rc)[J][3],
+                                             const double (&rd)[J][2], bool useW, double dw, Step (&o)[J], int lane,
+                                             double *rec, const KktRoles &R) {
+    const int N = P.N;
+    const double dt = P.dt;
+    // ---- stage records (stage-parallel) ----
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int k = lane * J + j;
+        if (k > N) continue;
+        const Stg &t = s[j];
+        double *q = rec + (size_t)k * KKT_REC;
+        const bool dyn = k < N;
+        q[KR_ZERO] = 0.0; q[KR_ONE] = 1.0; q[KR_DT] = dt;
+        q[KR_G + 0] = dyn ? t.a13 : 0.0; q[KR_G + 1] = dyn ? t.a23 : 0.0;
+        q[KR_G + 2] = dyn ? t.b11 : 0.0; q[KR_G + 3] = dyn ? t.b12 : 0.0;
+        q[KR_G + 4] = dyn ? t.b21 : 0.0; q[KR_G + 5] = dyn ? t.b22 : 0.0;
+                q[KR_H + 0] = (useW ? t.hxx : 0.0) + dw; q[KR_H + 1] = (useW ? t.hxy : 0.0); q[KR_H + 2] = 0.0;
+        q[KR_H + 3] = (useW ? t.hyy : 0.0) + dw; q[KR_H + 4] = 0.0; q[KR_H + 5] = (useW ? t.htt : 0.0) + dw;
+        q[KR_H + 6] = 0.0; q[KR_H + 7] = 0.0; q[KR_H + 8] = 0.0; q[KR_H + 9] = 0.0;
+        q[KR_H + 10] = dyn ? (useW ? t.htv : 0.0) : 0.0; q[KR_H + 11] = dyn ? (useW ? t.htw : 0.0) : 0.0;
+        q[KR_H + 12] = dyn ? ((useW ? t.hvv : 0.0) + dw + t.Dsig[0]) : 1.0;
+        q[KR_H + 13] = dyn ? (useW ? t.hvw : 0.0) : 0.0;
+        q[KR_H + 14] = dyn ? ((useW ? t.hww : 0.0) + dw + t.Dsig[1]) : 1.0;
+        const bool hasx = k >= 1;
+        q[KR_h + 0] = hasx ? t.rx[0] : 0.0; q[KR_h + 1] = hasx ? t.rx[1] : 0.0; q[KR_h + 2] = hasx ? t.rx[2] : 0.0;
+        q[KR_h + 3] = dyn ? (t.ru[0] + t.Dsig[0] * rd[j][0] + t.rs[0]) : 0.0;
+        q[KR_h + 4] = dyn ? (t.ru[1] + t.Dsig[1] * rd[j][1] + t.rs[1]) : 0.0;
+        q[KR_D + 0] = dyn ? -rc[j][0] : 0.0; q[KR_D + 1] = dyn ? -rc[j][1] : 0.0; q[KR_D + 2] = dyn ? -rc[j][2] : 0.0;
     }
     __syncwarp();
+    bool scanned = false;
     if (SCAN && J == 1) {
+        // parallel-in-time form: all cost-to-go matrices from a suffix scan over the lanes (kkt_backward_scan);
+        // 1 = done, 0 = wrong inertia, -1 = a local control block is not safely positive definite (serial form instead)
+        const int r = kkt_backward_scan(rec, rec + (size_t)(N + 1) * (KKT_REC + 6), N, dt, lane);
+        if (r == 0) return false;
+        scanned = r > 0;
+        if (!scanned && !kkt_backward_serial_ool(rec, N, R)) return false;
+    } else {
+        if (!kkt_backward_serial(rec, N, R)) return false;
+    }
+    __syncwarp();
+    if (scanned) {
         // (the scan routine has rolled the step out as a prefix scan of the closed-loop maps)
         const int k = lane;
         if (k <= N) {
@@ -1290,6 +1315,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
         double mu = P.mu_init, tau = fmax(TAU_MIN, 1.0 - mu);
         double theta_max = -1, theta_min = -1, dw_last = 0;
         int acceptable_count = 0;
+        bool tiny_last = false, tiny_flag = false; // BacktrackingLineSearch::tiny_step_last_iteration_, IpoptData::tiny_step_flag
         // filter: one entry per lane
         double fphi = 0, ftheta = 0;
         bool fvalid = false;
@@ -1370,26 +1396,33 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
             }
             if (iter >= P.max_iter) { status = B200MPC_MAXITER_EXCEEDED; break; }
 
-            // ---- barrier parameter update ----
-            for (;;) {
-                double cm = 0;
+            // ---- barrier parameter update (MonotoneMuUpdate).  A tiny step in two consecutive iterations forces a
+            // decrease; when mu cannot decrease any more: Search_Direction_Becomes_Too_Small ----
+            {
+                bool tflag = tiny_flag, stop = false;
+                tiny_flag = false;
+                for (;;) {
+                    double cm = 0;
 #pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    const bool dyn = (lane * J + j) < N;
+                    for (int j = 0; j < J; ++j) {
+                        const bool dyn = (lane * J + j) < N;
 #pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        const double sl = s[j].S[i] - P.sL[i], su = P.sU[i] - s[j].S[i];
-                        if (dyn) cm = fmax(cm, fmax(fabs(sl * s[j].vL[i] - mu), fabs(su * s[j].vU[i] - mu)));
+                        for (int i = 0; i < 2; i++) {
+                            const double sl = s[j].S[i] - P.sL[i], su = P.sU[i] - s[j].S[i];
+                            if (dyn) cm = fmax(cm, fmax(fabs(sl * s[j].vL[i] - mu), fabs(su * s[j].vU[i] - mu)));
+                        }
                     }
+                    cm = wmax(cm);
+                    const double Emu = fmax(dual_inf / sd, fmax(prim_inf, cm / sc));
+                    if (!(Emu <= K_EPS * mu) && !tflag) break;
+                    const double nm = fmax(fmin(K_MU * mu, pow(mu, TH_MU)), P.mu_floor);
+                    if (nm == mu) { stop = tflag; break; }
+                    mu = nm;
+                    tau = fmax(TAU_MIN, 1.0 - mu);
+                    fvalid = false;
+                    tflag = false;
                 }
-                cm = wmax(cm);
-                const double Emu = fmax(dual_inf / sd, fmax(prim_inf, cm / sc));
-                if (!(Emu <= K_EPS * mu)) break;
-                const double nm = fmax(fmin(K_MU * mu, pow(mu, TH_MU)), P.mu_floor);
-                if (nm == mu) break;
-                mu = nm;
-                tau = fmax(TAU_MIN, 1.0 - mu);
-                fvalid = false;
+                if (stop) { status = B200MPC_SEARCH_DIRECTION_TOO_SMALL; break; }
             }
 
             // ---- search direction with inertia correction ----
@@ -1466,6 +1499,57 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
             int acc = 0; // 0 none, 1 newton step, 2 corrected step
             bool fa = false;
             int ntrial = 0;
+            // BacktrackingLineSearch::DetectTinyStep: every primal component moves by less than tiny_step_tol = 10 eps
+            // (relative) and the point is nearly feasible -> the full step is taken without a line search
+            bool tiny;
+            {
+                int big = 0;
+                double c2 = 0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int k = lane * J + j;
+                    if (k >= 1 && k <= N) {
+#pragma unroll
+                        for (int i = 0; i < 3; i++) {
+                            if (!(fabs(st[j].dX[i]) <= TINY_STEP_TOL * (1.0 + fabs(s[j].X[i])))) big = 1;
+                        }
+                    }
+                    if (k < N) {
+#pragma unroll
+                        for (int i = 0; i < 3; i++) c2 += rc[j][i] * rc[j][i];
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            if (!(fabs(st[j].dU[i]) <= TINY_STEP_TOL * (1.0 + fabs(s[j].U[i])))) big = 1;
+                            if (!(fabs(st[j].dS[i]) <= TINY_STEP_TOL * (1.0 + fabs(s[j].S[i])))) big = 1;
+                            c2 += rd[j][i] * rd[j][i];
+                        }
+                    }
+                }
+                tiny = !wor(big);
+                if (tiny) tiny = sqrt(wsum(c2)) <= 1e-4;
+            }
+            if (tiny) {
+                double th_t, phi_t;
+                trial_eval<J, OBS>(P, sox, soy, ocs, s, st, alpha, mu, df, lane, th_t, phi_t);
+                if (isfinite(th_t) && isfinite(phi_t)) {
+                    (void)ls_acceptable(ref, alpha, phi_t, th_t, fphi, ftheta, fvalid, fa); // only for the filter-augmentation rule
+                    acc = 1;
+                    alpha_acc = alpha;
+                    if (tiny_last) tiny_flag = true;
+                    double dy = 0;
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+#pragma unroll
+                        for (int i = 0; i < 3; i++) dy = fmax(dy, fabs(st[j].dlam[i]));
+#pragma unroll
+                        for (int i = 0; i < 2; i++) dy = fmax(dy, fabs(st[j].dyd[i]));
+                    }
+                    tiny_last = wmax(dy) < TINY_STEP_Y_TOL;
+                } else {
+                    tiny = false;
+                }
+            }
+            if (!tiny) { tiny_flag = false; tiny_last = false; }
             while (!acc) {
                 double th_t, phi_t;
                 trial_eval<J, OBS>(P, sox, soy, ocs, s, st, alpha, mu, df, lane, th_t, phi_t);
@@ -1508,16 +1592,69 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
             }
 
             if (!acc) {
-                // restoration stand-in: roll the controls out (closed-form feasible point), restart multipliers
+                // Restoration stand-in.  Direction: towards the closed-form feasible point (U = S, X rolled out); the
+                // longest step t = 1, 1/2, ... along it is taken whose point passes IPOPT's restoration acceptance
+                // (finite, theta <= kappa_resto * theta, no excessive objective increase, acceptable to the augmented
+                // filter); the multipliers restart.
                 if (theta <= 1e-10 || n_resto >= MAX_RESTO) { status = B200MPC_RESTORATION_FAILED; break; }
                 filter_add(ref.phi - GAMMA_PHI * theta, (1 - GAMMA_THETA) * theta, fphi, ftheta, fvalid, ring, lane);
+                {
+                    // serial rollout X_{k+1} = F(X_k, S_k); the direction goes to the step record of the correction
+                    double y[3] = {x00, x01, x02};
+                    for (int l = 0; l <= N / J; ++l) {
+                        double z[3] = {y[0], y[1], y[2]};
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            const int ko = l * J + j;
+                            if (ko > N) continue;
+                            if (lane == l) {
+                                soc[j].dX[0] = z[0] - s[j].X[0]; soc[j].dX[1] = z[1] - s[j].X[1]; soc[j].dX[2] = z[2] - s[j].X[2];
+                            }
+                            if (ko < N) {
+                                double F[3];
+                                dyn_value(P, z, s[j].S, F);
+                                z[0] = F[0]; z[1] = F[1]; z[2] = F[2];
+                            }
+                        }
+                        y[0] = __shfl_sync(FULL, z[0], l); y[1] = __shfl_sync(FULL, z[1], l); y[2] = __shfl_sync(FULL, z[2], l);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int k = lane * J + j;
+                    if (k > N || k == 0) { soc[j].dX[0] = soc[j].dX[1] = soc[j].dX[2] = 0; }
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        soc[j].dU[i] = (k < N) ? (s[j].S[i] - s[j].U[i]) : 0.0;
+                        soc[j].dS[i] = 0;
+                    }
+                }
+                double t_acc = 0.0;
+                for (double t = 1.0; t >= RESTO_T_MIN; t *= 0.5) {
+                    double th_r, phi_r;
+                    trial_eval<J, OBS>(P, sox, soy, ocs, s, soc, t, mu, df, lane, th_r, phi_r);
+                    if (!isfinite(th_r) || !isfinite(phi_r)) continue;
+                    if (!(th_r <= KAPPA_RESTO * theta)) continue;
+                    if (phi_r > ref.phi) {
+                        double bas = 1.0;
+                        if (fabs(ref.phi) > 10.0) bas = log10(fabs(ref.phi));
+                        if (log10(phi_r - ref.phi) > OBJ_MAX_INC + bas) continue;
+                    }
+                    const bool rej = fvalid && !(cmp_le(phi_r, fphi, fphi) || cmp_le(th_r, ftheta, ftheta));
+                    if (__any_sync(FULL, rej)) continue;
+                    t_acc = t;
+                    break;
+                }
+                if (t_acc == 0.0) { status = B200MPC_RESTORATION_FAILED; break; }
                 double zm = 0;
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    const bool dyn = (lane * J + j) < N;
+                    const int k = lane * J + j;
+                    const bool dyn = k < N;
+                    if (k >= 1 && k <= N) { s[j].X[0] = s[j].Xt[0]; s[j].X[1] = s[j].Xt[1]; s[j].X[2] = s[j].Xt[2]; }
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
-                        if (dyn) { s[j].U[i] = s[j].S[i]; zm = fmax(zm, fmax(s[j].vL[i], s[j].vU[i])); }
+                        if (dyn) { s[j].U[i] = s[j].Ut[i]; zm = fmax(zm, fmax(s[j].vL[i], s[j].vU[i])); }
                         s[j].yd[i] = 0;
                     }
 #pragma unroll
@@ -1528,23 +1665,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
 #pragma unroll
                     for (int j = 0; j < J; ++j) { s[j].vL[0] = s[j].vL[1] = 1.0; s[j].vU[0] = s[j].vU[1] = 1.0; }
                 }
-                // serial rollout X_{k+1} = F(X_k, U_k)
-                double y[3] = {x00, x01, x02};
-                for (int l = 0; l <= N / J; ++l) {
-                    double z[3] = {y[0], y[1], y[2]};
-#pragma unroll
-                    for (int j = 0; j < J; ++j) {
-                        const int ko = l * J + j;
-                        if (ko > N) continue;
-                        if (lane == l) { s[j].X[0] = z[0]; s[j].X[1] = z[1]; s[j].X[2] = z[2]; }
-                        if (ko < N) {
-                            double F[3];
-                            dyn_value(P, z, s[j].U, F);
-                            z[0] = F[0]; z[1] = F[1]; z[2] = F[2];
-                        }
-                    }
-                    y[0] = __shfl_sync(FULL, z[0], l); y[1] = __shfl_sync(FULL, z[1], l); y[2] = __shfl_sync(FULL, z[2], l);
-                }
+                oc_valid = OBS && (P.obs_form != B200MPC_OBS_NONE); // ocs holds the sums of the accepted point
                 n_resto++;
                 iter++;
                 continue;
@@ -1739,6 +1860,8 @@ __global__ void __launch_bounds__(128) mpc_eval_kernel(const KParams P, const Ev
 #include "obstacles_kernel.cuh"
 #include "refgen_kernel.cuh"
 #include "control_kernel.cuh"
+#include "costmap_kernel.cuh"
+#include "sensor_kernel.cuh"
 
 // =============================================================================================================
 // Host side: C ABI
@@ -2660,5 +2783,266 @@ extern "C" int b200mpc_control_step_device(b200mpc_handle *h, int B, const doubl
     control_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     CU_TRY(h, cudaGetLastError());
     h->launches++;
+    return 0;
+}
+
+// ---- costmap inflation / dilation ---------------------------------------------------------------
+static void costmap_tile(int H, int W, int halo_h, int halo_w, size_t per_cell_extra, int &TH, int &TW, size_t &smem,
+                         bool with_tmp) {
+    // tile = as much of the grid as fits ~64 KB of shared memory (three CTAs per SM), rows first
+    TW = W < 128 ? W : 128;
+    TH = H < 64 ? H : 64;
+    for (;;) {
+        const size_t SH = (size_t)TH + halo_h, SW = (size_t)TW + halo_w;
+        smem = SH * SW * (8 + per_cell_extra) + (with_tmp ? SH * (size_t)TW * 8 : 0);
+        if (smem <= 64 * 1024 || (TH <= 8 && TW <= 16)) break;
+        if (TH > 8) TH = (TH + 1) / 2; else TW = (TW + 1) / 2;
+    }
+}
+
+extern "C" int b200mpc_dilate_batch_device(b200mpc_handle *h, int B, int H, int W, const double *grid, int kh, int kw,
+                                           uint8_t *out, void *stream) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || H < 1 || W < 1 || kh < 1 || kw < 1 || kh > 32 || kw > 32) return set_err(h, B200MPC_E_ARG, "B < 0, empty grid or kernel size outside [1,32]");
+    if (B == 0) return 0;
+    if (!grid || !out) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    DilateArgs a;
+    a.B = B; a.H = H; a.W = W; a.kh = kh; a.kw = kw; a.in = grid; a.out = out;
+    size_t smem;
+    costmap_tile(H, W, kh - 1, kw - 1, 0, a.TH, a.TW, smem, true);
+    if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(dilate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const long long tiles = (long long)B * ((H + a.TH - 1) / a.TH) * ((W + a.TW - 1) / a.TW);
+    const long long cap = (long long)h->sm_count * 6;
+    CU_TRY(h, cudaEventRecord(h->ev0, (cudaStream_t)stream));
+    dilate_kernel<<<(int)(tiles < cap ? tiles : cap), COSTMAP_THREADS, smem, (cudaStream_t)stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->ev1, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
+
+extern "C" int b200mpc_inflate_batch_device(b200mpc_handle *h, int B, int H, int W, const double *grid,
+                                            const double *inflation_matrix, int cells_inflation, double *out, void *stream) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || H < 1 || W < 1 || cells_inflation < 0 || cells_inflation > 32)
+        return set_err(h, B200MPC_E_ARG, "B < 0, empty grid or cells_inflation outside [0,32]");
+    if (B == 0) return 0;
+    if (!grid || !inflation_matrix || !out) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    InflateArgs a;
+    a.B = B; a.H = H; a.W = W; a.c = cells_inflation; a.in = grid; a.M = inflation_matrix; a.out = out;
+    size_t smem;
+    costmap_tile(H, W, 2 * cells_inflation, 2 * cells_inflation, 1, a.TH, a.TW, smem, false);
+    const int n = 2 * cells_inflation + 1;
+    smem += (size_t)n * n * 8 + 16;
+    if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const long long tiles = (long long)B * ((H + a.TH - 1) / a.TH) * ((W + a.TW - 1) / a.TW);
+    const long long cap = (long long)h->sm_count * 6;
+    CU_TRY(h, cudaEventRecord(h->ev0, (cudaStream_t)stream));
+    inflate_kernel<<<(int)(tiles < cap ? tiles : cap), COSTMAP_THREADS, smem, (cudaStream_t)stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->ev1, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
+
+extern "C" int b200mpc_local_costmap_batch_device(b200mpc_handle *h, int B, int n_beams, const double *scan,
+                                                  const double *beam_cos, const double *beam_sin, const double *yaw, double size,
+                                                  double resolution, int kh, int kw, uint8_t *out, void *stream) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || n_beams < 1 || kh < 1 || kw < 1 || kh > 32 || kw > 32) return set_err(h, B200MPC_E_ARG, "B < 0, n_beams < 1 or kernel size outside [1,32]");
+    if (!(size > 0) || !(resolution > 0)) return set_err(h, B200MPC_E_ARG, "size and resolution must be > 0");
+    if (B == 0) return 0;
+    if (!scan || !beam_cos || !beam_sin || !yaw || !out) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    LocalCostmapArgs a;
+    const double map_size = size * 2.0; // the publisher passes map_size = costmap_size * 2 (local_costmap_publisher.py:30)
+    a.B = B; a.n = n_beams; a.kh = kh; a.kw = kw;
+    a.nc = (int)(map_size / resolution);
+    if (a.nc < 1 || a.nc > 512) return set_err(h, B200MPC_E_ARG, "grid side int(2*size/resolution) out of range [1,512]");
+    a.wpr = (a.nc + 31) / 32;
+    a.scan = scan; a.bcos = beam_cos; a.bsin = beam_sin; a.yaw = yaw; a.half = map_size / 2; a.res = resolution;
+    a.value = 100; a.out = out;
+    const size_t smem = (size_t)LCM_WARPS * 2 * a.nc * a.wpr * 4;
+    if (smem > 200 * 1024) return set_err(h, B200MPC_E_ARG, "grid too large for the shared-memory staging");
+    if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(local_costmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int grid = (B + LCM_WARPS - 1) / LCM_WARPS;
+    const int cap = h->sm_count * 8;
+    if (grid > cap) grid = cap;
+    CU_TRY(h, cudaEventRecord(h->ev0, (cudaStream_t)stream));
+    local_costmap_kernel<<<grid, LCM_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->ev1, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
+
+// ---- sensor model and path preprocessing ------------------------------------------------------------------------------
+extern "C" int b200mpc_raycast_batch_device(b200mpc_handle *h, int B, int n_beams, const uint32_t *occ_bits, int H, int W,
+                                            double origin_x, double origin_y, double resolution, const double *pose,
+                                            int pose_stride, double angle_min, double angle_max, double range_min,
+                                            double range_max, double step, double *scan, void *stream) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || n_beams < 1 || H < 1 || W < 1 || pose_stride < 3) return set_err(h, B200MPC_E_ARG, "B < 0, n_beams < 1, empty map or pose_stride < 3");
+    if (!(resolution > 0) || !(step > 0) || !(range_max >= range_min)) return set_err(h, B200MPC_E_ARG, "resolution, step must be > 0 and range_max >= range_min");
+    if (B == 0) return 0;
+    if (!occ_bits || !pose || !scan) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    RaycastArgs a;
+    a.B = B; a.n = n_beams; a.H = H; a.W = W; a.wpr = (W + 31) / 32;
+    a.nsteps = (int)llrint((range_max - range_min) / step) + 1; // int(round((range_max - range_min) / step)) + 1
+    a.occ_bits = occ_bits; a.pose = pose; a.pose_stride = pose_stride;
+    a.angle_min = angle_min; a.angle_inc = angle_max - angle_min;
+    a.range_min = range_min; a.range_max = range_max; a.step = step;
+    a.ox = origin_x; a.oy = origin_y; a.res = resolution; a.scan = scan;
+    const size_t smem = (size_t)H * a.wpr * 4;
+    if (smem > 200 * 1024) return set_err(h, B200MPC_E_ARG, "map too large for the shared-memory staging (H * ceil(W/32) * 4 bytes <= 200 KB)");
+    if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(raycast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int grid = (B + RAY_WARPS - 1) / RAY_WARPS;
+    const int cap = h->sm_count * 4;
+    if (grid > cap) grid = cap;
+    CU_TRY(h, cudaEventRecord(h->ev0, (cudaStream_t)stream));
+    raycast_kernel<<<grid, RAY_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(h->ev1, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
+
+extern "C" int b200mpc_headings_batch_device(b200mpc_handle *h, int P, int K, const double *path_xy, double dt, double *heading,
+                                             double *velocity, double *omega, void *stream) {
+    if (!h) return B200MPC_E_ARG;
+    if (P < 0 || K < 2 || !(dt > 0)) return set_err(h, B200MPC_E_ARG, "P < 0, K < 2 or dt <= 0");
+    if (P == 0) return 0;
+    if (!path_xy || !heading || !velocity || !omega) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    HeadingsArgs a;
+    a.P = P; a.K = K; a.path_xy = path_xy; a.dt = dt; a.heading = heading; a.velocity = velocity; a.omega = omega;
+    long long blocks = ((long long)P * K + 255) / 256;
+    const long long cap = (long long)h->sm_count * 8;
+    headings_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+// host-buffer variants of the five producers above: stage through the handle's device buffer, blocking
+extern "C" int b200mpc_dilate_batch(b200mpc_handle *h, int B, int H, int W, const double *grid, int kh, int kw, uint8_t *out) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || H < 1 || W < 1) return set_err(h, B200MPC_E_ARG, "B < 0 or empty grid");
+    if (B == 0) return 0;
+    if (!grid || !out) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t cells = (size_t)B * H * W;
+    int rc = ensure_buf(h, stage_size(cells * 8) + stage_size(cells));
+    if (rc) return rc;
+    HostStage st{h, h->d_buf, 0};
+    cudaError_t e = cudaSuccess;
+    double *d_in = stage_in(st, grid, cells, e);
+    uint8_t *d_out = stage_in<uint8_t>(st, nullptr, cells, e);
+    CU_TRY(h, e);
+    rc = b200mpc_dilate_batch_device(h, B, H, W, d_in, kh, kw, d_out, h->stream);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(out, d_out, cells, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int b200mpc_inflate_batch(b200mpc_handle *h, int B, int H, int W, const double *grid, const double *inflation_matrix,
+                                     int cells_inflation, double *out) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || H < 1 || W < 1 || cells_inflation < 0) return set_err(h, B200MPC_E_ARG, "B < 0, empty grid or cells_inflation < 0");
+    if (B == 0) return 0;
+    if (!grid || !inflation_matrix || !out) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t cells = (size_t)B * H * W, nm = (size_t)(2 * cells_inflation + 1) * (2 * cells_inflation + 1);
+    int rc = ensure_buf(h, 2 * stage_size(cells * 8) + stage_size(nm * 8));
+    if (rc) return rc;
+    HostStage st{h, h->d_buf, 0};
+    cudaError_t e = cudaSuccess;
+    double *d_in = stage_in(st, grid, cells, e), *d_m = stage_in(st, inflation_matrix, nm, e);
+    double *d_out = stage_in<double>(st, nullptr, cells, e);
+    CU_TRY(h, e);
+    rc = b200mpc_inflate_batch_device(h, B, H, W, d_in, d_m, cells_inflation, d_out, h->stream);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(out, d_out, cells * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int b200mpc_local_costmap_batch(b200mpc_handle *h, int B, int n_beams, const double *scan, const double *beam_cos,
+                                           const double *beam_sin, const double *yaw, double size, double resolution, int kh,
+                                           int kw, uint8_t *out) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || n_beams < 1 || !(size > 0) || !(resolution > 0)) return set_err(h, B200MPC_E_ARG, "B < 0, n_beams < 1, size or resolution <= 0");
+    if (B == 0) return 0;
+    if (!scan || !beam_cos || !beam_sin || !yaw || !out) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int nc = (int)(size * 2.0 / resolution);
+    if (nc < 1 || nc > 512) return set_err(h, B200MPC_E_ARG, "grid side int(2*size/resolution) out of range [1,512]");
+    const size_t nb = (size_t)B, cells = nb * nc * nc;
+    int rc = ensure_buf(h, stage_size(nb * n_beams * 8) + 2 * stage_size((size_t)n_beams * 8) + stage_size(nb * 8) + stage_size(cells));
+    if (rc) return rc;
+    HostStage st{h, h->d_buf, 0};
+    cudaError_t e = cudaSuccess;
+    double *d_scan = stage_in(st, scan, nb * n_beams, e), *d_c = stage_in(st, beam_cos, (size_t)n_beams, e);
+    double *d_s = stage_in(st, beam_sin, (size_t)n_beams, e), *d_yaw = stage_in(st, yaw, nb, e);
+    uint8_t *d_out = stage_in<uint8_t>(st, nullptr, cells, e);
+    CU_TRY(h, e);
+    rc = b200mpc_local_costmap_batch_device(h, B, n_beams, d_scan, d_c, d_s, d_yaw, size, resolution, kh, kw, d_out, h->stream);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(out, d_out, cells, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int b200mpc_raycast_batch(b200mpc_handle *h, int B, int n_beams, const uint32_t *occ_bits, int H, int W, double origin_x,
+                                     double origin_y, double resolution, const double *pose, double angle_min, double angle_max,
+                                     double range_min, double range_max, double step, double *scan) {
+    if (!h) return B200MPC_E_ARG;
+    if (B < 0 || n_beams < 1 || H < 1 || W < 1) return set_err(h, B200MPC_E_ARG, "B < 0, n_beams < 1 or empty map");
+    if (B == 0) return 0;
+    if (!occ_bits || !pose || !scan) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t nb = (size_t)B, nw = (size_t)H * ((W + 31) / 32);
+    int rc = ensure_buf(h, stage_size(nw * 4) + stage_size(nb * 24) + stage_size(nb * n_beams * 8));
+    if (rc) return rc;
+    HostStage st{h, h->d_buf, 0};
+    cudaError_t e = cudaSuccess;
+    uint32_t *d_occ = stage_in(st, occ_bits, nw, e);
+    double *d_pose = stage_in(st, pose, nb * 3, e);
+    double *d_scan = stage_in<double>(st, nullptr, nb * n_beams, e);
+    CU_TRY(h, e);
+    rc = b200mpc_raycast_batch_device(h, B, n_beams, d_occ, H, W, origin_x, origin_y, resolution, d_pose, 3, angle_min, angle_max,
+                                      range_min, range_max, step, d_scan, h->stream);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(scan, d_scan, nb * n_beams * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int b200mpc_headings_batch(b200mpc_handle *h, int P, int K, const double *path_xy, double dt, double *heading,
+                                      double *velocity, double *omega) {
+    if (!h) return B200MPC_E_ARG;
+    if (P < 0 || K < 2) return set_err(h, B200MPC_E_ARG, "P < 0 or K < 2");
+    if (P == 0) return 0;
+    if (!path_xy || !heading || !velocity || !omega) return set_err(h, B200MPC_E_ARG, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t np_ = (size_t)P * K, nw = (size_t)P * (K - 1);
+    int rc = ensure_buf(h, stage_size(np_ * 16) + 2 * stage_size(np_ * 8) + stage_size(nw * 8));
+    if (rc) return rc;
+    HostStage st{h, h->d_buf, 0};
+    cudaError_t e = cudaSuccess;
+    double *d_xy = stage_in(st, path_xy, np_ * 2, e);
+    double *d_h = stage_in<double>(st, nullptr, np_, e), *d_v = stage_in<double>(st, nullptr, np_, e);
+    double *d_w = stage_in<double>(st, nullptr, nw, e);
+    CU_TRY(h, e);
+    rc = b200mpc_headings_batch_device(h, P, K, d_xy, dt, d_h, d_v, d_w, h->stream);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(heading, d_h, np_ * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(velocity, d_v, np_ * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(omega, d_w, nw * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -484,6 +484,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 L.status = B200MPC_MAXITER_EXCEEDED;
                 L.iter = 0; L.ls_extra = 0; L.n_resto = 0; L.acceptable_count = 0; L.ntrial = 0; L.soc_count = 0;
                 L.ring = 0; L.fmask = 0; L.keep = 0; L.soc_first = 1; L.moved = 0;
+                L.tiny = 0; L.tiny_last = 0; L.tiny_flag = 0; // (the two-sweep kernel does not detect tiny steps)
                 L.df = 1.0; L.mu = P.mu_init;
                 L.theta0 = -1; L.dw = 0; L.dw_last = 0; L.dw_b = 0;
                 L.alpha = 0; L.a_z = 0; L.alpha_soc = 0; L.a_z_soc = 0; L.a_min = 0; L.theta_soc_old = 0;

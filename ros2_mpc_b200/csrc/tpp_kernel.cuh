@@ -181,6 +181,7 @@ struct TppLane {
     int status, iter, ls_extra, n_resto, acceptable_count, ntrial, soc_count, ring;
     unsigned fmask;
     int keep, soc_first, moved;
+    int tiny, tiny_last, tiny_flag;                // tiny-step detection (BacktrackingLineSearch::DetectTinyStep and its two flags)
     double ymax_f;                                 // LSQ mode: largest slack-multiplier estimate seen by sweep F
     double dw_b;                                   // two-sweep kernel: delta_w of the factorisation in progress
 };
@@ -515,7 +516,7 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
 
 struct TppFwd {
     double a_max, a_z, gbd, ymax;
-    int bad;
+    int bad, tiny;
 };
 
 // staging of the forward sweep: slots 0-3 = K, kf rows of stage k, 4-7 = U, S, vL, vU of stage k,
@@ -549,6 +550,8 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
     double y0 = 0, y1 = 0, y2 = 0;
     double a_max = 1.0, a_z = 1.0, gbd = 0, ymax = 0;
     int bad = 0;
+    int big = 0;      // a primal component of the Newton step exceeds tiny_step_tol (relative)
+    double c2 = 0;    // squared 2-norm of the primal infeasibility of the current iterate
     double X[3];
     {
         const double2 a = tpp_ld2(wb + co * TPP_ROW_B, R_X01), b = tpp_ld2(wb + co * TPP_ROW_B, R_X2L0);
@@ -575,6 +578,9 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
         }
         if (!isfinite(y0) || !isfinite(y1) || !isfinite(y2)) bad = 1;
         tpp_st2(p, orow, y0, y1); tpp_st2(p, orow + 1, y2, 0.0);
+        if (k >= 1 && (!(fabs(y0) <= TINY_STEP_TOL * (1.0 + fabs(X[0]))) || !(fabs(y1) <= TINY_STEP_TOL * (1.0 + fabs(X[1]))) ||
+                       !(fabs(y2) <= TINY_STEP_TOL * (1.0 + fabs(X[2])))))
+            big = 1;
         if (k < N) {
             const double du0 = kf_.x + k0_.x * y0 + k0_.y * y1 + k1_.x * y2;
             const double du1 = kf_.y + k1_.y * y0 + k2_.x * y1 + k2_.y * y2;
@@ -614,7 +620,10 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
                     if (dvU < 0) a_z = fmin(a_z, -tau * vU * tpp_rcp(dvU));
                     if (!isfinite(ds) || !isfinite(dvL) || !isfinite(dvU)) bad = 1;
                     if (mode == BM_NEWTON) gbd += (-mu * isl + mu * isu) * ds + q.g[3 + i] * du[i];
+                    if (!(fabs(du[i]) <= TINY_STEP_TOL * (1.0 + fabs(U[i]))) || !(fabs(ds) <= TINY_STEP_TOL * (1.0 + fabs(S)))) big = 1;
+                    c2 += rdv[i] * rdv[i];
                 }
+                c2 += rc0 * rc0 + rc1 * rc1 + rc2 * rc2;
             }
             const double n0 = y0 + q.a13 * y2 + q.b11 * du0 + q.b12 * du1 - rc0;
             const double n1 = y1 + q.a23 * y2 + q.b21 * du0 + q.b22 * du1 - rc1;
@@ -624,10 +633,11 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
         }
     }
     o.a_max = a_max; o.a_z = a_z; o.gbd = gbd; o.ymax = ymax; o.bad = bad;
+    o.tiny = (!big && sqrt(c2) <= 1e-4) ? 1 : 0;
 }
 
 struct TppTrial {
-    double th, phi, ymax;
+    double th, phi, ymax, dymax; // dymax: largest multiplier step (defect and slack-equality multipliers), step modes
     int bad;
     TppNorms n;
 };
@@ -703,7 +713,7 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
     const double ikap = 1.0 / KAPPA_SIGMA;
     double Xn[3] = {0, 0, 0}, ln[3] = {0, 0, 0};
     double lo[3] = {0, 0, 0}, Lam[3] = {0, 0, 0}; // multipliers of stage k+1: at the current iterate / after a full step
-    double th = 0, slog = 0, pi = 0, di = 0, sy = 0, sz = 0, pmin = 1e300, pmax = -1e300, fs = 0, ymax = 0;
+    double th = 0, slog = 0, pi = 0, di = 0, sy = 0, sz = 0, pmin = 1e300, pmax = -1e300, fs = 0, ymax = 0, dymax = 0;
     int bad = 0;
     tpp_trial_stage(sb, wb + (size_t)N * TPP_STAGE_B, co, srow);
 #pragma unroll 1
@@ -750,7 +760,9 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
 #pragma unroll
                     for (int i = 0; i < 3; i++) {
                         X[i] += alpha * dX[i];
-                        lam[i] += alpha * (Lk[i] - lam[i]);
+                        const double dl = Lk[i] - lam[i];
+                        dymax = fmax(dymax, fabs(dl));
+                        lam[i] += alpha * dl;
                     }
                 } else {
                     ymax = fmax(ymax, fmax(fabs(Lk[0]), fmax(fabs(Lk[1]), fabs(Lk[2]))));
@@ -782,7 +794,9 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
                     const double dvU = mu * isu - vU[i] + vU[i] * isu * ds;
                     U[i] += alpha * du;
                     S[i] += alpha * ds;
-                    yd[i] += alpha * (Dsig * ds + rs);
+                    const double dyd = Dsig * ds + rs;
+                    dymax = fmax(dymax, fabs(dyd));
+                    yd[i] += alpha * dyd;
                     vL[i] += a_z * dvL;
                     vU[i] += a_z * dvU;
                     const double ml = mu * tpp_rcp(S[i] - P.sL[i]), mu_u = mu * tpp_rcp(P.sU[i] - S[i]);
@@ -842,7 +856,7 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
     }
     o.th = th;
     o.phi = df * fs - mu * slog;
-    o.ymax = ymax; o.bad = bad;
+    o.ymax = ymax; o.dymax = dymax; o.bad = bad;
     o.n.theta = th; o.n.prim_inf = pi; o.n.dual_inf = di; o.n.sum_y = sy; o.n.sum_z = sz;
     o.n.pmin = pmin; o.n.pmax = pmax; o.n.f = fs; o.n.slog = slog;
 }
@@ -899,8 +913,44 @@ __device__ __forceinline__ bool tpp_ls_acceptable(const TppLane &L, const double
     return tpp_filter_ok(fl, L.fmask, phi_t, th_t);
 }
 
-// Line search gave up on the Newton direction (alpha < alpha_min): restoration stand-in of the warp kernel — roll
-// the controls out (closed-form feasible point), restart the multipliers.  Writes the other iterate buffer.
+// Restoration stand-in (same rule as the warp kernel and the oracle).  The line search gave up on the Newton direction
+// (alpha < alpha_min).  Direction: towards the closed-form feasible point (U = S, X rolled out); the longest step
+// t = 1, 1/2, ... along it is taken whose point passes IPOPT's restoration acceptance (finite, theta <= kappa_resto * theta,
+// no excessive objective increase, acceptable to the augmented filter); the multipliers restart.
+// tpp_resto_eval: theta and objective of  current + t * direction  (direction in the R_SSTEP rows; S does not move).
+template <int SPEC>
+__device__ __noinline__ void tpp_resto_eval(const KParams &P, const char *wb, int co, const double *goal, double t, double *th_out,
+                                            double *f_out) {
+    const int N = P.N;
+    double th = 0, fs = 0;
+    double X[3];
+    {
+        const char *pc = wb + co * TPP_ROW_B;
+        const double2 a = tpp_ld2(pc, R_X01), b = tpp_ld2(pc, R_X2L0);
+        X[0] = a.x; X[1] = a.y; X[2] = b.x; // stage 0 does not move
+    }
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+        const char *p = wb + (size_t)k * TPP_STAGE_B;
+        const char *pc = p + co * TPP_ROW_B;
+        const double2 u2 = tpp_ld2(pc, R_U), s2 = tpp_ld2(pc, R_S), du2 = tpp_ld2(p, R_SSTEP + 2);
+        const double2 n01 = tpp_ld2(pc + TPP_STAGE_B, R_X01), n2 = tpp_ld2(pc + TPP_STAGE_B, R_X2L0);
+        const double2 d01 = tpp_ld2(p + TPP_STAGE_B, R_SSTEP), d2 = tpp_ld2(p + TPP_STAGE_B, R_SSTEP + 1);
+        const double U[2] = {u2.x + t * du2.x, u2.y + t * du2.y};
+        const double Xn[3] = {n01.x + t * d01.x, n01.y + t * d01.y, n2.x + t * d2.x};
+        double r[3], ub[2];
+        tpp_ref<SPEC>(P, goal, p, r, ub);
+        const double ln0[3] = {0, 0, 0};
+        TppLin q;
+        tpp_lin<false, SPEC>(P, r, ub, X, U, ln0, 1.0, q);
+        th += fabs(Xn[0] - q.F0) + fabs(Xn[1] - q.F1) + fabs(Xn[2] - q.F2) + fabs(U[0] - s2.x) + fabs(U[1] - s2.y);
+        fs += q.f;
+        X[0] = Xn[0]; X[1] = Xn[1]; X[2] = Xn[2];
+    }
+    *th_out = th;
+    *f_out = fs;
+}
+
 template <int SPEC>
 __device__ __forceinline__ void tpp_restore(const KParams &P, char *wb, double *fl, int cur, TppLane &L) {
     const int N = P.N;
@@ -908,32 +958,62 @@ __device__ __forceinline__ void tpp_restore(const KParams &P, char *wb, double *
     tpp_filter_add(fl, L, L.ref_phi - GAMMA_PHI * L.theta, (1 - GAMMA_THETA) * L.theta);
     const int co = cur * R_ITER, no = R_ITER - co;
     double zm = 0;
-#pragma unroll 2
-    for (int k = 0; k < N; ++k) {
-        const char *pc = wb + (size_t)k * TPP_STAGE_B + co * TPP_ROW_B;
-        const double2 a = tpp_ld2(pc, R_VL), b = tpp_ld2(pc, R_VU);
-        zm = fmax(zm, fmax(fmax(a.x, a.y), fmax(b.x, b.y)));
-    }
-    double y[3];
+    // direction -> R_SSTEP rows: (Xr - X) with Xr the roll-out of the slacks, (S - U)
     {
+        double y[3];
         const double2 a = tpp_ld2(wb + co * TPP_ROW_B, R_X01), b = tpp_ld2(wb + co * TPP_ROW_B, R_X2L0);
         y[0] = a.x; y[1] = a.y; y[2] = b.x;
+#pragma unroll 1
+        for (int k = 0; k <= N; ++k) {
+            char *p = wb + (size_t)k * TPP_STAGE_B;
+            const char *pc = p + co * TPP_ROW_B;
+            const double2 x01 = tpp_ld2(pc, R_X01), x2 = tpp_ld2(pc, R_X2L0);
+            tpp_st2(p, R_SSTEP, (k == 0) ? 0.0 : y[0] - x01.x, (k == 0) ? 0.0 : y[1] - x01.y);
+            tpp_st2(p, R_SSTEP + 1, (k == 0) ? 0.0 : y[2] - x2.x, 0.0);
+            if (k < N) {
+                const double2 u = tpp_ld2(pc, R_U), sv = tpp_ld2(pc, R_S), vl = tpp_ld2(pc, R_VL), vu = tpp_ld2(pc, R_VU);
+                zm = fmax(zm, fmax(fmax(vl.x, vl.y), fmax(vu.x, vu.y)));
+                tpp_st2(p, R_SSTEP + 2, sv.x - u.x, sv.y - u.y);
+                const double S[2] = {sv.x, sv.y};
+                double F[3];
+                tpp_dyn<SPEC>(P, y, S, F);
+                y[0] = F[0]; y[1] = F[1]; y[2] = F[2];
+            }
+        }
     }
+    double t_acc = 0.0;
+    const double phi_ref = L.ref_phi;
+    for (double t = 1.0; t >= RESTO_T_MIN; t *= 0.5) {
+        double th_r, f_r;
+        tpp_resto_eval<SPEC>(P, wb, co, L.goal, t, &th_r, &f_r);
+        const double phi_r = L.df * f_r - L.mu * L.slog; // the slacks do not move: the barrier term is the current one
+        if (!isfinite(th_r) || !isfinite(phi_r)) continue;
+        if (!(th_r <= KAPPA_RESTO * L.theta)) continue;
+        if (phi_r > phi_ref) {
+            double bas = 1.0;
+            if (fabs(phi_ref) > 10.0) bas = tpp_log10(fabs(phi_ref));
+            if (tpp_log10(phi_r - phi_ref) > OBJ_MAX_INC + bas) continue;
+        }
+        if (!tpp_filter_ok(fl, L.fmask, phi_r, th_r)) continue;
+        t_acc = t;
+        break;
+    }
+    if (t_acc == 0.0) { L.status = B200MPC_RESTORATION_FAILED; L.phase = PH_FIN; return; }
     const bool reset = zm > 1e3;
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-        const char *pc = wb + (size_t)k * TPP_STAGE_B + co * TPP_ROW_B;
+        const char *p = wb + (size_t)k * TPP_STAGE_B;
+        const char *pc = p + co * TPP_ROW_B;
         char *pw = wb + (size_t)k * TPP_STAGE_B + no * TPP_ROW_B;
-        tpp_st2(pw, R_X01, y[0], y[1]); tpp_st2(pw, R_X2L0, y[2], 0.0); tpp_st2(pw, R_L12, 0.0, 0.0);
+        const double2 x01 = tpp_ld2(pc, R_X01), x2 = tpp_ld2(pc, R_X2L0), d01 = tpp_ld2(p, R_SSTEP), d2 = tpp_ld2(p, R_SSTEP + 1);
+        tpp_st2(pw, R_X01, x01.x + t_acc * d01.x, x01.y + t_acc * d01.y);
+        tpp_st2(pw, R_X2L0, x2.x + t_acc * d2.x, 0.0);
+        tpp_st2(pw, R_L12, 0.0, 0.0);
         if (k < N) {
-            const double2 s = tpp_ld2(pc, R_S), a = tpp_ld2(pc, R_VL), b = tpp_ld2(pc, R_VU);
-            const double U[2] = {s.x, s.y};
-            tpp_st2(pw, R_U, U[0], U[1]); tpp_st2(pw, R_S, U[0], U[1]); tpp_st2(pw, R_YD, 0.0, 0.0);
+            const double2 u = tpp_ld2(pc, R_U), du = tpp_ld2(p, R_SSTEP + 2), s = tpp_ld2(pc, R_S), a = tpp_ld2(pc, R_VL), b = tpp_ld2(pc, R_VU);
+            tpp_st2(pw, R_U, u.x + t_acc * du.x, u.y + t_acc * du.y); tpp_st2(pw, R_S, s.x, s.y); tpp_st2(pw, R_YD, 0.0, 0.0);
             tpp_st2(pw, R_VL, reset ? 1.0 : a.x, reset ? 1.0 : a.y);
             tpp_st2(pw, R_VU, reset ? 1.0 : b.x, reset ? 1.0 : b.y);
-            double F[3];
-            tpp_dyn<SPEC>(P, y, U, F);
-            y[0] = F[0]; y[1] = F[1]; y[2] = F[2];
         }
     }
     L.moved = 1;
@@ -968,17 +1048,24 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L, co
         L.acceptable_count = 0;
     }
     if (L.iter >= P.max_iter) { L.status = B200MPC_MAXITER_EXCEEDED; return; }
-    // barrier parameter update
+    // barrier parameter update (a tiny step in two consecutive iterations forces a decrease; when mu cannot decrease any
+    // more: Search_Direction_Becomes_Too_Small)
     double mu = L.mu;
     bool changed = false;
+    bool tflag = L.tiny_flag != 0;
+    L.tiny_flag = 0;
     for (;;) {
         const double cm = fmax(fabs(n.pmax - mu), fabs(n.pmin - mu));
         const double Emu = fmax(n.dual_inf / sd, fmax(n.prim_inf, cm / sc));
-        if (!(Emu <= K_EPS * mu)) break;
+        if (!(Emu <= K_EPS * mu) && !tflag) break;
         const double nm = fmax(fmin(K_MU * mu, tpp_pow(mu, TH_MU)), P.mu_floor);
-        if (nm == mu) break;
+        if (nm == mu) {
+            if (tflag) { L.status = B200MPC_SEARCH_DIRECTION_TOO_SMALL; return; }
+            break;
+        }
         mu = nm;
         changed = true;
+        tflag = false;
     }
     if (changed) {
         L.mu = mu;
@@ -1047,6 +1134,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 L.status = B200MPC_MAXITER_EXCEEDED;
                 L.iter = 0; L.ls_extra = 0; L.n_resto = 0; L.acceptable_count = 0; L.ntrial = 0; L.soc_count = 0;
                 L.ring = 0; L.fmask = 0; L.keep = 0; L.soc_first = 1; L.moved = 0;
+                L.tiny = 0; L.tiny_last = 0; L.tiny_flag = 0;
                 L.df = 1.0; L.mu = P.mu_init;
                 L.theta0 = -1; L.dw = 0; L.dw_last = 0;
                 L.alpha = 0; L.a_z = 0; L.alpha_soc = 0; L.a_z_soc = 0; L.a_min = 0; L.theta_soc_old = 0;
@@ -1168,6 +1256,8 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                     L.alpha = f.a_max;
                     L.a_z = f.a_z;
                     L.ntrial = 0;
+                    L.tiny = f.tiny;
+                    if (!f.tiny) { L.tiny_flag = 0; L.tiny_last = 0; }
                     L.tmode = TM_STEP;
                     L.phase = PH_T;
                 }
@@ -1200,7 +1290,19 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 const bool soc = (tm == TM_STEP_SOC);
                 if (soc || L.ntrial++ > 0) L.ls_extra++;
                 bool fa;
-                if (tpp_ls_acceptable(L, fl, L.alpha, t.phi, t.th, fa)) {
+                bool ok = tpp_ls_acceptable(L, fl, L.alpha, t.phi, t.th, fa);
+                if (!soc && L.tiny) {
+                    // tiny step: the full step is accepted without a line search (unless it cannot be evaluated)
+                    L.tiny = 0;
+                    if (isfinite(t.th) && isfinite(t.phi)) {
+                        ok = true;
+                        if (L.tiny_last) L.tiny_flag = 1;
+                        L.tiny_last = (t.dymax < TINY_STEP_Y_TOL) ? 1 : 0;
+                    } else {
+                        L.tiny_flag = 0; L.tiny_last = 0;
+                    }
+                }
+                if (ok) {
                     if (!fa) tpp_filter_add(fl, L, L.ref_phi - GAMMA_PHI * L.theta, (1 - GAMMA_THETA) * L.theta);
                     L.iter++;
                     accepted = true;

@@ -5,8 +5,8 @@
   get_reference_trajectory  ros2_mpc/scripts/path_follower_local_planner.py:27-73    -> pf, puf (variant C)
 
 The per-control-step functions run on the GPU (libb200mpc.so: b200mpc_goals_batch, b200mpc_reftraj_batch; one warp per
-robot, bit-exact with the reference — see csrc/refgen_kernel.cuh).  get_headings is a per-path preprocessing step
-(arctan2 over the path once, not once per control step) and stays on the host.  The quirks of the reference are kept:
+robot, bit-exact with the reference — see csrc/refgen_kernel.cuh), and so does the per-path preprocessing get_headings
+(b200mpc_headings_batch, csrc/sensor_kernel.cuh).  The quirks of the reference are kept:
 headings are taken modulo 2 pi only in get_goal_for_mpc, the tracking reference tiles goal[:3] (x, y and whatever the
 caller stores third) within 0.5 m of the path end, and every array is padded with its last element."""
 import numpy as np
@@ -14,15 +14,14 @@ import numpy as np
 from .obstacles import _default_solver
 
 
-def get_headings(path_xy, dt):
-    """path_follower_local_planner.py:14-24 (host): heading (K,), velocity (K,), omega (K-1,)."""
+def get_headings(path_xy, dt, solver=None):
+    """Drop-in for get_headings(path_xy, dt) (path_follower_local_planner.py:14-23) on the GPU (b200mpc_headings_batch):
+    path_xy (K,2) -> heading (K,), velocity (K,), omega (K-1,); a batch (P,K,2) returns (P,K), (P,K), (P,K-1).
+    Velocities are bit-exact with the reference, headings to the last ulp of atan2."""
     path_xy = np.asarray(path_xy, dtype=np.float64)
-    path_heading = np.arctan2(path_xy[1:, 1] - path_xy[:-1, 1], path_xy[1:, 0] - path_xy[:-1, 0])
-    path_heading = np.append(path_heading, path_heading[-1])
-    path_omega = (path_heading[1:] - path_heading[:-1]) / 2
-    path_velocity = (np.linalg.norm(path_xy[1:, :] - path_xy[:-1, :], axis=1) / dt) * 2
-    path_velocity = np.append(path_velocity, path_velocity[-1])
-    return path_heading, path_velocity, path_omega
+    single = path_xy.ndim == 2
+    h, v, w = (solver or _default_solver()).headings_batch(path_xy[None] if single else path_xy, dt)
+    return (h[0], v[0], w[0]) if single else (h, v, w)
 
 
 def get_goals_batch(path_xy, path_heading, goal, pos, lookahead_dist_=0.5, solver=None):

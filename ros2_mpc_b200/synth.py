@@ -2,7 +2,7 @@
 
 Nothing here is on the measured path: these functions only build the inputs (x0, goal / reference, obstacle
 lists, initial controls) that the solve consumes.  The map is the reference's maps/map_carto.pgm, shipped as the
-derived fixture tests/golden/map_carto_occ.npz (tests/golden/make_map_fixture.py).
+derived data file ros2_mpc_b200/data/map_carto_occ.npz (tests/golden/make_map_fixture.py writes it).
 """
 import os
 
@@ -10,8 +10,7 @@ import numpy as np
 
 from . import obstacles as _obs
 
-_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-MAP_FIXTURE = os.path.join(_REPO, "tests", "golden", "map_carto_occ.npz")
+MAP_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "map_carto_occ.npz")
 
 
 def load_map(path=None):

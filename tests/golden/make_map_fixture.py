@@ -1,4 +1,4 @@
-"""Derive tests/golden/map_carto_occ.npz from the reference's map (run in the build container only).
+"""Derive ros2_mpc_b200/data/map_carto_occ.npz from the reference's map (run in the build container only).
 
 Reads /root/reference/maps/map_carto.pgm|yaml and applies the pixel convention of
 /root/reference/ros2_mpc/core/map_server.py:14-20 (pixel 0 -> occupied, 254/205 -> free, flipud so that row 0
@@ -41,7 +41,7 @@ def main():
     with open(os.path.join(REF, "map_carto.yaml")) as f:
         y = yaml.safe_load(f)
     occ = np.flipud(img == 0)  # map_server.py:16,20
-    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "map_carto_occ.npz")
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "ros2_mpc_b200", "data", "map_carto_occ.npz")
     free = np.flipud(img == 254)  # known-free pixels (205 = unknown)
     np.savez_compressed(out, occ_bits=np.packbits(occ), free_bits=np.packbits(free), shape=np.array(occ.shape),
                         resolution=float(y["resolution"]), origin=np.array(y["origin"][:2], dtype=np.float64))

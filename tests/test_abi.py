@@ -20,7 +20,10 @@ def test_header_declares_the_expected_entry_points():
                  "b200mpc_eval_batch", "b200mpc_last_error", "b200mpc_default_options",
                  "b200mpc_obstacles_batch", "b200mpc_obstacles_batch_device", "b200mpc_goals_batch",
                  "b200mpc_goals_batch_device", "b200mpc_reftraj_batch", "b200mpc_reftraj_batch_device",
-                 "b200mpc_control_step_device"):
+                 "b200mpc_control_step_device", "b200mpc_dilate_batch", "b200mpc_dilate_batch_device",
+                 "b200mpc_inflate_batch", "b200mpc_inflate_batch_device", "b200mpc_local_costmap_batch",
+                 "b200mpc_local_costmap_batch_device", "b200mpc_raycast_batch", "b200mpc_raycast_batch_device",
+                 "b200mpc_headings_batch", "b200mpc_headings_batch_device"):
         assert must in names
 
 

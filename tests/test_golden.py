@@ -125,15 +125,3 @@ def test_get_obstacles_live_against_reference_numba(obsg):
         g_ref = ru.convert_laser_scan_to_occupancy_grid(sc.copy(), a, 0.05, 4.0)
         g = ob.scan_to_occupancy_grid(sc[None], a, 0.05, 4.0)[0]
         assert np.array_equal(g, g_ref)
-
-
-def test_get_headings_matches_reference():
-    """Host-side per-path preprocessing (path_follower_local_planner.py:14-24) against the reference's own function."""
-    from ros2_mpc_b200 import references as rf
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "refgen_golden.npz"))
-    for pi in range(int(g["n_paths"])):
-        h, v, o = rf.get_headings(g[f"path{pi}_xy"], 0.2)
-        assert np.array_equal(h, g[f"path{pi}_heading"])
-        assert np.array_equal(v, g[f"path{pi}_velocity"])
-        assert np.array_equal(o, g[f"path{pi}_omega"])
-        assert len(o) == len(h) - 1
