@@ -12,6 +12,7 @@
  *                                                    mpc_point_stabilization.py:55-68, local_planner_tracking.py:65-80
  *                            (opti.set_initial / set_value / solve / sol.value), batched over independent problems
  *   b200mpc_solve_batch_device  same, caller-owned device buffers, asynchronous on a CUDA stream
+ *   b200mpc_solve_batch_multi   same, one batch sharded over the GPUs of a node (one host thread + handle per device)
  *   b200mpc_eval_batch    <- the NLP functions CasADi evaluates inside opti.solve():
  *                            rk4 :136-148, euler_integration (tracking) :132-137, define_cost_function :104-127,
  *                            define_obstacles_cost_function (mpc_point_stabilization.py:46-53)
@@ -157,6 +158,17 @@ int b200mpc_solve_batch_device(b200mpc_handle *h, int B, const double *x0, const
                                const double *obs_x, const double *obs_y, int obs_stride, const double *u_init,
                                double *X_out, double *U_out, double *cost_out, int32_t *status_out,
                                int32_t *iters_out, int32_t *ls_out, void *stream);
+
+/* Host-buffer solve of ONE batch on G devices of the node: `handles` are G handles created from the same
+ * parameters on G different devices; device g solves the contiguous slice [lo_g, hi_g) of the batch (sizes differ by at most
+ * one) on its own host thread and streams, reads its inputs from and writes its results straight into that slice of the
+ * caller's arrays (no gather copy, no collective).  Arguments and NULL rules as b200mpc_solve_batch; a shared obstacle list
+ * (obs_stride = 0) goes to every device.  Page-locked buffers are streamed per device as in b200mpc_solve_batch.
+ * Blocks until every device has finished; returns the first device's error code if one fails (text on handles[0]). */
+int b200mpc_solve_batch_multi(b200mpc_handle **handles, int G, int B, const double *x0, const double *xref,
+                              const double *uref, const double *obs_x, const double *obs_y, int obs_stride,
+                              const double *u_init, double *X_out, double *U_out, double *cost_out, int32_t *status_out,
+                              int32_t *iters_out, int32_t *ls_out);
 
 /* NLP function evaluation at given points (host buffers, blocking): for each problem b, X[b][N+1][3] (X[b][0]
  * must equal x0[b]), U[b][N][2], lam[b][N][3] (multipliers of c_k = X_k - F(X_{k-1},U_{k-1}), k = 1..N; NULL = 0):

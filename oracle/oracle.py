@@ -180,3 +180,36 @@ def evaluate(p, x0, xref, X, U, uref=None, obs_x=None, obs_y=None, lam=None, obj
                    _dp(obs_x), _dp(obs_y), _dp(X), _dp(U), _dp(lam), float(obj_scale),
                    _dp(f), _dp(c), _dp(g), _dp(st))
     return dict(f=float(f[0]), c=c, grad=g, stages=st)
+
+
+def kkt_certificate(p, x0, xref, X, U, uref=None, obs_x=None, obs_y=None, bound_tol=1e-6):
+    """Independent first-order optimality certificate of a returned point (X (N+1,3), U (N,2)), computed from orc_eval
+    only (no solver state): the multipliers of the shooting defects follow from the adjoint recursion
+    lam_N = -g_N, lam_k = A_k' lam_{k+1} - g_k, the reduced gradient w.r.t. U_k is g_u - B_k' lam_{k+1}; it must vanish
+    off the control bounds and point outwards on them.  Returns dict(defect, stationarity, gscale): the largest shooting
+    defect, the largest violation of the sign / zero conditions, and max(1, |grad f|_inf) to scale it by."""
+    N = p.N
+    X, U = _f64(X), _f64(U)
+    e = evaluate(p, x0, xref, X, U, uref=uref, obs_x=obs_x, obs_y=obs_y)
+    g, st = e["grad"], e["stages"]
+    lam = np.zeros((N + 2, 3))
+    for k in range(N, 0, -1):
+        gk = g[3 * (k - 1):3 * (k - 1) + 3]
+        if k == N:
+            lam[k] = -gk
+        else:
+            A = np.array([[1, 0, st[k, 0]], [0, 1, st[k, 1]], [0, 0, 1]])
+            lam[k] = A.T @ lam[k + 1] - gk
+    viol = 0.0
+    for k in range(N):
+        b11, b12, b21, b22 = st[k, 2:6]
+        Bm = np.array([[b11, b12], [b21, b22], [0, p.dt]])
+        rg = g[3 * N + 2 * k:3 * N + 2 * k + 2] - Bm.T @ lam[k + 1]
+        for i in range(2):
+            if U[k, i] <= p.u_lo[i] + bound_tol:
+                viol = max(viol, max(0.0, -rg[i]))
+            elif U[k, i] >= p.u_hi[i] - bound_tol:
+                viol = max(viol, max(0.0, rg[i]))
+            else:
+                viol = max(viol, abs(rg[i]))
+    return dict(defect=float(np.abs(e["c"]).max()), stationarity=float(viol), gscale=float(max(1.0, np.abs(g).max())))

@@ -57,6 +57,9 @@ def lib():
         L.b200mpc_last_error.restype = C.c_char_p
         L.b200mpc_solve_batch.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, C.c_int, dp, dp, dp, dp, ip, ip, ip]
         L.b200mpc_solve_batch.restype = C.c_int
+        L.b200mpc_solve_batch_multi.argtypes = [C.POINTER(vp), C.c_int, C.c_int, dp, dp, dp, dp, dp, C.c_int, dp, dp, dp, dp, ip,
+                                                ip, ip]
+        L.b200mpc_solve_batch_multi.restype = C.c_int
         # device entry point: raw addresses
         L.b200mpc_solve_batch_device.argtypes = [vp, C.c_int] + [vp] * 5 + [C.c_int] + [vp] * 7 + [vp]
         L.b200mpc_solve_batch_device.restype = C.c_int
@@ -224,11 +227,14 @@ class Solver:
         if out is None:
             out = dict(X=np.empty((B, N + 1, 3)), U=np.empty((B, N, 2)), cost=np.empty(B),
                        status=np.empty(B, np.int32), iters=np.empty(B, np.int32), ls=np.empty(B, np.int32))
-        rc = self._L.b200mpc_solve_batch(self._h, B, _dp(x0), _dp(xref), _dp(uref), _dp(obs_x), _dp(obs_y), stride,
-                                         _dp(u_init), _dp(out["X"]), _dp(out["U"]), _dp(out["cost"]),
-                                         _ip(out["status"]), _ip(out["iters"]), _ip(out["ls"]))
+        rc = self._solve_call(B, _dp(x0), _dp(xref), _dp(uref), _dp(obs_x), _dp(obs_y), stride,
+                              _dp(u_init), _dp(out["X"]), _dp(out["U"]), _dp(out["cost"]),
+                              _ip(out["status"]), _ip(out["iters"]), _ip(out["ls"]))
         self._check(rc)
         return out
+
+    def _solve_call(self, B, *ptrs):
+        return self._L.b200mpc_solve_batch(self._h, B, *ptrs)
 
     def obstacles_batch(self, scan, beam_cos, beam_sin, pos, yaw, size, resolution, slots):
         """Obstacle lists for B robots (host buffers).  scan (B,n); beam_cos/beam_sin (n,); pos (B,2); yaw (B,).
@@ -389,6 +395,39 @@ class Solver:
         h, v, w = np.empty((P, K)), np.empty((P, K)), np.empty((P, K - 1))
         self._check(self._L.b200mpc_headings_batch(self._h, P, K, _dp(path_xy), float(dt), _dp(h), _dp(v), _dp(w)))
         return h, v, w
+
+
+class MultiSolver(Solver):
+    """One batch sharded over several GPUs of the node (b200mpc_solve_batch_multi): a handle, a host thread and streams per
+    device, contiguous slices of the batch index, results written straight into the caller's arrays.  solve_batch has the
+    signature and the results of Solver.solve_batch; the per-device entry points act on the first device."""
+
+    def __init__(self, params, devices):
+        devices = [int(d) for d in devices]
+        if len(devices) < 1 or len(set(devices)) != len(devices):
+            raise ValueError("devices must be a non-empty list of distinct device indices")
+        self._solvers = [Solver(params, device=d) for d in devices]
+        first = self._solvers[0]
+        self._L, self.params, self._h, self.device, self.devices = first._L, params, first._h, first.device, devices
+        self._handles = (C.c_void_p * len(devices))(*[s._h for s in self._solvers])
+
+    def _solve_call(self, B, *ptrs):
+        return self._L.b200mpc_solve_batch_multi(self._handles, len(self._solvers), B, *ptrs)
+
+    def shard_kernel_ms(self):
+        """Device time of each shard's solve kernel of the most recent call."""
+        return [s.last_kernel_ms() for s in self._solvers]
+
+    def close(self):
+        for s in getattr(self, "_solvers", []):
+            s.close()
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class DevPtr:

@@ -29,10 +29,14 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <vector>
 
 #define FULL 0xffffffffu
 #ifndef B200MPC_MIN_CTAS
 #define B200MPC_MIN_CTAS 2
+#endif
+#ifndef B200MPC_MIN_CTAS_OBS
+#define B200MPC_MIN_CTAS_OBS 2 /* the obstacle instance of the warp kernel */
 #endif
 #ifndef B200MPC_TPP_MIN_CTAS
 #define B200MPC_TPP_MIN_CTAS 1
@@ -147,13 +151,23 @@ __device__ __forceinline__ void tpp_sincos_core(double x, double &sn, double &cs
 // sin / cos of th, th + hw, th + 2 hw (the RK4 stage angles) from two branch-free evaluations and the angle-addition
 // formulas; the three library sincos() calls they replace each hide a slow-path branch, which keeps the compiler from
 // interleaving their (independent) polynomial chains.  Library fallback for absurd arguments.
+// Library routines the solver reaches only off its hot path (huge angles, the filter's power laws) live out of line, one
+// copy each: inlined at every call site they made up a third of the kernel's code, which has to stream through a 32 KB
+// instruction cache (profiles/r2_warp_a_*: 1.9 cycles of instruction-fetch stall per issued instruction).
+__device__ __noinline__ void rk4_trig_far(double th, double hw, double *o) {
+    sincos(th, o + 0, o + 1);
+    sincos(th + hw, o + 2, o + 3);
+    sincos(th + 2.0 * hw, o + 4, o + 5);
+}
+__device__ __noinline__ double pow_ool(double a, double b) { return pow(a, b); }
+__device__ __noinline__ double log10_ool(double a) { return log10(a); }
 __device__ __forceinline__ void rk4_trig(double th, double hw, double &s0, double &c0, double &sm, double &cm, double &se,
                                          double &ce) {
     // (per-lane test, no warp vote: the callers sit inside per-stage branches that not every lane takes)
     if (!(fabs(th) <= 1e5) || !(fabs(hw) <= 1e5)) {
-        sincos(th, &s0, &c0);
-        sincos(th + hw, &sm, &cm);
-        sincos(th + 2.0 * hw, &se, &ce);
+        double o[6];
+        rk4_trig_far(th, hw, o);
+        s0 = o[0]; c0 = o[1]; sm = o[2]; cm = o[3]; se = o[4]; ce = o[5];
         return;
     }
     double sh, ch;
@@ -180,53 +194,131 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 // ---- K3: obstacle sum at one predicted position ---------------------------------------------------------
-// ox/oy are the problem's obstacle list staged in shared memory (all lanes read the same address: broadcast).
+// ox/oy are the problem's obstacle list staged in shared memory (all lanes read the same address: broadcast); lane = stage.
+// The reference pads the list with copies of its first point (get_obstacles, scripts/point_follower_local_planner.py:
+// 103-109; 160 x the sentinel (100, 100) when the scan hits nothing): the trailing run of copies of entry 0 is folded
+// into a weight w0 on entry 0, so only the first n_eff entries are walked (ObsList, set up when the list is staged).
+// Value, gradient and Hessian share one pass; the constant factors 2/r^2 of grad s and hess s are applied once after the
+// loop:  with p1 = phi'(s), p2 = phi''(s), d = (x - ox, y - oy):
+//     grad = (2/r^2) sum p1 d,     hess = (2/r^2)^2 sum p2 d d' + (2/r^2) (sum p1) I.
+// One out-of-line copy (the solver calls it from the linearisation, the line search, the second-order correction and the
+// restoration: inlined five times the loop alone was 20 KB of code for a 32 KB instruction cache).
+struct ObsList {
+    int n_eff;   // entries to walk (>= 1)
+    double w0;   // weight of entry 0: 1 + number of folded trailing copies
+};
+
+// e^q for the obstacle terms (q = c/s, usually 0 < q < 100; +inf / NaN when s = 0).  Branch-free, so that the compiler
+// interleaves the independent chains of the unrolled obstacle loop; Cody-Waite reduction by ln 2,
+// degree-13 Taylor polynomial on [-ln2/2, ln2/2] (relative error < 1e-17 before rounding), scaling by 2^k in two factors
+// (k reaches 1025 / -1075).  The coefficients sit in constant memory: as immediates each costs two instructions.
+__constant__ double OBS_EXP_C[12] = {
+    1.6059043836821613e-10, 2.0876756987868100e-09, 2.5052108385441720e-08, 2.7557319223985893e-07,   // 1/13! .. 1/10!
+    2.7557319223985888e-06, 2.4801587301587302e-05, 1.9841269841269841e-04, 1.3888888888888889e-03,   // 1/9! .. 1/6!
+    8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 1.4426950408889634};       // 1/5! 1/4! 1/3!, log2(e)
+__constant__ double OBS_EXP_LN2[2] = {6.93147180369123816490e-01, 1.90821492927058770002e-10};
+__device__ __forceinline__ double obs_exp(double q) {
+    const double kf = rint(q * OBS_EXP_C[11]);
+    double r = fma(-kf, OBS_EXP_LN2[0], q);
+    r = fma(-kf, OBS_EXP_LN2[1], r);
+    double p = fma(OBS_EXP_C[0], r, OBS_EXP_C[1]);
+#pragma unroll
+    for (int i = 2; i <= 10; i++) p = fma(p, r, OBS_EXP_C[i]);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    // 2^k in two factors; k is clamped so that the exponent arithmetic stays in range (the conversion saturates, NaN -> 0):
+    // arguments beyond the overflow / underflow thresholds are replaced below, a NaN argument gives NaN through p
+    const int k = max(min((int)kf, 1100), -1100), k1 = k >> 1, k2 = k - k1;
+    double e = (p * __hiloint2double((k1 + 1023) << 20, 0)) * __hiloint2double((k2 + 1023) << 20, 0);
+    e = (q > 709.782712893384) ? __longlong_as_double(0x7ff0000000000000ll) : e;
+    e = (q < -745.2) ? 0.0 : e;
+    return e;
+}
+
+__device__ __noinline__ void obstacle_eval(int form, double c, double ir2, const double *__restrict__ sox,
+                                           const double *__restrict__ soy, int n_eff, double w0, double x, double y,
+                                           double *out6) {
+    double v = 0, sp1 = 0, ax = 0, ay = 0, bxx = 0, bxy = 0, byy = 0;
+    if (form == B200MPC_OBS_EXPLOG) {
+        // phi(s) = exp(c/s):  phi' = -(c/s^2) phi,  phi'' = (c/s^2)(2/s + c/s^2) phi
+#define OBS_TERM_EXPLOG(J_, W_, USEW_)                                                                  \
+    do {                                                                                                \
+        const double dx = x - sox[J_], dy = y - soy[J_];                                                \
+        const double s_ = (dx * dx + dy * dy) * ir2;                                                    \
+        const double is = fast_rcp(s_); /* s = 0 (robot on an obstacle point): NaN instead of inf, invalid either way */ \
+        const double q = c * is;                                                                        \
+        double e = obs_exp(q);                                                                          \
+        if (USEW_) e *= (W_);                                                                           \
+        const double t = q * is;               /* c / s^2 */                                            \
+        const double te = t * e;               /* -phi' */                                              \
+        const double p2 = te * fma(2.0, is, t);                                                         \
+        const double p2x = p2 * dx;                                                                     \
+        v += e;                                                                                         \
+        sp1 -= te;                                                                                      \
+        ax = fma(-te, dx, ax);                                                                          \
+        ay = fma(-te, dy, ay);                                                                          \
+        bxx = fma(p2x, dx, bxx);                                                                        \
+        bxy = fma(p2x, dy, bxy);                                                                        \
+        byy = fma(p2 * dy, dy, byy);                                                                    \
+    } while (0)
+        OBS_TERM_EXPLOG(0, w0, true);
+#pragma unroll 4
+        for (int j = 1; j < n_eff; j++) OBS_TERM_EXPLOG(j, 1.0, false);
+#undef OBS_TERM_EXPLOG
+    } else {
+        // psi(s) = c exp(-s):  psi' = -psi,  psi'' = psi
+#define OBS_TERM_GAUSS(J_, W_, USEW_)                                                                   \
+    do {                                                                                                \
+        const double dx = x - sox[J_], dy = y - soy[J_];                                                \
+        const double s_ = (dx * dx + dy * dy) * ir2;                                                    \
+        double e = c * exp(-s_);                                                                        \
+        if (USEW_) e *= (W_);                                                                           \
+        const double p2x = e * dx;                                                                      \
+        v += e;                                                                                         \
+        sp1 -= e;                                                                                       \
+        ax = fma(-e, dx, ax);                                                                           \
+        ay = fma(-e, dy, ay);                                                                           \
+        bxx = fma(p2x, dx, bxx);                                                                        \
+        bxy = fma(p2x, dy, bxy);                                                                        \
+        byy = fma(e * dy, dy, byy);                                                                     \
+    } while (0)
+        OBS_TERM_GAUSS(0, w0, true);
+#pragma unroll 4
+        for (int j = 1; j < n_eff; j++) OBS_TERM_GAUSS(j, 1.0, false);
+#undef OBS_TERM_GAUSS
+    }
+    const double g1 = 2.0 * ir2, g2 = g1 * g1;
+    out6[0] = v;
+    out6[1] = g1 * ax;
+    out6[2] = g1 * ay;
+    out6[3] = fma(g2, bxx, g1 * sp1);
+    out6[4] = g2 * bxy;
+    out6[5] = fma(g2, byy, g1 * sp1);
+}
+
 template <bool DERIV>
-__device__ __forceinline__ void obstacle_sum(const KParams &P, const double *__restrict__ sox,
+__device__ __forceinline__ void obstacle_sum(const KParams &P, const ObsList &L, const double *__restrict__ sox,
                                              const double *__restrict__ soy, double x, double y, double &val,
                                              double &gx, double &gy, double &hxx, double &hxy, double &hyy) {
-    const double ir2 = P.inv_r2, c = P.obs_c;
-    double v = 0, ax = 0, ay = 0, bxx = 0, bxy = 0, byy = 0;
-    if (P.obs_form == B200MPC_OBS_EXPLOG) {
-#pragma unroll 4
-        for (int j = 0; j < P.M; j++) {
-            double dx = x - sox[j], dy = y - soy[j];
-            double s = (dx * dx + dy * dy) * ir2;
-            double is = fast_rcp(s); // s = 0 (robot on an obstacle point) gives NaN instead of inf: invalid number either way
-            double q = c * is;
-            double e = exp(q);
-            v += e;
-            if (DERIV) {
-                double t = q * is;          // c / s^2
-                double p1 = -t * e;         // phi'
-                double p2 = t * (2.0 * is + t) * e; // phi'' = c(2s+c)/s^4 * e
-                double sx = 2.0 * dx * ir2, sy = 2.0 * dy * ir2;
-                ax += p1 * sx;
-                ay += p1 * sy;
-                bxx += p2 * sx * sx + p1 * 2.0 * ir2;
-                bxy += p2 * sx * sy;
-                byy += p2 * sy * sy + p1 * 2.0 * ir2;
-            }
-        }
-    } else {
-#pragma unroll 4
-        for (int j = 0; j < P.M; j++) {
-            double dx = x - sox[j], dy = y - soy[j];
-            double s = (dx * dx + dy * dy) * ir2;
-            double e = c * exp(-s);
-            v += e;
-            if (DERIV) {
-                double sx = 2.0 * dx * ir2, sy = 2.0 * dy * ir2;
-                ax -= e * sx;
-                ay -= e * sy;
-                bxx += e * sx * sx - e * 2.0 * ir2;
-                bxy += e * sx * sy;
-                byy += e * sy * sy - e * 2.0 * ir2;
-            }
-        }
-    }
-    val = v;
-    if (DERIV) { gx = ax; gy = ay; hxx = bxx; hxy = bxy; hyy = byy; }
+    double o[6];
+    obstacle_eval(P.obs_form, P.obs_c, P.inv_r2, sox, soy, L.n_eff, L.w0, x, y, o);
+    val = o[0];
+    if (DERIV) { gx = o[1]; gy = o[2]; hxx = o[3]; hxy = o[4]; hyy = o[5]; }
+}
+
+// The list has been staged in shared memory by the whole warp: fold the trailing copies of entry 0 (warp-uniform result).
+__device__ __forceinline__ ObsList obstacle_list_setup(const double *sox, const double *soy, int M, int lane) {
+    const double x0 = sox[0], y0 = soy[0];
+    int last = 0; // highest index whose entry differs from entry 0
+    for (int i = lane; i < M; i += 32)
+        if (sox[i] != x0 || soy[i] != y0) last = i; // (a NaN entry differs from everything: it is walked)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(FULL, last, o));
+    ObsList L;
+    L.n_eff = last + 1;
+    L.w0 = 1.0 + (double)(M - L.n_eff);
+    return L;
 }
 
 // ---- per-stage register state ----------------------------------------------------------------------------
@@ -274,7 +366,7 @@ __device__ __forceinline__ void dyn_value(const KParams &P, const double X[3], c
 
 // Full stage evaluation: defect, Jacobian entries, objective gradient, Lagrangian Hessian, stage cost.
 // act: stage exists (k <= N); dyn: stage has controls and a successor (k < N); obs: obstacle sum on this stage.
-__device__ __forceinline__ double stage_full(const KParams &P, const double *sox, const double *soy, Stg &s,
+__device__ __forceinline__ double stage_full(const KParams &P, const ObsList &OL, const double *sox, const double *soy, Stg &s,
                                              const double Xn[3], const double ln[3], double df, bool act,
                                              bool dyn, bool obs, const double *oc = nullptr) {
     double fval = 0;
@@ -338,7 +430,7 @@ __device__ __forceinline__ double stage_full(const KParams &P, const double *sox
     if (obs && act) {
         double ov, gx, gy, oxx, oxy, oyy;
         if (oc) { ov = oc[0]; gx = oc[1]; gy = oc[2]; oxx = oc[3]; oxy = oc[4]; oyy = oc[5]; }
-        else obstacle_sum<true>(P, sox, soy, s.X[0], s.X[1], ov, gx, gy, oxx, oxy, oyy);
+        else obstacle_sum<true>(P, OL, sox, soy, s.X[0], s.X[1], ov, gx, gy, oxx, oxy, oyy);
         fval += ov;
         s.g[0] += df * gx;
         s.g[1] += df * gy;
@@ -350,7 +442,7 @@ __device__ __forceinline__ double stage_full(const KParams &P, const double *sox
 }
 
 // Value-only evaluation of a trial stage: defect (3) and stage cost.
-__device__ __forceinline__ double stage_value(const KParams &P, const double *sox, const double *soy,
+__device__ __forceinline__ double stage_value(const KParams &P, const ObsList &OL, const double *sox, const double *soy,
                                               const double X[3], const double U[2], const double r[3],
                                               const double ub[2], const double Xn[3], double ct[3], bool act,
                                               bool dyn, bool obs) {
@@ -369,7 +461,7 @@ __device__ __forceinline__ double stage_value(const KParams &P, const double *so
     }
     if (obs && act) {
         double ov, d0, d1, d2, d3, d4;
-        obstacle_sum<false>(P, sox, soy, X[0], X[1], ov, d0, d1, d2, d3, d4);
+        obstacle_sum<false>(P, OL, sox, soy, X[0], X[1], ov, d0, d1, d2, d3, d4);
         fval += ov;
     }
     return fval;
@@ -1070,7 +1162,7 @@ __device__ __forceinline__ double frac_to_bound(const KParams &P, const Stg (&s)
 
 // trial point curr + alpha*step: theta (1-norm) and barrier objective, both warp-uniform
 template <int J, bool OBS>
-__device__ __forceinline__ void trial_eval(const KParams &P, const double *sox, const double *soy, double *ocs, Stg (&s)[J],
+__device__ __forceinline__ void trial_eval(const KParams &P, const ObsList &OL, const double *sox, const double *soy, double *ocs, Stg (&s)[J],
                                            const Step (&o)[J], double alpha, double mu, double df, int lane,
                                            double &th_t, double &phi_t) {
 #pragma unroll
@@ -1093,12 +1185,12 @@ __device__ __forceinline__ void trial_eval(const KParams &P, const double *sox, 
         Stg &t = s[j];
         double Xn[3];
         NEXT3(Xn, Xt, j);
-        double fv = stage_value(P, sox, soy, t.Xt, t.Ut, t.r, t.ub, Xn, t.ct, act, dyn, false);
+        double fv = stage_value(P, OL, sox, soy, t.Xt, t.Ut, t.r, t.ub, Xn, t.ct, act, dyn, false);
         if (obs && act) {
             // value and derivatives: the accepted trial point is the next iterate, and its linearisation then takes
             // the sums from this per-stage cache in shared memory instead of walking the obstacle list again
             double ov, gx, gy, oxx, oxy, oyy;
-            obstacle_sum<true>(P, sox, soy, t.Xt[0], t.Xt[1], ov, gx, gy, oxx, oxy, oyy);
+            obstacle_sum<true>(P, OL, sox, soy, t.Xt[0], t.Xt[1], ov, gx, gy, oxx, oxy, oyy);
             double *oc = ocs + 6 * k;
             oc[0] = ov; oc[1] = gx; oc[2] = gy; oc[3] = oxx; oc[4] = oxy; oc[5] = oyy;
             fv += ov;
@@ -1124,12 +1216,12 @@ struct LsRef {
 };
 
 // FilterLSAcceptor::CheckAcceptabilityOfTrialPoint; the filter lives one entry per lane.
-__device__ __forceinline__ bool ls_acceptable(const LsRef &r, double alpha_test, double phi_t, double th_t,
-                                              double fphi, double ftheta, bool fvalid, bool &ftype_armijo) {
+__device__ __noinline__ bool ls_acceptable(const LsRef &r, double alpha_test, double phi_t, double th_t,
+                                           double fphi, double ftheta, bool fvalid, bool &ftype_armijo) {
     ftype_armijo = false;
     if (!isfinite(th_t) || !isfinite(phi_t)) return false;
     if (th_t > r.theta_max) return false;
-    const bool ftype = (r.gbd < 0) && (alpha_test * pow(-r.gbd, S_PHI) > DELTA_LS * pow(r.theta, S_THETA));
+    const bool ftype = (r.gbd < 0) && (alpha_test * pow_ool(-r.gbd, S_PHI) > DELTA_LS * pow_ool(r.theta, S_THETA));
     const bool armijo = cmp_le(phi_t - r.phi, ETA_PHI * alpha_test * r.gbd, r.phi);
     ftype_armijo = ftype && armijo;
     bool ok;
@@ -1138,8 +1230,8 @@ __device__ __forceinline__ bool ls_acceptable(const LsRef &r, double alpha_test,
     } else {
         if (phi_t > r.phi) {
             double bas = 1.0;
-            if (fabs(r.phi) > 10.0) bas = log10(fabs(r.phi));
-            if (log10(phi_t - r.phi) > OBJ_MAX_INC + bas) return false;
+            if (fabs(r.phi) > 10.0) bas = log10_ool(fabs(r.phi));
+            if (log10_ool(phi_t - r.phi) > OBJ_MAX_INC + bas) return false;
         }
         ok = cmp_le(th_t, (1 - GAMMA_THETA) * r.theta, r.theta) || cmp_le(phi_t - r.phi, -GAMMA_PHI * r.theta, r.phi);
     }
@@ -1179,9 +1271,13 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
 
     // ---- load the problem (coalesced: consecutive lanes read consecutive stages) ----
     const double x00 = A.x0[3 * (size_t)b], x01 = A.x0[3 * (size_t)b + 1], x02 = A.x0[3 * (size_t)b + 2];
+    ObsList OL;
+    OL.n_eff = 1; OL.w0 = 1.0;
     if (OBS && P.obs_form != B200MPC_OBS_NONE) {
         const double *gx = A.ox + (size_t)A.obs_stride * b, *gy = A.oy + (size_t)A.obs_stride * b;
         for (int i = lane; i < P.M; i += 32) { sox[i] = gx[i]; soy[i] = gy[i]; }
+        __syncwarp();
+        OL = obstacle_list_setup(sox, soy, P.M, lane);
     }
     __syncwarp();
 #pragma unroll
@@ -1241,7 +1337,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
             const bool obs = OBS && P.obs_form != B200MPC_OBS_NONE && k >= P.obs_k0 && k <= P.obs_k1;
             NEXT3(Xn0, X, j);
             NEXT3(ln0, lam, j);
-            fl += stage_full(P, sox, soy, s[j], Xn0, ln0, dfv, act, dyn, obs, (oc_valid && k <= N) ? ocs + 6 * k : nullptr);
+            fl += stage_full(P, OL, sox, soy, s[j], Xn0, ln0, dfv, act, dyn, obs, (oc_valid && k <= N) ? ocs + 6 * k : nullptr);
         }
         oc_valid = false;
         return wsum(fl);
@@ -1415,7 +1511,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                     cm = wmax(cm);
                     const double Emu = fmax(dual_inf / sd, fmax(prim_inf, cm / sc));
                     if (!(Emu <= K_EPS * mu) && !tflag) break;
-                    const double nm = fmax(fmin(K_MU * mu, pow(mu, TH_MU)), P.mu_floor);
+                    const double nm = fmax(fmin(K_MU * mu, pow_ool(mu, TH_MU)), P.mu_floor);
                     if (nm == mu) { stop = tflag; break; }
                     mu = nm;
                     tau = fmax(TAU_MIN, 1.0 - mu);
@@ -1491,7 +1587,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
             double a_min = GAMMA_THETA;
             if (ref.gbd < 0) {
                 a_min = fmin(GAMMA_THETA, GAMMA_PHI * theta / (-ref.gbd));
-                if (theta <= theta_min) a_min = fmin(a_min, DELTA_LS * pow(theta, S_THETA) / pow(-ref.gbd, S_PHI));
+                if (theta <= theta_min) a_min = fmin(a_min, DELTA_LS * pow_ool(theta, S_THETA) / pow_ool(-ref.gbd, S_PHI));
             }
             a_min *= ALPHA_MIN_FRAC;
 
@@ -1530,7 +1626,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
             }
             if (tiny) {
                 double th_t, phi_t;
-                trial_eval<J, OBS>(P, sox, soy, ocs, s, st, alpha, mu, df, lane, th_t, phi_t);
+                trial_eval<J, OBS>(P, OL, sox, soy, ocs, s, st, alpha, mu, df, lane, th_t, phi_t);
                 if (isfinite(th_t) && isfinite(phi_t)) {
                     (void)ls_acceptable(ref, alpha, phi_t, th_t, fphi, ftheta, fvalid, fa); // only for the filter-augmentation rule
                     acc = 1;
@@ -1552,7 +1648,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
             if (!tiny) { tiny_flag = false; tiny_last = false; }
             while (!acc) {
                 double th_t, phi_t;
-                trial_eval<J, OBS>(P, sox, soy, ocs, s, st, alpha, mu, df, lane, th_t, phi_t);
+                trial_eval<J, OBS>(P, OL, sox, soy, ocs, s, st, alpha, mu, df, lane, th_t, phi_t);
                 if (ntrial++ > 0) ls_extra++;
                 if (ls_acceptable(ref, alpha, phi_t, th_t, fphi, ftheta, fvalid, fa)) { acc = 1; alpha_acc = alpha; break; }
                 if (ntrial == 1 && P.max_soc > 0 && isfinite(th_t) && th_t >= theta) {
@@ -1580,7 +1676,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                         if (!KKT_SOLVE(P, s, csoc, dsoc, true, dw, soc, lane)) break;
                         alpha_soc = frac_to_bound<J>(P, s, soc, tau, lane);
                         double phi_s;
-                        trial_eval<J, OBS>(P, sox, soy, ocs, s, soc, alpha_soc, mu, df, lane, th_trial, phi_s);
+                        trial_eval<J, OBS>(P, OL, sox, soy, ocs, s, soc, alpha_soc, mu, df, lane, th_trial, phi_s);
                         ls_extra++;
                         if (ls_acceptable(ref, alpha, phi_s, th_trial, fphi, ftheta, fvalid, fa)) { acc = 2; alpha_acc = alpha_soc; }
                         else count++;
@@ -1632,13 +1728,13 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                 double t_acc = 0.0;
                 for (double t = 1.0; t >= RESTO_T_MIN; t *= 0.5) {
                     double th_r, phi_r;
-                    trial_eval<J, OBS>(P, sox, soy, ocs, s, soc, t, mu, df, lane, th_r, phi_r);
+                    trial_eval<J, OBS>(P, OL, sox, soy, ocs, s, soc, t, mu, df, lane, th_r, phi_r);
                     if (!isfinite(th_r) || !isfinite(phi_r)) continue;
                     if (!(th_r <= KAPPA_RESTO * theta)) continue;
                     if (phi_r > ref.phi) {
                         double bas = 1.0;
-                        if (fabs(ref.phi) > 10.0) bas = log10(fabs(ref.phi));
-                        if (log10(phi_r - ref.phi) > OBJ_MAX_INC + bas) continue;
+                        if (fabs(ref.phi) > 10.0) bas = log10_ool(fabs(ref.phi));
+                        if (log10_ool(phi_r - ref.phi) > OBJ_MAX_INC + bas) continue;
                     }
                     const bool rej = fvalid && !(cmp_le(phi_r, fphi, fphi) || cmp_le(th_r, ftheta, ftheta));
                     if (__any_sync(FULL, rej)) continue;
@@ -1733,7 +1829,7 @@ finish:
             const bool obs = OBS && P.obs_form != B200MPC_OBS_NONE && k >= P.obs_k0 && k <= P.obs_k1;
             double Xn[3], ct[3];
             NEXT3(Xn, X, j);
-            fl += stage_value(P, sox, soy, s[j].X, s[j].U, s[j].r, s[j].ub, Xn, ct, act, dyn, obs);
+            fl += stage_value(P, OL, sox, soy, s[j].X, s[j].U, s[j].r, s[j].ub, Xn, ct, act, dyn, obs);
         }
         const double fsum = wsum(fl);
 #pragma unroll
@@ -1759,12 +1855,12 @@ finish:
 }
 
 template <int J, bool OBS, bool SCAN>
-__global__ void __launch_bounds__(128, B200MPC_MIN_CTAS) mpc_solve_kernel(const KParams P, const BatchArgs A) {
+__global__ void __launch_bounds__(128, OBS ? B200MPC_MIN_CTAS_OBS : B200MPC_MIN_CTAS) mpc_solve_kernel(const KParams P, const BatchArgs A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int Mpad = (P.M + 3) & ~3;
     // per warp: the problem's obstacle lists (2*Mpad doubles) and the stage records of the KKT solve
-    const size_t per_warp = 2 * (size_t)Mpad + (size_t)(P.N + 1) * (KKT_REC + 6) + (J == 1 ? SCAN_NF * 32 : 0);
+    const size_t per_warp = 2 * (size_t)Mpad + (size_t)(P.N + 1) * (KKT_REC + 6) + (SCAN ? SCAN_NF * 32 : 0);
     double *sox = smem + (size_t)wid * per_warp, *soy = sox + Mpad, *rec = soy + Mpad;
     const KktRoles roles = kkt_roles(lane);
     for (;;) {
@@ -1786,9 +1882,13 @@ __global__ void __launch_bounds__(128) mpc_eval_kernel(const KParams P, const Ev
     const int N = P.N;
     const int b = blockIdx.x * (blockDim.x >> 5) + wid;
     if (b >= A.B) return;
+    ObsList OL;
+    OL.n_eff = 1; OL.w0 = 1.0;
     if (P.obs_form != B200MPC_OBS_NONE) {
         const double *gx = A.ox + (size_t)A.obs_stride * b, *gy = A.oy + (size_t)A.obs_stride * b;
         for (int i = lane; i < P.M; i += 32) { sox[i] = gx[i]; soy[i] = gy[i]; }
+        __syncwarp();
+        OL = obstacle_list_setup(sox, soy, P.M, lane);
     }
     __syncwarp();
     Stg s[J];
@@ -1824,7 +1924,7 @@ __global__ void __launch_bounds__(128) mpc_eval_kernel(const KParams P, const Ev
         const bool obs = P.obs_form != B200MPC_OBS_NONE && k >= P.obs_k0 && k <= P.obs_k1;
         NEXT3(Xn0, X, j);
         NEXT3(ln0, lam, j);
-        fl += stage_full(P, sox, soy, s[j], Xn0, ln0, A.obj_scale, act, dyn, obs);
+        fl += stage_full(P, OL, sox, soy, s[j], Xn0, ln0, A.obj_scale, act, dyn, obs);
     }
     const double f = wsum(fl);
     if (lane == 0 && A.f) A.f[b] = f;
@@ -1877,7 +1977,7 @@ struct b200mpc_handle {
     int J;
     int sm_count;
     int ctas;
-    size_t smem_bytes;
+    size_t smem_bytes, smem_scan_bytes; // dynamic shared memory of the warp kernel: serial-recursion / scan instance
     cudaStream_t stream;
     cudaEvent_t ev0, ev1;
     unsigned int *d_counter;
@@ -1961,8 +2061,9 @@ static cudaError_t configure_kernels(size_t smem) {
 }
 
 template <int J>
-static cudaError_t occupancy(int *blocks, size_t smem) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, mpc_solve_kernel<J, true, false>, 128, smem);
+static cudaError_t occupancy(int *blocks, size_t smem, bool obs) {
+    if (obs) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, mpc_solve_kernel<J, true, false>, 128, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, mpc_solve_kernel<J, false, false>, 128, smem);
 }
 
 extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
@@ -2033,8 +2134,9 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     h->J = (p->N + 1 + 31) / 32;
     const int Mpad = (k.M + 3) & ~3;
     // per warp: obstacle lists + the stage records of the lane-parallel KKT solve (KKT_REC doubles per stage)
-    h->smem_bytes = (size_t)4 * (2 * (size_t)Mpad + (size_t)(p->N + 1) * (KKT_REC + 6) + (h->J == 1 ? SCAN_NF * 32 : 0)) * sizeof(double);
-    if (h->smem_bytes > 227 * 1024) {
+    h->smem_bytes = (size_t)4 * (2 * (size_t)Mpad + (size_t)(p->N + 1) * (KKT_REC + 6)) * sizeof(double);
+    h->smem_scan_bytes = h->smem_bytes + (h->J == 1 ? (size_t)4 * SCAN_NF * 32 * sizeof(double) : 0); // scan instance: + its scratch
+    if (h->smem_scan_bytes > 227 * 1024) {
         set_err(nullptr, B200MPC_E_ARG, "N and M too large for the shared-memory staging of the warp kernel");
         b200mpc_destroy(h);
         return nullptr;
@@ -2053,12 +2155,12 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     // raised to the device's opt-in maximum once (a later handle with a smaller need must not lower it under an
     // earlier handle's launches); occupancy is computed for this handle's own size.
     const size_t smem_cap = prop.sharedMemPerBlockOptin;
-    if (h->smem_bytes > smem_cap) return fail("N and M too large for the shared memory of this device");
+    if (h->smem_scan_bytes > smem_cap) return fail("N and M too large for the shared memory of this device");
     switch (h->J) {
-        case 1: e = configure_kernels<1>(smem_cap); if (e == cudaSuccess) e = occupancy<1>(&blocks, h->smem_bytes); break;
-        case 2: e = configure_kernels<2>(smem_cap); if (e == cudaSuccess) e = occupancy<2>(&blocks, h->smem_bytes); break;
-        case 3: e = configure_kernels<3>(smem_cap); if (e == cudaSuccess) e = occupancy<3>(&blocks, h->smem_bytes); break;
-        default: e = configure_kernels<4>(smem_cap); if (e == cudaSuccess) e = occupancy<4>(&blocks, h->smem_bytes); break;
+        case 1: e = configure_kernels<1>(smem_cap); if (e == cudaSuccess) e = occupancy<1>(&blocks, h->smem_bytes, p->obs_form != B200MPC_OBS_NONE); break;
+        case 2: e = configure_kernels<2>(smem_cap); if (e == cudaSuccess) e = occupancy<2>(&blocks, h->smem_bytes, p->obs_form != B200MPC_OBS_NONE); break;
+        case 3: e = configure_kernels<3>(smem_cap); if (e == cudaSuccess) e = occupancy<3>(&blocks, h->smem_bytes, p->obs_form != B200MPC_OBS_NONE); break;
+        default: e = configure_kernels<4>(smem_cap); if (e == cudaSuccess) e = occupancy<4>(&blocks, h->smem_bytes, p->obs_form != B200MPC_OBS_NONE); break;
     }
     if (e != cudaSuccess) return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
     if (blocks < 1) blocks = 1;
@@ -2281,8 +2383,9 @@ static int launch_solve(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stre
     switch (h->J) {
 #define LAUNCH_WARP(JJ, SC)                                                                                \
     do {                                                                                                    \
-        if (h->prm.obs_form != B200MPC_OBS_NONE) mpc_solve_kernel<JJ, true, SC><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a); \
-        else mpc_solve_kernel<JJ, false, SC><<<grid, 128, h->smem_bytes, stream>>>(h->kp, a);              \
+        const size_t sm_ = SC ? h->smem_scan_bytes : h->smem_bytes;                                         \
+        if (h->prm.obs_form != B200MPC_OBS_NONE) mpc_solve_kernel<JJ, true, SC><<<grid, 128, sm_, stream>>>(h->kp, a); \
+        else mpc_solve_kernel<JJ, false, SC><<<grid, 128, sm_, stream>>>(h->kp, a);                        \
     } while (0)
         case 1: if (scan) LAUNCH_WARP(1, true); else LAUNCH_WARP(1, false); break;
         case 2: LAUNCH_WARP(2, false); break;
@@ -3044,5 +3147,51 @@ extern "C" int b200mpc_headings_batch(b200mpc_handle *h, int P, int K, const dou
     CU_TRY(h, cudaMemcpyAsync(velocity, d_v, np_ * 8, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaMemcpyAsync(omega, d_w, nw * 8, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- multi-GPU host-buffer solve ------------------------------------------------------------------------
+// Independent problems shard by batch index: device g gets the contiguous slice [lo_g, hi_g) (sizes differ by at most one),
+// one host thread and one handle (its own streams) per device, no collective; every device reads its inputs from and
+// writes its results straight into its slice of the caller's arrays — there is no gather copy.
+extern "C" int b200mpc_solve_batch_multi(b200mpc_handle **handles, int G, int B, const double *x0, const double *xref,
+                                         const double *uref, const double *obs_x, const double *obs_y, int obs_stride,
+                                         const double *u_init, double *X_out, double *U_out, double *cost_out,
+                                         int32_t *status_out, int32_t *iters_out, int32_t *ls_out) {
+    if (!handles || G < 1) return B200MPC_E_ARG;
+    for (int g = 0; g < G; g++)
+        if (!handles[g]) return B200MPC_E_ARG;
+    b200mpc_handle *h0 = handles[0];
+    if (B < 0) return set_err(h0, B200MPC_E_ARG, "B < 0");
+    for (int g = 1; g < G; g++) {
+        if (memcmp(&handles[g]->prm, &h0->prm, sizeof(b200mpc_params)) != 0)
+            return set_err(h0, B200MPC_E_ARG, "the handles of a multi-device solve must share one parameter set");
+        for (int k = 0; k < g; k++)
+            if (handles[k] == handles[g]) return set_err(h0, B200MPC_E_ARG, "a handle appears twice");
+    }
+    if (B == 0) return 0;
+    const int N = h0->prm.N;
+    const size_t w_ref = (h0->prm.ref_kind == B200MPC_REF_TRAJ) ? 3 * (size_t)N : 3;
+    std::vector<int> rcs(G, 0);
+    std::vector<std::thread> th;
+    th.reserve(G);
+    const int base = B / G, rem = B % G;
+    for (int g = 0; g < G; g++) {
+        const size_t lo = (size_t)g * base + (size_t)(g < rem ? g : rem);
+        const int n = base + (g < rem ? 1 : 0);
+        if (n == 0) continue;
+        th.emplace_back([=, &rcs]() {
+            rcs[g] = b200mpc_solve_batch(handles[g], n, x0 + lo * 3, xref + lo * w_ref, uref ? uref + lo * 2 * N : nullptr,
+                                         (obs_x && obs_stride) ? obs_x + lo * obs_stride : obs_x,
+                                         (obs_y && obs_stride) ? obs_y + lo * obs_stride : obs_y, obs_stride,
+                                         u_init ? u_init + lo * 2 * N : nullptr, X_out ? X_out + lo * 3 * (N + 1) : nullptr,
+                                         U_out ? U_out + lo * 2 * N : nullptr, cost_out ? cost_out + lo : nullptr,
+                                         status_out ? status_out + lo : nullptr, iters_out ? iters_out + lo : nullptr,
+                                         ls_out ? ls_out + lo : nullptr);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int g = 0; g < G; g++)
+        if (rcs[g]) return set_err(h0, rcs[g], std::string("device ") + std::to_string(handles[g]->device) + ": " + handles[g]->err);
     return 0;
 }

@@ -9,7 +9,8 @@ Reference surface mirrored (names, argument meaning, return values, error behavi
   Mpc.perform_mpc(u0, x0, pf, puf, obstacles_x=None, obstacles_y=None)
         variant C -> (x_opt (3,N+1), u_opt[:, 0])                         (local_planner_tracking.py:65-80)
   A failed solve raises RuntimeError carrying IPOPT's return_status name, as opti.solve() does.
-Extension: perform_mpc_batch(...) solves B independent problems in one kernel launch.
+Extension: perform_mpc_batch(...) solves B independent problems in one kernel launch; Mpc(devices=[0, 1, ...]) shards that
+batch over several GPUs of the node (contiguous slices, no collective, results written into one set of host arrays).
 """
 import numpy as np
 
@@ -30,7 +31,7 @@ class SolveError(RuntimeError):
 class _MpcBase:
     variant = None
 
-    def __init__(self, params_path=None, device=0, N=None, obstacles=None, **overrides):
+    def __init__(self, params_path=None, device=0, N=None, obstacles=None, devices=None, **overrides):
         params = load_params(params_path)
         self.params = params
         self.dt = params["dt"]
@@ -42,7 +43,8 @@ class _MpcBase:
         self.n_controls = 2
         self._p = make_params(self.variant, params, N=self.N, obstacles=obstacles, **overrides)
         self.n_obstacles = self._p.M
-        self._solver = _shim.Solver(self._p, device=device)
+        # devices=[0, 1, ...]: perform_mpc_batch shards its batch over these GPUs (one handle + host thread per device)
+        self._solver = _shim.MultiSolver(self._p, devices) if devices else _shim.Solver(self._p, device=device)
         # opti.parameter values persist between calls until set again
         self._obs_x = None
         self._obs_y = None

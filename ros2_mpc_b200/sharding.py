@@ -12,15 +12,24 @@ def contiguous_shard(B, rank, world):
     return lo, hi
 
 
-def solve_sharded(solve_fn, arrays, B, rank, world, dist=None, device=None):
+def solve_sharded(solve_fn, arrays, B, rank, world, dist=None, device=None, shared=()):
     """Each rank calls solve_fn(slice of every array) on its shard; rank 0 receives the concatenated outputs.
 
-    solve_fn maps a dict of input arrays (sliced along axis 0; entries that are None or not batch-shaped are
-    passed through) to a dict of output arrays with the shard's batch on axis 0.  Returns the full-batch dict on
-    rank 0 and None elsewhere.  With world == 1 no process group is needed."""
+    solve_fn maps a dict of input arrays to a dict of output arrays with the shard's batch on axis 0.  Every numpy array
+    in `arrays` is batch-shaped (leading dimension B) and is sliced, EXCEPT the keys named in `shared` (one obstacle list
+    for all problems, tables, ...) and None entries, which are passed through whole.  A batched array whose leading
+    dimension is not B is an error — nothing is inferred from shapes.  Returns the full-batch dict on rank 0 and None
+    elsewhere.  With world == 1 no process group is needed."""
     lo, hi = contiguous_shard(B, rank, world)
-    local_in = {k: (v[lo:hi] if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == B else v)
-                for k, v in arrays.items()}
+    local_in = {}
+    for k, v in arrays.items():
+        if v is None or k in shared or not isinstance(v, np.ndarray):
+            local_in[k] = v
+            continue
+        if v.ndim < 1 or v.shape[0] != B:
+            raise ValueError(f"array {k!r} has leading dimension {v.shape[:1]}, expected the batch size {B} "
+                             "(name it in `shared` if it is not per problem)")
+        local_in[k] = v[lo:hi]
     local_out = solve_fn(local_in)
     if world == 1:
         return local_out

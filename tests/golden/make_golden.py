@@ -156,6 +156,35 @@ def make_nlp_golden(mpcs):
     np.savez_compressed(os.path.join(HERE, "nlp_golden.npz"), **out)
 
 
+def make_gauss_golden(mpcs):
+    """Variant B's obstacle cost (local_planner_point_stabilization.py:60-67): built by the reference, then dropped from its
+    objective (:127).  The reference's own method is called on the traced problem and its expression evaluated at seeded
+    points with obstacle lists close to the trajectory; appended to nlp_golden.npz as Bobs_*."""
+    from casadi import evaluate  # the stand-in's evaluator
+    mpc = mpcs["B"]
+    opti = mpc.opti
+    rng = np.random.default_rng(4242)
+    N = 30
+    expr = mpc.define_obstacles_cost_function(cost_factor=5.0)   # params["reverse_factor"], as :43-45 passes it
+    x0 = np.array([0.4, -0.3, 0.9])
+    ang = rng.uniform(0, 2 * np.pi, 160); rr = rng.uniform(0.1, 0.8, 160)
+    obs_x = x0[0] + rr * np.cos(ang); obs_y = x0[1] + rr * np.sin(ang)
+    opti.set_value(mpc.P, np.concatenate([x0, np.array([1.1, 0.2, 0.5])]))
+    opti.set_value(mpc.obstacles_x, obs_x); opti.set_value(mpc.obstacles_y, obs_y)
+    npts = 6
+    Xs = rng.normal(0, 0.3, (npts, N + 1, 3)) + x0
+    Xs[:, 0, :] = x0
+    Us = rng.uniform(-0.1, 0.1, (npts, N, 2))
+    f = np.empty(npts)
+    for i in range(npts):
+        z = opti_vector(N, Xs[i], Us[i])
+        f[i] = evaluate(expr.nodes(), opti._env(z))[0]
+    g = dict(np.load(os.path.join(HERE, "nlp_golden.npz")))
+    g.update(Bobs_x0=x0, Bobs_obs_x=obs_x, Bobs_obs_y=obs_y, Bobs_X=Xs, Bobs_U=Us, Bobs_f=f)
+    np.savez_compressed(os.path.join(HERE, "nlp_golden.npz"), **g)
+    print("gauss obstacle cost golden", f[:3])
+
+
 def make_solve_golden(mpcs):
     out = {}
     N = 30
@@ -204,4 +233,5 @@ if __name__ == "__main__":
     make_obstacles_golden()
     mpcs = build_reference_mpcs()
     make_nlp_golden(mpcs)
+    make_gauss_golden(mpcs)
     make_solve_golden(mpcs)

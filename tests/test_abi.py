@@ -16,7 +16,7 @@ def _declared_functions():
 
 def test_header_declares_the_expected_entry_points():
     names = _declared_functions()
-    for must in ("b200mpc_create", "b200mpc_destroy", "b200mpc_solve_batch", "b200mpc_solve_batch_device",
+    for must in ("b200mpc_create", "b200mpc_destroy", "b200mpc_solve_batch", "b200mpc_solve_batch_device", "b200mpc_solve_batch_multi",
                  "b200mpc_eval_batch", "b200mpc_last_error", "b200mpc_default_options",
                  "b200mpc_obstacles_batch", "b200mpc_obstacles_batch_device", "b200mpc_goals_batch",
                  "b200mpc_goals_batch_device", "b200mpc_reftraj_batch", "b200mpc_reftraj_batch_device",

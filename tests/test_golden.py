@@ -125,3 +125,25 @@ def test_get_obstacles_live_against_reference_numba(obsg):
         g_ref = ru.convert_laser_scan_to_occupancy_grid(sc.copy(), a, 0.05, 4.0)
         g = ob.scan_to_occupancy_grid(sc[None], a, 0.05, 4.0)[0]
         assert np.array_equal(g, g_ref)
+
+
+def test_oracle_gauss_obstacle_cost_matches_reference_sources(nlp):
+    """Variant B's obstacle cost, c*exp(-s) (local_planner_point_stabilization.py:60-67; built, then dropped from the
+    objective): the oracle's gauss form against values of the reference's own method traced through the casadi stand-in."""
+    p1, p0 = O.variant_params("B", obstacles=True), O.variant_params("B")
+    x0, goal = nlp["Bobs_x0"], np.array([1.1, 0.2, 0.5])
+    for i in range(nlp["Bobs_X"].shape[0]):
+        X, U = nlp["Bobs_X"][i], nlp["Bobs_U"][i]
+        f1 = O.evaluate(p1, x0, goal, X, U, obs_x=nlp["Bobs_obs_x"], obs_y=nlp["Bobs_obs_y"])["f"]
+        f0 = O.evaluate(p0, x0, goal, X, U)["f"]
+        assert abs((f1 - f0) - nlp["Bobs_f"][i]) <= 1e-12 * nlp["Bobs_f"][i]
+
+
+def test_kkt_certificate_helper_on_a_converged_and_a_perturbed_point():
+    p = O.variant_params("B")
+    x0, goal = np.array([0.0, 0.0, 0.0]), np.array([1.0, 1.0, 0.0])
+    r = O.solve(p, x0, goal)
+    c = O.kkt_certificate(p, x0, goal, r["X"].T, r["U"].T)
+    assert c["defect"] <= 1e-8 and c["stationarity"] <= 1e-6 * c["gscale"]
+    U = r["U"].T.copy(); U[3, 1] -= 0.05
+    assert O.kkt_certificate(p, x0, goal, r["X"].T, U)["stationarity"] > 1e-3

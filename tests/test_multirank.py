@@ -30,7 +30,19 @@ def _worker(rank, world, port, q):
         r = O.solve_batch(p, a["x0"], a["goal"], nthreads=1)
         return dict(X=r["X"], U=r["U"], status=r["status"])
 
-    out = solve_sharded(solve_fn, dict(x0=x0, goal=goal), B, rank, world, dist=dist)
+    # a shared table whose length happens to equal the batch size must not be sliced (it is named in `shared`)
+    table = np.arange(B, dtype=np.float64)
+
+    def solve_fn_checked(a):
+        assert a["table"].shape == (B,) and np.array_equal(a["table"], table)
+        return solve_fn(a)
+
+    out = solve_sharded(solve_fn_checked, dict(x0=x0, goal=goal, table=table), B, rank, world, dist=dist, shared=("table",))
+    try:
+        solve_sharded(solve_fn, dict(x0=x0, goal=goal, table=table[:3]), B, rank, world, dist=dist)
+        raise AssertionError("a mis-shaped batched array must be rejected")
+    except ValueError:
+        pass
     dist.barrier()
     if rank == 0:
         full = O.solve_batch(p, x0, goal, nthreads=1)
@@ -58,3 +70,14 @@ def test_two_rank_sharded_solve_matches_single_rank():
     tags = dict(res)
     assert "ok" in tags, res
     assert sorted(tags["ok"] + tags["rank1"]) == [5, 6]  # 11 problems -> shards of 6 and 5
+
+
+def test_contiguous_shards_cover_the_batch():
+    """The C ABI (b200mpc_solve_batch_multi) and sharding.contiguous_shard use the same rule: sizes differ by at most one."""
+    from ros2_mpc_b200.sharding import contiguous_shard
+    for B, G in ((11, 2), (1048576, 8), (5, 8), (0, 3), (4096, 3)):
+        sl = [contiguous_shard(B, g, G) for g in range(G)]
+        assert sl[0][0] == 0 and sl[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+        sizes = [h - l for l, h in sl]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
