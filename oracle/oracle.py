@@ -182,14 +182,23 @@ def evaluate(p, x0, xref, X, U, uref=None, obs_x=None, obs_y=None, lam=None, obj
     return dict(f=float(f[0]), c=c, grad=g, stages=st)
 
 
-def kkt_certificate(p, x0, xref, X, U, uref=None, obs_x=None, obs_y=None, bound_tol=1e-6):
+def kkt_certificate(p, x0, xref, X, U, uref=None, obs_x=None, obs_y=None, u_init=None, bound_tol=1e-6):
     """Independent first-order optimality certificate of a returned point (X (N+1,3), U (N,2)), computed from orc_eval
     only (no solver state): the multipliers of the shooting defects follow from the adjoint recursion
     lam_N = -g_N, lam_k = A_k' lam_{k+1} - g_k, the reduced gradient w.r.t. U_k is g_u - B_k' lam_{k+1}; it must vanish
-    off the control bounds and point outwards on them.  Returns dict(defect, stationarity, gscale): the largest shooting
-    defect, the largest violation of the sign / zero conditions, and max(1, |grad f|_inf) to scale it by."""
+    off the control bounds and point outwards on them.
+    IPOPT's convergence test is on the SCALED problem: objective scaling df = min(1, 100 / |grad f|_inf) at the starting
+    point (X = 0, U = u_init), and the dual infeasibility is divided by s_d = max(100, (|lam|_1 + |z|_1) / n) / 100.
+    Returns dict(defect, stationarity (unscaled, controls within bound_tol of a bound count as active), df,
+    scaled (= df * stationarity / s_d), complementarity (= df * max z_i * distance to the bound z_i acts on: the scaled
+    complementarity IPOPT drives to mu; it covers interior controls, active bounds and everything between))."""
     N = p.N
-    X, U = _f64(X), _f64(U)
+    x0, X, U = _f64(x0), _f64(X), _f64(U)
+    Xs = np.zeros((N + 1, 3)); Xs[0] = x0
+    Us = np.zeros((N, 2)) if u_init is None else _f64(u_init).reshape(N, 2)
+    gs = evaluate(p, x0, xref, Xs, Us, uref=uref, obs_x=obs_x, obs_y=obs_y)["grad"]
+    gmax = float(np.abs(gs).max())
+    df = max(min(1.0, 100.0 / gmax), 1e-8) if gmax > 100.0 else 1.0
     e = evaluate(p, x0, xref, X, U, uref=uref, obs_x=obs_x, obs_y=obs_y)
     g, st = e["grad"], e["stages"]
     lam = np.zeros((N + 2, 3))
@@ -200,16 +209,24 @@ def kkt_certificate(p, x0, xref, X, U, uref=None, obs_x=None, obs_y=None, bound_
         else:
             A = np.array([[1, 0, st[k, 0]], [0, 1, st[k, 1]], [0, 0, 1]])
             lam[k] = A.T @ lam[k + 1] - gk
-    viol = 0.0
+    # stationarity in u with bound multipliers z_L, z_U >= 0:  rg - z_L + z_U = 0  ->  z_L = max(rg, 0), z_U = max(-rg, 0);
+    # what remains to be checked is complementarity, z_L (u - lo) and z_U (hi - u) (an interior control needs rg = 0, a
+    # control on a bound needs the right sign: both are "the product is small")
+    viol, zsum, compl = 0.0, 0.0, 0.0
     for k in range(N):
         b11, b12, b21, b22 = st[k, 2:6]
         Bm = np.array([[b11, b12], [b21, b22], [0, p.dt]])
         rg = g[3 * N + 2 * k:3 * N + 2 * k + 2] - Bm.T @ lam[k + 1]
+        zsum += 2.0 * float(np.abs(rg).sum())   # the multiplier of U - S = 0 and the active bound multiplier
         for i in range(2):
-            if U[k, i] <= p.u_lo[i] + bound_tol:
+            dl, dh = max(U[k, i] - p.u_lo[i], 0.0), max(p.u_hi[i] - U[k, i], 0.0)
+            compl = max(compl, rg[i] * dl if rg[i] > 0 else -rg[i] * dh)
+            if dl <= bound_tol:
                 viol = max(viol, max(0.0, -rg[i]))
-            elif U[k, i] >= p.u_hi[i] - bound_tol:
+            elif dh <= bound_tol:
                 viol = max(viol, max(0.0, rg[i]))
             else:
                 viol = max(viol, abs(rg[i]))
-    return dict(defect=float(np.abs(e["c"]).max()), stationarity=float(viol), gscale=float(max(1.0, np.abs(g).max())))
+    sd = max(100.0, df * (float(np.abs(lam).sum()) + zsum) / (9 * N)) / 100.0
+    return dict(defect=float(np.abs(e["c"]).max()), stationarity=float(viol), df=float(df), scaled=float(df * viol / sd),
+                complementarity=float(df * compl))

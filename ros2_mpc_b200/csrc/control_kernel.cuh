@@ -33,8 +33,10 @@ __device__ __forceinline__ double ctl_pymod(double a, double m) {
     else r = copysign(0.0, m);
     return r;
 }
+// np.linalg.norm of one 2-vector = sqrt(x.dot(x)); the BLAS dot product fuses the second product into the sum
+// (tests/golden/control_golden.npz has cases exactly on both thresholds)
 __device__ __forceinline__ double ctl_norm2(double dx, double dy) {
-    return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    return sqrt(__fma_rn(dy, dy, __dmul_rn(dx, dx)));
 }
 
 __global__ void __launch_bounds__(128) control_step_kernel(const ControlArgs a) {

@@ -42,6 +42,12 @@ __device__ __forceinline__ double refgen_pymod(double a, double m) {
 __device__ __forceinline__ double refgen_norm2(double dx, double dy) {
     return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
+// np.linalg.norm of ONE 2-vector (no axis argument): sqrt(x.dot(x)), and the BLAS dot product fuses the second product
+// into the sum: sqrt(fma(dy, dy, dx*dx)) — one rounding less than the axis=1 form above (measured against numpy on 20 000
+// vectors; it decides comparisons that land within an ulp of a threshold)
+__device__ __forceinline__ double refgen_norm2_dot(double dx, double dy) {
+    return sqrt(__fma_rn(dy, dy, __dmul_rn(dx, dx)));
+}
 // np.argmin ordering: smaller value wins, a NaN beats everything, ties go to the lower index
 __device__ __forceinline__ bool refgen_better(double a, int ia, double b, int ib) {
     const bool an = (a != a), bn = (b != b);
@@ -65,7 +71,7 @@ __global__ void __launch_bounds__(REFGEN_WARPS * 32) goals_kernel(const RefGenAr
         const double *g = a.goal + (size_t)b * a.goal_stride;
         const double px = a.pos[(size_t)b * a.pos_stride], py = a.pos[(size_t)b * a.pos_stride + 1];
         double *out = a.out_goal + (size_t)b * 3;
-        if (refgen_norm2(g[0] - px, g[1] - py) < a.lookahead) {
+        if (refgen_norm2_dot(g[0] - px, g[1] - py) < a.lookahead) {
             if (lane == 0) { out[0] = g[0]; out[1] = g[1]; out[2] = refgen_pymod(g[4], two_pi); }
             if (lane == 0 && a.nearest) a.nearest[b] = -1;
             continue;
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(REFGEN_WARPS * 32) reftraj_kernel(const RefGen
             if (imin == 0x7fffffff || refgen_better(d, k, vmin, imin)) { vmin = d; imin = k; }
         }
         refgen_argmin(vmin, imin);
-        const bool at_end = refgen_norm2(x - pxy[2 * (a.K - 1)], y - pxy[2 * (a.K - 1) + 1]) < 0.5;
+        const bool at_end = refgen_norm2_dot(x - pxy[2 * (a.K - 1)], y - pxy[2 * (a.K - 1) + 1]) < 0.5;
         const double *g = a.goal + (size_t)b * a.goal_stride;
         double *pxf = a.pxf + (size_t)b * 3 * a.N, *puf = a.puf + (size_t)b * 2 * a.N;
         for (int i = lane; i < a.N; i += 32) {
