@@ -1180,9 +1180,18 @@ int orc_solve(const orc_params *p, const double *x0, const double *xref, const d
 
         if (!acc) {
             /* Restoration stand-in.  IPOPT would switch to its feasibility-restoration NLP here.  For a
-             * multiple-shooting transcription a feasible point is available in closed form (roll the
-             * controls out), so the stand-in augments the filter with the current point, sets U := S
-             * (strictly inside the bounds), rolls X out and restarts the multipliers. */
+             * multiple-shooting transcription feasible points are available in closed form (roll the
+             * controls out), so the stand-in augments the filter with the current point and moves to a
+             * point that IPOPT's restoration acceptance test admits (theta <= kappa_resto * theta,
+             * acceptable to the filter), then restarts the multipliers:
+             *   stage 1  along the direction to "U := S, X rolled out" (S fixed), longest step
+             *            t = 1, 1/2, ... 1/1024 that passes (incl. the obj_max_inc test);
+             *   stage 2  (only if stage 1 found nothing: the roll-out runs into an obstacle point, where
+             *            exp(c/s) overflows) the family "plan shrunk towards standing still":
+             *            S_l = u_c + l (S - u_c), U := S_l, X rolled out, l = 1/2, 1/4, ... 1/1024, 0
+             *            (u_c = the zero control pushed into the interior of its box); the member with the
+             *            lowest barrier objective is taken.  l = 0 is the robot standing at x0, which is
+             *            finite whenever the starting point was, so stage 2 always ends with a point. */
             if (theta <= 1e-10 || stt.n_resto >= MAX_RESTO) { status = ORC_RESTORATION_FAILED; break; }
             filter_add(&filt, ref.phi - GAMMA_PHI * theta, (1 - GAMMA_THETA) * theta);
             /* restoration direction: towards the closed-form feasible point (U = S, X rolled out) */
@@ -1205,9 +1214,41 @@ int orc_solve(const orc_params *p, const double *x0, const double *xref, const d
                 t_acc = t;
                 break;
             }
+            if (t_acc == 0.0) {
+                /* stage 2: the family of feasible points "the plan shrunk towards standing still": S_l = uc + l (S - uc),
+                 * U = S_l, X rolled out, l = 1/2, 1/4, ..., 0; the member with the lowest barrier objective is taken */
+                double uc[2];
+                for (int i = 0; i < 2; i++) {
+                    double lo = w->sL[i], hi = w->sU[i];
+                    double pl = fmin(BOUND_PUSH * fmax(1.0, fabs(lo)), BOUND_FRAC * (hi - lo));
+                    double pu = fmin(BOUND_PUSH * fmax(1.0, fabs(hi)), BOUND_FRAC * (hi - lo));
+                    uc[i] = fmin(fmax(0.0, lo + pl), hi - pu);
+                }
+                double lam = 0.5, best = INFINITY, lam_best = -1.0;
+                for (int pass = 0; pass < 2; pass++) {
+                    for (;;) {
+                        if (pass == 1) lam = lam_best;
+                        for (int i = 0; i < n2; i++) w->St[i] = uc[i & 1] + lam * (w->S[i] - uc[i & 1]);
+                        rollout(p, x0, w->St, w->Xt);
+                        for (int i = 0; i < n2; i++) { w->soc.dU[i] = w->St[i] - w->U[i]; w->soc.dS[i] = w->St[i] - w->S[i]; }
+                        for (int i = 0; i < n3; i++) w->soc.dX[i] = w->Xt[i] - w->X[i];
+                        if (pass == 1) break;
+                        double th_r, phi_r;
+                        trial_eval(w, &q, &w->soc, 1.0, mu, df, &th_r, &phi_r);
+                        if (trace) fprintf(stderr, "   resto2 lam %.4g th %.4e phi %.6e filt %d\n", lam, th_r, phi_r, filter_acceptable(&filt, phi_r, th_r));
+                        if (isfinite(th_r) && isfinite(phi_r) && th_r <= KAPPA_RESTO * theta && filter_acceptable(&filt, phi_r, th_r) && phi_r < best) {
+                            best = phi_r; lam_best = lam;
+                        }
+                        if (lam == 0.0) break;
+                        lam = (lam * 0.5 >= RESTO_T_MIN) ? lam * 0.5 : 0.0;
+                    }
+                    if (lam_best < 0.0) break;
+                    if (pass == 1) t_acc = 1.0;
+                }
+            }
             if (t_acc == 0.0) { status = ORC_RESTORATION_FAILED; break; }
             for (int i = 3; i < n3; i++) w->X[i] += t_acc * w->soc.dX[i];
-            for (int i = 0; i < n2; i++) w->U[i] += t_acc * w->soc.dU[i];
+            for (int i = 0; i < n2; i++) { w->U[i] += t_acc * w->soc.dU[i]; w->S[i] += t_acc * w->soc.dS[i]; }
             double zmax = 0;
             for (int i = 0; i < n2; i++) zmax = fmax(zmax, fmax(w->vL[i], w->vU[i]));
             if (zmax > 1e3)

@@ -1688,14 +1688,32 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
             }
 
             if (!acc) {
-                // Restoration stand-in.  Direction: towards the closed-form feasible point (U = S, X rolled out); the
-                // longest step t = 1, 1/2, ... along it is taken whose point passes IPOPT's restoration acceptance
-                // (finite, theta <= kappa_resto * theta, no excessive objective increase, acceptable to the augmented
-                // filter); the multipliers restart.
+                // Restoration stand-in (same rule as oracle/mpc_oracle.c).  The filter is augmented with the current point, then
+                //   stage 1: along the direction to the closed-form feasible point (U = S, X rolled out; S fixed) the longest
+                //            step t = 1, 1/2, ... is taken whose point passes IPOPT's restoration acceptance (finite,
+                //            theta <= kappa_resto * theta, no excessive objective increase, acceptable to the filter);
+                //   stage 2: if there is none (the roll-out runs into an obstacle point), the family "plan shrunk towards
+                //            standing still": S_l = u_c + l (S - u_c), U = S_l, X rolled out, l = 1/2, 1/4, ..., 0; the member
+                //            with the lowest barrier objective is taken.
+                // The multipliers restart.
                 if (theta <= 1e-10 || n_resto >= MAX_RESTO) { status = B200MPC_RESTORATION_FAILED; break; }
                 filter_add(ref.phi - GAMMA_PHI * theta, (1 - GAMMA_THETA) * theta, fphi, ftheta, fvalid, ring, lane);
-                {
-                    // serial rollout X_{k+1} = F(X_k, S_k); the direction goes to the step record of the correction
+                double uc[2];
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const double lo = P.sL[i], hi = P.sU[i];
+                    const double pl = fmin(BOUND_PUSH * fmax(1.0, fabs(lo)), BOUND_FRAC * (hi - lo));
+                    const double pu = fmin(BOUND_PUSH * fmax(1.0, fabs(hi)), BOUND_FRAC * (hi - lo));
+                    uc[i] = fmin(fmax(0.0, lo + pl), hi - pu);
+                }
+                // direction to "U = S_l, S = S_l, X rolled out" into the step record of the correction (l < 0: S_l = S exactly)
+                auto resto_direction = [&](double lam) {
+                    double tS[J][2];
+#pragma unroll
+                    for (int j = 0; j < J; ++j)
+#pragma unroll
+                        for (int i = 0; i < 2; i++) tS[j][i] = (lam < 0.0) ? s[j].S[i] : uc[i] + lam * (s[j].S[i] - uc[i]);
+                    // serial rollout X_{k+1} = F(X_k, S_l,k)
                     double y[3] = {x00, x01, x02};
                     for (int l = 0; l <= N / J; ++l) {
                         double z[3] = {y[0], y[1], y[2]};
@@ -1708,23 +1726,24 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                             }
                             if (ko < N) {
                                 double F[3];
-                                dyn_value(P, z, s[j].S, F);
+                                dyn_value(P, z, tS[j], F);
                                 z[0] = F[0]; z[1] = F[1]; z[2] = F[2];
                             }
                         }
                         y[0] = __shfl_sync(FULL, z[0], l); y[1] = __shfl_sync(FULL, z[1], l); y[2] = __shfl_sync(FULL, z[2], l);
                     }
-                }
 #pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    const int k = lane * J + j;
-                    if (k > N || k == 0) { soc[j].dX[0] = soc[j].dX[1] = soc[j].dX[2] = 0; }
+                    for (int j = 0; j < J; ++j) {
+                        const int k = lane * J + j;
+                        if (k > N || k == 0) { soc[j].dX[0] = soc[j].dX[1] = soc[j].dX[2] = 0; }
 #pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        soc[j].dU[i] = (k < N) ? (s[j].S[i] - s[j].U[i]) : 0.0;
-                        soc[j].dS[i] = 0;
+                        for (int i = 0; i < 2; i++) {
+                            soc[j].dU[i] = (k < N) ? (tS[j][i] - s[j].U[i]) : 0.0;
+                            soc[j].dS[i] = (k < N) ? (tS[j][i] - s[j].S[i]) : 0.0;
+                        }
                     }
-                }
+                };
+                resto_direction(-1.0);
                 double t_acc = 0.0;
                 for (double t = 1.0; t >= RESTO_T_MIN; t *= 0.5) {
                     double th_r, phi_r;
@@ -1741,6 +1760,29 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                     t_acc = t;
                     break;
                 }
+                if (t_acc == 0.0) {
+                    double lam = 0.5, best = __longlong_as_double(0x7ff0000000000000ll), lam_best = -1.0;
+                    for (;;) {
+                        resto_direction(lam);
+                        double th_r, phi_r;
+                        trial_eval<J, OBS>(P, OL, sox, soy, ocs, s, soc, 1.0, mu, df, lane, th_r, phi_r);
+                        bool okc = isfinite(th_r) && isfinite(phi_r) && (th_r <= KAPPA_RESTO * theta) && (phi_r < best);
+                        if (okc) {
+                            const bool rej = fvalid && !(cmp_le(phi_r, fphi, fphi) || cmp_le(th_r, ftheta, ftheta));
+                            okc = !__any_sync(FULL, rej);
+                        }
+                        if (okc) { best = phi_r; lam_best = lam; }
+                        if (lam == 0.0) break;
+                        lam = (lam * 0.5 >= RESTO_T_MIN) ? lam * 0.5 : 0.0;
+                    }
+                    if (lam_best >= 0.0) {
+                        // the trial record (and the obstacle cache) must belong to the point that is taken
+                        resto_direction(lam_best);
+                        double th_r, phi_r;
+                        trial_eval<J, OBS>(P, OL, sox, soy, ocs, s, soc, 1.0, mu, df, lane, th_r, phi_r);
+                        t_acc = 1.0;
+                    }
+                }
                 if (t_acc == 0.0) { status = B200MPC_RESTORATION_FAILED; break; }
                 double zm = 0;
 #pragma unroll
@@ -1750,7 +1792,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                     if (k >= 1 && k <= N) { s[j].X[0] = s[j].Xt[0]; s[j].X[1] = s[j].Xt[1]; s[j].X[2] = s[j].Xt[2]; }
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
-                        if (dyn) { s[j].U[i] = s[j].Ut[i]; zm = fmax(zm, fmax(s[j].vL[i], s[j].vU[i])); }
+                        if (dyn) { s[j].U[i] = s[j].Ut[i]; s[j].S[i] = s[j].St[i]; zm = fmax(zm, fmax(s[j].vL[i], s[j].vU[i])); }
                         s[j].yd[i] = 0;
                     }
 #pragma unroll

@@ -100,7 +100,7 @@ __device__ __forceinline__ void tppf_forward(const KParams &P, char *wb, char *s
             tpp_ref<SPEC>(P, goal, p, r, ub);
             const double ln0[3] = {0, 0, 0};
             TppLin q;
-            tpp_lin<false, SPEC>(P, r, ub, X, U, ln0, df, q);
+            tpp_lin<false, SPEC>(P, r, ub, X, U, ln0, df, q, tpp_obs_zero());
             double rc0, rc1, rc2, rdv[2] = {U[0] - Sv[0], U[1] - Sv[1]};
             if (mode == BM_LSQ) {
                 rc0 = rc1 = rc2 = 0;
@@ -283,7 +283,7 @@ __device__ __forceinline__ void tppf_trial_backward(const KParams &P, char *wb, 
             tpp_st2(pw, R_U, U[0], U[1]); tpp_st2(pw, R_S, S[0], S[1]); tpp_st2(pw, R_YD, yd[0], yd[1]);
             tpp_st2(pw, R_VL, vL[0], vL[1]); tpp_st2(pw, R_VU, vU[0], vU[1]);
             TppLin q;
-            tpp_lin<true, SPEC>(P, r, ub, X, U, ln, df, q);
+            tpp_lin<true, SPEC>(P, r, ub, X, U, ln, df, q, tpp_obs_zero());
             const double c[3] = {Xn[0] - q.F0, Xn[1] - q.F1, Xn[2] - q.F2};
             fs += q.f;
 #pragma unroll

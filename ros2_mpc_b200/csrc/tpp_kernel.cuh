@@ -47,11 +47,15 @@
 // The lane kernels are instantiated per problem family (template parameter SPEC), so that the integrator and the kind of
 // reference are compile-time constants and the other family's code leaves the sweeps' loop bodies (instruction cache):
 //   SPEC 0  generic (run-time switches)   SPEC 1  RK4 + fixed goal (variants A, B)   SPEC 2  Euler + trajectory (variant C)
+//   SPEC 3  RK4 + fixed goal + obstacle cost (variant A).  The generic instance handles the obstacle cost through a run-time
+//           switch; instances 1 and 2 carry no obstacle code at all.
 #define TPP_SPEC_GENERIC 0
 #define TPP_SPEC_RK4_GOAL 1
 #define TPP_SPEC_EULER_TRAJ 2
-#define TPP_IS_EULER(P) (SPEC == TPP_SPEC_RK4_GOAL ? false : (SPEC == TPP_SPEC_EULER_TRAJ ? true : ((P).integrator == B200MPC_EULER)))
-#define TPP_IS_GOAL(P) (SPEC == TPP_SPEC_RK4_GOAL ? true : (SPEC == TPP_SPEC_EULER_TRAJ ? false : ((P).ref_kind == B200MPC_REF_GOAL)))
+#define TPP_SPEC_RK4_GOAL_OBS 3
+#define TPP_IS_EULER(P) ((SPEC == TPP_SPEC_RK4_GOAL || SPEC == TPP_SPEC_RK4_GOAL_OBS) ? false : (SPEC == TPP_SPEC_EULER_TRAJ ? true : ((P).integrator == B200MPC_EULER)))
+#define TPP_IS_GOAL(P) ((SPEC == TPP_SPEC_RK4_GOAL || SPEC == TPP_SPEC_RK4_GOAL_OBS) ? true : (SPEC == TPP_SPEC_EULER_TRAJ ? false : ((P).ref_kind == B200MPC_REF_GOAL)))
+#define TPP_HAS_OBS(P) (SPEC == TPP_SPEC_RK4_GOAL_OBS ? true : (SPEC == TPP_SPEC_GENERIC ? ((P).obs_form != B200MPC_OBS_NONE) : false))
 #ifndef TPP_BWD_EAGER
 #define TPP_BWD_EAGER 1 /* backward sweep: read all staged rows at the top of the stage and issue the next copy at once */
 #endif
@@ -67,7 +71,9 @@ enum {
     R_CS = 26,   // second-order-correction right-hand sides: (cs0,cs1) (cs2,-) (ds0,ds1)
     R_REF = 29,  // per-stage references (trajectory tracking only): (r0,r1) (r2,-) (ub0,ub1)
     R_KB = 32,   // two-sweep kernel (tpp_fused.cuh) only: (kfb0,kfb1), barrier-parameter coefficient of the gain kf
-    TPP_NR = 33
+    R_OC = 33,   // obstacle cost only: value, gradient and Hessian of the stage's obstacle sum at the iterate of buffer 0 / 1
+                 // (unscaled): (val,gx) (gy,hxx) (hxy,hyy); rows 33-35 belong to iterate buffer 0, rows 36-38 to buffer 1
+    TPP_NR = 39
 };
 #define TPP_ROW_B 512
 #define TPP_STAGE_B (TPP_NR * TPP_ROW_B)
@@ -184,6 +190,7 @@ struct TppLane {
     int tiny, tiny_last, tiny_flag;                // tiny-step detection (BacktrackingLineSearch::DetectTinyStep and its two flags)
     double ymax_f;                                 // LSQ mode: largest slack-multiplier estimate seen by sweep F
     double dw_b;                                   // two-sweep kernel: delta_w of the factorisation in progress
+    int n_eff;                                     // obstacle cost: entries of the problem's obstacle list to walk (ObsList)
 };
 #define TPP_LANE_STRIDE (((sizeof(TppLane) + 7) / 8) | 1) /* in doubles, odd */
 
@@ -217,18 +224,36 @@ __device__ __forceinline__ void tpp_trig(double th, double hw, double &s0, doubl
 
 struct TppLin {
     double a13, a23, b11, b12, b21, b22, F0, F1, F2;
-    double hxx, hyy, htt, htv, htw, hvv, hvw, hww;
+    double hxx, hxy, hyy, htt, htv, htw, hvv, hvw, hww;
     double g[5], f;
 };
+
+// Obstacle sum of one stage (unscaled): value, gradient, Hessian — read from the stage's cache rows (R_OC), which the
+// obstacle block of the kernel (tpp_obstacle_block) fills before the sweeps that need them.
+struct TppObs {
+    double v, gx, gy, hxx, hxy, hyy;
+};
+__device__ __forceinline__ TppObs tpp_obs_zero() {
+    TppObs o;
+    o.v = 0; o.gx = 0; o.gy = 0; o.hxx = 0; o.hxy = 0; o.hyy = 0;
+    return o;
+}
+// cache rows of iterate buffer `buf` at the stage whose record starts at p
+__device__ __forceinline__ TppObs tpp_obs_load(const char *p, int buf) {
+    const double2 a = tpp_ld2(p, R_OC + 3 * buf), b = tpp_ld2(p, R_OC + 3 * buf + 1), c = tpp_ld2(p, R_OC + 3 * buf + 2);
+    TppObs o;
+    o.v = a.x; o.gx = a.y; o.gy = b.x; o.hxx = b.y; o.hxy = c.x; o.hyy = c.y;
+    return o;
+}
 
 // K1+K2 of a stage with controls (k < N): integration step, Jacobian entries, stage cost and its gradient; with
 // HESS also the Lagrangian Hessian block (ln = multiplier of the defect X_{k+1} - F(X_k, U_k)).
 template <bool HESS, int SPEC>
 __device__ __forceinline__ void tpp_lin(const KParams &P, const double r[3], const double ub[2], const double X[3],
-                                        const double U[2], const double ln[3], double df, TppLin &o) {
+                                        const double U[2], const double ln[3], double df, TppLin &o, const TppObs &oc) {
     const double dt = P.dt, th = X[2], v = U[0], w = U[1];
     o.b12 = 0; o.b22 = 0;
-    o.htw = 0; o.hvw = 0; o.hww = 0;
+    o.htw = 0; o.hvw = 0; o.hww = 0; o.hxy = 0;
     if (TPP_IS_EULER(P)) {
         double sn, cs;
         tpp_sincos1(th, &sn, &cs);
@@ -276,6 +301,16 @@ __device__ __forceinline__ void tpp_lin(const KParams &P, const double r[3], con
         o.htt = df * 2.0 * P.Q[2] + o.htt;
         o.hvv = df * (2.0 * P.R[0] + P.kappa * P.kappa * er);
         o.hww = df * 2.0 * P.R[1] + o.hww;
+    }
+    if (TPP_HAS_OBS(P)) {
+        o.f += oc.v;
+        o.g[0] = fma(df, oc.gx, o.g[0]);
+        o.g[1] = fma(df, oc.gy, o.g[1]);
+        if (HESS) {
+            o.hxx = fma(df, oc.hxx, o.hxx);
+            o.hyy = fma(df, oc.hyy, o.hyy);
+            o.hxy = df * oc.hxy;
+        }
     }
 }
 
@@ -391,7 +426,7 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
             double r[3], ub[2];
             tpp_ref<SPEC>(P, goal, p, r, ub);
             TppLin q;
-            tpp_lin<true, SPEC>(P, r, ub, X, U, ln, df, q);
+            tpp_lin<true, SPEC>(P, r, ub, X, U, ln, df, q, tpp_obs_zero());
 #if !TPP_BWD_EAGER
             const double2 s2 = tpp_sld(sb, R_S), yd2 = tpp_sld(sb, R_YD), vl2 = tpp_sld(sb, R_VL), vu2 = tpp_sld(sb, R_VU);
             tpp_consume(x01, x2l0, l12, u2);
@@ -593,7 +628,7 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
             tpp_ref<SPEC>(P, goal, p, r, ub);
             const double ln0[3] = {0, 0, 0};
             TppLin q;
-            tpp_lin<false, SPEC>(P, r, ub, X, U, ln0, df, q);
+            tpp_lin<false, SPEC>(P, r, ub, X, U, ln0, df, q, tpp_obs_zero());
             double rc0, rc1, rc2, rdv[2] = {U[0] - Sv[0], U[1] - Sv[1]};
             if (mode == BM_LSQ) {
                 rc0 = rc1 = rc2 = 0;
@@ -809,7 +844,7 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
             tpp_st2(pw, R_U, U[0], U[1]); tpp_st2(pw, R_S, S[0], S[1]); tpp_st2(pw, R_YD, yd[0], yd[1]);
             tpp_st2(pw, R_VL, vL[0], vL[1]); tpp_st2(pw, R_VU, vU[0], vU[1]);
             TppLin q;
-            tpp_lin<false, SPEC>(P, r, ub, X, U, ln, df, q);
+            tpp_lin<false, SPEC>(P, r, ub, X, U, ln, df, q, tpp_obs_zero());
             const double c[3] = {Xn[0] - q.F0, Xn[1] - q.F1, Xn[2] - q.F2};
             fs += q.f;
 #pragma unroll
@@ -914,15 +949,20 @@ __device__ __forceinline__ bool tpp_ls_acceptable(const TppLane &L, const double
 }
 
 // Restoration stand-in (same rule as the warp kernel and the oracle).  The line search gave up on the Newton direction
-// (alpha < alpha_min).  Direction: towards the closed-form feasible point (U = S, X rolled out); the longest step
-// t = 1, 1/2, ... along it is taken whose point passes IPOPT's restoration acceptance (finite, theta <= kappa_resto * theta,
-// no excessive objective increase, acceptable to the augmented filter); the multipliers restart.
-// tpp_resto_eval: theta and objective of  current + t * direction  (direction in the R_SSTEP rows; S does not move).
+// (alpha < alpha_min).  The filter is augmented with the current point, then
+//   stage 1: along the direction to the closed-form feasible point (U = S, X rolled out; S fixed) the longest step
+//            t = 1, 1/2, ... is taken whose point passes IPOPT's restoration acceptance (finite, theta <= kappa_resto * theta,
+//            no excessive objective increase, acceptable to the augmented filter);
+//   stage 2: if there is none, the family "plan shrunk towards standing still": S_l = u_c + l (S - u_c), U = S_l, X rolled out,
+//            l = 1/2, 1/4, ..., 0; the member with the lowest barrier objective is taken.
+// The multipliers restart.
+// tpp_resto_eval: theta, objective and log-barrier sum of  current + t * direction  (direction (dX, dU) in the R_SSTEP rows;
+// the slack step is dU + (U - S) when move_s, else the slacks stay).
 template <int SPEC>
-__device__ __noinline__ void tpp_resto_eval(const KParams &P, const char *wb, int co, const double *goal, double t, double *th_out,
-                                            double *f_out) {
+__device__ __noinline__ void tpp_resto_eval(const KParams &P, const char *wb, int co, const double *goal, double t, int move_s,
+                                            double *th_out, double *f_out, double *slog_out) {
     const int N = P.N;
-    double th = 0, fs = 0;
+    double th = 0, fs = 0, slog = 0;
     double X[3];
     {
         const char *pc = wb + co * TPP_ROW_B;
@@ -937,18 +977,57 @@ __device__ __noinline__ void tpp_resto_eval(const KParams &P, const char *wb, in
         const double2 n01 = tpp_ld2(pc + TPP_STAGE_B, R_X01), n2 = tpp_ld2(pc + TPP_STAGE_B, R_X2L0);
         const double2 d01 = tpp_ld2(p + TPP_STAGE_B, R_SSTEP), d2 = tpp_ld2(p + TPP_STAGE_B, R_SSTEP + 1);
         const double U[2] = {u2.x + t * du2.x, u2.y + t * du2.y};
+        double S[2] = {s2.x, s2.y};
+        if (move_s) {
+            S[0] = s2.x + t * (du2.x + (u2.x - s2.x));
+            S[1] = s2.y + t * (du2.y + (u2.y - s2.y));
+            const double l0 = S[0] - P.sL[0], l1 = P.sU[0] - S[0], l2 = S[1] - P.sL[1], l3 = P.sU[1] - S[1];
+            const bool inside = (l0 > 0.0) && (l1 > 0.0) && (l2 > 0.0) && (l3 > 0.0);
+            slog += log(inside ? (l0 * l1) * (l2 * l3) : -1.0);
+        }
         const double Xn[3] = {n01.x + t * d01.x, n01.y + t * d01.y, n2.x + t * d2.x};
         double r[3], ub[2];
         tpp_ref<SPEC>(P, goal, p, r, ub);
         const double ln0[3] = {0, 0, 0};
         TppLin q;
-        tpp_lin<false, SPEC>(P, r, ub, X, U, ln0, 1.0, q);
-        th += fabs(Xn[0] - q.F0) + fabs(Xn[1] - q.F1) + fabs(Xn[2] - q.F2) + fabs(U[0] - s2.x) + fabs(U[1] - s2.y);
+        tpp_lin<false, SPEC>(P, r, ub, X, U, ln0, 1.0, q, tpp_obs_zero());
+        th += fabs(Xn[0] - q.F0) + fabs(Xn[1] - q.F1) + fabs(Xn[2] - q.F2) + fabs(U[0] - S[0]) + fabs(U[1] - S[1]);
         fs += q.f;
         X[0] = Xn[0]; X[1] = Xn[1]; X[2] = Xn[2];
     }
     *th_out = th;
     *f_out = fs;
+    *slog_out = slog;
+}
+
+// restoration direction -> R_SSTEP rows: (Xr - X) with Xr the roll-out of the target slacks S_l, (S_l - U);
+// lam < 0: S_l = S exactly (stage 1).  Returns the largest bound multiplier.
+template <int SPEC>
+__device__ __noinline__ double tpp_resto_direction(const KParams &P, char *wb, int co, double lam, double uc0, double uc1) {
+    const int N = P.N;
+    double zm = 0;
+    double y[3];
+    const double2 a = tpp_ld2(wb + co * TPP_ROW_B, R_X01), b = tpp_ld2(wb + co * TPP_ROW_B, R_X2L0);
+    y[0] = a.x; y[1] = a.y; y[2] = b.x;
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+        char *p = wb + (size_t)k * TPP_STAGE_B;
+        const char *pc = p + co * TPP_ROW_B;
+        const double2 x01 = tpp_ld2(pc, R_X01), x2 = tpp_ld2(pc, R_X2L0);
+        tpp_st2(p, R_SSTEP, (k == 0) ? 0.0 : y[0] - x01.x, (k == 0) ? 0.0 : y[1] - x01.y);
+        tpp_st2(p, R_SSTEP + 1, (k == 0) ? 0.0 : y[2] - x2.x, 0.0);
+        if (k < N) {
+            const double2 u = tpp_ld2(pc, R_U), sv = tpp_ld2(pc, R_S), vl = tpp_ld2(pc, R_VL), vu = tpp_ld2(pc, R_VU);
+            zm = fmax(zm, fmax(fmax(vl.x, vl.y), fmax(vu.x, vu.y)));
+            double S[2] = {sv.x, sv.y};
+            if (lam >= 0.0) { S[0] = uc0 + lam * (sv.x - uc0); S[1] = uc1 + lam * (sv.y - uc1); }
+            tpp_st2(p, R_SSTEP + 2, S[0] - u.x, S[1] - u.y);
+            double F[3];
+            tpp_dyn<SPEC>(P, y, S, F);
+            y[0] = F[0]; y[1] = F[1]; y[2] = F[2];
+        }
+    }
+    return zm;
 }
 
 template <int SPEC>
@@ -957,35 +1036,13 @@ __device__ __forceinline__ void tpp_restore(const KParams &P, char *wb, double *
     if (L.theta <= 1e-10 || L.n_resto >= MAX_RESTO) { L.status = B200MPC_RESTORATION_FAILED; L.phase = PH_FIN; return; }
     tpp_filter_add(fl, L, L.ref_phi - GAMMA_PHI * L.theta, (1 - GAMMA_THETA) * L.theta);
     const int co = cur * R_ITER, no = R_ITER - co;
-    double zm = 0;
-    // direction -> R_SSTEP rows: (Xr - X) with Xr the roll-out of the slacks, (S - U)
-    {
-        double y[3];
-        const double2 a = tpp_ld2(wb + co * TPP_ROW_B, R_X01), b = tpp_ld2(wb + co * TPP_ROW_B, R_X2L0);
-        y[0] = a.x; y[1] = a.y; y[2] = b.x;
-#pragma unroll 1
-        for (int k = 0; k <= N; ++k) {
-            char *p = wb + (size_t)k * TPP_STAGE_B;
-            const char *pc = p + co * TPP_ROW_B;
-            const double2 x01 = tpp_ld2(pc, R_X01), x2 = tpp_ld2(pc, R_X2L0);
-            tpp_st2(p, R_SSTEP, (k == 0) ? 0.0 : y[0] - x01.x, (k == 0) ? 0.0 : y[1] - x01.y);
-            tpp_st2(p, R_SSTEP + 1, (k == 0) ? 0.0 : y[2] - x2.x, 0.0);
-            if (k < N) {
-                const double2 u = tpp_ld2(pc, R_U), sv = tpp_ld2(pc, R_S), vl = tpp_ld2(pc, R_VL), vu = tpp_ld2(pc, R_VU);
-                zm = fmax(zm, fmax(fmax(vl.x, vl.y), fmax(vu.x, vu.y)));
-                tpp_st2(p, R_SSTEP + 2, sv.x - u.x, sv.y - u.y);
-                const double S[2] = {sv.x, sv.y};
-                double F[3];
-                tpp_dyn<SPEC>(P, y, S, F);
-                y[0] = F[0]; y[1] = F[1]; y[2] = F[2];
-            }
-        }
-    }
+    const double zm = tpp_resto_direction<SPEC>(P, wb, co, -1.0, 0.0, 0.0);
     double t_acc = 0.0;
+    int move_s = 0;
     const double phi_ref = L.ref_phi;
     for (double t = 1.0; t >= RESTO_T_MIN; t *= 0.5) {
-        double th_r, f_r;
-        tpp_resto_eval<SPEC>(P, wb, co, L.goal, t, &th_r, &f_r);
+        double th_r, f_r, sl_r;
+        tpp_resto_eval<SPEC>(P, wb, co, L.goal, t, 0, &th_r, &f_r, &sl_r);
         const double phi_r = L.df * f_r - L.mu * L.slog; // the slacks do not move: the barrier term is the current one
         if (!isfinite(th_r) || !isfinite(phi_r)) continue;
         if (!(th_r <= KAPPA_RESTO * L.theta)) continue;
@@ -997,6 +1054,34 @@ __device__ __forceinline__ void tpp_restore(const KParams &P, char *wb, double *
         if (!tpp_filter_ok(fl, L.fmask, phi_r, th_r)) continue;
         t_acc = t;
         break;
+    }
+    if (t_acc == 0.0) {
+        double uc[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const double lo = P.sL[i], hi = P.sU[i];
+            const double pl = fmin(BOUND_PUSH * fmax(1.0, fabs(lo)), BOUND_FRAC * (hi - lo));
+            const double pu = fmin(BOUND_PUSH * fmax(1.0, fabs(hi)), BOUND_FRAC * (hi - lo));
+            uc[i] = fmin(fmax(0.0, lo + pl), hi - pu);
+        }
+        double lam = 0.5, best = __longlong_as_double(0x7ff0000000000000ll), lam_best = -1.0;
+        for (;;) {
+            (void)tpp_resto_direction<SPEC>(P, wb, co, lam, uc[0], uc[1]);
+            double th_r, f_r, sl_r;
+            tpp_resto_eval<SPEC>(P, wb, co, L.goal, 1.0, 1, &th_r, &f_r, &sl_r);
+            const double phi_r = L.df * f_r - L.mu * sl_r;
+            if (isfinite(th_r) && isfinite(phi_r) && (th_r <= KAPPA_RESTO * L.theta) && (phi_r < best) &&
+                tpp_filter_ok(fl, L.fmask, phi_r, th_r)) {
+                best = phi_r; lam_best = lam;
+            }
+            if (lam == 0.0) break;
+            lam = (lam * 0.5 >= RESTO_T_MIN) ? lam * 0.5 : 0.0;
+        }
+        if (lam_best >= 0.0) {
+            (void)tpp_resto_direction<SPEC>(P, wb, co, lam_best, uc[0], uc[1]);
+            t_acc = 1.0;
+            move_s = 1;
+        }
     }
     if (t_acc == 0.0) { L.status = B200MPC_RESTORATION_FAILED; L.phase = PH_FIN; return; }
     const bool reset = zm > 1e3;
@@ -1011,7 +1096,9 @@ __device__ __forceinline__ void tpp_restore(const KParams &P, char *wb, double *
         tpp_st2(pw, R_L12, 0.0, 0.0);
         if (k < N) {
             const double2 u = tpp_ld2(pc, R_U), du = tpp_ld2(p, R_SSTEP + 2), s = tpp_ld2(pc, R_S), a = tpp_ld2(pc, R_VL), b = tpp_ld2(pc, R_VU);
-            tpp_st2(pw, R_U, u.x + t_acc * du.x, u.y + t_acc * du.y); tpp_st2(pw, R_S, s.x, s.y); tpp_st2(pw, R_YD, 0.0, 0.0);
+            double S[2] = {s.x, s.y};
+            if (move_s) { S[0] = s.x + t_acc * (du.x + (u.x - s.x)); S[1] = s.y + t_acc * (du.y + (u.y - s.y)); }
+            tpp_st2(pw, R_U, u.x + t_acc * du.x, u.y + t_acc * du.y); tpp_st2(pw, R_S, S[0], S[1]); tpp_st2(pw, R_YD, 0.0, 0.0);
             tpp_st2(pw, R_VL, reset ? 1.0 : a.x, reset ? 1.0 : a.y);
             tpp_st2(pw, R_VU, reset ? 1.0 : b.x, reset ? 1.0 : b.y);
         }
