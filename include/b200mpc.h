@@ -291,8 +291,9 @@ int b200mpc_headings_batch_device(b200mpc_handle *h, int P, int K, const double 
                                   double *velocity, double *omega, void *stream);
 
 /* Forces one of the two solve kernels (default B200MPC_KERNEL_AUTO; the environment variable B200MPC_KERNEL=warp|lane
- * sets the default of new handles).  Both kernels run the same algorithm; results agree to rounding.  The
- * lane-per-problem kernel does not carry the obstacle cost (obs_form != NONE always uses the warp kernel). */
+ * sets the default of new handles).  Both kernels run the same algorithm; results agree to rounding (with the obstacle
+ * cost active the problem is non-convex and rounding can tip a solve to another local optimum).  AUTO takes the
+ * lane-per-problem kernel from 30 720 problems on (131 072 with the obstacle cost). */
 int b200mpc_set_kernel(b200mpc_handle *h, int kind);
 /* B200MPC_KERNEL_WARP / _LANE: the kernel the most recent solve used. */
 int b200mpc_last_kernel_kind(const b200mpc_handle *h);

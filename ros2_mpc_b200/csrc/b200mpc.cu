@@ -26,6 +26,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -90,7 +91,22 @@ struct BatchArgs {
     double *X, *U, *cost;
     int *status, *iters, *ls;
     unsigned int *counter;
+    // Straggler hand-over (lane kernel -> warp kernel).  A lane-kernel launch lasts as long as its slowest problem, and a
+    // trip of a nearly empty warp costs what a trip of a full one does, so the lane kernel EXPORTS the complete solver
+    // state of a problem (record below) when the problem has taken hand_iter iterations, or when the work queue is empty
+    // and its warp has thinned out; a second launch of the warp kernel (resume = the same records) picks those problems
+    // up exactly where they stood — per-iteration latency 20 us instead of a 0.3-0.5 ms trip.
+    double *hand_rec = nullptr;          // [hand_cap][HAND_REC(N)] records, or NULL (no hand-over)
+    unsigned int *hand_count = nullptr;  // records written (lane kernel) / to read (warp kernel); may exceed hand_cap: clamp
+    int hand_cap = 0, hand_iter = 0, hand_thin = 0;
+    int resume = 0;                      // warp kernel: 1 = the batch IS the list of records (B is ignored)
 };
+// record of one exported problem (doubles): per stage the eight iterate rows of the lane kernel's workspace
+// (X0 X1 | X2 lam0 | lam1 lam2 | U | S | yd | vL | vU), 16 scalars, the filter (32 x (phi, theta))
+#define HAND_SCAL(N) (16 * ((N) + 1))
+#define HAND_FILT(N) (HAND_SCAL(N) + 16)
+#define HAND_REC(N) (HAND_FILT(N) + 64)
+enum { HS_B = 0, HS_MU, HS_DF, HS_THETA0, HS_DWLAST, HS_ITER, HS_LS, HS_NRESTO, HS_ACCEPT, HS_TINYLAST, HS_TINYFLAG, HS_FMASK, HS_RING };
 
 struct EvalArgs {
     int B, obs_stride;
@@ -236,6 +252,57 @@ __device__ __forceinline__ double obs_exp(double q) {
     return e;
 }
 
+// One term of the exp(c/s) sum.  ptxas lays independent FP64 chains out one after the other (it minimises registers; a
+// four-term loop written side by side comes out term by term all the same), and a warp then issues one instruction per
+// FP64 latency (profiles/r2_warp_a_v1, r2_lane_a_v1: 53-62 % of the obstacle loop's samples are fixed-latency waits).  So
+// the parallelism is put INSIDE the term: the exponential's polynomial in Estrin form (4 levels instead of a 13-step Horner
+// chain), the reciprocal with one second-order correction, and the derivative factors formed next to the reduction.
+// c > 0 (the reference: reverse_factor 5.0 / cost_factor 0.5), so q = c/s >= 0 and 2^k is applied by an integer add to the
+// exponent field (k <= 1024 whenever q is below the overflow threshold, and then p < 1: the result is a normal number).
+struct ObsAcc {
+    double v, sp1, ax, ay, bxx, bxy, byy;
+};
+template <bool USEW>
+__device__ __forceinline__ void obs_term_explog(double c, double ir2, double x, double y, double ox, double oy, double w, ObsAcc &A) {
+    const double dx = x - ox, dy = y - oy;
+    const double s = (dx * dx + dy * dy) * ir2;
+    double y0; // s = 0 (robot on an obstacle point): NaN instead of inf, invalid either way
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(s));
+    const double e1 = fma(-s, y0, 1.0);   // |e1| <= 2^-23: 1/s = y0 (1 + e1 + e1^2) to 2^-69
+    const double e2 = fma(e1, e1, e1);
+    const double is = fma(y0, e2, y0);
+    const double q = c * is;
+    const double kf = rint(q * OBS_EXP_C[11]);
+    const double t = q * is;              // c / s^2
+    const double tt = fma(2.0, is, t);
+    double r = fma(-kf, OBS_EXP_LN2[0], q);
+    r = fma(-kf, OBS_EXP_LN2[1], r);
+    // e^r, |r| <= ln2 / 2, degree 13 (relative error < 1e-17 before rounding)
+    const double r2 = r * r;
+    const double b0 = 1.0 + r, b1 = fma(OBS_EXP_C[10], r, 0.5), b2 = fma(OBS_EXP_C[8], r, OBS_EXP_C[9]),
+                 b3 = fma(OBS_EXP_C[6], r, OBS_EXP_C[7]), b4 = fma(OBS_EXP_C[4], r, OBS_EXP_C[5]),
+                 b5 = fma(OBS_EXP_C[2], r, OBS_EXP_C[3]), b6 = fma(OBS_EXP_C[0], r, OBS_EXP_C[1]);
+    const double r4 = r2 * r2;
+    const double c0 = fma(b1, r2, b0), c1 = fma(b3, r2, b2), c2 = fma(b5, r2, b4);
+    const double r8 = r4 * r4;
+    const double d0 = fma(c1, r4, c0), d1 = fma(b6, r4, c2);
+    const double p = fma(d1, r8, d0);
+    const int k = (int)kf; // (saturating conversion; NaN -> 0, and then p is NaN)
+    double e = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    e = (q > 709.782712893384) ? __longlong_as_double(0x7ff0000000000000ll) : e;
+    if (USEW) e *= w;
+    const double te = t * e;              // -phi'
+    const double p2 = te * tt;            // phi'' = (c/s^2)(2/s + c/s^2) phi
+    const double p2x = p2 * dx;
+    A.v += e;
+    A.sp1 -= te;
+    A.ax = fma(-te, dx, A.ax);
+    A.ay = fma(-te, dy, A.ay);
+    A.bxx = fma(p2x, dx, A.bxx);
+    A.bxy = fma(p2x, dy, A.bxy);
+    A.byy = fma(p2 * dy, dy, A.byy);
+}
+
 __device__ __noinline__ void obstacle_eval(int form, double c, double ir2, const double *__restrict__ sox,
                                            const double *__restrict__ soy, int n_eff, double w0, double x, double y,
                                            double *out6) {
@@ -262,9 +329,18 @@ __device__ __noinline__ void obstacle_eval(int form, double c, double ir2, const
         bxy = fma(p2x, dy, bxy);                                                                        \
         byy = fma(p2 * dy, dy, byy);                                                                    \
     } while (0)
-        OBS_TERM_EXPLOG(0, w0, true);
+        if (c > 0.0) {
+            ObsAcc A;
+            A.v = 0; A.sp1 = 0; A.ax = 0; A.ay = 0; A.bxx = 0; A.bxy = 0; A.byy = 0;
+            obs_term_explog<true>(c, ir2, x, y, sox[0], soy[0], w0, A);
 #pragma unroll 4
-        for (int j = 1; j < n_eff; j++) OBS_TERM_EXPLOG(j, 1.0, false);
+            for (int j = 1; j < n_eff; j++) obs_term_explog<false>(c, ir2, x, y, sox[j], soy[j], 1.0, A);
+            v = A.v; sp1 = A.sp1; ax = A.ax; ay = A.ay; bxx = A.bxx; bxy = A.bxy; byy = A.byy;
+        } else {
+            OBS_TERM_EXPLOG(0, w0, true);
+#pragma unroll 1
+            for (int j = 1; j < n_eff; j++) OBS_TERM_EXPLOG(j, 1.0, false);
+        }
 #undef OBS_TERM_EXPLOG
     } else {
         // psi(s) = c exp(-s):  psi' = -psi,  psi'' = psi
@@ -1263,7 +1339,9 @@ __device__ __forceinline__ void filter_add(double phi, double theta, double &fph
 // that the out-of-line call does not cost the serial-form instance registers.
 template <int J, bool OBS, bool SCAN>
 __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane, double *sox, double *soy, double *rec,
-                          const KktRoles &roles) {
+                          const KktRoles &roles, const double *hrec = nullptr) {
+    // hrec: record of a problem the lane kernel handed over (BatchArgs::hand_rec): the solve resumes at the top of the
+    // interior-point loop with the exported iterate, barrier parameter, filter and counters instead of starting cold
     const int N = P.N;
     Stg s[J];
     Step st[J], soc[J];
@@ -1317,12 +1395,25 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
             t.vL[i] = 1.0; t.vU[i] = 1.0; t.yd[i] = 0;
             t.Dsig[i] = 1.0; t.rs[i] = 0;
         }
+        if (hrec && k <= N) {
+            const double *q = hrec + 16 * k;
+            if (k >= 1) { t.X[0] = q[0]; t.X[1] = q[1]; t.X[2] = q[2]; t.lam[0] = q[3]; t.lam[1] = q[4]; t.lam[2] = q[5]; }
+            if (dyn) {
+                t.U[0] = q[6]; t.U[1] = q[7]; t.S[0] = q[8]; t.S[1] = q[9]; t.yd[0] = q[10]; t.yd[1] = q[11];
+                t.vL[0] = q[12]; t.vL[1] = q[13]; t.vU[0] = q[14]; t.vU[1] = q[15];
+            }
+        }
     }
 
     int status = B200MPC_MAXITER_EXCEEDED;
     int iter = 0, ls_extra = 0, n_resto = 0;
     double df = 1.0;
     double fcur = 0;
+    if (hrec) {
+        const double *q = hrec + HAND_SCAL(N);
+        iter = (int)q[HS_ITER]; ls_extra = (int)q[HS_LS]; n_resto = (int)q[HS_NRESTO];
+        df = q[HS_DF];
+    }
 
     bool oc_valid = false; // ocs holds the obstacle sums of the current iterate (it was the accepted trial point)
     double *ocs = rec + (size_t)(N + 1) * KKT_REC; // per stage: value, gradient (2), Hessian (3) of the obstacle sum
@@ -1344,7 +1435,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
     };
 
     // ---- objective scaling from the gradient at the starting point; invalid-number check ----
-    {
+    if (!hrec) {
         fcur = eval_point(1.0);
         double gmax = 0;
         int bad = 0;
@@ -1373,7 +1464,7 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
     }
 
     // ---- least-squares multiplier estimate ----
-    {
+    if (!hrec) {
         fcur = eval_point(df);
         double ymax = 0;
 #pragma unroll
@@ -1416,6 +1507,18 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
         double fphi = 0, ftheta = 0;
         bool fvalid = false;
         int ring = 0;
+        if (hrec) {
+            const double *q = hrec + HAND_SCAL(N);
+            mu = q[HS_MU]; tau = fmax(TAU_MIN, 1.0 - mu);
+            theta_max = 1e4 * q[HS_THETA0]; theta_min = 1e-4 * q[HS_THETA0];
+            dw_last = q[HS_DWLAST];
+            acceptable_count = (int)q[HS_ACCEPT];
+            tiny_last = q[HS_TINYLAST] != 0.0; tiny_flag = q[HS_TINYFLAG] != 0.0;
+            const unsigned fm = (unsigned)q[HS_FMASK];
+            ring = (int)q[HS_RING];
+            fvalid = (fm >> lane) & 1u;
+            fphi = hrec[HAND_FILT(N) + 2 * lane]; ftheta = hrec[HAND_FILT(N) + 2 * lane + 1];
+        }
 
         for (;;) {
             // ---- evaluate the current point ----
@@ -1905,6 +2008,19 @@ __global__ void __launch_bounds__(128, OBS ? B200MPC_MIN_CTAS_OBS : B200MPC_MIN_
     const size_t per_warp = 2 * (size_t)Mpad + (size_t)(P.N + 1) * (KKT_REC + 6) + (SCAN ? SCAN_NF * 32 : 0);
     double *sox = smem + (size_t)wid * per_warp, *soy = sox + Mpad, *rec = soy + Mpad;
     const KktRoles roles = kkt_roles(lane);
+    if (A.resume) {
+        // second launch behind the lane kernel: the batch is the list of problems it handed over
+        const int n = (int)min(*A.hand_count, (unsigned)A.hand_cap);
+        for (;;) {
+            int r = 0;
+            if (lane == 0) r = (int)atomicAdd(A.counter, 1u);
+            r = __shfl_sync(FULL, r, 0);
+            if (r >= n) break;
+            const double *hrec = A.hand_rec + (size_t)r * HAND_REC(P.N);
+            solve_one<J, OBS, SCAN>(P, A, (int)hrec[HAND_SCAL(P.N) + HS_B], lane, sox, soy, rec, roles, hrec);
+        }
+        return;
+    }
     for (;;) {
         int b = 0;
         if (lane == 0) b = (int)atomicAdd(A.counter, 1u);
@@ -2031,6 +2147,13 @@ struct b200mpc_handle {
     int kernel_kind;   // B200MPC_KERNEL_AUTO / _WARP / _LANE
     int last_kind;     // kernel used by the most recent solve
     int tpp_ctas;
+    size_t tpp_obs_smem; // bytes of per-warp obstacle-list buffers behind TPP_SMEM_BYTES (0: lists are read from global memory)
+    int tpp_cta_sync;
+    // straggler hand-over from the lane kernel to the warp kernel (BatchArgs::hand_rec)
+    int hand_iter, hand_thin;   // hand_iter <= 0: off
+    double *d_hand;
+    size_t hand_cap;
+    unsigned int *d_hand_count;
     int kkt_scan_mode; // warp kernel: -1 scan recursion for batches that leave warps idle, 0 never, 1 always
     int lane_spec;     // template instance of the lane kernels (TPP_SPEC_*)
     int lane_fused;    // 1: two-sweep lane kernel (tpp_fused.cuh), 0: three-sweep lane kernel (tpp_kernel.cuh)
@@ -2213,17 +2336,40 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     h->lane_spec = TPP_SPEC_GENERIC;
     if (p->integrator == B200MPC_RK4 && p->ref_kind == B200MPC_REF_GOAL) h->lane_spec = TPP_SPEC_RK4_GOAL;
     if (p->integrator == B200MPC_EULER && p->ref_kind == B200MPC_REF_TRAJ) h->lane_spec = TPP_SPEC_EULER_TRAJ;
+    if (p->obs_form != B200MPC_OBS_NONE) // obstacle cost: the instance of variant A, or the generic one (run-time switch)
+        h->lane_spec = (h->lane_spec == TPP_SPEC_RK4_GOAL) ? TPP_SPEC_RK4_GOAL_OBS : TPP_SPEC_GENERIC;
     if (getenv("B200MPC_LANE_GENERIC")) h->lane_spec = TPP_SPEC_GENERIC;
     {
-        const void *fns[6] = {(const void *)mpc_solve_tpp_kernel<0>, (const void *)mpc_solve_tpp_kernel<1>,
+        const void *fns[7] = {(const void *)mpc_solve_tpp_kernel<0>, (const void *)mpc_solve_tpp_kernel<1>,
                               (const void *)mpc_solve_tpp_kernel<2>, (const void *)mpc_solve_tppf_kernel<0>,
-                              (const void *)mpc_solve_tppf_kernel<1>, (const void *)mpc_solve_tppf_kernel<2>};
-        for (int i = 0; i < 6; i++)
-            if ((e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tpp_smem)) != cudaSuccess)
+                              (const void *)mpc_solve_tppf_kernel<1>, (const void *)mpc_solve_tppf_kernel<2>,
+                              (const void *)mpc_solve_tpp_kernel<3>};
+        // obstacle cost: one obstacle list per warp behind the kernel's own shared memory, if it fits
+        h->tpp_obs_smem = 0;
+        if (p->obs_form != B200MPC_OBS_NONE) {
+            const size_t lists = (size_t)(TPP_THREADS / 32) * 2 * (size_t)((p->M + 3) & ~3) * sizeof(double);
+            if (tpp_smem + lists <= smem_cap) h->tpp_obs_smem = lists;
+        }
+        for (int i = 0; i < 7; i++) {
+            const bool with_lists = (i == 0 || i == 6);
+            if ((e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(tpp_smem + (with_lists ? h->tpp_obs_smem : 0)))) != cudaSuccess)
                 return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
+        }
     }
+    // hand-over threshold: about twice the mean iteration count of the family (variant A ~60, variants B / C ~22)
+    // (measured, 1 M problems: variant B 198.2 -> 190.4 ms with 60 / 8; variant A: the launch no longer lasts as long as its
+    // slowest problem, 1354 -> 417 ms for 65 536 problems with one 3000-iteration straggler)
+    h->hand_iter = (p->obs_form != B200MPC_OBS_NONE) ? 192 : 60;
+    h->hand_thin = (p->obs_form != B200MPC_OBS_NONE) ? 4 : 8;
+    if (const char *eh = getenv("B200MPC_HAND_ITER")) h->hand_iter = atoi(eh);
+    if (const char *eh = getenv("B200MPC_HAND_THIN")) h->hand_thin = atoi(eh);
+    h->d_hand = nullptr; h->hand_cap = 0; h->d_hand_count = nullptr;
+    h->tpp_cta_sync = (p->obs_form != B200MPC_OBS_NONE) ? 0 : 1; // (tpp_kernel.cuh, TppArgs::cta_sync)
+    if (const char *es = getenv("B200MPC_LANE_SYNC")) h->tpp_cta_sync = (es[0] == '1');
     h->lane_fused = B200MPC_LANE_FUSED_DEFAULT;
     if (const char *ef = getenv("B200MPC_LANE_FUSED")) h->lane_fused = (ef[0] == '1');
+    if (p->obs_form != B200MPC_OBS_NONE) h->lane_fused = 0; // the two-sweep kernel has no obstacle cost
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tblocks, mpc_solve_tpp_kernel<0>, TPP_THREADS, tpp_smem)) != cudaSuccess)
         return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
     if (tblocks < 1) tblocks = 1;
@@ -2250,6 +2396,8 @@ extern "C" void b200mpc_destroy(b200mpc_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->d_buf) cudaFree(h->d_buf);
+    if (h->d_hand) cudaFree(h->d_hand);
+    if (h->d_hand_count) cudaFree(h->d_hand_count);
     if (h->d_ws) cudaFree(h->d_ws);
     if (h->d_filt) cudaFree(h->d_filt);
     if (h->d_stats) cudaFree(h->d_stats);
@@ -2330,8 +2478,6 @@ extern "C" int b200mpc_set_kernel(b200mpc_handle *h, int kind) {
     if (!h) return B200MPC_E_ARG;
     if (kind != B200MPC_KERNEL_AUTO && kind != B200MPC_KERNEL_WARP && kind != B200MPC_KERNEL_LANE)
         return set_err(h, B200MPC_E_ARG, "unknown kernel kind");
-    if (kind == B200MPC_KERNEL_LANE && h->prm.obs_form != B200MPC_OBS_NONE)
-        return set_err(h, B200MPC_E_ARG, "the lane-per-problem kernel does not carry the obstacle cost");
     h->kernel_kind = kind;
     return 0;
 }
@@ -2358,8 +2504,29 @@ struct StreamWords {
     int chunk;
 };
 
-static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stream, const StreamWords *sw = nullptr) {
+static int launch_warp_kernel(b200mpc_handle *h, const BatchArgs &a, int grid, bool scan, cudaStream_t stream);
+
+static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a_in, cudaStream_t stream, const StreamWords *sw = nullptr) {
     const int N = h->prm.N;
+    BatchArgs a = a_in;
+    // straggler hand-over (not for streamed host-buffer solves: their per-chunk completion flags count lane-kernel results)
+    const bool hand = h->hand_iter > 0 && !sw;
+    if (hand) {
+        const size_t cap = (size_t)std::max(4096, a.B / 8);
+        if (cap > h->hand_cap) {
+            if (h->d_hand) { cudaFree(h->d_hand); h->d_hand = nullptr; h->hand_cap = 0; }
+            cudaError_t e = cudaMalloc(&h->d_hand, cap * HAND_REC(N) * sizeof(double));
+            if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc(hand-over records): ") + cudaGetErrorString(e));
+            h->hand_cap = cap;
+        }
+        if (!h->d_hand_count) {
+            cudaError_t e = cudaMalloc(&h->d_hand_count, sizeof(unsigned int));
+            if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+        CU_TRY(h, cudaMemsetAsync(h->d_hand_count, 0, sizeof(unsigned int), stream));
+        a.hand_rec = h->d_hand; a.hand_count = h->d_hand_count; a.hand_cap = (int)h->hand_cap;
+        a.hand_iter = h->hand_iter; a.hand_thin = h->hand_thin;
+    }
     const size_t nwarps = (size_t)h->tpp_ctas * (TPP_THREADS / 32);
     if (!h->d_ws) {
         const size_t ws_bytes = nwarps * (size_t)(N + 1) * TPP_STAGE_B;
@@ -2380,6 +2547,9 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t 
     t.a = a; t.ws = h->d_ws; t.filt = h->d_filt; t.stats = h->d_stats;
     t.avail = sw ? sw->avail : nullptr; t.done = sw ? sw->done : nullptr; t.flags = sw ? sw->flags : nullptr;
     t.chunk = sw ? sw->chunk : 1;
+    t.cta_sync = h->lane_fused ? 1 : h->tpp_cta_sync;
+    t.obs_smem = h->tpp_obs_smem ? 1 : 0;
+    const size_t smem_obs = TPP_SMEM_BYTES + h->tpp_obs_smem;
     CU_TRY(h, cudaEventRecord(h->ev0, stream));
     const int spec = h->lane_spec;
     if (h->lane_fused) {
@@ -2388,22 +2558,37 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a, cudaStream_t 
         else mpc_solve_tppf_kernel<TPP_SPEC_GENERIC><<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
     } else {
         if (spec == TPP_SPEC_RK4_GOAL) mpc_solve_tpp_kernel<TPP_SPEC_RK4_GOAL><<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
+        else if (spec == TPP_SPEC_RK4_GOAL_OBS) mpc_solve_tpp_kernel<TPP_SPEC_RK4_GOAL_OBS><<<grid, TPP_THREADS, smem_obs, stream>>>(h->kp, t);
         else if (spec == TPP_SPEC_EULER_TRAJ) mpc_solve_tpp_kernel<TPP_SPEC_EULER_TRAJ><<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
-        else mpc_solve_tpp_kernel<TPP_SPEC_GENERIC><<<grid, TPP_THREADS, TPP_SMEM_BYTES, stream>>>(h->kp, t);
+        else mpc_solve_tpp_kernel<TPP_SPEC_GENERIC><<<grid, TPP_THREADS, smem_obs, stream>>>(h->kp, t);
     }
     CU_TRY(h, cudaGetLastError());
+    if (hand) {
+        // the problems the lane kernel handed over: warp kernel, resuming from the records (their number stays on the device)
+        BatchArgs r = a;
+        r.resume = 1;
+        CU_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), stream));
+        const int rc = launch_warp_kernel(h, r, h->ctas, false, stream);
+        if (rc) return rc;
+        h->launches++;
+    }
     CU_TRY(h, cudaEventRecord(h->ev1, stream));
     h->launches++;
     h->last_kind = B200MPC_KERNEL_LANE;
     return 0;
 }
 
-// Kernel choice: the lane-per-problem kernel needs enough problems to fill the machine with lanes; below that
-// (and whenever the obstacle cost is active) the warp-per-problem kernel is used.
+// Kernel choice: the lane-per-problem kernel needs enough problems to fill the machine with lanes; below that the
+// warp-per-problem kernel is used.  With the obstacle cost a lane-kernel launch lasts as long as its slowest problems
+// (hundreds of trips), so the crossover lies higher.
+#ifndef B200MPC_LANE_KERNEL_MIN_BATCH_OBS
+#define B200MPC_LANE_KERNEL_MIN_BATCH_OBS 131072
+#endif
 static int choose_kernel(const b200mpc_handle *h, int B) {
     int kind = h->kernel_kind;
-    if (h->prm.obs_form != B200MPC_OBS_NONE) kind = B200MPC_KERNEL_WARP;
-    else if (kind == B200MPC_KERNEL_AUTO) kind = (B >= B200MPC_LANE_KERNEL_MIN_BATCH) ? B200MPC_KERNEL_LANE : B200MPC_KERNEL_WARP;
+    const bool obs = h->prm.obs_form != B200MPC_OBS_NONE;
+    if (kind == B200MPC_KERNEL_AUTO)
+        kind = (B >= (obs ? B200MPC_LANE_KERNEL_MIN_BATCH_OBS : B200MPC_LANE_KERNEL_MIN_BATCH)) ? B200MPC_KERNEL_LANE : B200MPC_KERNEL_WARP;
     return kind;
 }
 
@@ -2420,8 +2605,16 @@ static int launch_solve(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stre
     // total work: it is used while the batch leaves warps of the persistent grid idle, i.e. when latency is what
     // the caller sees; a batch that fills the machine keeps the lane-parallel serial form (+17 % solves/s there).
     const bool scan = (h->kkt_scan_mode >= 0) ? (h->kkt_scan_mode == 1) : (a.B <= h->ctas * 4);
-    h->kp.kkt_scan = scan ? 1 : 0;
     CU_TRY(h, cudaEventRecord(h->ev0, stream));
+    const int rc = launch_warp_kernel(h, a, grid, scan, stream);
+    if (rc) return rc;
+    CU_TRY(h, cudaEventRecord(h->ev1, stream));
+    h->launches++;
+    return 0;
+}
+
+static int launch_warp_kernel(b200mpc_handle *h, const BatchArgs &a, int grid, bool scan, cudaStream_t stream) {
+    h->kp.kkt_scan = scan ? 1 : 0;
     switch (h->J) {
 #define LAUNCH_WARP(JJ, SC)                                                                                \
     do {                                                                                                    \
@@ -2436,8 +2629,6 @@ static int launch_solve(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stre
 #undef LAUNCH_WARP
     }
     CU_TRY(h, cudaGetLastError());
-    CU_TRY(h, cudaEventRecord(h->ev1, stream));
-    h->launches++;
     return 0;
 }
 
@@ -2547,7 +2738,7 @@ extern "C" int b200mpc_solve_batch(b200mpc_handle *h, int B, const double *x0, c
     double *d_X = (double *)take(sz_X), *d_U = (double *)take(sz_U), *d_c = (double *)take(sz_c);
     int *d_st = (int *)take(sz_i), *d_it = (int *)take(sz_i), *d_ls = (int *)take(sz_i);
     cudaStream_t s = h->stream;
-    if (choose_kernel(h, B) == B200MPC_KERNEL_LANE && B >= B200MPC_STREAM_MIN_BATCH && !getenv("B200MPC_NO_STREAMING") &&
+    if (choose_kernel(h, B) == B200MPC_KERNEL_LANE && B >= B200MPC_STREAM_MIN_BATCH && !getenv("B200MPC_NO_STREAMING") && !obs &&
         is_pinned(x0) && is_pinned(X_out) && is_pinned(U_out)) {
         // ---- streamed solve: inputs arrive and results leave in chunks while the persistent kernel runs ----
         // copy stream:   [chunk c inputs H2D][avail := end of chunk c] ...          (the kernel waits for `avail`)

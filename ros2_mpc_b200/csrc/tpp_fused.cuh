@@ -215,7 +215,7 @@ __device__ __forceinline__ void tppf_trial_backward(const KParams &P, char *wb, 
                     Lk[0] = -dwk * dX[0]; Lk[1] = -dwk * dX[1]; Lk[2] = -dwk * dX[2];
                 } else {
                     const double Uc[2] = {u2.x, u2.y};
-                    tpp_costate<SPEC>(P, r, X, Uc, lo, Lam, dX, duv, lsq ? 1.0 : df, dwk, !lsq, Lk);
+                    tpp_costate<SPEC>(P, r, X, Uc, lo, Lam, dX, duv, lsq ? 1.0 : df, dwk, !lsq, Lk, tpp_obs_zero());
                 }
                 Lam[0] = Lk[0]; Lam[1] = Lk[1]; Lam[2] = Lk[2];
                 chk = fma(0.0, (Lk[0] + Lk[1]) + Lk[2], chk); // 0*inf = NaN and NaN sticks: one test after the sweep

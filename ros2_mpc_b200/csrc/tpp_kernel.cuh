@@ -80,7 +80,7 @@ enum {
 #define TPP_STAGE_SLOTS 11                       /* staging rows per warp: the trial sweep needs 11 */
 #define TPP_STAGE_SMEM (TPP_STAGE_SLOTS * TPP_ROW_B) /* bytes of shared-memory staging per warp */
 
-enum { PH_LOAD = 0, PH_B = 1, PH_F = 2, PH_T = 3, PH_BACKTRACK = 4, PH_FIN = 6, PH_DONE = 7 };
+enum { PH_LOAD = 0, PH_B = 1, PH_F = 2, PH_T = 3, PH_BACKTRACK = 4, PH_EXPORT = 5, PH_FIN = 6, PH_DONE = 7 };
 enum { BM_NEWTON = 0, BM_SOC = 1, BM_LSQ = 2 };
 enum { TM_EVAL = 1, TM_LSQ = 2, TM_STEP = 3, TM_STEP_SOC = 4 };
 
@@ -156,6 +156,8 @@ struct TppArgs {
     unsigned *done;            // [chunks] finished problems per chunk
     unsigned *flags;           // [chunks] host-mapped: set to 1 when the chunk's results are complete in device memory
     int chunk;                 // problems per chunk
+    int cta_sync;              // 1: the warps of a CTA run the sweeps in lock-step (instruction cache); 0: every warp on its own
+    int obs_smem;              // 1: the dynamic shared memory has room for one obstacle list per warp (behind TPP_SMEM_BYTES)
 };
 #ifndef TPP_STATS
 #define TPP_STATS 0
@@ -191,6 +193,7 @@ struct TppLane {
     double ymax_f;                                 // LSQ mode: largest slack-multiplier estimate seen by sweep F
     double dw_b;                                   // two-sweep kernel: delta_w of the factorisation in progress
     int n_eff;                                     // obstacle cost: entries of the problem's obstacle list to walk (ObsList)
+    int hslot;                                     // hand-over (BatchArgs::hand_rec): the record this problem is exported to
 };
 #define TPP_LANE_STRIDE (((sizeof(TppLane) + 7) / 8) | 1) /* in doubles, odd */
 
@@ -409,11 +412,17 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
         const double X[3] = {x01.x, x01.y, x2l0.x};
         double lam[3] = {0, 0, 0};
         if (k >= 1) { lam[0] = x2l0.y; lam[1] = l12.x; lam[2] = l12.y; }
+        // obstacle sum of the stage at the current iterate (cache rows; zeros outside the stages that carry the cost)
+        TppObs oc = tpp_obs_zero();
+        if (TPP_HAS_OBS(P)) {
+            oc = tpp_obs_load(p, cur);
+            if (k > 1) tpp_l2_prefetch(p - 2 * TPP_STAGE_B, R_OC + 3 * cur, 3);
+        }
 #if TPP_BWD_EAGER
         TPP_BWD_PREFETCH();
 #endif
         if (k == N) {
-            // terminal stage: no cost, no controls
+            // terminal stage: no tracking cost, no controls (the obstacle cost of variant A covers it)
 #if !TPP_BWD_EAGER
             tpp_consume(x01, x2l0, l12, u2);
             TPP_BWD_PREFETCH();
@@ -421,12 +430,22 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
             q00 = dw; q01 = 0; q02 = 0; q11 = dw; q12 = 0; q22 = dw;
             if (mode == BM_LSQ) { v0 = 0; v1 = 0; v2 = 0; }
             else { v0 = lam[0]; v1 = lam[1]; v2 = lam[2]; }
+            if (TPP_HAS_OBS(P)) {
+                const double g0 = df * oc.gx, g1 = df * oc.gy;
+                v0 += g0; v1 += g1;
+                if (useW) { q00 = fma(df, oc.hxx, q00); q01 = df * oc.hxy; q11 = fma(df, oc.hyy, q11); }
+                if (mode == BM_LSQ) {
+                    fs += oc.v;
+                    if (!isfinite(g0) || !isfinite(g1)) bad = 1;
+                    gmax = fmax(gmax, fmax(fabs(g0), fabs(g1)));
+                }
+            }
         } else {
             const double U[2] = {u2.x, u2.y};
             double r[3], ub[2];
             tpp_ref<SPEC>(P, goal, p, r, ub);
             TppLin q;
-            tpp_lin<true, SPEC>(P, r, ub, X, U, ln, df, q, tpp_obs_zero());
+            tpp_lin<true, SPEC>(P, r, ub, X, U, ln, df, q, oc);
 #if !TPP_BWD_EAGER
             const double2 s2 = tpp_sld(sb, R_S), yd2 = tpp_sld(sb, R_YD), vl2 = tpp_sld(sb, R_VL), vu2 = tpp_sld(sb, R_VU);
             tpp_consume(x01, x2l0, l12, u2);
@@ -487,7 +506,7 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
                     tpp_st2(p, R_CS, rc[0], rc[1]); tpp_st2(p, R_CS + 1, rc[2], 0.0); tpp_st2(p, R_CS + 2, rd[0], rd[1]);
                 }
             }
-            const double hxx = useW ? q.hxx : 0.0, hyy = useW ? q.hyy : 0.0;
+            const double hxx = useW ? q.hxx : 0.0, hyy = useW ? q.hyy : 0.0, hxy = useW ? q.hxy : 0.0;
             const double htt = useW ? q.htt : 0.0, htv = useW ? q.htv : 0.0, htw = useW ? q.htw : 0.0;
             const double hvv = useW ? q.hvv : 0.0, hvw = useW ? q.hvw : 0.0, hww = useW ? q.hww : 0.0;
             const double a = q.a13, b = q.a23, b11 = q.b11, b12 = q.b12, b21 = q.b21, b22 = q.b22;
@@ -501,7 +520,7 @@ __device__ __forceinline__ void tpp_backward(const KParams &P, const BatchArgs &
             const double t1 = q12 + a * q01 + b * q11;
             const double t2 = q22 + a * q02 + b * q12;
             // Qxx = Hxx + A'PA
-            const double x00 = hxx + dw + q00, x01_ = q01, x11 = hyy + dw + q11;
+            const double x00 = hxx + dw + q00, x01_ = hxy + q01, x11 = hyy + dw + q11;
             const double x02 = t0, x12 = t1, x22 = htt + dw + t2 + a * t0 + b * t1;
             // PB columns
             const double e0 = b11 * q00 + b21 * q01, e1 = b11 * q01 + b21 * q11;
@@ -616,6 +635,14 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
         if (k >= 1 && (!(fabs(y0) <= TINY_STEP_TOL * (1.0 + fabs(X[0]))) || !(fabs(y1) <= TINY_STEP_TOL * (1.0 + fabs(X[1]))) ||
                        !(fabs(y2) <= TINY_STEP_TOL * (1.0 + fabs(X[2])))))
             big = 1;
+        // obstacle gradient of the stage at the current iterate (directional derivative of the objective)
+        TppObs oc = tpp_obs_zero();
+        if (TPP_HAS_OBS(P) && mode == BM_NEWTON) {
+            const double2 a = tpp_ld2(p, R_OC + 3 * cur), b = tpp_ld2(p, R_OC + 3 * cur + 1);
+            oc.gx = a.y; oc.gy = b.x;
+            if (k + 2 <= N) tpp_l2_prefetch(p + 2 * TPP_STAGE_B, R_OC + 3 * cur, 2);
+            if (k == N) gbd += df * (oc.gx * y0 + oc.gy * y1);
+        }
         if (k < N) {
             const double du0 = kf_.x + k0_.x * y0 + k0_.y * y1 + k1_.x * y2;
             const double du1 = kf_.y + k1_.y * y0 + k2_.x * y1 + k2_.y * y2;
@@ -628,7 +655,7 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
             tpp_ref<SPEC>(P, goal, p, r, ub);
             const double ln0[3] = {0, 0, 0};
             TppLin q;
-            tpp_lin<false, SPEC>(P, r, ub, X, U, ln0, df, q, tpp_obs_zero());
+            tpp_lin<false, SPEC>(P, r, ub, X, U, ln0, df, q, oc);
             double rc0, rc1, rc2, rdv[2] = {U[0] - Sv[0], U[1] - Sv[1]};
             if (mode == BM_LSQ) {
                 rc0 = rc1 = rc2 = 0;
@@ -693,7 +720,8 @@ __device__ __forceinline__ void tpp_trial_stage(char *sb, const char *p, int co,
 template <int SPEC>
 __device__ __forceinline__ void tpp_costate(const KParams &P, const double r[3], const double X[3], const double U[2],
                                             const double lo[3], const double Ln[3], const double dX[3],
-                                            const double dU[2], double df, double dw, bool useW, double Lk[3]) {
+                                            const double dU[2], double df, double dw, bool useW, double Lk[3],
+                                            const TppObs &oc) {
     const double dt = P.dt, th = X[2], v = U[0], w = U[1];
     double a13, a23, htt, htv, htw = 0;
     if (TPP_IS_EULER(P)) {
@@ -727,6 +755,15 @@ __device__ __forceinline__ void tpp_costate(const KParams &P, const double r[3],
     Lk[0] = Ln[0] - g0 - hxx * dX[0];
     Lk[1] = Ln[1] - g1 - hyy * dX[1];
     Lk[2] = Ln[2] + a13 * Ln[0] + a23 * Ln[1] - g2 - hth * dX[2] - htv * dU[0] - htw * dU[1];
+    if (TPP_HAS_OBS(P)) {
+        // obstacle sum of the stage: gradient, and (Newton system only) its Hessian block
+        Lk[0] -= df * oc.gx;
+        Lk[1] -= df * oc.gy;
+        if (useW) {
+            Lk[0] -= df * (oc.hxx * dX[0] + oc.hxy * dX[1]);
+            Lk[1] -= df * (oc.hxy * dX[0] + oc.hyy * dX[1]);
+        }
+    }
 }
 
 // ---- sweep T: write curr + alpha*step into the other iterate buffer and evaluate that point -------------------------
@@ -775,6 +812,14 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
         double X[3] = {x01.x, x01.y, x2l0.x};
         double lam[3] = {0, 0, 0};
         const double duv[2] = {du2.x, du2.y};
+        // obstacle sums of the stage: at the current iterate (costate recursion) and at the point being evaluated (the
+        // obstacle block has put them into the cache rows of the other buffer)
+        TppObs occ = tpp_obs_zero(), oct = tpp_obs_zero();
+        if (TPP_HAS_OBS(P)) {
+            if (step || lsq) occ = tpp_obs_load(p, cur);
+            oct = tpp_obs_load(p, 1 - cur);
+            if (k > 1) tpp_l2_prefetch(p - 2 * TPP_STAGE_B, R_OC, 6);
+        }
         if (k >= 1) {
             lam[0] = x2l0.y; lam[1] = l12.x; lam[2] = l12.y;
             const double lcur[3] = {lam[0], lam[1], lam[2]};
@@ -783,18 +828,27 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
                 const double dwk = lsq ? 1.0 : dw;
                 double Lk[3];
                 if (k == N) {
-                    // terminal stage: no cost, no controls
+                    // terminal stage: no tracking cost, no controls
                     Lk[0] = -dwk * dX[0]; Lk[1] = -dwk * dX[1]; Lk[2] = -dwk * dX[2];
+                    if (TPP_HAS_OBS(P)) {
+                        const double dfv = lsq ? 1.0 : df;
+                        Lk[0] -= dfv * occ.gx;
+                        Lk[1] -= dfv * occ.gy;
+                        if (!lsq) {
+                            Lk[0] -= dfv * (occ.hxx * dX[0] + occ.hxy * dX[1]);
+                            Lk[1] -= dfv * (occ.hxy * dX[0] + occ.hyy * dX[1]);
+                        }
+                    }
                 } else {
                     const double Uc[2] = {u2.x, u2.y};
-                    tpp_costate<SPEC>(P, r, X, Uc, lo, Lam, dX, duv, lsq ? 1.0 : df, dwk, !lsq, Lk);
+                    tpp_costate<SPEC>(P, r, X, Uc, lo, Lam, dX, duv, lsq ? 1.0 : df, dwk, !lsq, Lk, occ);
                 }
                 Lam[0] = Lk[0]; Lam[1] = Lk[1]; Lam[2] = Lk[2];
                 if (!isfinite(Lk[0]) || !isfinite(Lk[1]) || !isfinite(Lk[2])) bad = 1;
                 if (step) {
 #pragma unroll
                     for (int i = 0; i < 3; i++) {
-                        X[i] += alpha * dX[i];
+                        X[i] = fma(alpha, dX[i], X[i]); // (the obstacle block forms the same point with the same operation)
                         const double dl = Lk[i] - lam[i];
                         dymax = fmax(dymax, fabs(dl));
                         lam[i] += alpha * dl;
@@ -844,7 +898,7 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
             tpp_st2(pw, R_U, U[0], U[1]); tpp_st2(pw, R_S, S[0], S[1]); tpp_st2(pw, R_YD, yd[0], yd[1]);
             tpp_st2(pw, R_VL, vL[0], vL[1]); tpp_st2(pw, R_VU, vU[0], vU[1]);
             TppLin q;
-            tpp_lin<false, SPEC>(P, r, ub, X, U, ln, df, q, tpp_obs_zero());
+            tpp_lin<false, SPEC>(P, r, ub, X, U, ln, df, q, oct);
             const double c[3] = {Xn[0] - q.F0, Xn[1] - q.F1, Xn[2] - q.F2};
             fs += q.f;
 #pragma unroll
@@ -882,8 +936,15 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
             // barrier term: one logarithm per stage; a slack outside its bounds gives NaN like log(negative) would
             slog += log(inside ? prod : -1.0);
         } else if (k >= 1) {
-            // terminal state: no cost; its stationarity residual is the multiplier itself
-            di = fmax(di, fmax(fabs(lam[0]), fmax(fabs(lam[1]), fabs(lam[2]))));
+            // terminal state: no tracking cost; its stationarity residual is the multiplier itself (plus the gradient of
+            // the obstacle sum, where the terminal stage carries it)
+            double r0 = lam[0], r1 = lam[1];
+            if (TPP_HAS_OBS(P)) {
+                r0 = fma(df, oct.gx, r0);
+                r1 = fma(df, oct.gy, r1);
+                fs += oct.v;
+            }
+            di = fmax(di, fmax(fabs(r0), fmax(fabs(r1), fabs(lam[2]))));
             sy += fabs(lam[0]) + fabs(lam[1]) + fabs(lam[2]);
         }
         Xn[0] = X[0]; Xn[1] = X[1]; Xn[2] = X[2];
@@ -894,6 +955,65 @@ __device__ __forceinline__ void tpp_trial(const KParams &P, const BatchArgs &A, 
     o.ymax = ymax; o.dymax = dymax; o.bad = bad;
     o.n.theta = th; o.n.prim_inf = pi; o.n.dual_inf = di; o.n.sum_y = sy; o.n.sum_z = sz;
     o.n.pmin = pmin; o.n.pmax = pmax; o.n.f = fs; o.n.slog = slog;
+}
+
+// ---- obstacle block: the obstacle sums the next sweep needs, for the lanes in `mask` ---------------------------------------
+// One problem at a time, by the whole warp with lane <-> stage (obstacle_eval of b200mpc.cu, the routine of the warp kernel):
+// the problem's obstacle list is read straight from the caller's arrays (every lane reads the same entry: one broadcast
+// transaction, served by L1 after the first stage touched it), the stage's position comes from the lane's column of the
+// workspace,  point = X of buffer `cur` (+ alpha * the step in rows `srow`, when srow >= 0),  and value / gradient / Hessian
+// go to the cache rows of buffer `dst`.  A lane-per-problem walk would have to re-read each lane's 2.5 KB list for every
+// stage (or tile the stages); this way a list is read once per evaluation, the padding fold (n_eff) is per problem, and
+// lanes that are not about to evaluate a point cost nothing.
+// copy_rows: the point does not move (multiplier estimate): the cache rows are copied instead.
+// the first n entries of a problem's obstacle list -> the warp's list buffer in shared memory (olist; NULL: stay in global)
+__device__ __forceinline__ void tpp_stage_list(const double *&gx, const double *&gy, int n, double *olist, int Mpad) {
+    if (!olist) return;
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) { olist[i] = gx[i]; olist[Mpad + i] = gy[i]; }
+    __syncwarp();
+    gx = olist; gy = olist + Mpad;
+}
+
+template <int SPEC>
+__device__ __noinline__ void tpp_obstacle_block(const KParams &P, const BatchArgs &A, char *wbase, unsigned mask, int cur,
+                                                int dst, int b_mine, int neff_mine, double alpha_mine, int srow_mine,
+                                                int copy_mine, double *olist) {
+    const int lane = threadIdx.x & 31, N = P.N;
+    const int co = cur * R_ITER;
+    const int Mpad = (P.M + 3) & ~3;
+    for (unsigned m = mask; m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        const size_t b = (size_t)__shfl_sync(FULL, b_mine, j);
+        const int ne = __shfl_sync(FULL, neff_mine, j);
+        const double al = __shfl_sync(FULL, alpha_mine, j);
+        const int sr = __shfl_sync(FULL, srow_mine, j);
+        const int cp = __shfl_sync(FULL, copy_mine, j);
+        const double *gx = A.ox + (size_t)A.obs_stride * b, *gy = A.oy + (size_t)A.obs_stride * b;
+        if (!cp) tpp_stage_list(gx, gy, ne, olist, Mpad);
+        const double w0 = 1.0 + (double)(P.M - ne);
+        for (int k = lane; k <= N; k += 32) {
+            char *p = wbase + (size_t)k * TPP_STAGE_B + j * 16;
+            if (cp) {
+                const double2 a = tpp_ld2(p, R_OC + 3 * cur), c = tpp_ld2(p, R_OC + 3 * cur + 1), d = tpp_ld2(p, R_OC + 3 * cur + 2);
+                tpp_st2(p, R_OC + 3 * dst, a.x, a.y); tpp_st2(p, R_OC + 3 * dst + 1, c.x, c.y); tpp_st2(p, R_OC + 3 * dst + 2, d.x, d.y);
+                continue;
+            }
+            const double2 x = tpp_ld2(p + co * TPP_ROW_B, R_X01);
+            double px = x.x, py = x.y;
+            if (sr >= 0) {
+                const double2 d = tpp_ld2(p, sr);
+                px = fma(al, d.x, px);
+                py = fma(al, d.y, py);
+            }
+            double o6[6] = {0, 0, 0, 0, 0, 0};
+            if (k >= P.obs_k0 && k <= P.obs_k1) obstacle_eval(P.obs_form, P.obs_c, P.inv_r2, gx, gy, ne, w0, px, py, o6);
+            tpp_st2(p, R_OC + 3 * dst, o6[0], o6[1]); tpp_st2(p, R_OC + 3 * dst + 1, o6[2], o6[3]);
+            tpp_st2(p, R_OC + 3 * dst + 2, o6[4], o6[5]);
+        }
+    }
+    __syncwarp();
 }
 
 // ---- filter (32 entries per lane, kept in the workspace) --------------------------------------------------------------
@@ -1110,6 +1230,170 @@ __device__ __forceinline__ void tpp_restore(const KParams &P, char *wb, double *
     L.phase = PH_T;
 }
 
+// Restoration stand-in of the instances with the obstacle cost: the same rule, but every candidate needs the obstacle sums of
+// all stages, so the WARP evaluates the candidates of one problem at a time (lane <-> stage, sums by butterfly reductions)
+// while the problem's own lane builds the directions, keeps its filter and takes the decisions.
+// tpp_resto_eval_coop: theta, objective and log-barrier sum of  current + t * direction  of the problem in column wbj.
+template <int SPEC>
+__device__ __forceinline__ void tpp_resto_eval_coop(const KParams &P, const double *gx, const double *gy, int n_eff, const char *wbj,
+                                                    int co, const double goal[3], double t, int move_s, double &th_out,
+                                                    double &f_out, double &slog_out) {
+    const int lane = threadIdx.x & 31, N = P.N;
+    const double w0 = 1.0 + (double)(P.M - n_eff);
+    double th = 0, fs = 0, slog = 0;
+    for (int k = lane; k <= N; k += 32) {
+        const char *p = wbj + (size_t)k * TPP_STAGE_B;
+        const char *pc = p + co * TPP_ROW_B;
+        const double2 x01 = tpp_ld2(pc, R_X01), x2 = tpp_ld2(pc, R_X2L0), dx01 = tpp_ld2(p, R_SSTEP), dx2 = tpp_ld2(p, R_SSTEP + 1);
+        const double X[3] = {x01.x + t * dx01.x, x01.y + t * dx01.y, x2.x + t * dx2.x}; // (the direction rows of stage 0 are zero)
+        TppObs oc = tpp_obs_zero();
+        if (k >= P.obs_k0 && k <= P.obs_k1) {
+            double o6[6];
+            obstacle_eval(P.obs_form, P.obs_c, P.inv_r2, gx, gy, n_eff, w0, X[0], X[1], o6);
+            oc.v = o6[0];
+        }
+        if (k < N) {
+            const double2 u2 = tpp_ld2(pc, R_U), s2 = tpp_ld2(pc, R_S), du2 = tpp_ld2(p, R_SSTEP + 2);
+            const double2 n01 = tpp_ld2(pc + TPP_STAGE_B, R_X01), n2 = tpp_ld2(pc + TPP_STAGE_B, R_X2L0);
+            const double2 d01 = tpp_ld2(p + TPP_STAGE_B, R_SSTEP), d2 = tpp_ld2(p + TPP_STAGE_B, R_SSTEP + 1);
+            const double U[2] = {u2.x + t * du2.x, u2.y + t * du2.y};
+            double S[2] = {s2.x, s2.y};
+            if (move_s) {
+                S[0] = s2.x + t * (du2.x + (u2.x - s2.x));
+                S[1] = s2.y + t * (du2.y + (u2.y - s2.y));
+                const double l0 = S[0] - P.sL[0], l1 = P.sU[0] - S[0], l2 = S[1] - P.sL[1], l3 = P.sU[1] - S[1];
+                const bool inside = (l0 > 0.0) && (l1 > 0.0) && (l2 > 0.0) && (l3 > 0.0);
+                slog += log(inside ? (l0 * l1) * (l2 * l3) : -1.0);
+            }
+            const double Xn[3] = {n01.x + t * d01.x, n01.y + t * d01.y, n2.x + t * d2.x};
+            double r[3], ub[2];
+            tpp_ref<SPEC>(P, goal, p, r, ub);
+            const double ln0[3] = {0, 0, 0};
+            TppLin q;
+            tpp_lin<false, SPEC>(P, r, ub, X, U, ln0, 1.0, q, oc);
+            th += fabs(Xn[0] - q.F0) + fabs(Xn[1] - q.F1) + fabs(Xn[2] - q.F2) + fabs(U[0] - S[0]) + fabs(U[1] - S[1]);
+            fs += q.f;
+        } else {
+            fs += oc.v;
+        }
+    }
+    __syncwarp();
+    th_out = wsum(th); f_out = wsum(fs); slog_out = wsum(slog);
+}
+
+template <int SPEC>
+__device__ __noinline__ void tpp_restore_obs(const KParams &P, const BatchArgs &A, char *wbase, double *fl, int cur, TppLane &L,
+                                             unsigned mask, double *olist) {
+    const int lane = threadIdx.x & 31, N = P.N;
+    const int Mpad = (P.M + 3) & ~3;
+    const int co = cur * R_ITER, no = R_ITER - co;
+    double uc[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const double lo = P.sL[i], hi = P.sU[i];
+        const double pl = fmin(BOUND_PUSH * fmax(1.0, fabs(lo)), BOUND_FRAC * (hi - lo));
+        const double pu = fmin(BOUND_PUSH * fmax(1.0, fabs(hi)), BOUND_FRAC * (hi - lo));
+        uc[i] = fmin(fmax(0.0, lo + pl), hi - pu);
+    }
+    for (unsigned m = mask; m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        char *wbj = wbase + j * 16; // the problem's column of the workspace
+        int go = 0;
+        double zm = 0;
+        if (lane == j) {
+            if (L.theta <= 1e-10 || L.n_resto >= MAX_RESTO) { L.status = B200MPC_RESTORATION_FAILED; L.phase = PH_FIN; }
+            else {
+                tpp_filter_add(fl, L, L.ref_phi - GAMMA_PHI * L.theta, (1 - GAMMA_THETA) * L.theta);
+                zm = tpp_resto_direction<SPEC>(P, wbj, co, -1.0, 0.0, 0.0);
+                go = 1;
+            }
+        }
+        __syncwarp();
+        if (!__shfl_sync(FULL, go, j)) continue;
+        const size_t pb = (size_t)__shfl_sync(FULL, L.b, j);
+        const int ne = __shfl_sync(FULL, L.n_eff, j);
+        const double theta = __shfl_sync(FULL, L.theta, j), df = __shfl_sync(FULL, L.df, j), mu = __shfl_sync(FULL, L.mu, j);
+        const double slog_cur = __shfl_sync(FULL, L.slog, j), phi_ref = __shfl_sync(FULL, L.ref_phi, j);
+        const double goal[3] = {__shfl_sync(FULL, L.goal[0], j), __shfl_sync(FULL, L.goal[1], j), __shfl_sync(FULL, L.goal[2], j)};
+        const double *gx = A.ox + (size_t)A.obs_stride * pb, *gy = A.oy + (size_t)A.obs_stride * pb;
+        tpp_stage_list(gx, gy, ne, olist, Mpad);
+        double t_acc = 0.0;
+        int move_s = 0;
+        for (double t = 1.0; t >= RESTO_T_MIN; t *= 0.5) {
+            double th_r, f_r, sl_r;
+            tpp_resto_eval_coop<SPEC>(P, gx, gy, ne, wbj, co, goal, t, 0, th_r, f_r, sl_r);
+            const double phi_r = df * f_r - mu * slog_cur; // the slacks do not move: the barrier term is the current one
+            int ok = 0;
+            if (lane == j) {
+                ok = isfinite(th_r) && isfinite(phi_r) && (th_r <= KAPPA_RESTO * theta);
+                if (ok && phi_r > phi_ref) {
+                    double bas = 1.0;
+                    if (fabs(phi_ref) > 10.0) bas = tpp_log10(fabs(phi_ref));
+                    if (tpp_log10(phi_r - phi_ref) > OBJ_MAX_INC + bas) ok = 0;
+                }
+                if (ok && !tpp_filter_ok(fl, L.fmask, phi_r, th_r)) ok = 0;
+            }
+            if (__shfl_sync(FULL, ok, j)) { t_acc = t; break; }
+        }
+        if (t_acc == 0.0) {
+            double lam = 0.5, best = __longlong_as_double(0x7ff0000000000000ll), lam_best = -1.0;
+            for (;;) {
+                if (lane == j) (void)tpp_resto_direction<SPEC>(P, wbj, co, lam, uc[0], uc[1]);
+                __syncwarp();
+                double th_r, f_r, sl_r;
+                tpp_resto_eval_coop<SPEC>(P, gx, gy, ne, wbj, co, goal, 1.0, 1, th_r, f_r, sl_r);
+                const double phi_r = df * f_r - mu * sl_r;
+                int ok = 0;
+                if (lane == j)
+                    ok = isfinite(th_r) && isfinite(phi_r) && (th_r <= KAPPA_RESTO * theta) && (phi_r < best) &&
+                         tpp_filter_ok(fl, L.fmask, phi_r, th_r);
+                if (__shfl_sync(FULL, ok, j)) { best = phi_r; lam_best = lam; }
+                if (lam == 0.0) break;
+                lam = (lam * 0.5 >= RESTO_T_MIN) ? lam * 0.5 : 0.0;
+            }
+            if (lam_best >= 0.0) {
+                if (lane == j) (void)tpp_resto_direction<SPEC>(P, wbj, co, lam_best, uc[0], uc[1]);
+                __syncwarp();
+                t_acc = 1.0;
+                move_s = 1;
+            }
+        }
+        if (t_acc == 0.0) {
+            if (lane == j) { L.status = B200MPC_RESTORATION_FAILED; L.phase = PH_FIN; }
+            continue;
+        }
+        // the accepted point goes to the other iterate buffer (stage-parallel), its obstacle sums to that buffer's cache rows
+        const bool reset = __shfl_sync(FULL, zm, j) > 1e3;
+        for (int k = lane; k <= N; k += 32) {
+            const char *p = wbj + (size_t)k * TPP_STAGE_B;
+            const char *pc = p + co * TPP_ROW_B;
+            char *pw = wbj + (size_t)k * TPP_STAGE_B + no * TPP_ROW_B;
+            const double2 x01 = tpp_ld2(pc, R_X01), x2 = tpp_ld2(pc, R_X2L0), d01 = tpp_ld2(p, R_SSTEP), d2 = tpp_ld2(p, R_SSTEP + 1);
+            tpp_st2(pw, R_X01, fma(t_acc, d01.x, x01.x), fma(t_acc, d01.y, x01.y));
+            tpp_st2(pw, R_X2L0, x2.x + t_acc * d2.x, 0.0);
+            tpp_st2(pw, R_L12, 0.0, 0.0);
+            if (k < N) {
+                const double2 u = tpp_ld2(pc, R_U), du = tpp_ld2(p, R_SSTEP + 2), sv = tpp_ld2(pc, R_S), a = tpp_ld2(pc, R_VL), c = tpp_ld2(pc, R_VU);
+                double S[2] = {sv.x, sv.y};
+                if (move_s) { S[0] = sv.x + t_acc * (du.x + (u.x - sv.x)); S[1] = sv.y + t_acc * (du.y + (u.y - sv.y)); }
+                tpp_st2(pw, R_U, u.x + t_acc * du.x, u.y + t_acc * du.y); tpp_st2(pw, R_S, S[0], S[1]); tpp_st2(pw, R_YD, 0.0, 0.0);
+                tpp_st2(pw, R_VL, reset ? 1.0 : a.x, reset ? 1.0 : a.y);
+                tpp_st2(pw, R_VU, reset ? 1.0 : c.x, reset ? 1.0 : c.y);
+            }
+        }
+        __syncwarp();
+        tpp_obstacle_block<SPEC>(P, A, wbase, 1u << j, cur, 1 - cur, L.b, L.n_eff, t_acc, R_SSTEP, 0, olist);
+        if (lane == j) {
+            L.moved = 1;
+            L.n_resto++;
+            L.iter++;
+            L.tmode = TM_EVAL;
+            L.phase = PH_T;
+        }
+    }
+    __syncwarp();
+}
+
 // Top of an interior-point iteration: convergence tests, barrier update; leaves the lane in phase B (Newton) or
 // finishes the problem.  n = residual norms of the (new) current iterate.
 __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L, const TppNorms &n) {
@@ -1172,7 +1456,11 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L, co
 #define TPP_SYNC 1
 #endif
 #if TPP_SYNC == 1
-#define TPP_BLOCK_SYNC() __syncthreads()
+#define TPP_BLOCK_SYNC()                     \
+    do {                                     \
+        if (T.cta_sync) __syncthreads();     \
+        else __syncwarp();                   \
+    } while (0)
 #else
 #define TPP_BLOCK_SYNC() __syncwarp() /* TPP_SYNC == 2: the CTA only meets once per trip (at the exit test) */
 #endif
@@ -1194,6 +1482,8 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
     L.phase = PH_LOAD;
     L.b = -1;
     L.moved = 0;
+    // obstacle cost: the warp's list buffer (the list of the problem whose sums the warp is forming)
+    double *olist = (TPP_HAS_OBS(P) && T.obs_smem) ? reinterpret_cast<double *>(tpp_smem + TPP_SMEM_BYTES) + (size_t)wid * 2 * ((P.M + 3) & ~3) : nullptr;
     int cur = 0; // warp-uniform: the buffer holding the current iterates during this trip
 
     for (;;) {
@@ -1273,8 +1563,20 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             }
         }
         __syncwarp();
+        if (TPP_HAS_OBS(P)) {
+            // new problems: length of the obstacle list without its padding, obstacle sums of the starting point
+            const unsigned nm = __ballot_sync(FULL, newb >= 0);
+            for (unsigned m = nm; m; m &= m - 1) {
+                const int j = __ffs(m) - 1;
+                const size_t b = (size_t)__shfl_sync(FULL, newb, j);
+                const ObsList OL = obstacle_list_setup(A.ox + (size_t)A.obs_stride * b, A.oy + (size_t)A.obs_stride * b, P.M, lane);
+                if (lane == j) L.n_eff = OL.n_eff;
+            }
+            __syncwarp();
+            if (nm) tpp_obstacle_block<SPEC>(P, A, wbase, nm, cur, cur, L.b, L.n_eff, 0.0, -1, 0, olist);
+        }
 #if TPP_SYNC
-        if (__syncthreads_and(L.phase == PH_DONE)) break;
+        if (T.cta_sync ? __syncthreads_and(L.phase == PH_DONE) : __all_sync(FULL, L.phase == PH_DONE)) break;
 #else
         if (__all_sync(FULL, L.phase == PH_DONE)) break;
 #endif
@@ -1356,6 +1658,28 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             }
         }
 
+        // ---- block O: obstacle sums of the points sweep T is about to evaluate (into the cache rows of the other buffer) ----
+        if (TPP_HAS_OBS(P)) {
+            TPP_BLOCK_SYNC();
+            const int tm = L.tmode;
+            const unsigned om = __ballot_sync(FULL, tpp_opaque(L.phase) == PH_T);
+            if (om) {
+                const int srow = (tm == TM_STEP) ? R_STEP : ((tm == TM_STEP_SOC) ? R_SSTEP : -1);
+                const double al = (tm == TM_STEP_SOC) ? L.alpha_soc : L.alpha;
+                // multiplier estimate / evaluation after a restoration: the point is the current one, whose sums are cached
+                const int cp = (tm == TM_LSQ || tm == TM_EVAL) ? 1 : 0;
+                tpp_obstacle_block<SPEC>(P, A, wbase, om, cur, 1 - cur, L.b, L.n_eff, al, srow, cp, olist);
+            }
+        }
+
+        // hand-over threshold of this trip: hand_iter iterations; 0 once the work queue is empty and the warp has thinned out
+        int hcap = A.hand_iter;
+        if (A.hand_rec) {
+            const int ph = tpp_opaque(L.phase);
+            const unsigned act = __ballot_sync(FULL, ph != PH_DONE && ph != PH_LOAD);
+            if (__popc(act) <= A.hand_thin && *reinterpret_cast<volatile unsigned *>(A.counter) >= (unsigned)A.B) hcap = 0;
+        }
+
         // ---- block T ----
         TPP_BLOCK_SYNC();
         if (tpp_opaque(L.phase) == PH_T) {
@@ -1417,21 +1741,36 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 }
             }
             if (accepted) {
-                // top of the next iteration: convergence tests, barrier update
                 L.moved = 1;
-                tpp_iterate_top(P, L, t.n);
+                // a straggler leaves for the warp kernel here, at the top of an iteration, with its state as it stands
+                bool leave = false;
+                if (A.hand_rec && L.iter >= hcap) {
+                    const unsigned slot = atomicAdd(A.hand_count, 1u);
+                    if (slot < (unsigned)A.hand_cap) { L.hslot = (int)slot; L.phase = PH_EXPORT; leave = true; }
+                }
+                // top of the next iteration: convergence tests, barrier update
+                if (!leave) tpp_iterate_top(P, L, t.n);
             }
         }
 
         // ---- rare: backtracking / restoration stand-in ----
         __syncwarp();
-        if (tpp_opaque(L.phase) == PH_BACKTRACK) {
-            L.alpha *= 0.5;
-            if (L.alpha < L.a_min) {
+        {
+            int resto = 0;
+            if (tpp_opaque(L.phase) == PH_BACKTRACK) {
+                L.alpha *= 0.5;
+                if (L.alpha < L.a_min) {
+                    resto = 1;
+                } else {
+                    L.tmode = TM_STEP;
+                    L.phase = PH_T;
+                }
+            }
+            if (TPP_HAS_OBS(P)) {
+                const unsigned rm = __ballot_sync(FULL, resto);
+                if (rm) tpp_restore_obs<SPEC>(P, A, wbase, fl, cur, L, rm, olist);
+            } else if (resto) {
                 tpp_restore<SPEC>(P, wb, fl, cur, L);
-            } else {
-                L.tmode = TM_STEP;
-                L.phase = PH_T;
             }
         }
 
@@ -1457,6 +1796,32 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                     if (k < N) u = tpp_ld2(pc, R_U);
                     xo[3 * k] = a.x; xo[3 * k + 1] = a.y; xo[3 * k + 2] = c.x;
                     if (k < N) uo[k] = u;
+                }
+            }
+            // hand-over records: iterate rows of the new current buffer, filter, solver scalars
+            if (A.hand_rec) {
+                const bool ex = (ph == PH_EXPORT);
+                for (unsigned m = __ballot_sync(FULL, ex); m; m &= m - 1) {
+                    const int j = __ffs(m) - 1;
+                    const int co = __shfl_sync(FULL, myco, j);
+                    double *hr = A.hand_rec + (size_t)__shfl_sync(FULL, L.hslot, j) * HAND_REC(N);
+                    for (int k = lane; k <= N; k += 32) {
+                        const char *pc = wbase + (size_t)k * TPP_STAGE_B + co * TPP_ROW_B + j * 16;
+                        double2 *o = reinterpret_cast<double2 *>(hr + 16 * k);
+#pragma unroll
+                        for (int f = 0; f < R_ITER; f++) o[f] = tpp_ld2(pc, f);
+                    }
+                    const double *flj = T.filt + gw * (64 * 32) + j;
+                    hr[HAND_FILT(N) + lane] = flj[lane * 32];
+                    hr[HAND_FILT(N) + 32 + lane] = flj[(32 + lane) * 32];
+                }
+                if (ex) {
+                    double *q = A.hand_rec + (size_t)L.hslot * HAND_REC(N) + HAND_SCAL(N);
+                    q[HS_B] = (double)L.b; q[HS_MU] = L.mu; q[HS_DF] = L.df; q[HS_THETA0] = L.theta0; q[HS_DWLAST] = L.dw_last;
+                    q[HS_ITER] = (double)L.iter; q[HS_LS] = (double)L.ls_extra; q[HS_NRESTO] = (double)L.n_resto;
+                    q[HS_ACCEPT] = (double)L.acceptable_count; q[HS_TINYLAST] = (double)L.tiny_last;
+                    q[HS_TINYFLAG] = (double)L.tiny_flag; q[HS_FMASK] = (double)L.fmask; q[HS_RING] = (double)L.ring;
+                    L.phase = PH_LOAD;
                 }
             }
             if (fin) {
@@ -1495,6 +1860,14 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                     for (int f = 0; f < R_ITER; f++) v[f] = tpp_ld2(pc, f);
 #pragma unroll
                     for (int f = 0; f < R_ITER; f++) tpp_st2(pw, f, v[f].x, v[f].y);
+                    if (TPP_HAS_OBS(P)) {
+                        char *ps = wbase + (size_t)k * TPP_STAGE_B + j * 16;
+#pragma unroll
+                        for (int f = 0; f < 3; f++) {
+                            const double2 c = tpp_ld2(ps, R_OC + 3 * cur + f);
+                            tpp_st2(ps, R_OC + 3 * (1 - cur) + f, c.x, c.y);
+                        }
+                    }
                 }
             }
             L.moved = 0;
