@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--no-latency", action="store_true", help="skip the 300 single solves (profiling runs)")
     ap.add_argument("--ref-sample", type=int, default=0, help="problems per step of the reference arm (0 = auto)")
     ap.add_argument("--no-variant-a", action="store_true", help="skip the second record (obstacle-active variant A)")
+    ap.add_argument("--a-seeds", type=int, default=64, help="warm-start seeds of the variant-A config-4 batch (x 4096 robots)")
     return ap.parse_args()
 
 
@@ -411,7 +412,7 @@ def costmap_lines(solver, torch, dev, params, hbm_peak, robots=4096, tile=32, re
     return out
 
 
-def variant_a_record(torch, dev, params, local_rank, fp64_peak, steps, do_cpu):
+def variant_a_record(torch, dev, params, local_rank, fp64_peak, steps, do_cpu, a_seeds=64):
     """Second record (rank 0, one GPU): the obstacle-active variant A (mpc_point_stabilization.py: exp(c/s) over 31 x 160
     stage-obstacle pairs), config 3 (4096 problems, one launch at a time and double-buffered over two handles / streams so
     that the stragglers of one batch overlap the next) and a config-4-style batch (4096 robots x 16 seeds), with roofline,
@@ -484,21 +485,28 @@ def variant_a_record(torch, dev, params, local_rank, fp64_peak, steps, do_cpu):
     rec["config3"]["e2e"] = {"value": int(np.isin(oh["status"], (0, 1)).sum()) / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                              "h2d_bytes_per_step": inb * B3, "d2h_bytes_per_step": outb * B3}
     del d3a, d3b
-    # config-4-style batch
-    wl4 = build_workload("A", 4096, 16, 0, params)
+    # config-4-style batch: 4096 robots x 64 warm-start seeds.  From 131 072 problems on the automatic choice is the
+    # lane-per-problem kernel with the obstacle cost (+ the warp kernel resuming the stragglers it hands over).
+    wl4 = build_workload("A", 4096, a_seeds, 0, params)
     d4 = dev_buffers(wl4)
     B4 = wl4["B"]
     launch(S1, d4, B4, s1)
     ms4 = time_steps([(S1, d4, s1)], B4, 3)
+    kind4 = S1.last_kernel_kind
     st4 = d4["status"].cpu().numpy(); it4 = d4["iters"].cpu().numpy(); ls4 = d4["ls"].cpu().numpy()
     conv4 = int(np.isin(st4, (0, 1)).sum())
     W4 = float(algorithmic_flops(p, it4, ls4).sum())
+    out4 = {k: d4[k].cpu().numpy() for k in ("X", "U", "cost", "status", "iters")}
     rec["config4"] = {
-        "workload": "config4 with the obstacle-active variant: 4096 robots x 16 warm-start seeds = 65536 problems",
-        "problems": B4, "converged_fraction": conv4 / B4, "mean_iterations": float(it4.mean()), "ms_per_step": ms4,
-        "value": conv4 / (ms4 * 1e-3), "unit": UNIT,
+        "workload": f"config4 with the obstacle-active variant: 4096 robots x {a_seeds} warm-start seeds = {B4} problems",
+        "kernel": ("mpc_solve_tpp_kernel<3> (lane per problem, obstacle sums by the warp into per-stage cache rows) + "
+                   "mpc_solve_kernel<1,true,false> resuming the stragglers") if kind4 == _shim.KERNEL_LANE else rec["kernel"],
+        "problems": B4, "converged_fraction": conv4 / B4, "mean_iterations": float(it4.mean()), "max_iterations": int(it4.max()),
+        "ms_per_step": ms4, "value": conv4 / (ms4 * 1e-3), "unit": UNIT,
+        "status_counts": {int(k): int(v) for k, v in zip(*np.unique(st4, return_counts=True))},
         "roofline": {"bound": "fp64", "achieved": W4 / (ms4 * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": W4 / (ms4 * 1e-3) / 1e12 / fp64_peak if fp64_peak else None, "algorithmic_flops_per_launch": W4},
+        "parity": parity_sample("A", params, wl4, out4, n=256),
     }
     S1.close(); S2.close()
     if do_cpu:
@@ -757,7 +765,8 @@ def main():
     torch.cuda.empty_cache()
     if rank == 0:
         if world == 1 and not args.no_variant_a:
-            line["variant_a"] = variant_a_record(torch, dev, params, local_rank, fp64_peak, args.steps, not args.no_cpu_baseline)
+            line["variant_a"] = variant_a_record(torch, dev, params, local_rank, fp64_peak, args.steps, not args.no_cpu_baseline,
+                                                 a_seeds=args.a_seeds)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

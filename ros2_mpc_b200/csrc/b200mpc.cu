@@ -2529,7 +2529,7 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a_in, cudaStream
     }
     const size_t nwarps = (size_t)h->tpp_ctas * (TPP_THREADS / 32);
     if (!h->d_ws) {
-        const size_t ws_bytes = nwarps * (size_t)(N + 1) * TPP_STAGE_B;
+        const size_t ws_bytes = nwarps * (size_t)(N + 1) * TPP_STAGE_B_MAX;
         cudaError_t e = cudaMalloc(&h->d_ws, ws_bytes);
         if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e));
         e = cudaMalloc(&h->d_filt, nwarps * 64 * 32 * sizeof(double));
@@ -2549,6 +2549,7 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a_in, cudaStream
     t.chunk = sw ? sw->chunk : 1;
     t.cta_sync = h->lane_fused ? 1 : h->tpp_cta_sync;
     t.obs_smem = h->tpp_obs_smem ? 1 : 0;
+    t.stage_b = (h->lane_spec == TPP_SPEC_GENERIC || h->lane_spec == TPP_SPEC_RK4_GOAL_OBS) ? TPP_STAGE_B_OF(TPP_SPEC_GENERIC) : TPP_STAGE_B_OF(TPP_SPEC_RK4_GOAL);
     const size_t smem_obs = TPP_SMEM_BYTES + h->tpp_obs_smem;
     CU_TRY(h, cudaEventRecord(h->ev0, stream));
     const int spec = h->lane_spec;

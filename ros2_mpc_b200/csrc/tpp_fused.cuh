@@ -33,6 +33,7 @@ enum { PHF_LOAD = 0, PHF_TB = 1, PHF_F = 2, PHF_BACKTRACK = 4, PHF_FIN = 6, PHF_
 enum { TMF_INIT = 0, TMF_EVAL = 1, TMF_LSQ = 2, TMF_STEP = 3, TMF_STEP_SOC = 4, TMF_HOLD = 5 };
 
 // ---- sweep F (as tpp_forward, gains kf = kf_a + mu kf_b, iterate read from buffer `buf`) ----------------------------
+template <int SPEC>
 __device__ __forceinline__ void tppf_forward_stage(char *sb, const char *p, int co, bool has_next) {
 #pragma unroll
     for (int i = 0; i < 4; i++) tpp_cp16(sb + i * TPP_ROW_B, p + (R_K + i) * TPP_ROW_B);
@@ -65,7 +66,7 @@ __device__ __forceinline__ void tppf_forward(const KParams &P, char *wb, char *s
         const double2 a = tpp_ld2(wb + co * TPP_ROW_B, R_X01), b = tpp_ld2(wb + co * TPP_ROW_B, R_X2L0);
         X[0] = a.x; X[1] = a.y; X[2] = b.x;
     }
-    tppf_forward_stage(sb, wb, co, N > 0);
+    tppf_forward_stage<SPEC>(sb, wb, co, N > 0);
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
         const int mode = tpp_opaque(bmode0);
@@ -77,7 +78,7 @@ __device__ __forceinline__ void tppf_forward(const KParams &P, char *wb, char *s
         tpp_consume(k0_, k1_, k2_, kfa_);
         tpp_consume(kfb_, u2, s2, vl2);
         tpp_consume(vu2, xn01, xn2, xn2);
-        if (k < N) tppf_forward_stage(sb, p + TPP_STAGE_B, co, k + 1 < N);
+        if (k < N) tppf_forward_stage<SPEC>(sb, p + TPP_STAGE_B, co, k + 1 < N);
         if (k + 2 <= N) {
             tppf_l2_prefetch(p + 2 * TPP_STAGE_B, R_K, 4);
             tppf_l2_prefetch(p + 2 * TPP_STAGE_B, R_KB, 1);

@@ -73,10 +73,15 @@ enum {
     R_KB = 32,   // two-sweep kernel (tpp_fused.cuh) only: (kfb0,kfb1), barrier-parameter coefficient of the gain kf
     R_OC = 33,   // obstacle cost only: value, gradient and Hessian of the stage's obstacle sum at the iterate of buffer 0 / 1
                  // (unscaled): (val,gx) (gy,hxx) (hxy,hyy); rows 33-35 belong to iterate buffer 0, rows 36-38 to buffer 1
+    TPP_NR_BASE = 33, // rows per stage of the instances without the obstacle cost
     TPP_NR = 39
 };
 #define TPP_ROW_B 512
-#define TPP_STAGE_B (TPP_NR * TPP_ROW_B)
+// bytes per stage record: the instances that can carry the obstacle cost (generic, RK4 + goal + obstacles) have the cache rows
+// (a larger stage stride costs the others 5-7 %: measured 193.7 -> 205 ms per 1 M variant-B problems with 39 rows everywhere)
+#define TPP_STAGE_B_OF(SPEC_) ((((SPEC_) == TPP_SPEC_GENERIC || (SPEC_) == TPP_SPEC_RK4_GOAL_OBS) ? (int)TPP_NR : (int)TPP_NR_BASE) * TPP_ROW_B)
+#define TPP_STAGE_B TPP_STAGE_B_OF(SPEC)
+#define TPP_STAGE_B_MAX (TPP_NR * TPP_ROW_B)
 #define TPP_STAGE_SLOTS 11                       /* staging rows per warp: the trial sweep needs 11 */
 #define TPP_STAGE_SMEM (TPP_STAGE_SLOTS * TPP_ROW_B) /* bytes of shared-memory staging per warp */
 
@@ -158,6 +163,7 @@ struct TppArgs {
     int chunk;                 // problems per chunk
     int cta_sync;              // 1: the warps of a CTA run the sweeps in lock-step (instruction cache); 0: every warp on its own
     int obs_smem;              // 1: the dynamic shared memory has room for one obstacle list per warp (behind TPP_SMEM_BYTES)
+    int stage_b;               // bytes per stage record of the launched instance (TPP_STAGE_B_OF)
 };
 #ifndef TPP_STATS
 #define TPP_STATS 0
@@ -193,7 +199,7 @@ struct TppLane {
     double ymax_f;                                 // LSQ mode: largest slack-multiplier estimate seen by sweep F
     double dw_b;                                   // two-sweep kernel: delta_w of the factorisation in progress
     int n_eff;                                     // obstacle cost: entries of the problem's obstacle list to walk (ObsList)
-    int hslot;                                     // hand-over (BatchArgs::hand_rec): the record this problem is exported to
+    int hslot, hcap;                               // hand-over (BatchArgs::hand_rec): record the problem is exported to; iteration threshold
 };
 #define TPP_LANE_STRIDE (((sizeof(TppLane) + 7) / 8) | 1) /* in doubles, odd */
 
@@ -575,6 +581,7 @@ struct TppFwd {
 
 // staging of the forward sweep: slots 0-3 = K, kf rows of stage k, 4-7 = U, S, vL, vU of stage k,
 // 8-9 = (X0,X1) (X2,lam0) of stage k+1
+template <int SPEC>
 __device__ __forceinline__ void tpp_forward_stage(char *sb, const char *p, int co, bool has_next) {
 #pragma unroll
     for (int i = 0; i < 4; i++) tpp_cp16(sb + i * TPP_ROW_B, p + (R_K + i) * TPP_ROW_B);
@@ -611,7 +618,7 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
         const double2 a = tpp_ld2(wb + co * TPP_ROW_B, R_X01), b = tpp_ld2(wb + co * TPP_ROW_B, R_X2L0);
         X[0] = a.x; X[1] = a.y; X[2] = b.x;
     }
-    tpp_forward_stage(sb, wb, co, N > 0);
+    tpp_forward_stage<SPEC>(sb, wb, co, N > 0);
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
         const int mode = tpp_opaque(bmode0);
@@ -623,7 +630,7 @@ __device__ __forceinline__ void tpp_forward(const KParams &P, const BatchArgs &A
         tpp_consume(k0_, k1_, k2_, kf_);
         tpp_consume(u2, s2, vl2, vu2);
         tpp_consume(xn01, xn2, xn2, xn2);
-        if (k < N) tpp_forward_stage(sb, p + TPP_STAGE_B, co, k + 1 < N);
+        if (k < N) tpp_forward_stage<SPEC>(sb, p + TPP_STAGE_B, co, k + 1 < N);
         if (k + 2 <= N) {
             tpp_l2_prefetch(p + 2 * TPP_STAGE_B, R_K, 4);
             tpp_l2_prefetch(p + 2 * TPP_STAGE_B + co * TPP_ROW_B, R_U, 2);
@@ -1455,16 +1462,71 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L, co
 #ifndef TPP_SYNC
 #define TPP_SYNC 1
 #endif
+#ifndef TPP_EXP_NO_HANDOVER
+#define TPP_EXP_NO_HANDOVER 0
+#endif
+// lock-step is a run-time choice only for the instances that can carry the obstacle cost
+#define TPP_CTA_SYNC ((SPEC == TPP_SPEC_RK4_GOAL || SPEC == TPP_SPEC_EULER_TRAJ) ? true : (T.cta_sync != 0))
+#define TPP_HAND (TPP_EXP_NO_HANDOVER ? false : (A.hand_rec != nullptr))
 #if TPP_SYNC == 1
 #define TPP_BLOCK_SYNC()                     \
     do {                                     \
-        if (T.cta_sync) __syncthreads();     \
+        if (TPP_CTA_SYNC) __syncthreads();   \
         else __syncwarp();                   \
     } while (0)
 #else
 #define TPP_BLOCK_SYNC() __syncwarp() /* TPP_SYNC == 2: the CTA only meets once per trip (at the exit test) */
 #endif
 #define TPP_SMEM_BYTES ((size_t)(TPP_THREADS / 32) * TPP_STAGE_SMEM + (size_t)TPP_THREADS * TPP_LANE_STRIDE * sizeof(double))
+
+// ---- straggler hand-over (BatchArgs::hand_rec).  Out of line: inlined, the export code costs the sweeps registers
+// (measured: +80 B of spills per thread and 8 % of the throughput of variant B, whether or not a problem is ever exported).
+// Once per trip, whole warp: (1) the records of the lanes that decided to leave (phase PH_EXPORT: iterate rows of buffer
+// myco, filter, solver scalars); a lane that finds the record buffer full stays and re-evaluates its point (one trip);
+// (2) the threshold of the next trip: hand_iter iterations, 0 once the work queue is empty and the warp has thinned out.
+__device__ __noinline__ void tpp_hand_trip(const KParams &P, const TppArgs &T, char *wbase, size_t gw, TppLane &L, int myco) {
+    const BatchArgs &A = T.a;
+    const int N = P.N, lane = threadIdx.x & 31;
+    const int stage_b = T.stage_b;
+    int ex = (L.phase == PH_EXPORT);
+    if (ex) {
+        const unsigned slot = atomicAdd(A.hand_count, 1u);
+        if (slot < (unsigned)A.hand_cap) {
+            L.hslot = (int)slot;
+        } else {
+            ex = 0;
+            L.hslot = -2; // no further attempts
+            L.tmode = TM_EVAL;
+            L.phase = PH_T;
+        }
+    }
+    for (unsigned m = __ballot_sync(FULL, ex); m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        const int co = __shfl_sync(FULL, myco, j);
+        double *hr = A.hand_rec + (size_t)__shfl_sync(FULL, L.hslot, j) * HAND_REC(N);
+        for (int k = lane; k <= N; k += 32) {
+            const char *pc = wbase + (size_t)k * stage_b + co * TPP_ROW_B + j * 16;
+            double2 *o = reinterpret_cast<double2 *>(hr + 16 * k);
+#pragma unroll
+            for (int f = 0; f < R_ITER; f++) o[f] = tpp_ld2(pc, f);
+        }
+        const double *flj = T.filt + gw * (64 * 32) + j;
+        hr[HAND_FILT(N) + lane] = flj[lane * 32];
+        hr[HAND_FILT(N) + 32 + lane] = flj[(32 + lane) * 32];
+    }
+    if (ex) {
+        double *q = A.hand_rec + (size_t)L.hslot * HAND_REC(N) + HAND_SCAL(N);
+        q[HS_B] = (double)L.b; q[HS_MU] = L.mu; q[HS_DF] = L.df; q[HS_THETA0] = L.theta0; q[HS_DWLAST] = L.dw_last;
+        q[HS_ITER] = (double)L.iter; q[HS_LS] = (double)L.ls_extra; q[HS_NRESTO] = (double)L.n_resto;
+        q[HS_ACCEPT] = (double)L.acceptable_count; q[HS_TINYLAST] = (double)L.tiny_last;
+        q[HS_TINYFLAG] = (double)L.tiny_flag; q[HS_FMASK] = (double)L.fmask; q[HS_RING] = (double)L.ring;
+        L.phase = PH_LOAD;
+    }
+    const int ph = L.phase;
+    const unsigned act = __ballot_sync(FULL, ph != PH_DONE && ph != PH_LOAD);
+    const bool thin = __popc(act) <= A.hand_thin && *reinterpret_cast<volatile unsigned *>(A.counter) >= (unsigned)A.B;
+    L.hcap = (L.hslot == -2) ? 0x7fffffff : (thin ? 0 : A.hand_iter);
+}
 
 template <int SPEC>
 __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_tpp_kernel(const KParams P, const TppArgs T) {
@@ -1520,6 +1582,8 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 L.bmode = BM_LSQ;
                 L.tmode = TM_LSQ;
                 L.phase = PH_B;
+                L.hslot = -1;
+                L.hcap = A.hand_iter;
             }
         }
         __syncwarp();
@@ -1576,7 +1640,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             if (nm) tpp_obstacle_block<SPEC>(P, A, wbase, nm, cur, cur, L.b, L.n_eff, 0.0, -1, 0, olist);
         }
 #if TPP_SYNC
-        if (T.cta_sync ? __syncthreads_and(L.phase == PH_DONE) : __all_sync(FULL, L.phase == PH_DONE)) break;
+        if (TPP_CTA_SYNC ? __syncthreads_and(L.phase == PH_DONE) : __all_sync(FULL, L.phase == PH_DONE)) break;
 #else
         if (__all_sync(FULL, L.phase == PH_DONE)) break;
 #endif
@@ -1672,14 +1736,6 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             }
         }
 
-        // hand-over threshold of this trip: hand_iter iterations; 0 once the work queue is empty and the warp has thinned out
-        int hcap = A.hand_iter;
-        if (A.hand_rec) {
-            const int ph = tpp_opaque(L.phase);
-            const unsigned act = __ballot_sync(FULL, ph != PH_DONE && ph != PH_LOAD);
-            if (__popc(act) <= A.hand_thin && *reinterpret_cast<volatile unsigned *>(A.counter) >= (unsigned)A.B) hcap = 0;
-        }
-
         // ---- block T ----
         TPP_BLOCK_SYNC();
         if (tpp_opaque(L.phase) == PH_T) {
@@ -1744,10 +1800,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 L.moved = 1;
                 // a straggler leaves for the warp kernel here, at the top of an iteration, with its state as it stands
                 bool leave = false;
-                if (A.hand_rec && L.iter >= hcap) {
-                    const unsigned slot = atomicAdd(A.hand_count, 1u);
-                    if (slot < (unsigned)A.hand_cap) { L.hslot = (int)slot; L.phase = PH_EXPORT; leave = true; }
-                }
+                if (TPP_HAND && L.iter >= L.hcap) { L.phase = PH_EXPORT; leave = true; }
                 // top of the next iteration: convergence tests, barrier update
                 if (!leave) tpp_iterate_top(P, L, t.n);
             }
@@ -1799,31 +1852,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 }
             }
             // hand-over records: iterate rows of the new current buffer, filter, solver scalars
-            if (A.hand_rec) {
-                const bool ex = (ph == PH_EXPORT);
-                for (unsigned m = __ballot_sync(FULL, ex); m; m &= m - 1) {
-                    const int j = __ffs(m) - 1;
-                    const int co = __shfl_sync(FULL, myco, j);
-                    double *hr = A.hand_rec + (size_t)__shfl_sync(FULL, L.hslot, j) * HAND_REC(N);
-                    for (int k = lane; k <= N; k += 32) {
-                        const char *pc = wbase + (size_t)k * TPP_STAGE_B + co * TPP_ROW_B + j * 16;
-                        double2 *o = reinterpret_cast<double2 *>(hr + 16 * k);
-#pragma unroll
-                        for (int f = 0; f < R_ITER; f++) o[f] = tpp_ld2(pc, f);
-                    }
-                    const double *flj = T.filt + gw * (64 * 32) + j;
-                    hr[HAND_FILT(N) + lane] = flj[lane * 32];
-                    hr[HAND_FILT(N) + 32 + lane] = flj[(32 + lane) * 32];
-                }
-                if (ex) {
-                    double *q = A.hand_rec + (size_t)L.hslot * HAND_REC(N) + HAND_SCAL(N);
-                    q[HS_B] = (double)L.b; q[HS_MU] = L.mu; q[HS_DF] = L.df; q[HS_THETA0] = L.theta0; q[HS_DWLAST] = L.dw_last;
-                    q[HS_ITER] = (double)L.iter; q[HS_LS] = (double)L.ls_extra; q[HS_NRESTO] = (double)L.n_resto;
-                    q[HS_ACCEPT] = (double)L.acceptable_count; q[HS_TINYLAST] = (double)L.tiny_last;
-                    q[HS_TINYFLAG] = (double)L.tiny_flag; q[HS_FMASK] = (double)L.fmask; q[HS_RING] = (double)L.ring;
-                    L.phase = PH_LOAD;
-                }
-            }
+            if (TPP_HAND) tpp_hand_trip(P, T, wbase, gw, L, myco);
             if (fin) {
                 const size_t b = (size_t)L.b;
                 if (A.cost) A.cost[b] = L.f;

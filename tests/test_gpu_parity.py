@@ -218,9 +218,12 @@ def test_horizon_sweep_config5(env, N, field):
     out = S.solve_batch(w["x0"], w["goal"], obs_x=ox, obs_y=oy)
     ref = O.solve_batch(po, w["x0"], w["goal"], obs_x=ox, obs_y=oy)
     cert = lambda b, X, U: O.kkt_certificate(po, w["x0"][b], w["goal"][b], X, U, obs_x=ox[b], obs_y=oy[b])  # noqa: E731
-    # the stated field at N = 100: every predicted position sits inside the obstacle annulus, a fifth of the problems converge
+    # the stated field at N = 100: every predicted position sits inside the obstacle annulus, a fifth of the problems converge.
+    # The stated field starts 0.3 m from the nearest obstacle point: the iteration is chaotic there, and with 48 problems the
+    # count of problems that an ulp in exp() tips to another status / optimum moves between 2 and 4 from build to build
+    # (each "another optimum" is certified as a KKT point below): 10 % for the stated field, 5 % for the easier one.
     hard = field == "stated" and N == 100
-    nst, nopt = _assert_parity(out, ref, need_frac=0.15 if hard else 0.3, nonconvex_slack=0.1 if hard else 0.05, certify=cert)
+    nst, nopt = _assert_parity(out, ref, need_frac=0.15 if hard else 0.3, nonconvex_slack=0.1 if field == "stated" else 0.05, certify=cert)
     print(f"config 5 {field} N={N}: converged {np.isin(ref['status'], (0, 1)).mean():.2f}, another status {nst}, another optimum {nopt}, "
           f"status counts {dict(zip(*np.unique(out['status'], return_counts=True)))}")
     S.close()
