@@ -2361,7 +2361,10 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     // (measured, 1 M problems: variant B 198.2 -> 190.4 ms with 60 / 8; variant A: the launch no longer lasts as long as its
     // slowest problem, 1354 -> 417 ms for 65 536 problems with one 3000-iteration straggler)
     h->hand_iter = (p->obs_form != B200MPC_OBS_NONE) ? 192 : 60;
-    h->hand_thin = (p->obs_form != B200MPC_OBS_NONE) ? 4 : 8;
+    // hand_thin: also hand over every problem of a warp that has thinned out to <= hand_thin active lanes once the work queue is
+    // empty.  Off (-1) by default: which problems that rule catches depends on the timing of the launch, and results would
+    // no longer be bit-identical from run to run (the two kernels agree to rounding, not to the bit).
+    h->hand_thin = -1;
     if (const char *eh = getenv("B200MPC_HAND_ITER")) h->hand_iter = atoi(eh);
     if (const char *eh = getenv("B200MPC_HAND_THIN")) h->hand_thin = atoi(eh);
     h->d_hand = nullptr; h->hand_cap = 0; h->d_hand_count = nullptr;
@@ -2382,7 +2385,7 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     if ((e = cudaStreamCreateWithFlags(&h->ostream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cudaGetErrorString(e));
     if ((e = cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming)) != cudaSuccess) return fail(cudaGetErrorString(e));
     if ((e = cudaMalloc(&h->d_sync, (1 + B200MPC_MAX_CHUNKS) * sizeof(unsigned int))) != cudaSuccess) return fail(cudaGetErrorString(e));
-    if ((e = cudaHostAlloc(&h->h_sync, 2 * B200MPC_MAX_CHUNKS * sizeof(unsigned int), cudaHostAllocMapped)) != cudaSuccess)
+    if ((e = cudaHostAlloc(&h->h_sync, (2 * B200MPC_MAX_CHUNKS + 1) * sizeof(unsigned int), cudaHostAllocMapped)) != cudaSuccess)
         return fail(cudaGetErrorString(e));
     if ((e = cudaHostGetDevicePointer(&h->h_sync_dev, h->h_sync, 0)) != cudaSuccess) return fail(cudaGetErrorString(e));
     h->small_cap = (size_t)1 << 20;
@@ -2502,6 +2505,7 @@ struct StreamWords {
     const unsigned *avail;
     unsigned *done, *flags;
     int chunk;
+    const unsigned *abort = nullptr; // host-mapped: set by the host when the streamed call fails
 };
 
 static int launch_warp_kernel(b200mpc_handle *h, const BatchArgs &a, int grid, bool scan, cudaStream_t stream);
@@ -2547,6 +2551,7 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a_in, cudaStream
     t.a = a; t.ws = h->d_ws; t.filt = h->d_filt; t.stats = h->d_stats;
     t.avail = sw ? sw->avail : nullptr; t.done = sw ? sw->done : nullptr; t.flags = sw ? sw->flags : nullptr;
     t.chunk = sw ? sw->chunk : 1;
+    t.abort = sw ? sw->abort : nullptr;
     t.cta_sync = h->lane_fused ? 1 : h->tpp_cta_sync;
     t.obs_smem = h->tpp_obs_smem ? 1 : 0;
     t.stage_b = (h->lane_spec == TPP_SPEC_GENERIC || h->lane_spec == TPP_SPEC_RK4_GOAL_OBS) ? TPP_STAGE_B_OF(TPP_SPEC_GENERIC) : TPP_STAGE_B_OF(TPP_SPEC_RK4_GOAL);
@@ -2739,8 +2744,13 @@ extern "C" int b200mpc_solve_batch(b200mpc_handle *h, int B, const double *x0, c
     double *d_X = (double *)take(sz_X), *d_U = (double *)take(sz_U), *d_c = (double *)take(sz_c);
     int *d_st = (int *)take(sz_i), *d_it = (int *)take(sz_i), *d_ls = (int *)take(sz_i);
     cudaStream_t s = h->stream;
+    // every buffer the streamed path touches must be page-locked: a pageable one turns its copies into staged, effectively
+    // synchronous ones, and the overlap (and the ordering the watermark relies on) is gone
+    const bool all_pinned = is_pinned(x0) && is_pinned(xref) && (!traj || is_pinned(uref)) && (!u_init || is_pinned(u_init)) &&
+                            is_pinned(X_out) && is_pinned(U_out) && is_pinned(status_out) && (!cost_out || is_pinned(cost_out)) &&
+                            (!iters_out || is_pinned(iters_out)) && (!ls_out || is_pinned(ls_out));
     if (choose_kernel(h, B) == B200MPC_KERNEL_LANE && B >= B200MPC_STREAM_MIN_BATCH && !getenv("B200MPC_NO_STREAMING") && !obs &&
-        is_pinned(x0) && is_pinned(X_out) && is_pinned(U_out)) {
+        all_pinned) {
         // ---- streamed solve: inputs arrive and results leave in chunks while the persistent kernel runs ----
         // copy stream:   [chunk c inputs H2D][avail := end of chunk c] ...          (the kernel waits for `avail`)
         // kernel:        finishes problems in roughly ascending order; the lane completing chunk c raises flags[c]
@@ -2753,24 +2763,39 @@ extern "C" int b200mpc_solve_batch(b200mpc_handle *h, int B, const double *x0, c
         nchunks = (B + chunk - 1) / chunk;
         volatile unsigned int *flags = h->h_sync;
         unsigned int *marks = h->h_sync + B200MPC_MAX_CHUNKS;
+        volatile unsigned int *abort_word = h->h_sync + 2 * B200MPC_MAX_CHUNKS; // the kernel's wait on the watermark gives up when set
+        *abort_word = 0;
+        // any failure from here on: release the persistent kernel (it may be waiting for inputs that will never arrive), drain
+        // the three streams so that nothing of this call is in flight when the staging buffer is reused, then report
+        auto bail = [&](int code, const std::string &msg) {
+            *abort_word = 1;
+            cudaStreamSynchronize(s); cudaStreamSynchronize(h->cstream); cudaStreamSynchronize(h->ostream);
+            cudaGetLastError();
+            return set_err(h, code, msg);
+        };
+#define CU_TRY_S(call)                                                                                  \
+    do {                                                                                                \
+        const cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return bail(B200MPC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
         for (int c = 0; c < nchunks; c++) {
             flags[c] = 0;
             const long long end = (long long)(c + 1) * chunk;
             marks[c] = (unsigned)(end < B ? end : B);
         }
-        CU_TRY(h, cudaMemsetAsync(h->d_sync, 0, (1 + B200MPC_MAX_CHUNKS) * sizeof(unsigned int), s));
-        CU_TRY(h, cudaEventRecord(h->ev_sync, s));
-        CU_TRY(h, cudaStreamWaitEvent(h->cstream, h->ev_sync, 0));
-        CU_TRY(h, cudaStreamWaitEvent(h->ostream, h->ev_sync, 0)); // earlier work on the staging buffer is complete
+        CU_TRY_S(cudaMemsetAsync(h->d_sync, 0, (1 + B200MPC_MAX_CHUNKS) * sizeof(unsigned int), s));
+        CU_TRY_S(cudaEventRecord(h->ev_sync, s));
+        CU_TRY_S(cudaStreamWaitEvent(h->cstream, h->ev_sync, 0));
+        CU_TRY_S(cudaStreamWaitEvent(h->ostream, h->ev_sync, 0)); // earlier work on the staging buffer is complete
         const size_t w_ref = traj ? 3 * N : 3;
         for (int c = 0; c < nchunks; c++) {
             const size_t b0 = (size_t)c * chunk, n = marks[c] - b0;
             cudaStream_t cs = h->cstream;
-            CU_TRY(h, cudaMemcpyAsync(d_x0 + b0 * 3, x0 + b0 * 3, n * 3 * 8, cudaMemcpyHostToDevice, cs));
-            CU_TRY(h, cudaMemcpyAsync(d_xref + b0 * w_ref, xref + b0 * w_ref, n * w_ref * 8, cudaMemcpyHostToDevice, cs));
-            if (traj) CU_TRY(h, cudaMemcpyAsync(d_uref + b0 * 2 * N, uref + b0 * 2 * N, n * 2 * N * 8, cudaMemcpyHostToDevice, cs));
-            if (u_init) CU_TRY(h, cudaMemcpyAsync(d_ui + b0 * 2 * N, u_init + b0 * 2 * N, n * 2 * N * 8, cudaMemcpyHostToDevice, cs));
-            CU_TRY(h, cudaMemcpyAsync(h->d_sync, marks + c, sizeof(unsigned int), cudaMemcpyHostToDevice, cs));
+            CU_TRY_S(cudaMemcpyAsync(d_x0 + b0 * 3, x0 + b0 * 3, n * 3 * 8, cudaMemcpyHostToDevice, cs));
+            CU_TRY_S(cudaMemcpyAsync(d_xref + b0 * w_ref, xref + b0 * w_ref, n * w_ref * 8, cudaMemcpyHostToDevice, cs));
+            if (traj) CU_TRY_S(cudaMemcpyAsync(d_uref + b0 * 2 * N, uref + b0 * 2 * N, n * 2 * N * 8, cudaMemcpyHostToDevice, cs));
+            if (u_init) CU_TRY_S(cudaMemcpyAsync(d_ui + b0 * 2 * N, u_init + b0 * 2 * N, n * 2 * N * 8, cudaMemcpyHostToDevice, cs));
+            CU_TRY_S(cudaMemcpyAsync(h->d_sync, marks + c, sizeof(unsigned int), cudaMemcpyHostToDevice, cs));
         }
         BatchArgs a;
         a.B = B; a.obs_stride = obs_stride;
@@ -2779,32 +2804,37 @@ extern "C" int b200mpc_solve_batch(b200mpc_handle *h, int B, const double *x0, c
         a.counter = h->d_counter;
         StreamWords sw;
         sw.avail = h->d_sync; sw.done = h->d_sync + 1; sw.flags = h->h_sync_dev; sw.chunk = chunk;
+        sw.abort = h->h_sync_dev + 2 * B200MPC_MAX_CHUNKS;
         rc = launch_solve_tpp(h, a, s, &sw);
-        if (rc) return rc;
+        if (rc) return bail(rc, h->err);
         for (int c = 0; c < nchunks; c++) {
             unsigned spins = 0;
             while (!flags[c]) {
                 if ((++spins & 0x3ff) == 0) {
                     const cudaError_t q = cudaStreamQuery(s);
                     if (q == cudaSuccess) break; // kernel finished: every chunk is complete
-                    if (q != cudaErrorNotReady) return set_err(h, B200MPC_E_CUDA, std::string("solve kernel: ") + cudaGetErrorString(q));
+                    if (q != cudaErrorNotReady) return bail(B200MPC_E_CUDA, std::string("solve kernel: ") + cudaGetErrorString(q));
+                    const cudaError_t qc = cudaStreamQuery(h->cstream); // a failed input copy would leave the kernel waiting
+                    if (qc != cudaSuccess && qc != cudaErrorNotReady)
+                        return bail(B200MPC_E_CUDA, std::string("input copy: ") + cudaGetErrorString(qc));
                     std::this_thread::yield();
                 }
             }
             const size_t b0 = (size_t)c * chunk, n = marks[c] - b0;
             cudaStream_t os = h->ostream;
-            CU_TRY(h, cudaMemcpyAsync(X_out + b0 * 3 * (N + 1), d_X + b0 * 3 * (N + 1), n * 3 * (N + 1) * 8, cudaMemcpyDeviceToHost, os));
-            CU_TRY(h, cudaMemcpyAsync(U_out + b0 * 2 * N, d_U + b0 * 2 * N, n * 2 * N * 8, cudaMemcpyDeviceToHost, os));
-            if (cost_out) CU_TRY(h, cudaMemcpyAsync(cost_out + b0, d_c + b0, n * 8, cudaMemcpyDeviceToHost, os));
-            CU_TRY(h, cudaMemcpyAsync(status_out + b0, d_st + b0, n * 4, cudaMemcpyDeviceToHost, os));
-            if (iters_out) CU_TRY(h, cudaMemcpyAsync(iters_out + b0, d_it + b0, n * 4, cudaMemcpyDeviceToHost, os));
-            if (ls_out) CU_TRY(h, cudaMemcpyAsync(ls_out + b0, d_ls + b0, n * 4, cudaMemcpyDeviceToHost, os));
+            CU_TRY_S(cudaMemcpyAsync(X_out + b0 * 3 * (N + 1), d_X + b0 * 3 * (N + 1), n * 3 * (N + 1) * 8, cudaMemcpyDeviceToHost, os));
+            CU_TRY_S(cudaMemcpyAsync(U_out + b0 * 2 * N, d_U + b0 * 2 * N, n * 2 * N * 8, cudaMemcpyDeviceToHost, os));
+            if (cost_out) CU_TRY_S(cudaMemcpyAsync(cost_out + b0, d_c + b0, n * 8, cudaMemcpyDeviceToHost, os));
+            CU_TRY_S(cudaMemcpyAsync(status_out + b0, d_st + b0, n * 4, cudaMemcpyDeviceToHost, os));
+            if (iters_out) CU_TRY_S(cudaMemcpyAsync(iters_out + b0, d_it + b0, n * 4, cudaMemcpyDeviceToHost, os));
+            if (ls_out) CU_TRY_S(cudaMemcpyAsync(ls_out + b0, d_ls + b0, n * 4, cudaMemcpyDeviceToHost, os));
         }
-        CU_TRY(h, cudaStreamSynchronize(s));
-        CU_TRY(h, cudaStreamSynchronize(h->cstream));
-        CU_TRY(h, cudaStreamSynchronize(h->ostream));
+        CU_TRY_S(cudaStreamSynchronize(s));
+        CU_TRY_S(cudaStreamSynchronize(h->cstream));
+        CU_TRY_S(cudaStreamSynchronize(h->ostream));
         h->last_streamed = nchunks;
         return 0;
+#undef CU_TRY_S
     }
     CU_TRY(h, cudaMemcpyAsync(d_x0, x0, nb * 3 * 8, cudaMemcpyHostToDevice, s));
     CU_TRY(h, cudaMemcpyAsync(d_xref, xref, nb * (traj ? 3 * N : 3) * 8, cudaMemcpyHostToDevice, s));

@@ -474,7 +474,10 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 newb = b;
                 L.b = b;
                 if (T.avail) {
-                    while (*reinterpret_cast<const volatile unsigned *>(T.avail) <= (unsigned)b) __nanosleep(500);
+                    while (*reinterpret_cast<const volatile unsigned *>(T.avail) <= (unsigned)b) {
+                        if (T.abort && *reinterpret_cast<const volatile unsigned *>(T.abort)) break; // call given up by the host
+                        __nanosleep(500);
+                    }
                     __threadfence();
                 }
                 L.goal[0] = L.goal[1] = L.goal[2] = 0;

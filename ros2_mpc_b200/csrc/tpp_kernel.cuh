@@ -161,6 +161,7 @@ struct TppArgs {
     unsigned *done;            // [chunks] finished problems per chunk
     unsigned *flags;           // [chunks] host-mapped: set to 1 when the chunk's results are complete in device memory
     int chunk;                 // problems per chunk
+    const unsigned *abort;     // host-mapped word: non-zero = the host gave the call up (a copy failed): stop waiting for inputs
     int cta_sync;              // 1: the warps of a CTA run the sweeps in lock-step (instruction cache); 0: every warp on its own
     int obs_smem;              // 1: the dynamic shared memory has room for one obstacle list per warp (behind TPP_SMEM_BYTES)
     int stage_b;               // bytes per stage record of the launched instance (TPP_STAGE_B_OF)
@@ -1559,10 +1560,14 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             } else {
                 newb = b;
                 L.b = b;
+                bool gone = false; // streamed call given up by the host
                 if (T.avail) {
                     // streamed inputs: wait until the copy stream has delivered this problem (only ever at the start
                     // of a batch: the copies run 20x faster than the problems are consumed)
-                    while (*reinterpret_cast<const volatile unsigned *>(T.avail) <= (unsigned)b) __nanosleep(500);
+                    while (*reinterpret_cast<const volatile unsigned *>(T.avail) <= (unsigned)b) {
+                        if (T.abort && *reinterpret_cast<const volatile unsigned *>(T.abort)) { gone = true; break; }
+                        __nanosleep(500);
+                    }
                     __threadfence();
                 }
                 L.goal[0] = L.goal[1] = L.goal[2] = 0;
@@ -1584,6 +1589,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 L.phase = PH_B;
                 L.hslot = -1;
                 L.hcap = A.hand_iter;
+                if (gone) { L.phase = PH_DONE; newb = -1; }
             }
         }
         __syncwarp();

@@ -609,11 +609,14 @@ def test_lane_kernel_horizon_sweep(env, N):
 
 
 @pytest.mark.parametrize("variant", ["B", "C"])
-def test_streamed_host_solve_matches_plain(env, variant):
+def test_streamed_host_solve_matches_plain(env, variant, monkeypatch):
     """Page-locked host buffers: the batch is streamed (chunked H2D while the kernel runs, per-chunk D2H on
     completion flags).  Every problem must come out bit-identical to the plain copy-in / solve / copy-out path,
-    including a ragged last chunk."""
+    including a ragged last chunk.  (A streamed solve finishes every problem in the lane kernel — the per-chunk flags count
+    its results — while the plain path hands its stragglers to the warp kernel, which agrees to rounding, not to the bit:
+    the hand-over is switched off for the bit-wise comparison and compared at the parity tolerances below.)"""
     import torch
+    monkeypatch.setenv("B200MPC_HAND_ITER", "0")
     shim, synth = env["shim"], env["synth"]
     w = synth.robots_on_map(B=4096, seed=5)
     rep, B = 33, 33 * 4096 - 77
@@ -644,6 +647,13 @@ def test_streamed_host_solve_matches_plain(env, variant):
         for k in ("status", "iters", "ls", "cost", "X", "U"):
             assert np.array_equal(st[k], plain[k]), (k, rnd)
     S.close()
+    # default handle: plain path with the straggler hand-over against the streamed result
+    monkeypatch.delenv("B200MPC_HAND_ITER")
+    S = shim.Solver(env["make"](variant, env["y"]))
+    handed = S.solve_batch(x0, xr, **kw)
+    S.close()
+    _assert_parity(handed, {k: np.array(v) for k, v in st.items()}, need_frac=1.0)
+    assert (handed["iters"] == st["iters"]).mean() >= 0.999
 
 
 # ---- obstacle-list construction on the GPU ----------------------------------------------------
