@@ -43,8 +43,11 @@
  * are reported in status_out with IPOPT's ApplicationReturnStatus values (the reference raises RuntimeError from
  * opti.solve() for any status other than Solve_Succeeded / Solved_To_Acceptable_Level).
  * A handle is bound to one device and is not thread-safe (one handle per thread and device), matching the
- * reference's one-Mpc-per-process usage.  There is no CPU fallback: every entry point fails if no CUDA device
- * is available.
+ * reference's one-Mpc-per-process usage.  ONE solve may be in flight per handle: the work-queue counter, the lane
+ * kernel's workspace, the hand-over records and the timing events belong to the handle, so a second
+ * b200mpc_solve_batch_device on another stream has to wait for the first (use one handle per stream; two handles
+ * alternating overlap the tail of one batch with the start of the next).  There is no CPU fallback: every entry point
+ * fails if no CUDA device is available.
  *
  * Layouts (all FP64, problem-major, "stage-major" inside a problem):
  *   x0      [B][3]                 initial state (x, y, theta)                       = P[0:3]
