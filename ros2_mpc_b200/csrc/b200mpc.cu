@@ -2148,7 +2148,7 @@ struct b200mpc_handle {
     int last_kind;     // kernel used by the most recent solve
     int tpp_ctas;
     size_t tpp_obs_smem; // bytes of per-warp obstacle-list buffers behind TPP_SMEM_BYTES (0: lists are read from global memory)
-    int tpp_cta_sync;
+    int tpp_cta_sync, tpp_b_passes;
     // straggler hand-over from the lane kernel to the warp kernel (BatchArgs::hand_rec)
     int hand_iter, hand_thin;   // hand_iter <= 0: off
     double *d_hand;
@@ -2369,6 +2369,11 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     if (const char *eh = getenv("B200MPC_HAND_THIN")) h->hand_thin = atoi(eh);
     h->d_hand = nullptr; h->hand_cap = 0; h->d_hand_count = nullptr;
     h->tpp_cta_sync = (p->obs_form != B200MPC_OBS_NONE) ? 0 : 1; // (tpp_kernel.cuh, TppArgs::cta_sync)
+    // two executions of block B per trip (TppArgs::b_passes): 15 % (variants B / C) to 49 % (variant A) of the factorisations need
+    // an inertia correction, which used to cost the lane a whole trip; measured on 1 M cold variant-B problems
+    // 181.7 / 165.5 / 174.7 ms with 1 / 2 / 3 executions, variant C 181.7 -> 173.7 ms, variant A (262 144) 895 -> 863 ms
+    h->tpp_b_passes = 2;
+    if (const char *eb = getenv("B200MPC_LANE_BPASSES")) h->tpp_b_passes = std::max(1, atoi(eb));
     if (const char *es = getenv("B200MPC_LANE_SYNC")) h->tpp_cta_sync = (es[0] == '1');
     h->lane_fused = B200MPC_LANE_FUSED_DEFAULT;
     if (const char *ef = getenv("B200MPC_LANE_FUSED")) h->lane_fused = (ef[0] == '1');
@@ -2376,6 +2381,7 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tblocks, mpc_solve_tpp_kernel<0>, TPP_THREADS, tpp_smem)) != cudaSuccess)
         return fail(std::string("kernel configuration: ") + cudaGetErrorString(e));
     if (tblocks < 1) tblocks = 1;
+    if (const char *ec = getenv("B200MPC_LANE_CTAS_PER_SM")) tblocks = std::max(1, std::min(tblocks, atoi(ec))); // tuning experiments
     h->tpp_ctas = tblocks * h->sm_count;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cudaGetErrorString(e));
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail(cudaGetErrorString(e));
@@ -2554,6 +2560,7 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a_in, cudaStream
     t.abort = sw ? sw->abort : nullptr;
     t.cta_sync = h->lane_fused ? 1 : h->tpp_cta_sync;
     t.obs_smem = h->tpp_obs_smem ? 1 : 0;
+    t.b_passes = h->tpp_b_passes;
     t.stage_b = (h->lane_spec == TPP_SPEC_GENERIC || h->lane_spec == TPP_SPEC_RK4_GOAL_OBS) ? TPP_STAGE_B_OF(TPP_SPEC_GENERIC) : TPP_STAGE_B_OF(TPP_SPEC_RK4_GOAL);
     const size_t smem_obs = TPP_SMEM_BYTES + h->tpp_obs_smem;
     CU_TRY(h, cudaEventRecord(h->ev0, stream));

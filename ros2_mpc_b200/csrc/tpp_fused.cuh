@@ -474,8 +474,9 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 newb = b;
                 L.b = b;
                 if (T.avail) {
+                    unsigned spins = 0;
                     while (*reinterpret_cast<const volatile unsigned *>(T.avail) <= (unsigned)b) {
-                        if (T.abort && *reinterpret_cast<const volatile unsigned *>(T.abort)) break; // call given up by the host
+                        if ((++spins & 1023u) == 0 && T.abort && *reinterpret_cast<const volatile unsigned *>(T.abort)) break; // call given up by the host
                         __nanosleep(500);
                     }
                     __threadfence();

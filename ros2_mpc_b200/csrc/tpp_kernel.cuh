@@ -165,6 +165,7 @@ struct TppArgs {
     int cta_sync;              // 1: the warps of a CTA run the sweeps in lock-step (instruction cache); 0: every warp on its own
     int obs_smem;              // 1: the dynamic shared memory has room for one obstacle list per warp (behind TPP_SMEM_BYTES)
     int stage_b;               // bytes per stage record of the launched instance (TPP_STAGE_B_OF)
+    int b_passes;              // executions of block B per trip (>= 1)
 };
 #ifndef TPP_STATS
 #define TPP_STATS 0
@@ -1564,8 +1565,11 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 if (T.avail) {
                     // streamed inputs: wait until the copy stream has delivered this problem (only ever at the start
                     // of a batch: the copies run 20x faster than the problems are consumed)
+                    // (the abort word lives in host memory: it is looked at every 1024th round — tens of thousands of waiting
+                    // lanes reading it over PCIe every round slowed the very input copies they wait for: 204 -> 217 ms)
+                    unsigned spins = 0;
                     while (*reinterpret_cast<const volatile unsigned *>(T.avail) <= (unsigned)b) {
-                        if (T.abort && *reinterpret_cast<const volatile unsigned *>(T.abort)) { gone = true; break; }
+                        if ((++spins & 1023u) == 0 && T.abort && *reinterpret_cast<const volatile unsigned *>(T.abort)) { gone = true; break; }
                         __nanosleep(500);
                     }
                     __threadfence();
@@ -1651,7 +1655,11 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
         if (__all_sync(FULL, L.phase == PH_DONE)) break;
 #endif
 
-        // ---- block B ----
+        // ---- block B ----  (b_passes > 1: a lane whose factorisation has the wrong inertia repeats the sweep with the next
+        // delta_w in the same trip instead of costing itself a whole trip: with the obstacle cost half of the iterations need
+        // an inertia correction, and block B is a small part of a trip there)
+#pragma unroll 1
+        for (int bpass = 0; bpass < T.b_passes; bpass++) {
         TPP_BLOCK_SYNC();
         if (tpp_opaque(L.phase) == PH_B) {
             TppBwd r;
@@ -1683,6 +1691,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 L.dw = nd;
                 if (nd > DW_MAX) { L.status = B200MPC_ERROR_IN_STEP_COMPUTATION; L.phase = PH_FIN; }
             }
+        }
         }
 
         // ---- block F ----
