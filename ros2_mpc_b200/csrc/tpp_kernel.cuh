@@ -1000,6 +1000,12 @@ __device__ __noinline__ void tpp_obstacle_block(const KParams &P, const BatchArg
         const int sr = __shfl_sync(FULL, srow_mine, j);
         const int cp = __shfl_sync(FULL, copy_mine, j);
         const double *gx = A.ox + (size_t)A.obs_stride * b, *gy = A.oy + (size_t)A.obs_stride * b;
+        if (const unsigned rest = m & (m - 1)) {
+            // the next problem's list on its way into L2 while this one is evaluated (lanes 0-15: x, 16-31: y; 128 B each)
+            const size_t bn = (size_t)__shfl_sync(FULL, b_mine, __ffs(rest) - 1);
+            const double *pn = ((lane < 16) ? A.ox : A.oy) + (size_t)A.obs_stride * bn + (lane & 15) * 16;
+            if ((lane & 15) * 16 < P.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn));
+        }
         if (!cp) tpp_stage_list(gx, gy, ne, olist, Mpad);
         const double w0 = 1.0 + (double)(P.M - ne);
         for (int k = lane; k <= N; k += 32) {
