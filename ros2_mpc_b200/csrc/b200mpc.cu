@@ -99,7 +99,13 @@ struct BatchArgs {
     double *hand_rec = nullptr;          // [hand_cap][HAND_REC(N)] records, or NULL (no hand-over)
     unsigned int *hand_count = nullptr;  // records written (lane kernel) / to read (warp kernel); may exceed hand_cap: clamp
     int hand_cap = 0, hand_iter = 0, hand_thin = 0;
-    int resume = 0;                      // warp kernel: 1 = the batch IS the list of records (B is ignored)
+    // warp kernel, resume != 0: the batch IS the list of records resume_rec[min(*resume_count, resume_cap)] (B is ignored).
+    // The warp kernel exports as well (hand_rec != NULL: problems reaching hand_iter iterations): a batch that does not fill
+    // the machine several times over is solved as a cascade of iteration-bounded launches, so that its long problems run
+    // side by side in the last launches instead of one behind the other at the end of a single one.
+    int resume = 0, resume_cap = 0;
+    const double *resume_rec = nullptr;
+    const unsigned int *resume_count = nullptr;
 };
 // record of one exported problem (doubles): per stage the eight iterate rows of the lane kernel's workspace
 // (X0 X1 | X2 lam0 | lam1 lam2 | U | S | yd | vL | vU), 16 scalars, the filter (32 x (phi, theta))
@@ -1507,9 +1513,11 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
         double fphi = 0, ftheta = 0;
         bool fvalid = false;
         int ring = 0;
+        double theta0 = -1; // max(1, theta at the starting point): theta_max / theta_min are 1e4 / 1e-4 times it
         if (hrec) {
             const double *q = hrec + HAND_SCAL(N);
             mu = q[HS_MU]; tau = fmax(TAU_MIN, 1.0 - mu);
+            theta0 = q[HS_THETA0];
             theta_max = 1e4 * q[HS_THETA0]; theta_min = 1e-4 * q[HS_THETA0];
             dw_last = q[HS_DWLAST];
             acceptable_count = (int)q[HS_ACCEPT];
@@ -1521,6 +1529,39 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
         }
 
         for (;;) {
+            // ---- iteration-bounded launch: a problem that has taken hand_iter iterations leaves with its complete state
+            //      (the record the lane kernel writes, tpp_hand_trip) and is resumed by the next launch ----
+            if (A.hand_rec && iter >= A.hand_iter) {
+                unsigned slot = 0;
+                if (lane == 0) slot = atomicAdd(A.hand_count, 1u);
+                slot = __shfl_sync(FULL, slot, 0);
+                if (slot < (unsigned)A.hand_cap) {
+                    double *hr = A.hand_rec + (size_t)slot * HAND_REC(N);
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        const int k = lane * J + j;
+                        if (k <= N) {
+                            double *q = hr + 16 * k;
+                            q[0] = s[j].X[0]; q[1] = s[j].X[1]; q[2] = s[j].X[2];
+                            q[3] = s[j].lam[0]; q[4] = s[j].lam[1]; q[5] = s[j].lam[2];
+                            q[6] = s[j].U[0]; q[7] = s[j].U[1]; q[8] = s[j].S[0]; q[9] = s[j].S[1];
+                            q[10] = s[j].yd[0]; q[11] = s[j].yd[1]; q[12] = s[j].vL[0]; q[13] = s[j].vL[1];
+                            q[14] = s[j].vU[0]; q[15] = s[j].vU[1];
+                        }
+                    }
+                    hr[HAND_FILT(N) + 2 * lane] = fphi; hr[HAND_FILT(N) + 2 * lane + 1] = ftheta;
+                    const unsigned fm = __ballot_sync(FULL, fvalid);
+                    if (lane == 0) {
+                        double *q = hr + HAND_SCAL(N);
+                        q[HS_B] = (double)b; q[HS_MU] = mu; q[HS_DF] = df; q[HS_THETA0] = theta0; q[HS_DWLAST] = dw_last;
+                        q[HS_ITER] = (double)iter; q[HS_LS] = (double)ls_extra; q[HS_NRESTO] = (double)n_resto;
+                        q[HS_ACCEPT] = (double)acceptable_count; q[HS_TINYLAST] = tiny_last ? 1.0 : 0.0;
+                        q[HS_TINYFLAG] = tiny_flag ? 1.0 : 0.0; q[HS_FMASK] = (double)fm; q[HS_RING] = (double)ring;
+                    }
+                    __syncwarp();
+                    return;
+                }
+            }
             // ---- evaluate the current point ----
             fcur = eval_point(df);
             double theta, prim_inf, dual_inf, sum_y, sum_z, compl0;
@@ -1573,8 +1614,9 @@ __device__ void solve_one(const KParams &P, const BatchArgs &A, int b, int lane,
                 sum_y = wsum(sy); sum_z = wsum(sz); compl0 = wmax(c0);
             }
             if (theta_max < 0) {
-                theta_max = 1e4 * fmax(1.0, theta);
-                theta_min = 1e-4 * fmax(1.0, theta);
+                theta0 = fmax(1.0, theta);
+                theta_max = 1e4 * theta0;
+                theta_min = 1e-4 * theta0;
             }
             const double sd = fmax(S_MAX, (sum_y + sum_z) / (double)(9 * N)) / S_MAX;
             const double sc = fmax(S_MAX, sum_z / (double)(4 * N)) / S_MAX;
@@ -2009,14 +2051,15 @@ __global__ void __launch_bounds__(128, OBS ? B200MPC_MIN_CTAS_OBS : B200MPC_MIN_
     double *sox = smem + (size_t)wid * per_warp, *soy = sox + Mpad, *rec = soy + Mpad;
     const KktRoles roles = kkt_roles(lane);
     if (A.resume) {
-        // second launch behind the lane kernel: the batch is the list of problems it handed over
-        const int n = (int)min(*A.hand_count, (unsigned)A.hand_cap);
+        // a launch behind the lane kernel or behind an iteration-bounded launch of this kernel: the batch is the list of
+        // problems that one handed over
+        const int n = (int)min(*A.resume_count, (unsigned)A.resume_cap);
         for (;;) {
             int r = 0;
             if (lane == 0) r = (int)atomicAdd(A.counter, 1u);
             r = __shfl_sync(FULL, r, 0);
             if (r >= n) break;
-            const double *hrec = A.hand_rec + (size_t)r * HAND_REC(P.N);
+            const double *hrec = A.resume_rec + (size_t)r * HAND_REC(P.N);
             solve_one<J, OBS, SCAN>(P, A, (int)hrec[HAND_SCAL(P.N) + HS_B], lane, sox, soy, rec, roles, hrec);
         }
         return;
@@ -2151,9 +2194,10 @@ struct b200mpc_handle {
     int tpp_cta_sync, tpp_b_passes;
     // straggler hand-over from the lane kernel to the warp kernel (BatchArgs::hand_rec)
     int hand_iter, hand_thin;   // hand_iter <= 0: off
-    double *d_hand;
-    size_t hand_cap;
-    unsigned int *d_hand_count;
+    double *d_hand[2];          // two record buffers: a launch reads one and writes the other
+    size_t hand_cap[2];
+    unsigned int *d_hand_count; // [2]
+    int warp_caps[4], n_warp_caps; // iteration bounds of the warp kernel's cascade (launch p exports at warp_caps[p]; the last launch has none)
     int kkt_scan_mode; // warp kernel: -1 scan recursion for batches that leave warps idle, 0 never, 1 always
     int lane_spec;     // template instance of the lane kernels (TPP_SPEC_*)
     int lane_fused;    // 1: two-sweep lane kernel (tpp_fused.cuh), 0: three-sweep lane kernel (tpp_kernel.cuh)
@@ -2367,7 +2411,22 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     h->hand_thin = -1;
     if (const char *eh = getenv("B200MPC_HAND_ITER")) h->hand_iter = atoi(eh);
     if (const char *eh = getenv("B200MPC_HAND_THIN")) h->hand_thin = atoi(eh);
-    h->d_hand = nullptr; h->hand_cap = 0; h->d_hand_count = nullptr;
+    h->d_hand[0] = h->d_hand[1] = nullptr; h->hand_cap[0] = h->hand_cap[1] = 0; h->d_hand_count = nullptr;
+    // warp kernel, batches of more than two waves of the persistent grid: optional cascade of iteration-bounded launches
+    // (B200MPC_WARP_CAPS="64,160").  OFF by default — measured, it loses: config 3 variant A 29.7 ms in one launch, 33.2 ms
+    // as 64 / 160 / rest; variant B 3.79 vs 4.25 ms with a bound of 32.  The persistent grid already starts a new problem the
+    // moment a warp is free, a single launch lasts about as long as its longest problem alone (343 iterations sharing an SM
+    // with seven other warps), and every bounded launch adds a tail of its own.
+    h->n_warp_caps = 0;
+    if (const char *ew = getenv("B200MPC_WARP_CAPS")) { // "64,160" | "0" (off)
+        h->n_warp_caps = 0;
+        for (const char *q = ew; *q && h->n_warp_caps < 4;) {
+            const int v = atoi(q);
+            if (v > 0) h->warp_caps[h->n_warp_caps++] = v;
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+    }
     h->tpp_cta_sync = (p->obs_form != B200MPC_OBS_NONE) ? 0 : 1; // (tpp_kernel.cuh, TppArgs::cta_sync)
     // two executions of block B per trip (TppArgs::b_passes): 15 % (variants B / C) to 49 % (variant A) of the factorisations need
     // an inertia correction, which used to cost the lane a whole trip; measured on 1 M cold variant-B problems
@@ -2405,7 +2464,8 @@ extern "C" void b200mpc_destroy(b200mpc_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->d_buf) cudaFree(h->d_buf);
-    if (h->d_hand) cudaFree(h->d_hand);
+    if (h->d_hand[0]) cudaFree(h->d_hand[0]);
+    if (h->d_hand[1]) cudaFree(h->d_hand[1]);
     if (h->d_hand_count) cudaFree(h->d_hand_count);
     if (h->d_ws) cudaFree(h->d_ws);
     if (h->d_filt) cudaFree(h->d_filt);
@@ -2516,30 +2576,36 @@ struct StreamWords {
 
 static int launch_warp_kernel(b200mpc_handle *h, const BatchArgs &a, int grid, bool scan, cudaStream_t stream);
 
-static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a_in, cudaStream_t stream, const StreamWords *sw = nullptr) {
+// record buffer `which` (0 / 1) with room for `cap` problems, its counter zeroed on `stream`
+static int ensure_hand_buffer(b200mpc_handle *h, int which, size_t cap, cudaStream_t stream) {
     const int N = h->prm.N;
+    if (cap > h->hand_cap[which]) {
+        if (h->d_hand[which]) { cudaFree(h->d_hand[which]); h->d_hand[which] = nullptr; h->hand_cap[which] = 0; }
+        cudaError_t e = cudaMalloc(&h->d_hand[which], cap * HAND_REC(N) * sizeof(double));
+        if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc(hand-over records): ") + cudaGetErrorString(e));
+        h->hand_cap[which] = cap;
+    }
+    if (!h->d_hand_count) {
+        cudaError_t e = cudaMalloc(&h->d_hand_count, 2 * sizeof(unsigned int));
+        if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    CU_TRY(h, cudaMemsetAsync(h->d_hand_count + which, 0, sizeof(unsigned int), stream));
+    return 0;
+}
+
+static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a_in, cudaStream_t stream, const StreamWords *sw = nullptr) {
     BatchArgs a = a_in;
     // straggler hand-over (not for streamed host-buffer solves: their per-chunk completion flags count lane-kernel results)
     const bool hand = h->hand_iter > 0 && !sw;
     if (hand) {
-        const size_t cap = (size_t)std::max(4096, a.B / 8);
-        if (cap > h->hand_cap) {
-            if (h->d_hand) { cudaFree(h->d_hand); h->d_hand = nullptr; h->hand_cap = 0; }
-            cudaError_t e = cudaMalloc(&h->d_hand, cap * HAND_REC(N) * sizeof(double));
-            if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc(hand-over records): ") + cudaGetErrorString(e));
-            h->hand_cap = cap;
-        }
-        if (!h->d_hand_count) {
-            cudaError_t e = cudaMalloc(&h->d_hand_count, sizeof(unsigned int));
-            if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-        }
-        CU_TRY(h, cudaMemsetAsync(h->d_hand_count, 0, sizeof(unsigned int), stream));
-        a.hand_rec = h->d_hand; a.hand_count = h->d_hand_count; a.hand_cap = (int)h->hand_cap;
+        const int rc = ensure_hand_buffer(h, 0, (size_t)std::max(4096, a.B / 8), stream);
+        if (rc) return rc;
+        a.hand_rec = h->d_hand[0]; a.hand_count = h->d_hand_count; a.hand_cap = (int)h->hand_cap[0];
         a.hand_iter = h->hand_iter; a.hand_thin = h->hand_thin;
     }
     const size_t nwarps = (size_t)h->tpp_ctas * (TPP_THREADS / 32);
     if (!h->d_ws) {
-        const size_t ws_bytes = nwarps * (size_t)(N + 1) * TPP_STAGE_B_MAX;
+        const size_t ws_bytes = nwarps * (size_t)(h->prm.N + 1) * TPP_STAGE_B_MAX;
         cudaError_t e = cudaMalloc(&h->d_ws, ws_bytes);
         if (e != cudaSuccess) return set_err(h, B200MPC_E_NOMEM, std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e));
         e = cudaMalloc(&h->d_filt, nwarps * 64 * 32 * sizeof(double));
@@ -2579,7 +2645,8 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a_in, cudaStream
     if (hand) {
         // the problems the lane kernel handed over: warp kernel, resuming from the records (their number stays on the device)
         BatchArgs r = a;
-        r.resume = 1;
+        r.resume = 1; r.resume_rec = a.hand_rec; r.resume_count = a.hand_count; r.resume_cap = a.hand_cap;
+        r.hand_rec = nullptr; r.hand_count = nullptr; r.hand_cap = 0; r.hand_iter = 0;
         CU_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), stream));
         const int rc = launch_warp_kernel(h, r, h->ctas, false, stream);
         if (rc) return rc;
@@ -2619,10 +2686,29 @@ static int launch_solve(b200mpc_handle *h, const BatchArgs &a, cudaStream_t stre
     // the caller sees; a batch that fills the machine keeps the lane-parallel serial form (+17 % solves/s there).
     const bool scan = (h->kkt_scan_mode >= 0) ? (h->kkt_scan_mode == 1) : (a.B <= h->ctas * 4);
     CU_TRY(h, cudaEventRecord(h->ev0, stream));
-    const int rc = launch_warp_kernel(h, a, grid, scan, stream);
-    if (rc) return rc;
+    // A batch of more than two waves of the persistent grid goes as a cascade of iteration-bounded launches: launch p hands
+    // the problems that reach warp_caps[p] iterations to launch p + 1 (records in two alternating buffers, counts on the
+    // device), so the long problems run side by side in the last launches instead of one behind the other at the end.
+    const int ncaps = (a.B > 2 * h->ctas * 4) ? h->n_warp_caps : 0;
+    BatchArgs cur = a;
+    for (int pass = 0; pass <= ncaps; pass++) {
+        if (pass < ncaps) {
+            const int w = pass & 1;
+            const int rc = ensure_hand_buffer(h, w, (size_t)a.B, stream);
+            if (rc) return rc;
+            cur.hand_rec = h->d_hand[w]; cur.hand_count = h->d_hand_count + w; cur.hand_cap = (int)h->hand_cap[w];
+            cur.hand_iter = h->warp_caps[pass];
+        } else {
+            cur.hand_rec = nullptr; cur.hand_count = nullptr; cur.hand_cap = 0; cur.hand_iter = 0;
+        }
+        if (pass > 0) CU_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), stream));
+        const int rc = launch_warp_kernel(h, cur, pass == 0 ? grid : h->ctas, scan, stream);
+        if (rc) return rc;
+        h->launches++;
+        // the next launch resumes what this one exported
+        cur.resume = 1; cur.resume_rec = cur.hand_rec; cur.resume_count = cur.hand_count; cur.resume_cap = cur.hand_cap;
+    }
     CU_TRY(h, cudaEventRecord(h->ev1, stream));
-    h->launches++;
     return 0;
 }
 

@@ -1051,6 +1051,30 @@ def test_fleet_with_obstacle_cost_runs_on_the_device(env):
     assert np.linalg.norm(state[:, :2] - start[:, :2], axis=1).max() > 0.1   # the fleet moves
 
 
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_iteration_bounded_warp_kernel_launches(env, variant, monkeypatch):
+    """The warp kernel can export a problem's solver state as the lane kernel does and resume it in a later launch
+    (B200MPC_WARP_CAPS: a cascade of iteration-bounded launches; off by default, it does not pay).  With bounds of 5 and 12
+    iterations nearly every problem crosses two launch boundaries; results must be bit-identical to the single launch."""
+    shim, synth = env["shim"], env["synth"]
+    w = synth.robots_on_map(B=4096, seed=9)
+    xr, kw = _inputs(env, variant, w)
+    S = shim.Solver(env["make"](variant, env["y"]))
+    S.set_kernel(shim.KERNEL_WARP)
+    one = S.solve_batch(w["x0"], xr, **kw)
+    S.close()
+    monkeypatch.setenv("B200MPC_WARP_CAPS", "5,12")
+    S = shim.Solver(env["make"](variant, env["y"]))
+    monkeypatch.delenv("B200MPC_WARP_CAPS")
+    S.set_kernel(shim.KERNEL_WARP)
+    n0 = S.launch_count
+    out = S.solve_batch(w["x0"], xr, **kw)
+    assert S.launch_count - n0 == 3
+    S.close()
+    for k in ("status", "iters", "ls", "cost", "X", "U"):
+        assert np.array_equal(out[k], one[k], equal_nan=True), k
+
+
 def test_handles_with_different_shared_memory_needs_coexist(env, robots):
     """The warp kernel's dynamic shared-memory limit is a per-kernel attribute shared by all handles of the process: a
     handle created later with a smaller need (no obstacle lists) must not break the launches of an earlier one."""
