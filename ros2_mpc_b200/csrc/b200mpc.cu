@@ -3270,6 +3270,19 @@ extern "C" int b200mpc_dilate_batch_device(b200mpc_handle *h, int B, int H, int 
     DilateArgs a;
     a.B = B; a.H = H; a.W = W; a.kh = kh; a.kw = kw; a.in = grid; a.out = out;
     size_t smem;
+    const size_t whole = 2 * (size_t)H * W * sizeof(double);
+    if (whole <= 110 * 1024 && (kh - 1) / 2 < H && (kw - 1) / 2 < W) {
+        // the whole grid and its row maxima fit: one CTA per grid, the grid is read once (two CTAs per SM at 80 x 80)
+        a.TH = H; a.TW = W;
+        CU_TRY(h, cudaFuncSetAttribute(dilate_whole_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        const long long cap = (long long)h->sm_count * 2;
+        CU_TRY(h, cudaEventRecord(h->ev0, (cudaStream_t)stream));
+        dilate_whole_kernel<<<(int)(B < cap ? B : cap), COSTMAP_THREADS, whole, (cudaStream_t)stream>>>(a);
+        CU_TRY(h, cudaGetLastError());
+        CU_TRY(h, cudaEventRecord(h->ev1, (cudaStream_t)stream));
+        h->launches++;
+        return 0;
+    }
     costmap_tile(H, W, kh - 1, kw - 1, 0, a.TH, a.TW, smem, true);
     if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(dilate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const long long tiles = (long long)B * ((H + a.TH - 1) / a.TH) * ((W + a.TW - 1) / a.TW);
