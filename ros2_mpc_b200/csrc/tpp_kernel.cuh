@@ -1530,10 +1530,14 @@ __device__ __noinline__ void tpp_hand_trip(const KParams &P, const TppArgs &T, c
         q[HS_TINYFLAG] = (double)L.tiny_flag; q[HS_FMASK] = (double)L.fmask; q[HS_RING] = (double)L.ring;
         L.phase = PH_LOAD;
     }
-    const int ph = L.phase;
-    const unsigned act = __ballot_sync(FULL, ph != PH_DONE && ph != PH_LOAD);
-    const bool thin = __popc(act) <= A.hand_thin && *reinterpret_cast<volatile unsigned *>(A.counter) >= (unsigned)A.B;
-    L.hcap = (L.hslot == -2) ? 0x7fffffff : (thin ? 0 : A.hand_iter);
+    if (A.hand_thin >= 0) { // (off by default: the work-queue counter is not even looked at then)
+        const int ph = L.phase;
+        const unsigned act = __ballot_sync(FULL, ph != PH_DONE && ph != PH_LOAD);
+        const bool thin = __popc(act) <= A.hand_thin && *reinterpret_cast<volatile unsigned *>(A.counter) >= (unsigned)A.B;
+        L.hcap = (L.hslot == -2) ? 0x7fffffff : (thin ? 0 : A.hand_iter);
+    } else if (L.hslot == -2) {
+        L.hcap = 0x7fffffff;
+    }
 }
 
 template <int SPEC>
@@ -1873,7 +1877,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 }
             }
             // hand-over records: iterate rows of the new current buffer, filter, solver scalars
-            if (TPP_HAND) tpp_hand_trip(P, T, wbase, gw, L, myco);
+            if (TPP_HAND && (A.hand_thin >= 0 || __any_sync(FULL, ph == PH_EXPORT))) tpp_hand_trip(P, T, wbase, gw, L, myco);
             if (fin) {
                 const size_t b = (size_t)L.b;
                 if (A.cost) A.cost[b] = L.f;
