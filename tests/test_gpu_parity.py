@@ -1075,6 +1075,27 @@ def test_iteration_bounded_warp_kernel_launches(env, variant, monkeypatch):
         assert np.array_equal(out[k], one[k], equal_nan=True), k
 
 
+def test_restoration_second_stage_on_both_kernels(env):
+    """The problems of tests/golden/resto_golden.npz (first restoration stage finds nothing: the roll-out runs into an obstacle
+    point) on the warp kernel and on the lane kernel (warp-cooperative restoration): status, optimum and iteration count of
+    the oracle, and the cost scipy's SLSQP reaches where it converges."""
+    O, shim = env["O"], env["shim"]
+    g = np.load(os.path.join(G, "resto_golden.npz"))
+    po = O.variant_params("A", env["y"])
+    kw = dict(obs_x=g["obs_x"], obs_y=g["obs_y"])
+    ref = O.solve_batch(po, g["x0"], g["goal"], **kw)
+    assert (ref["status"] == 0).all()
+    for kind in (shim.KERNEL_WARP, shim.KERNEL_LANE):
+        S = shim.Solver(env["make"]("A", env["y"]))
+        S.set_kernel(kind)
+        out = S.solve_batch(g["x0"], g["goal"], **kw)
+        S.close()
+        _assert_parity(out, ref, need_frac=1.0)
+        assert np.array_equal(out["iters"], ref["iters"])
+        ok = np.isfinite(g["slsqp_cost"])
+        assert np.all(np.abs(out["cost"][ok] - g["slsqp_cost"][ok]) <= COST_RTOL * np.abs(g["slsqp_cost"][ok]))
+
+
 def test_handles_with_different_shared_memory_needs_coexist(env, robots):
     """The warp kernel's dynamic shared-memory limit is a per-kernel attribute shared by all handles of the process: a
     handle created later with a smaller need (no obstacle lists) must not break the launches of an earlier one."""

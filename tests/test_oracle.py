@@ -5,6 +5,7 @@ The reference has no tests or golden vectors, so these are
 Riccati backend with an independent dense LDL^T of the full KKT matrix, analytic known answers, and agreement of
 the optimum with scipy's SLSQP on the same multiple-shooting NLP."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -276,3 +277,21 @@ def test_batch_matches_single_and_threads():
     assert np.array_equal(r1["X"], r3["X"]) and np.array_equal(r1["status"], r3["status"])
     s = O.solve(p, x0[5], goal[5])
     assert np.array_equal(s["X"].T, r1["X"][5]) and s["cost"] == r1["cost"][5]
+
+
+def test_restoration_second_stage_reaches_the_third_party_optimum():
+    """Four config-3 problems of the obstacle-active variant on which the roll-out of the slacks runs into an obstacle point
+    (tests/golden/make_resto_golden.py): with the first restoration stage alone the solve ended Restoration_Failed at a
+    cost of 2.5e8 ... 4.6e24; the second stage (the plan shrunk towards standing still, lowest barrier objective) lets all
+    four converge, and where scipy's SLSQP reaches a KKT point from the same cold start it is the same optimum."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resto_golden.npz"))
+    p = O.variant_params("A")
+    for n in range(len(g["index"])):
+        kw = dict(obs_x=g["obs_x"][n], obs_y=g["obs_y"][n])
+        r = O.solve(p, g["x0"][n], g["goal"][n], **kw)
+        assert r["status"] == 0 and r["stats"]["n_resto"] >= 1, (int(g["index"][n]), r["status"], r["stats"])
+        c = O.kkt_certificate(p, g["x0"][n], g["goal"][n], r["X"].T.copy(), r["U"].T.copy(), **kw)
+        assert c["defect"] <= 1e-8 and c["complementarity"] <= 1e-6, c
+        if np.isfinite(g["slsqp_cost"][n]):
+            assert abs(r["cost"] - g["slsqp_cost"][n]) <= 1e-5 * abs(g["slsqp_cost"][n])
+    assert np.isfinite(g["slsqp_cost"]).sum() >= 2
