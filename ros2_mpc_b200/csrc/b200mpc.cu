@@ -2404,7 +2404,7 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     // hand-over threshold: about twice the mean iteration count of the family (variant A ~60, variants B / C ~22)
     // (measured, 1 M problems: variant B 198.2 -> 190.4 ms with 60 / 8; variant A: the launch no longer lasts as long as its
     // slowest problem, 1354 -> 417 ms for 65 536 problems with one 3000-iteration straggler)
-    h->hand_iter = (p->obs_form != B200MPC_OBS_NONE) ? 192 : 60;
+    h->hand_iter = (p->obs_form != B200MPC_OBS_NONE) ? 128 : 60;
     // hand_thin: also hand over every problem of a warp that has thinned out to <= hand_thin active lanes once the work queue is
     // empty.  Off (-1) by default: which problems that rule catches depends on the timing of the launch, and results would
     // no longer be bit-identical from run to run (the two kernels agree to rounding, not to the bit).
@@ -2598,7 +2598,9 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a_in, cudaStream
     // straggler hand-over (not for streamed host-buffer solves: their per-chunk completion flags count lane-kernel results)
     const bool hand = h->hand_iter > 0 && !sw;
     if (hand) {
-        const int rc = ensure_hand_buffer(h, 0, (size_t)std::max(4096, a.B / 8), stream);
+        // room for a quarter of the batch: a lane that finds the buffer full stays in the lane kernel for good, and a
+        // 3000-iteration problem left there holds the launch for seconds (measured with room for an eighth and a threshold of 96)
+        const int rc = ensure_hand_buffer(h, 0, (size_t)a.B / 4 + 4096, stream);
         if (rc) return rc;
         a.hand_rec = h->d_hand[0]; a.hand_count = h->d_hand_count; a.hand_cap = (int)h->hand_cap[0];
         a.hand_iter = h->hand_iter; a.hand_thin = h->hand_thin;
