@@ -1602,7 +1602,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
                 L.tmode = TM_LSQ;
                 L.phase = PH_B;
                 L.hslot = -1;
-                L.hcap = A.hand_iter;
+                L.hcap = (A.hand_iter_tail > 0 && (long long)b >= (long long)A.B - (long long)(gridDim.x * blockDim.x)) ? A.hand_iter_tail : A.hand_iter;
                 if (gone) { L.phase = PH_DONE; newb = -1; }
             }
         }
