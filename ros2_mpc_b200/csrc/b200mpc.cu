@@ -2613,6 +2613,7 @@ static int launch_solve_tpp(b200mpc_handle *h, const BatchArgs &a_in, cudaStream
         const int rc = ensure_hand_buffer(h, 0, (size_t)a.B / 4 + 4096, stream);
         if (rc) return rc;
         a.hand_rec = h->d_hand[0]; a.hand_count = h->d_hand_count; a.hand_cap = (int)h->hand_cap[0];
+        if (const char *ec = getenv("B200MPC_HAND_CAP")) a.hand_cap = std::min(a.hand_cap, std::max(0, atoi(ec))); // tests: the buffer-full path
         a.hand_iter = h->hand_iter; a.hand_thin = h->hand_thin;
         a.hand_iter_tail = h->hand_iter_tail;
     }

@@ -565,6 +565,25 @@ def test_straggler_handover_lane_to_warp_kernel(env, robots, variant, monkeypatc
     assert np.mean((out["iters"] == ref["iters"])[both]) >= (0.9 if variant == "A" else 0.99)
 
 
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_straggler_handover_with_a_full_record_buffer(env, robots, variant, monkeypatch):
+    """A lane that wants to leave but finds the record buffer full stays in the lane kernel for good (it re-evaluates its
+    point and goes on).  Room for 16 records and a threshold of 3: 16 problems change kernels, the others take the
+    buffer-full path; every problem must still match the oracle."""
+    O, shim = env["O"], env["shim"]
+    xr, kw = _inputs(env, variant, robots)
+    ref = O.solve_batch(O.variant_params(variant, env["y"]), robots["x0"], xr, **kw)
+    monkeypatch.setenv("B200MPC_HAND_ITER", "3")
+    monkeypatch.setenv("B200MPC_HAND_CAP", "16")
+    S = shim.Solver(env["make"](variant, env["y"]))
+    S.set_kernel(shim.KERNEL_LANE)
+    out = S.solve_batch(robots["x0"], xr, **kw)
+    S.close()
+    _assert_parity(out, ref, need_frac=0.9 if variant == "A" else 1.0, nonconvex_slack=0.02 if variant == "A" else 0.0)
+    both = np.isin(out["status"], (0, 1)) & np.isin(ref["status"], (0, 1))
+    assert np.mean((out["iters"] == ref["iters"])[both]) >= (0.9 if variant == "A" else 0.99)
+
+
 def test_lane_kernel_edge_cases(env, robots):
     O, shim = env["O"], env["shim"]
     po = O.variant_params("B", env["y"])
