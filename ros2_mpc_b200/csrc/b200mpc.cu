@@ -3284,6 +3284,33 @@ extern "C" int b200mpc_dilate_batch_device(b200mpc_handle *h, int B, int H, int 
     DilateArgs a;
     a.B = B; a.H = H; a.W = W; a.kh = kh; a.kw = kw; a.in = grid; a.out = out;
     size_t smem;
+    if (kh == 10 && kw == 10) {
+        // the structuring element of both costmap publishers: strip kernel (integer maxima by doubling, registers)
+        DilateStripArgs s;
+        s.B = B; s.H = H; s.W = W; s.in = grid; s.out = out;
+        auto layout = [&](int TH, int TW) {
+            s.TH = TH; s.TW = TW;
+            const int nsx = (TW + DIL_SEG - 1) / DIL_SEG, nsy = (TH + DIL_SEG - 1) / DIL_SEG;
+            s.PS = (nsx * DIL_SEG + kw - 1) | 1;
+            s.PT = TW | 1;
+            s.src_rows = (TH == H && TW == W) ? H : TH + kh - 1;
+            const size_t ints = (size_t)s.src_rows * s.PS + (size_t)(nsy * DIL_SEG + kh - 1) * s.PT;
+            s.obuf_off = (int)((ints * 4 + 15) & ~(size_t)15);
+            return (size_t)s.obuf_off + (((size_t)TH * TW + 15) & ~(size_t)15);
+        };
+        smem = layout(H, W);
+        if (smem > 72 * 1024) smem = layout(H < 80 ? H : 80, W < 80 ? W : 80);
+        if (smem > 48 * 1024)
+            CU_TRY(h, cudaFuncSetAttribute(dilate_strip_kernel<10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        const long long tiles = (long long)B * ((H + s.TH - 1) / s.TH) * ((W + s.TW - 1) / s.TW);
+        const long long cap = (long long)h->sm_count * 3;
+        CU_TRY(h, cudaEventRecord(h->ev0, (cudaStream_t)stream));
+        dilate_strip_kernel<10, 10><<<(int)(tiles < cap ? tiles : cap), DIL_THREADS, smem, (cudaStream_t)stream>>>(s);
+        CU_TRY(h, cudaGetLastError());
+        CU_TRY(h, cudaEventRecord(h->ev1, (cudaStream_t)stream));
+        h->launches++;
+        return 0;
+    }
     const size_t whole = 2 * (size_t)H * W * sizeof(double);
     if (whole <= 110 * 1024 && (kh - 1) / 2 < H && (kw - 1) / 2 < W) {
         // the whole grid and its row maxima fit: one CTA per grid, the grid is read once (two CTAs per SM at 80 x 80)

@@ -117,6 +117,13 @@ def test_gpu_dilate_matches_opencv(gold, built):
     out = cm.dilate(grids)
     for b in (0, 100, 256):
         assert np.array_equal(out[b], np_dilate(grids[b], 10, 10))
+    # the 10 x 10 strip kernel on other shapes: whole grid with an odd width, smaller than the structuring element, tiled
+    # (several tiles per grid, ragged last tiles), arbitrary non-negative values (truncated toward zero by the cast)
+    for shape in ((33, 47), (7, 5), (1, 1), (81, 80), (80, 82), (100, 200), (224, 314), (161, 19)):
+        g = np.round(rng.uniform(0, 255.9, (3,) + shape), 2) * (rng.random((3,) + shape) < 0.05)
+        o = cm.dilate(g)
+        for b in range(3):
+            assert np.array_equal(o[b], np_dilate(g[b], 10, 10)), shape
 
 
 @pytest.mark.gpu
