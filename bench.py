@@ -396,7 +396,7 @@ def costmap_lines(solver, torch, dev, params, hbm_peak, robots=4096, tile=32, re
                                           D(dbs.data_ptr()), D(yaw.data_ptr()), float(params["costmap_size"]),
                                           float(params["resolution"]), 10, 10, D(img.data_ptr()), D(stream.cuda_stream)))
     by = 8 * n + nc * nc + 8
-    out = {"local_costmap": {"kernel": "local_costmap_kernel", "robots_per_launch": B, "ms_per_launch": ms,
+    out = {"local_costmap": {"kernel": "local_costmap_kernel<10,10>", "robots_per_launch": B, "ms_per_launch": ms,
                              "robots_per_s": B / (ms * 1e-3), "bound": "hbm", "algorithmic_bytes_per_robot": by,
                              "achieved_gbs": by * B / (ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                              "frac": by * B / (ms * 1e-3) / 1e9 / hbm_peak}}

@@ -3303,6 +3303,7 @@ extern "C" int b200mpc_dilate_batch_device(b200mpc_handle *h, int B, int H, int 
         if (smem > 48 * 1024)
             CU_TRY(h, cudaFuncSetAttribute(dilate_strip_kernel<10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
         const long long tiles = (long long)B * ((H + s.TH - 1) / s.TH) * ((W + s.TW - 1) / s.TW);
+        if (tiles >= (1ll << 31)) return set_err(h, B200MPC_E_ARG, "too many tiles for one launch (B x tiles per grid >= 2^31)");
         const long long cap = (long long)h->sm_count * 3;
         CU_TRY(h, cudaEventRecord(h->ev0, (cudaStream_t)stream));
         dilate_strip_kernel<10, 10><<<(int)(tiles < cap ? tiles : cap), DIL_THREADS, smem, (cudaStream_t)stream>>>(s);
@@ -3378,14 +3379,17 @@ extern "C" int b200mpc_local_costmap_batch_device(b200mpc_handle *h, int B, int 
     a.wpr = (a.nc + 31) / 32;
     a.scan = scan; a.bcos = beam_cos; a.bsin = beam_sin; a.yaw = yaw; a.half = map_size / 2; a.res = resolution;
     a.value = 100; a.out = out;
-    const size_t smem = (size_t)LCM_WARPS * 2 * a.nc * a.wpr * 4;
+    const size_t smem = (size_t)LCM_WARPS * 2 * a.nc * a.wpr * 4 + 2048; // + the byte-expansion table of the compile-time instance
     if (smem > 200 * 1024) return set_err(h, B200MPC_E_ARG, "grid too large for the shared-memory staging");
-    if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(local_costmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    // the publishers' structuring element on a grid whose rows are whole 16-byte pieces: compile-time passes
+    const bool fast = (kh == 10 && kw == 10 && a.nc % 16 == 0 && (reinterpret_cast<size_t>(out) & 15) == 0);
+    void (*kern)(const LocalCostmapArgs) = fast ? local_costmap_kernel<10, 10> : local_costmap_kernel<0, 0>;
+    if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int grid = (B + LCM_WARPS - 1) / LCM_WARPS;
     const int cap = h->sm_count * 8;
     if (grid > cap) grid = cap;
     CU_TRY(h, cudaEventRecord(h->ev0, (cudaStream_t)stream));
-    local_costmap_kernel<<<grid, LCM_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
+    kern<<<grid, LCM_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaEventRecord(h->ev1, (cudaStream_t)stream));
     h->launches++;

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(COSTMAP_THREADS) dilate_whole_kernel(const Dil
 // One CTA per tile (tile = whole grid when it fits: the 80 x 80 local costmap is exactly 320 strips per pass).
 #define DIL_THREADS 320
 #define DIL_SEG 20
+#define DIL_LD 1
 #define DIL_NEG (-2147483647 - 1)
 
 __device__ __forceinline__ int dil_cvt(double v) { return (v != v) ? DIL_NEG : __double2int_rz(v); }
@@ -158,7 +159,7 @@ struct DilateStripArgs {
 };
 
 template <int KH, int KW>
-__global__ void __launch_bounds__(DIL_THREADS) dilate_strip_kernel(const DilateStripArgs a) {
+__global__ void __launch_bounds__(DIL_THREADS, 3) dilate_strip_kernel(const DilateStripArgs a) {
     extern __shared__ __align__(16) unsigned char cm_smem[];
     constexpr int ah = KH / 2, aw = KW / 2;
     const int H = a.H, W = a.W, TH = a.TH, TW = a.TW, PS = a.PS, PT = a.PT;
@@ -181,23 +182,36 @@ __global__ void __launch_bounds__(DIL_THREADS) dilate_strip_kernel(const DilateS
             tmp[(j < ah ? j : H + j) * PT + x] = DIL_NEG;
         }
     }
-    for (long long t = blockIdx.x; t < (long long)a.B * per_grid; t += gridDim.x) {
-        const int b = (int)(t / per_grid), tt = (int)(t - (long long)b * per_grid);
-        const int y0 = (tt / tiles_x) * TH, x0 = (tt % tiles_x) * TW;
+    // (loop-invariant index arithmetic of the vectorised staging: this thread's first cell, the step between its loads)
+    const int half = (H * W) >> 1;
+    const int dy = (2 * DIL_THREADS) / W, dx = 2 * DIL_THREADS - dy * W;
+    const int ys = (2 * (int)threadIdx.x) / W, xs = 2 * (int)threadIdx.x - ys * W;
+    const int ntiles = a.B * per_grid; // (the host keeps B * tiles per grid below 2^31)
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int b = whole ? t : t / per_grid, tt = whole ? 0 : t - b * per_grid;
+        const int ty = whole ? 0 : tt / tiles_x;
+        const int y0 = ty * TH, x0 = (tt - ty * tiles_x) * TW;
         const double *g = a.in + (size_t)b * H * W;
         // staged rows that lie inside the image: r in [r_lo, r_hi)
         const int r_lo = max(0, ah - y0), r_hi = min(SH, H - y0 + ah), nr = r_hi - r_lo;
         if (vec_in) {
             const double2 *g2 = reinterpret_cast<const double2 *>(g);
-            const int half = (H * W) >> 1, step = 2 * DIL_THREADS;
-            const int dy = step / W, dx = step - dy * W;
-            int cell = 2 * threadIdx.x, y = cell / W, x = cell - y * W;
-            for (int i = threadIdx.x; i < half; i += DIL_THREADS) {
-                const double2 v = __ldcs(g2 + i);
-                int *d = src + y * PS + aw + x;
-                d[0] = dil_cvt(v.x); d[1] = dil_cvt(v.y);
-                x += dx; y += dy;
-                if (x >= W) { x -= W; y++; }
+            int y = ys, x = xs;
+            // DIL_LD loads in flight per thread before the first conversion waits for one
+            for (int i0 = threadIdx.x; i0 < half; i0 += DIL_LD * DIL_THREADS) {
+                double2 v[DIL_LD];
+#pragma unroll
+                for (int u = 0; u < DIL_LD; u++)
+                    if (i0 + u * DIL_THREADS < half) v[u] = __ldcs(g2 + i0 + u * DIL_THREADS);
+#pragma unroll
+                for (int u = 0; u < DIL_LD; u++) {
+                    if (i0 + u * DIL_THREADS < half) {
+                        int *d = src + y * PS + aw + x;
+                        d[0] = dil_cvt(v[u].x); d[1] = dil_cvt(v[u].y);
+                    }
+                    x += dx; y += dy;
+                    if (x >= W) { x -= W; y++; }
+                }
             }
         } else {
             for (int i = threadIdx.x; i < nr * CW; i += DIL_THREADS) {
@@ -322,6 +336,30 @@ struct LocalCostmapArgs {
 // OR of the row shifted by -lo .. +hi bit positions (bit x of the result = any bit in [x - hi, x + lo] ... see caller)
 __device__ __forceinline__ unsigned lcm_word(const unsigned *row, int wpr, int w) { return (w >= 0 && w < wpr) ? row[w] : 0u; }
 
+// KH = KW = 0: structuring element from the arguments (generic passes).  KH, KW > 0: compile-time element and a grid side
+// that is a multiple of 16 (the publishers' case, 10 x 10 on 80 x 80): the shifts of the horizontal pass unroll, the
+// vertical pass takes strips of LCM_VSEG rows per lane (window ORs by doubling in registers, as dil_window_max does for
+// maxima) and leaves its words in shared memory, and the byte expansion reads ONE word per 16-byte store; the index
+// divisions are multiplications (profiles/r2_lcm_v1_ncu_summary.txt: the generic passes were 68 % of the kernel's
+// instructions, the kernel issue-bound at 78 % of the issue slots).
+#define LCM_VSEG 8
+template <int K, int NOUT>
+__device__ __forceinline__ void lcm_window_or(unsigned (&v)[NOUT + K - 1]) {
+    constexpr int LEN = NOUT + K - 1;
+    constexpr int P = K >= 32 ? 32 : K >= 16 ? 16 : K >= 8 ? 8 : K >= 4 ? 4 : K >= 2 ? 2 : 1;
+#pragma unroll
+    for (int q = 1; q < P; q <<= 1) {
+#pragma unroll
+        for (int j = 0; j < LEN; j++)
+            if (j + 2 * q <= LEN) v[j] |= v[j + q];
+    }
+    if (K > P) {
+#pragma unroll
+        for (int t = 0; t < NOUT; t++) v[t] |= v[t + K - P];
+    }
+}
+
+template <int KH, int KW>
 __global__ void __launch_bounds__(LCM_WARPS * 32) local_costmap_kernel(const LocalCostmapArgs a) {
     extern __shared__ __align__(16) unsigned char cm_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -334,10 +372,21 @@ __global__ void __launch_bounds__(LCM_WARPS * 32) local_costmap_kernel(const Loc
     // a set bit (ys, xs) lights the outputs y in [ys - (kh-1-ah), ys + ah], x in [xs - (kw-1-aw), xs + aw]
     const int left = a.kw - 1 - aw, right = aw, up = a.kh - 1 - ah, down = ah;
     const unsigned v4 = 0x01010101u * a.value;
+    // compile-time element: table byte of 8 cells -> their 8 image bytes, behind the warps' buffers (two loads per 16-byte store)
+    uint2 *lut = reinterpret_cast<uint2 *>(cm_smem + (size_t)LCM_WARPS * per_warp);
+    if (KH > 0) {
+        for (int e = threadIdx.x; e < 256; e += LCM_WARPS * 32)
+            lut[e] = make_uint2((((e & 0xfu) * 0x00204081u) & 0x01010101u) * a.value, ((((e >> 4) & 0xfu) * 0x00204081u) & 0x01010101u) * a.value);
+        __syncthreads();
+    }
     for (int b = blockIdx.x * LCM_WARPS + wid; b < a.B; b += gridDim.x * LCM_WARPS) {
         for (int w = lane; w < nc * wpr; w += 32) bits[w] = 0u;
         __syncwarp();
         const double *sc = a.scan + (size_t)b * a.n;
+        {   // the warp's next scan on its way into L2 while this one is processed (one 128-byte line per lane)
+            const long long bn = (long long)b + (long long)gridDim.x * LCM_WARPS;
+            if (bn < a.B && lane * 16 < a.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.scan + (size_t)bn * a.n + lane * 16));
+        }
         double sn, cs;
         sincos(a.yaw[b], &sn, &cs);
         const double nsn = -sn;
@@ -388,41 +437,84 @@ __global__ void __launch_bounds__(LCM_WARPS * 32) local_costmap_kernel(const Loc
             }
         }
         __syncwarp();
-        // horizontal pass: hor[y] bit x = OR of bits[y] over xs in [x - right, x + left]
-        for (int i = lane; i < nc * wpr; i += 32) {
-            const int y = i / wpr, w = i - y * wpr;
-            const unsigned *row = bits + y * wpr;
-            const unsigned lo = lcm_word(row, wpr, w - 1), mid = row[w], hi = lcm_word(row, wpr, w + 1);
-            unsigned acc = mid;
-            for (int s = 1; s <= right; s++) acc |= __funnelshift_l(lo, mid, s);  // sources at lower x
-            for (int s = 1; s <= left; s++) acc |= __funnelshift_r(mid, hi, s);   // sources at higher x
-            hor[i] = acc;
-        }
-        __syncwarp();
-        // vertical pass + expansion to bytes: out[y] = OR of hor[ys] over ys in [y - down, y + up]
-        unsigned char *o = a.out + (size_t)b * nc * nc;
-        const int groups = (nc + 15) / 16; // 16 cells per store
-        for (int i = lane; i < nc * groups; i += 32) {
-            const int y = i / groups, gx = (i - y * groups) * 16;
-            const int w = gx >> 5, sh = gx & 31;
-            unsigned acc = 0u;
-            const int ya = max(0, y - down), yb = min(nc - 1, y + up);
-            for (int ys = ya; ys <= yb; ys++) acc |= hor[ys * wpr + w];
-            const unsigned m16 = (acc >> sh) & 0xffffu;
-            unsigned q[4];
+        if (KH > 0) {
+            // ---- compile-time element ----
+            constexpr int kleft = KW - 1 - KW / 2, kright = KW / 2, kdown = KH / 2; // (rows above: KH - 1 - kdown)
+            const unsigned mw = (1u << 20) / (unsigned)wpr + 1u; // i / wpr = (i * mw) >> 20 for i < 2^20 / wpr (i < 8192, wpr <= 16)
+            for (int i = lane; i < nc * wpr; i += 32) {
+                const int y = (int)(((unsigned)i * mw) >> 20), w = i - y * wpr;
+                const unsigned *row = bits + y * wpr;
+                const unsigned lo = lcm_word(row, wpr, w - 1), mid = row[w], hi = lcm_word(row, wpr, w + 1);
+                unsigned acc = mid;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const unsigned nib = (m16 >> (4 * u)) & 0xfu;
-                // spread 4 bits to 4 bytes (0x00 / 0x01 each), then scale by the cell value
-                const unsigned spread = (nib * 0x00204081u) & 0x01010101u;
-                q[u] = spread * a.value;
+                for (int s = 1; s <= kright; s++) acc |= __funnelshift_l(lo, mid, s);
+#pragma unroll
+                for (int s = 1; s <= kleft; s++) acc |= __funnelshift_r(mid, hi, s);
+                hor[i] = acc;
             }
-            (void)v4;
-            unsigned char *dst = o + (size_t)y * nc + gx;
-            if (gx + 16 <= nc && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
-                __stcs(reinterpret_cast<uint4 *>(dst), make_uint4(q[0], q[1], q[2], q[3]));
-            } else {
-                for (int u = 0; u < 16 && gx + u < nc; u++) dst[u] = (unsigned char)((q[u >> 2] >> (8 * (u & 3))) & 0xffu);
+            __syncwarp();
+            // vertical pass: lane <-> (strip of LCM_VSEG rows, word column); ver[y] = OR of hor[ys], ys in [y - kdown, y + KH - 1 - kdown]
+            unsigned *ver = bits; // (the occupancy bits are dead)
+            const int nstrips = (nc + LCM_VSEG - 1) / LCM_VSEG;
+            for (int i = lane; i < nstrips * wpr; i += 32) {
+                const int st = (int)(((unsigned)i * mw) >> 20), w = i - st * wpr;
+                const int yb = st * LCM_VSEG - kdown;
+                unsigned v[LCM_VSEG + KH - 1];
+#pragma unroll
+                for (int j = 0; j < LCM_VSEG + KH - 1; j++) v[j] = ((unsigned)(yb + j) < (unsigned)nc) ? hor[(yb + j) * wpr + w] : 0u;
+                lcm_window_or<KH, LCM_VSEG>(v);
+#pragma unroll
+                for (int j = 0; j < LCM_VSEG; j++)
+                    if (st * LCM_VSEG + j < nc) ver[(st * LCM_VSEG + j) * wpr + w] = v[j];
+            }
+            __syncwarp();
+            // bytes: 16 cells per store, consecutive lanes write consecutive 16-byte pieces of the image
+            unsigned char *o = a.out + (size_t)b * nc * nc;
+            const int groups = nc >> 4;
+            const unsigned mg = (1u << 20) / (unsigned)groups + 1u; // i < nc * groups <= 16384 < 2^20 / groups
+            for (int i = lane; i < nc * groups; i += 32) {
+                const int y = (int)(((unsigned)i * mg) >> 20), g = i - y * groups;
+                const unsigned m16 = (ver[y * wpr + (g >> 1)] >> ((g & 1) << 4)) & 0xffffu;
+                const uint2 qa = lut[m16 & 0xffu], qb = lut[m16 >> 8];
+                __stcs(reinterpret_cast<uint4 *>(o) + i, make_uint4(qa.x, qa.y, qb.x, qb.y));
+            }
+        } else {
+            // horizontal pass: hor[y] bit x = OR of bits[y] over xs in [x - right, x + left]
+            for (int i = lane; i < nc * wpr; i += 32) {
+                const int y = i / wpr, w = i - y * wpr;
+                const unsigned *row = bits + y * wpr;
+                const unsigned lo = lcm_word(row, wpr, w - 1), mid = row[w], hi = lcm_word(row, wpr, w + 1);
+                unsigned acc = mid;
+                for (int s = 1; s <= right; s++) acc |= __funnelshift_l(lo, mid, s);  // sources at lower x
+                for (int s = 1; s <= left; s++) acc |= __funnelshift_r(mid, hi, s);   // sources at higher x
+                hor[i] = acc;
+            }
+            __syncwarp();
+            // vertical pass + expansion to bytes: out[y] = OR of hor[ys] over ys in [y - down, y + up]
+            unsigned char *o = a.out + (size_t)b * nc * nc;
+            const int groups = (nc + 15) / 16; // 16 cells per store
+            for (int i = lane; i < nc * groups; i += 32) {
+                const int y = i / groups, gx = (i - y * groups) * 16;
+                const int w = gx >> 5, sh = gx & 31;
+                unsigned acc = 0u;
+                const int ya = max(0, y - down), yb = min(nc - 1, y + up);
+                for (int ys = ya; ys <= yb; ys++) acc |= hor[ys * wpr + w];
+                const unsigned m16 = (acc >> sh) & 0xffffu;
+                unsigned q[4];
+    #pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const unsigned nib = (m16 >> (4 * u)) & 0xfu;
+                    // spread 4 bits to 4 bytes (0x00 / 0x01 each), then scale by the cell value
+                    const unsigned spread = (nib * 0x00204081u) & 0x01010101u;
+                    q[u] = spread * a.value;
+                }
+                (void)v4;
+                unsigned char *dst = o + (size_t)y * nc + gx;
+                if (gx + 16 <= nc && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
+                    __stcs(reinterpret_cast<uint4 *>(dst), make_uint4(q[0], q[1], q[2], q[3]));
+                } else {
+                    for (int u = 0; u < 16 && gx + u < nc; u++) dst[u] = (unsigned char)((q[u >> 2] >> (8 * (u & 3))) & 0xffu);
+                }
             }
         }
         __syncwarp();

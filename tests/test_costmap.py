@@ -142,6 +142,8 @@ def test_gpu_local_costmap_matches_reference(gold, built):
     from ros2_mpc_b200 import obstacles as ob
     grid = np.unpackbits(gold["lcm_grid_bits"])[:B * 6400].reshape(B, 80, 80) * 100.0
     assert np.array_equal(cm.dilate(grid), ref)
+    # another structuring element takes the kernel's generic passes: same image as the generic dilation of the grid
+    assert np.array_equal(cm.local_costmap(scans, gold["lcm_angles"], 0.05, 2.0, yaw, ksize=(7, 4)), cm.dilate(grid, (7, 4)))
 
 
 @pytest.mark.gpu
