@@ -70,6 +70,10 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) obstacles_kernel(const ObsBuil
         for (int w = lane; w < a.nwords; w += 32) bits[w] = 0u;
         __syncwarp();
         const double *sc = a.scan + (size_t)b * a.n;
+        {   // the warp's next scan on its way into L2 while this one is processed (one 128-byte line per lane)
+            const long long bn = (long long)b + (long long)gridDim.x * OBS_WARPS;
+            if (bn < a.B && lane * 16 < a.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.scan + (size_t)bn * a.n + lane * 16));
+        }
         // ---- cell indices, occupancy bits in rotated np.where order ----
         // (an infinite coordinate would have to be replaced by the scan's largest finite one, utils.py:30-31: that
         //  needs a second pass, taken only if one shows up — the rotation-by-0.0 product turns the infinities of
