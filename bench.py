@@ -406,7 +406,7 @@ def costmap_lines(solver, torch, dev, params, hbm_peak, robots=4096, tile=32, re
     ms = timed(lambda: solver.device_call("b200mpc_dilate_batch_device", G, nc, nc, D(grids.data_ptr()), 10, 10,
                                           D(dimg.data_ptr()), D(stream.cuda_stream)))
     by = 9 * nc * nc
-    out["dilate"] = {"kernel": "dilate_strip_kernel<10,10>", "grids_per_launch": G, "ms_per_launch": ms, "bound": "hbm",
+    out["dilate"] = {"kernel": "dilate_strip_tma_kernel<10,10>", "grids_per_launch": G, "ms_per_launch": ms, "bound": "hbm",
                      "algorithmic_bytes_per_grid": by, "achieved_gbs": by * G / (ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                      "frac": by * G / (ms * 1e-3) / 1e9 / hbm_peak}
     return out

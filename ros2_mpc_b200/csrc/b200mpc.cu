@@ -3299,6 +3299,26 @@ extern "C" int b200mpc_dilate_batch_device(b200mpc_handle *h, int B, int H, int 
             return (size_t)s.obuf_off + (((size_t)TH * TW + 15) & ~(size_t)15);
         };
         smem = layout(H, W);
+        s.raw_bytes = 0; s.bar_off = 0;
+        {
+            // whole grid fetched by the TMA engine (bulk copy of H*W*8 contiguous bytes), two CTAs per SM
+            const size_t raw = (((size_t)H * W * 8) + 127) & ~(size_t)127;
+            const size_t total = raw + smem + 16;
+            const char *tma_env = getenv("B200MPC_DILATE_TMA");
+            if ((W & 1) == 0 && (reinterpret_cast<size_t>(grid) & 15) == 0 && total <= 113 * 1024 && !(tma_env && tma_env[0] == '0')) {
+                s.raw_bytes = (int)raw;
+                s.bar_off = (int)(raw + smem);
+                s.obuf_off += (int)raw;
+                CU_TRY(h, cudaFuncSetAttribute(dilate_strip_tma_kernel<10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+                const int cap = h->sm_count * 2;
+                CU_TRY(h, cudaEventRecord(h->ev0, (cudaStream_t)stream));
+                dilate_strip_tma_kernel<10, 10><<<B < cap ? B : cap, DIL_THREADS, total, (cudaStream_t)stream>>>(s);
+                CU_TRY(h, cudaGetLastError());
+                CU_TRY(h, cudaEventRecord(h->ev1, (cudaStream_t)stream));
+                h->launches++;
+                return 0;
+            }
+        }
         if (smem > 72 * 1024) smem = layout(H < 80 ? H : 80, W < 80 ? W : 80);
         if (smem > 48 * 1024)
             CU_TRY(h, cudaFuncSetAttribute(dilate_strip_kernel<10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));

@@ -154,6 +154,7 @@ struct DilateStripArgs {
     int PS, PT;            // row strides (ints) of the staged tile and of the row maxima, both odd
     int src_rows;          // rows of the staged tile
     int obuf_off;          // byte offset of the output image in shared memory (multiple of 16)
+    int raw_bytes, bar_off; // TMA instance: bytes of the raw float64 grid in front of the int32 tile, offset of the mbarrier
     const double *in;      // [B][H][W]
     unsigned char *out;    // [B][H][W]
 };
@@ -234,9 +235,14 @@ __global__ void __launch_bounds__(DIL_THREADS, 3) dilate_strip_kernel(const Dila
             for (int j = 0; j < DIL_SEG + KW - 1; j++) v[j] = p[j];
             dil_window_max<KW, DIL_SEG>(v);
             int *q = tmp + (r_lo + rr) * PT + s * DIL_SEG;
+            if ((s + 1) * DIL_SEG <= TW) {
 #pragma unroll
-            for (int j = 0; j < DIL_SEG; j++)
-                if (s * DIL_SEG + j < TW) q[j] = v[j];
+                for (int j = 0; j < DIL_SEG; j++) q[j] = v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < DIL_SEG; j++)
+                    if (s * DIL_SEG + j < TW) q[j] = v[j];
+            }
         }
         __syncthreads();
         // columns: consecutive threads take consecutive columns
@@ -247,9 +253,15 @@ __global__ void __launch_bounds__(DIL_THREADS, 3) dilate_strip_kernel(const Dila
 #pragma unroll
             for (int j = 0; j < DIL_SEG + KH - 1; j++) v[j] = p[j * PT];
             dil_window_max<KH, DIL_SEG>(v);
+            unsigned char *ob = obuf + (s * DIL_SEG) * TW + x;
+            if ((s + 1) * DIL_SEG <= TH) {
 #pragma unroll
-            for (int j = 0; j < DIL_SEG; j++)
-                if (s * DIL_SEG + j < TH) obuf[(s * DIL_SEG + j) * TW + x] = (unsigned char)v[j];
+                for (int j = 0; j < DIL_SEG; j++) ob[j * TW] = (unsigned char)v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < DIL_SEG; j++)
+                    if (s * DIL_SEG + j < TH) ob[j * TW] = (unsigned char)v[j];
+            }
         }
         __syncthreads();
         unsigned char *o = a.out + (size_t)b * H * W;
@@ -267,6 +279,123 @@ __global__ void __launch_bounds__(DIL_THREADS, 3) dilate_strip_kernel(const Dila
         }
         // no barrier here: the next tile's staging writes src and the halo rows of tmp only (both last read before the
         // barrier above), and obuf is not written again before two more barriers
+    }
+}
+
+// dilate_strip_tma_kernel<KH, KW> — whole-grid tiles of the strip kernel with the grid fetched by the TMA engine: ONE thread
+// issues a bulk copy (cp.async.bulk global -> shared, completion counted in bytes on an mbarrier) of the next grid's
+// H*W*8 contiguous bytes as soon as the current grid has been converted to int32, so the fetch overlaps the row pass, the
+// column pass and the stores of the current grid; no thread spends registers or issue slots on global loads and none
+// waits for them at the head of a tile (profiles/r2_dilate_strip_ncu_summary.txt: 56 % of the strip kernel's stall samples).
+// Two CTAs per SM (raw grid 51 KB + int32 tile 28 KB + row maxima 29 KB + image 6 KB for 80 x 80).
+__device__ __forceinline__ unsigned dil_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dil_tma_fetch(unsigned bar, unsigned dst, const void *src, unsigned bytes) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the generic-proxy reads of the buffer are done (barrier before)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    for (unsigned off = 0; off < bytes; off += 16384u) {
+        const unsigned n = (bytes - off < 16384u) ? bytes - off : 16384u;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                     "l"(reinterpret_cast<const char *>(src) + off), "r"(n), "r"(bar)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ bool dil_mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+template <int KH, int KW>
+__global__ void __launch_bounds__(DIL_THREADS, 2) dilate_strip_tma_kernel(const DilateStripArgs a) {
+    extern __shared__ __align__(16) unsigned char cm_smem[];
+    constexpr int ah = KH / 2, aw = KW / 2;
+    const int H = a.H, W = a.W, PS = a.PS, PT = a.PT, HW = H * W;
+    const int NSX = (W + DIL_SEG - 1) / DIL_SEG, NSY = (H + DIL_SEG - 1) / DIL_SEG;
+    const double2 *raw2 = reinterpret_cast<const double2 *>(cm_smem);      // [H*W] float64, written by the TMA engine
+    int *src = reinterpret_cast<int *>(cm_smem + a.raw_bytes);             // [H][PS]
+    int *tmp = src + (size_t)H * PS;                                       // [NSY*SEG + KH - 1][PT]
+    unsigned char *obuf = cm_smem + a.obuf_off;                            // [H][W]
+    const unsigned bar = dil_smem_addr(cm_smem + a.bar_off), raw_s = dil_smem_addr(cm_smem);
+    const unsigned bytes = (unsigned)HW * 8u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < H * (KW - 1); i += DIL_THREADS) {
+        const int r = i / (KW - 1), j = i - r * (KW - 1);
+        src[r * PS + (j < aw ? j : W + j)] = DIL_NEG;
+    }
+    for (int i = threadIdx.x; i < (KH - 1) * W; i += DIL_THREADS) {
+        const int j = i / W, x = i - j * W;
+        tmp[(j < ah ? j : H + j) * PT + x] = DIL_NEG;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && (int)blockIdx.x < a.B) dil_tma_fetch(bar, raw_s, a.in + (size_t)blockIdx.x * HW, bytes);
+    const int half = HW >> 1;
+    const int dy = (2 * DIL_THREADS) / W, dx = 2 * DIL_THREADS - dy * W;
+    const int ys = (2 * (int)threadIdx.x) / W, xs = 2 * (int)threadIdx.x - ys * W;
+    unsigned parity = 0;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        while (!dil_mbar_try_wait(bar, parity)) {}
+        parity ^= 1u;
+        {
+            int y = ys, x = xs;
+            for (int i = threadIdx.x; i < half; i += DIL_THREADS) {
+                const double2 v = raw2[i];
+                int *d = src + y * PS + aw + x;
+                d[0] = dil_cvt(v.x); d[1] = dil_cvt(v.y);
+                x += dx; y += dy;
+                if (x >= W) { x -= W; y++; }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && b + (int)gridDim.x < a.B) dil_tma_fetch(bar, raw_s, a.in + (size_t)(b + gridDim.x) * HW, bytes);
+        for (int i = threadIdx.x; i < H * NSX; i += DIL_THREADS) {
+            const int s = i / H, rr = i - s * H;
+            const int *p = src + rr * PS + s * DIL_SEG;
+            int v[DIL_SEG + KW - 1];
+#pragma unroll
+            for (int j = 0; j < DIL_SEG + KW - 1; j++) v[j] = p[j];
+            dil_window_max<KW, DIL_SEG>(v);
+            int *q = tmp + (ah + rr) * PT + s * DIL_SEG;
+            if ((s + 1) * DIL_SEG <= W) {
+#pragma unroll
+                for (int j = 0; j < DIL_SEG; j++) q[j] = v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < DIL_SEG; j++)
+                    if (s * DIL_SEG + j < W) q[j] = v[j];
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < W * NSY; i += DIL_THREADS) {
+            const int s = i / W, x = i - s * W;
+            const int *p = tmp + (s * DIL_SEG) * PT + x;
+            int v[DIL_SEG + KH - 1];
+#pragma unroll
+            for (int j = 0; j < DIL_SEG + KH - 1; j++) v[j] = p[j * PT];
+            dil_window_max<KH, DIL_SEG>(v);
+            unsigned char *ob = obuf + (s * DIL_SEG) * W + x;
+            if ((s + 1) * DIL_SEG <= H) {
+#pragma unroll
+                for (int j = 0; j < DIL_SEG; j++) ob[j * W] = (unsigned char)v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < DIL_SEG; j++)
+                    if (s * DIL_SEG + j < H) ob[j * W] = (unsigned char)v[j];
+            }
+        }
+        __syncthreads();
+        unsigned char *o = a.out + (size_t)b * HW;
+        if ((HW & 15) == 0 && ((reinterpret_cast<size_t>(o) & 15) == 0)) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(obuf);
+            uint4 *d4 = reinterpret_cast<uint4 *>(o);
+            for (int i = threadIdx.x; i < HW >> 4; i += DIL_THREADS) __stcs(d4 + i, s4[i]);
+        } else {
+            for (int i = threadIdx.x; i < HW; i += DIL_THREADS) o[i] = obuf[i];
+        }
+        // (src is next written after the mbarrier wait, tmp after the barrier behind the conversion, obuf after two more)
     }
 }
 
