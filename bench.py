@@ -459,6 +459,14 @@ def variant_a_record(torch, dev, params, local_rank, fp64_peak, steps, do_cpu, a
     ms_single = time_steps([(S1, d3a, s1)], B3, k3)
     kms3 = S1.last_kernel_ms()
     ms_double = time_steps([(S1, d3a, s1), (S2, d3b, s2)], B3, k3)
+    # four handles / streams: a batch's stragglers last about as long as its body, so two batches in flight do not hide them all
+    extra = [(_shim.Solver(p, device=local_rank), dev_buffers(wl3), torch.cuda.Stream(device=dev)) for _ in range(2)]
+    for S, d, st in extra:
+        launch(S, d, B3, st)
+    ms_quad = time_steps([(S1, d3a, s1), (S2, d3b, s2)] + extra, B3, 2 * k3)
+    for S, _, _ in extra:
+        S.close()
+    del extra
     st3 = d3a["status"].cpu().numpy(); it3 = d3a["iters"].cpu().numpy(); ls3 = d3a["ls"].cpu().numpy()
     conv3 = int(np.isin(st3, (0, 1)).sum())
     W3 = float(algorithmic_flops(p, it3, ls3).sum())
@@ -470,6 +478,8 @@ def variant_a_record(torch, dev, params, local_rank, fp64_peak, steps, do_cpu, a
         "double_buffered": {"ms_per_step": ms_double, "value": conv3 / (ms_double * 1e-3), "unit": UNIT,
                             "how": "consecutive batches alternate between two handles / streams: the persistent CTAs of the "
                                    "next batch start on the SMs the stragglers of the previous one have left"},
+        "four_in_flight": {"ms_per_step": ms_quad, "value": conv3 / (ms_quad * 1e-3), "unit": UNIT,
+                           "how": "the same with four handles / streams (a stream of independent 4096-problem batches)"},
         "roofline": {"bound": "fp64", "achieved": W3 / (ms_double * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": W3 / (ms_double * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
                      "algorithmic_flops_per_launch": W3, "traffic": None},
