@@ -3371,9 +3371,21 @@ extern "C" int b200mpc_inflate_batch_device(b200mpc_handle *h, int B, int H, int
     costmap_tile(H, W, 2 * cells_inflation, 2 * cells_inflation, 1, a.TH, a.TW, smem, false);
     const int n = 2 * cells_inflation + 1;
     smem += (size_t)n * n * 8 + 16;
-    if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const long long tiles = (long long)B * ((H + a.TH - 1) / a.TH) * ((W + a.TW - 1) / a.TW);
     const long long cap = (long long)h->sm_count * 6;
+    if (cells_inflation <= 15) {
+        // sources as bit rows (a window row of <= 31 bits is one funnel shift)
+        const size_t SH = (size_t)a.TH + 2 * cells_inflation, SW = (size_t)a.TW + 2 * cells_inflation;
+        const size_t sb = SH * SW * 8 + (size_t)n * n * 8 + SH * ((SW + 31) / 32 + 1) * 4;
+        if (sb > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(inflate_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU_TRY(h, cudaEventRecord(h->ev0, (cudaStream_t)stream));
+        inflate_bits_kernel<<<(int)(tiles < cap ? tiles : cap), COSTMAP_THREADS, sb, (cudaStream_t)stream>>>(a);
+        CU_TRY(h, cudaGetLastError());
+        CU_TRY(h, cudaEventRecord(h->ev1, (cudaStream_t)stream));
+        h->launches++;
+        return 0;
+    }
+    if (smem > 48 * 1024) CU_TRY(h, cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU_TRY(h, cudaEventRecord(h->ev0, (cudaStream_t)stream));
     inflate_kernel<<<(int)(tiles < cap ? tiles : cap), COSTMAP_THREADS, smem, (cudaStream_t)stream>>>(a);
     CU_TRY(h, cudaGetLastError());

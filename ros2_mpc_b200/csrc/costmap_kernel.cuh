@@ -449,6 +449,66 @@ __global__ void __launch_bounds__(COSTMAP_THREADS) inflate_kernel(const InflateA
     }
 }
 
+// inflate_bits_kernel — the same gather for cells_inflation <= 15 with the stamping sources as BIT rows: a window row is one
+// funnel shift of two words, and only its set bits are visited.  Sources are sparse (obstacle cells), so a cell costs
+// 2c+1 window extractions instead of (2c+1)^2 byte tests.  Staging is one warp per tile row: coalesced loads, the source
+// predicate of 32 cells becomes one word by a warp vote.
+__global__ void __launch_bounds__(COSTMAP_THREADS) inflate_bits_kernel(const InflateArgs a) {
+    extern __shared__ __align__(16) unsigned char cm_smem[];
+    const int c = a.c, n = 2 * c + 1;
+    const int SH = a.TH + 2 * c, SW = a.TW + 2 * c;
+    const int WPR = (SW + 31) / 32 + 1;                           // + one word so that the funnel shift may read w + 1
+    double *src = reinterpret_cast<double *>(cm_smem);            // [SH][SW] original values
+    double *Ms = src + (size_t)SH * SW;                           // [n][n]
+    unsigned *obits = reinterpret_cast<unsigned *>(Ms + (size_t)n * n); // [SH][WPR] bit cc of row r = staged cell (r, cc) is a source
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = COSTMAP_THREADS / 32;
+    const int tiles_x = (a.W + a.TW - 1) / a.TW, tiles_y = (a.H + a.TH - 1) / a.TH;
+    const int per_grid = tiles_x * tiles_y;
+    const unsigned nmask = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
+    for (int i = threadIdx.x; i < n * n; i += COSTMAP_THREADS) Ms[i] = a.M[i];
+    for (int r = threadIdx.x; r < SH; r += COSTMAP_THREADS) obits[r * WPR + WPR - 1] = 0u;
+    for (long long t = blockIdx.x; t < (long long)a.B * per_grid; t += gridDim.x) {
+        const int b = (int)(t / per_grid), tt = (int)(t % per_grid);
+        const int y0 = (tt / tiles_x) * a.TH, x0 = (tt % tiles_x) * a.TW;
+        const double *g = a.in + (size_t)b * a.H * a.W;
+        for (int r = wid; r < SH; r += nw) {
+            const int y = y0 + r - c;
+            const bool yin = (y >= 0 && y < a.H), ysrc = (y >= c && y + c < a.H);
+            for (int c0 = 0; c0 < SW; c0 += 32) {
+                const int cc = c0 + lane, x = x0 + cc - c;
+                const bool inside = yin && cc < SW && x >= 0 && x < a.W;
+                const double v = inside ? __ldcs(g + (size_t)y * a.W + x) : 1.0;
+                if (cc < SW) src[r * SW + cc] = v;
+                // a source: original value exactly 0 and the whole window inside the grid (costmap.py:10-14)
+                const unsigned word = __ballot_sync(0xffffffffu, inside && ysrc && v == 0.0 && x >= c && x + c < a.W);
+                if (lane == 0) obits[r * WPR + (c0 >> 5)] = word;
+            }
+        }
+        __syncthreads();
+        double *o = a.out + (size_t)b * a.H * a.W;
+        for (int i = threadIdx.x; i < a.TH * a.TW; i += COSTMAP_THREADS) {
+            const int r = i / a.TW, cc = i - r * a.TW;
+            const int y = y0 + r, x = x0 + cc;
+            if (y >= a.H || x >= a.W) continue;
+            double m = src[(size_t)(r + c) * SW + cc + c];
+            const int w = cc >> 5, sh = cc & 31;
+            // window bit j <-> staged column cc + j <-> dx = c - j, inflation-matrix entry [dy + c][2c - j]
+            for (int dy = -c; dy <= c; dy++) {
+                const unsigned *brow = obits + (r + c - dy) * WPR + w;
+                unsigned bits = __funnelshift_r(brow[0], brow[1], sh) & nmask;
+                const double *mrow = Ms + (size_t)(dy + c) * n + 2 * c;
+                while (bits) {
+                    const int j = __ffs(bits) - 1;
+                    m = fmin(m, mrow[-j]);
+                    bits &= bits - 1;
+                }
+            }
+            o[(size_t)y * a.W + x] = m;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- scan -> occupancy bits -> dilated uint8 image, one warp per robot ------------------------------------------------
 struct LocalCostmapArgs {
     int B, n, nc, kh, kw, wpr;   // wpr = 32-bit words per grid row

@@ -101,6 +101,17 @@ def test_gpu_inflate_matches_reference(gold, built):
     out = cm.inflate_global(batch, M, c)
     for k in range(3):
         assert np.array_equal(out[k], np_inflate(batch[k], M, c))
+    # an inflation matrix without any symmetry (an index flip would hide behind the reference's ring matrix), on the bit-row
+    # kernel (cells_inflation <= 15: 3, 15) and on the generic one (16); grids wider than one tile and narrower than a window
+    rng = np.random.default_rng(11)
+    for (H, W, cc) in ((80, 80, 3), (70, 150, 15), (90, 140, 16), (9, 40, 4), (33, 33, 0)):
+        gg = np.full((2, H, W), 100.0)
+        gg[rng.random((2, H, W)) < 0.2] = 37.5
+        gg[rng.random((2, H, W)) < 0.02] = 0.0
+        Mr = np.round(rng.uniform(1, 99, (2 * cc + 1, 2 * cc + 1)), 3)
+        oo = cm.inflate_global(gg, Mr, cc)
+        for k in range(2):
+            assert np.array_equal(oo[k], np_inflate(gg[k], Mr, cc)), (H, W, cc)
     for i in range(int(gold["n_local"])):
         o = cm.inflate_local(g, M, c, gold[f"local{i}_pos"], int(gold[f"local{i}_size"]))
         assert o.shape == gold[f"local{i}_out"].shape and np.array_equal(o, gold[f"local{i}_out"]), i
