@@ -409,6 +409,19 @@ def costmap_lines(solver, torch, dev, params, hbm_peak, robots=4096, tile=32, re
     out["dilate"] = {"kernel": "dilate_strip_tma_kernel<10,10>", "grids_per_launch": G, "ms_per_launch": ms, "bound": "hbm",
                      "algorithmic_bytes_per_grid": by, "achieved_gbs": by * G / (ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                      "frac": by * G / (ms * 1e-3) / 1e9 / hbm_peak}
+    # inflate_global (utils/costmap.py:5-20) with the reference's gradient matrix, inflation_radius / resolution cells: grids of
+    # free cells (100) with 1 % obstacle cells (0 = stamping sources)
+    from ros2_mpc_b200 import costmap as cmod  # noqa: PLC0415
+    ci = max(1, int(round(params["inflation_radius"] / params["resolution"])))
+    M = t(cmod.get_inflation_matrix(ci))
+    igr = torch.where(torch.rand((G, nc, nc), device=dev) < 0.01, 0.0, 100.0).to(torch.float64)
+    iout = torch.empty_like(igr)
+    ms = timed(lambda: solver.device_call("b200mpc_inflate_batch_device", G, nc, nc, D(igr.data_ptr()), D(M.data_ptr()), ci,
+                                          D(iout.data_ptr()), D(stream.cuda_stream)))
+    by = 16 * nc * nc
+    out["inflate"] = {"kernel": "inflate_bits_kernel", "grids_per_launch": G, "cells_inflation": ci, "ms_per_launch": ms, "bound": "hbm",
+                      "algorithmic_bytes_per_grid": by, "achieved_gbs": by * G / (ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                      "frac": by * G / (ms * 1e-3) / 1e9 / hbm_peak}
     return out
 
 

@@ -3373,7 +3373,8 @@ extern "C" int b200mpc_inflate_batch_device(b200mpc_handle *h, int B, int H, int
     smem += (size_t)n * n * 8 + 16;
     const long long tiles = (long long)B * ((H + a.TH - 1) / a.TH) * ((W + a.TW - 1) / a.TW);
     const long long cap = (long long)h->sm_count * 6;
-    if (cells_inflation <= 15) {
+    const char *ib_env = getenv("B200MPC_INFLATE_BITS");
+    if (cells_inflation <= 15 && !(ib_env && ib_env[0] == '0')) {
         // sources as bit rows (a window row of <= 31 bits is one funnel shift)
         const size_t SH = (size_t)a.TH + 2 * cells_inflation, SW = (size_t)a.TW + 2 * cells_inflation;
         const size_t sb = SH * SW * 8 + (size_t)n * n * 8 + SH * ((SW + 31) / 32 + 1) * 4;
