@@ -123,17 +123,20 @@ struct EvalArgs {
 };
 
 // ---- warp reductions (butterfly: every lane ends with the same bits) ------------------------------------
-__device__ __forceinline__ double wsum(double v) {
+#ifndef WRED_INLINE
+#define WRED_INLINE __forceinline__
+#endif
+__device__ WRED_INLINE double wsum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
-__device__ __forceinline__ double wmax(double v) {
+__device__ WRED_INLINE double wmax(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
     return v;
 }
-__device__ __forceinline__ double wmin(double v) {
+__device__ WRED_INLINE double wmin(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
     return v;
