@@ -1476,11 +1476,27 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L, co
 // lock-step is a run-time choice only for the instances that can carry the obstacle cost
 #define TPP_CTA_SYNC ((SPEC == TPP_SPEC_RK4_GOAL || SPEC == TPP_SPEC_EULER_TRAJ) ? true : (T.cta_sync != 0))
 #define TPP_HAND (TPP_EXP_NO_HANDOVER ? false : (A.hand_rec != nullptr))
+// cta_sync == 2 (instances with a run-time choice only): lock-step among the warps that share a scheduler (warp index mod 4:
+// three of the twelve warps) — they share that scheduler's instruction buffer, and a barrier of three waits for less
+// imbalance than a barrier of twelve.  Named barriers 1-4, 32 * (warps / 4) threads each.
+__device__ __forceinline__ void tpp_group_sync(int wid) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (wid & 3)), "r"((TPP_THREADS / 32 / 4) * 32) : "memory");
+}
+__device__ __forceinline__ bool tpp_group_and(int wid, bool pred) {
+    int r;
+    asm volatile("{\n.reg .pred p, q;\nsetp.ne.s32 q, %3, 0;\nbar.red.and.pred p, %1, %2, q;\nselp.s32 %0, 1, 0, p;\n}"
+                 : "=r"(r) : "r"(1 + (wid & 3)), "r"((TPP_THREADS / 32 / 4) * 32), "r"((int)pred) : "memory");
+    return r != 0;
+}
+// (compile-time off for the instances without the obstacle cost: measured there, the group barrier is slower than the CTA's,
+// 205.9 vs 186 ms per 1 M problems, and the mere run-time choice costs those instances 112 B of spills and 13 %)
+#define TPP_GROUP_SYNC ((SPEC == TPP_SPEC_RK4_GOAL || SPEC == TPP_SPEC_EULER_TRAJ) ? false : (T.cta_sync == 2))
 #if TPP_SYNC == 1
-#define TPP_BLOCK_SYNC()                     \
-    do {                                     \
-        if (TPP_CTA_SYNC) __syncthreads();   \
-        else __syncwarp();                   \
+#define TPP_BLOCK_SYNC()                          \
+    do {                                          \
+        if (TPP_GROUP_SYNC) tpp_group_sync(wid);  \
+        else if (TPP_CTA_SYNC) __syncthreads();   \
+        else __syncwarp();                        \
     } while (0)
 #else
 #define TPP_BLOCK_SYNC() __syncwarp() /* TPP_SYNC == 2: the CTA only meets once per trip (at the exit test) */
@@ -1660,7 +1676,8 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             if (nm) tpp_obstacle_block<SPEC>(P, A, wbase, nm, cur, cur, L.b, L.n_eff, 0.0, -1, 0, olist);
         }
 #if TPP_SYNC
-        if (TPP_CTA_SYNC ? __syncthreads_and(L.phase == PH_DONE) : __all_sync(FULL, L.phase == PH_DONE)) break;
+        if (TPP_GROUP_SYNC ? tpp_group_and(wid, L.phase == PH_DONE)
+                           : (TPP_CTA_SYNC ? (bool)__syncthreads_and(L.phase == PH_DONE) : (bool)__all_sync(FULL, L.phase == PH_DONE))) break;
 #else
         if (__all_sync(FULL, L.phase == PH_DONE)) break;
 #endif
