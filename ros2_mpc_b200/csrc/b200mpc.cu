@@ -2446,7 +2446,7 @@ extern "C" b200mpc_handle *b200mpc_create(const b200mpc_params *p, int device) {
     // 181.7 / 165.5 / 174.7 ms with 1 / 2 / 3 executions, variant C 181.7 -> 173.7 ms, variant A (262 144) 895 -> 863 ms
     h->tpp_b_passes = 2;
     if (const char *eb = getenv("B200MPC_LANE_BPASSES")) h->tpp_b_passes = std::max(1, atoi(eb));
-    if (const char *es = getenv("B200MPC_LANE_SYNC")) h->tpp_cta_sync = (es[0] == '2') ? 2 : (es[0] == '1');
+    if (const char *es = getenv("B200MPC_LANE_SYNC")) h->tpp_cta_sync = (es[0] >= '0' && es[0] <= '3') ? es[0] - '0' : h->tpp_cta_sync;
     h->lane_fused = B200MPC_LANE_FUSED_DEFAULT;
     if (const char *ef = getenv("B200MPC_LANE_FUSED")) h->lane_fused = (ef[0] == '1');
     if (p->obs_form != B200MPC_OBS_NONE) h->lane_fused = 0; // the two-sweep kernel has no obstacle cost

@@ -1479,22 +1479,25 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L, co
 // cta_sync == 2 (instances with a run-time choice only): lock-step among the warps that share a scheduler (warp index mod 4:
 // three of the twelve warps) — they share that scheduler's instruction buffer, and a barrier of three waits for less
 // imbalance than a barrier of twelve.  Named barriers 1-4, 32 * (warps / 4) threads each.
-__device__ __forceinline__ void tpp_group_sync(int wid) {
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + (wid & 3)), "r"((TPP_THREADS / 32 / 4) * 32) : "memory");
+// (cta_sync == 3: two groups, even and odd warps — six warps on two schedulers each; measured against the groups of three)
+__device__ __forceinline__ void tpp_group_sync(int wid, int mode) {
+    const int gm = (mode == 3) ? 1 : 3;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (wid & gm)), "r"((TPP_THREADS / 32 / (gm + 1)) * 32) : "memory");
 }
-__device__ __forceinline__ bool tpp_group_and(int wid, bool pred) {
+__device__ __forceinline__ bool tpp_group_and(int wid, int mode, bool pred) {
     int r;
+    const int gm = (mode == 3) ? 1 : 3;
     asm volatile("{\n.reg .pred p, q;\nsetp.ne.s32 q, %3, 0;\nbar.red.and.pred p, %1, %2, q;\nselp.s32 %0, 1, 0, p;\n}"
-                 : "=r"(r) : "r"(1 + (wid & 3)), "r"((TPP_THREADS / 32 / 4) * 32), "r"((int)pred) : "memory");
+                 : "=r"(r) : "r"(1 + (wid & gm)), "r"((TPP_THREADS / 32 / (gm + 1)) * 32), "r"((int)pred) : "memory");
     return r != 0;
 }
 // (compile-time off for the instances without the obstacle cost: measured there, the group barrier is slower than the CTA's,
 // 205.9 vs 186 ms per 1 M problems, and the mere run-time choice costs those instances 112 B of spills and 13 %)
-#define TPP_GROUP_SYNC ((SPEC == TPP_SPEC_RK4_GOAL || SPEC == TPP_SPEC_EULER_TRAJ) ? false : (T.cta_sync == 2))
+#define TPP_GROUP_SYNC ((SPEC == TPP_SPEC_RK4_GOAL || SPEC == TPP_SPEC_EULER_TRAJ) ? false : (T.cta_sync >= 2))
 #if TPP_SYNC == 1
 #define TPP_BLOCK_SYNC()                          \
     do {                                          \
-        if (TPP_GROUP_SYNC) tpp_group_sync(wid);  \
+        if (TPP_GROUP_SYNC) tpp_group_sync(wid, T.cta_sync);  \
         else if (TPP_CTA_SYNC) __syncthreads();   \
         else __syncwarp();                        \
     } while (0)
@@ -1676,7 +1679,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             if (nm) tpp_obstacle_block<SPEC>(P, A, wbase, nm, cur, cur, L.b, L.n_eff, 0.0, -1, 0, olist);
         }
 #if TPP_SYNC
-        if (TPP_GROUP_SYNC ? tpp_group_and(wid, L.phase == PH_DONE)
+        if (TPP_GROUP_SYNC ? tpp_group_and(wid, T.cta_sync, L.phase == PH_DONE)
                            : (TPP_CTA_SYNC ? (bool)__syncthreads_and(L.phase == PH_DONE) : (bool)__all_sync(FULL, L.phase == PH_DONE))) break;
 #else
         if (__all_sync(FULL, L.phase == PH_DONE)) break;
