@@ -1493,11 +1493,15 @@ __device__ __forceinline__ bool tpp_group_and(int wid, int mode, bool pred) {
 }
 // (compile-time off for the instances without the obstacle cost: measured there, the group barrier is slower than the CTA's,
 // 205.9 vs 186 ms per 1 M problems, and the mere run-time choice costs those instances 112 B of spills and 13 %)
-#define TPP_GROUP_SYNC ((SPEC == TPP_SPEC_RK4_GOAL || SPEC == TPP_SPEC_EULER_TRAJ) ? false : (T.cta_sync >= 2))
+#ifndef TPP_STATIC_GROUP
+#define TPP_STATIC_GROUP 0 /* build knob: 2 / 3 = the instances without the obstacle cost use the group barrier of that mode */
+#endif
+#define TPP_GROUP_SYNC ((SPEC == TPP_SPEC_RK4_GOAL || SPEC == TPP_SPEC_EULER_TRAJ) ? (TPP_STATIC_GROUP != 0) : (T.cta_sync >= 2))
+#define TPP_GROUP_MODE ((SPEC == TPP_SPEC_RK4_GOAL || SPEC == TPP_SPEC_EULER_TRAJ) ? TPP_STATIC_GROUP : T.cta_sync)
 #if TPP_SYNC == 1
 #define TPP_BLOCK_SYNC()                          \
     do {                                          \
-        if (TPP_GROUP_SYNC) tpp_group_sync(wid, T.cta_sync);  \
+        if (TPP_GROUP_SYNC) tpp_group_sync(wid, TPP_GROUP_MODE);  \
         else if (TPP_CTA_SYNC) __syncthreads();   \
         else __syncwarp();                        \
     } while (0)
@@ -1679,7 +1683,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
             if (nm) tpp_obstacle_block<SPEC>(P, A, wbase, nm, cur, cur, L.b, L.n_eff, 0.0, -1, 0, olist);
         }
 #if TPP_SYNC
-        if (TPP_GROUP_SYNC ? tpp_group_and(wid, T.cta_sync, L.phase == PH_DONE)
+        if (TPP_GROUP_SYNC ? tpp_group_and(wid, TPP_GROUP_MODE, L.phase == PH_DONE)
                            : (TPP_CTA_SYNC ? (bool)__syncthreads_and(L.phase == PH_DONE) : (bool)__all_sync(FULL, L.phase == PH_DONE))) break;
 #else
         if (__all_sync(FULL, L.phase == PH_DONE)) break;
