@@ -1773,7 +1773,7 @@ __global__ void __launch_bounds__(TPP_THREADS, B200MPC_TPP_MIN_CTAS) mpc_solve_t
 
         // ---- block O: obstacle sums of the points sweep T is about to evaluate (into the cache rows of the other buffer) ----
         if (TPP_HAS_OBS(P)) {
-            TPP_BLOCK_SYNC();
+            TPP_BLOCK_SYNC(); // (without this meeting: 736.5 vs 740.7 ms per 262 144 problems — immaterial)
             const int tm = L.tmode;
             const unsigned om = __ballot_sync(FULL, tpp_opaque(L.phase) == PH_T);
             if (om) {
