@@ -1479,6 +1479,7 @@ __device__ __forceinline__ void tpp_iterate_top(const KParams &P, TppLane &L, co
 // cta_sync == 2 (instances with a run-time choice only): lock-step among the warps that share a scheduler (warp index mod 4:
 // three of the twelve warps) — they share that scheduler's instruction buffer, and a barrier of three waits for less
 // imbalance than a barrier of twelve.  Named barriers 1-4, 32 * (warps / 4) threads each.
+static_assert((TPP_THREADS / 32) % 4 == 0, "the scheduler-group barriers count on the same number of warps per scheduler");
 // (cta_sync == 3: two groups, even and odd warps — six warps on two schedulers each; measured against the groups of three)
 __device__ __forceinline__ void tpp_group_sync(int wid, int mode) {
     const int gm = (mode == 3) ? 1 : 3;
