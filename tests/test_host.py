@@ -131,3 +131,27 @@ def test_gpu_only_helpers_fail_loudly_without_a_device(built):
     # the numpy mirror itself (workload generation, checker) of course runs
     ox, oy, cnt = ob.get_obstacles(scan, np.array([0.0, 6.28]), 2.0, 0.05, np.zeros((1, 2)), np.zeros(1), 160)
     assert ox.shape == (1, 160) and cnt[0] > 0
+
+
+def test_bench_strong_scaling_shards_tile_the_batch():
+    """bench.py's strong-scaling leg: rank r of n takes the seed blocks [r*S/n, (r+1)*S/n) of ONE batch — the shards, put
+    end to end, are the whole batch (every array), for the variants with and without per-problem obstacle lists."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    y = load_params()
+    robots, seeds, world = 16, 8, 4
+    for variant in ("B", "A", "C"):
+        whole = bench.build_workload(variant, robots, seeds, 0, y)
+        parts = [bench.build_workload(variant, robots, seeds, 0, y, seed_lo=r * seeds // world, seed_hi=(r + 1) * seeds // world)
+                 for r in range(world)]
+        assert sum(p["B"] for p in parts) == whole["B"] == robots * seeds
+        for k in ("x0", "xref", "uref", "u_init", "obs_x", "obs_y"):
+            if whole[k] is None:
+                assert all(p[k] is None for p in parts)
+            else:
+                assert np.array_equal(np.concatenate([p[k] for p in parts]), whole[k]), (variant, k)
+        # weak scaling: another rank's batch differs in its warm-start seeds only
+        other = bench.build_workload(variant, robots, seeds, seeds, y)
+        assert np.array_equal(other["x0"], whole["x0"]) and not np.array_equal(other["u_init"], whole["u_init"])
