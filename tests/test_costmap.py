@@ -193,3 +193,31 @@ def test_gpu_get_headings_matches_reference(built):
     xy = np.stack([g["path0_xy"], g["path0_xy"][::-1]])
     hb, vb, ob_ = rf.get_headings(xy, 0.2)
     assert hb.shape == (2, len(g["path0_xy"])) and np.array_equal(vb[0], g["path0_velocity"])
+
+
+def test_window_maximum_by_doubling_is_the_window_maximum():
+    """The strip kernels' register scheme (costmap_kernel.cuh: dil_window_max / lcm_window_or), restated: in-place doubling to the
+    largest power of two P <= K, then one combine of two overlapping windows of P.  Any K up to 32, maxima and ORs."""
+    rng = np.random.default_rng(3)
+    nout = 20
+    for K in range(1, 33):
+        ln = nout + K - 1
+        P = 1 << (K.bit_length() - 1)
+        for op, v in ((max, list(rng.integers(-1000, 1000, ln))), (lambda a, b: a | b, list(rng.integers(0, 1 << 32, ln)))):
+            ref = v[:]
+            want = []
+            for t in range(nout):
+                acc = ref[t]
+                for j in range(1, K):
+                    acc = op(acc, ref[t + j])
+                want.append(acc)
+            q = 1
+            while q < P:
+                for j in range(ln):
+                    if j + 2 * q <= ln:
+                        v[j] = op(v[j], v[j + q])
+                q <<= 1
+            if K > P:
+                for t in range(nout):
+                    v[t] = op(v[t], v[t + K - P])
+            assert v[:nout] == want, K
